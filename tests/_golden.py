@@ -1,0 +1,65 @@
+"""Load a golden case (tests/golden/*.npz, written by tests/golden/make_golden.py from the
+unmodified reference) and turn it into oracle objects / injection sequences."""
+import json
+import os
+
+import numpy as np
+
+from oracle import npbnn_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CHAIN_CASES = ["c1_classify", "c2_regress_emp1", "c2_regress_emp0", "syn_swish_cauchy", "syn_genrelu_laplace",
+               "syn_uniform_bound", "syn_classw_temp", "syn_instw", "syn_adapt", "syn_block_mask",
+               "syn_regress_error"]
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    return z, meta
+
+
+def n_layers(meta):
+    return len(meta["n_nodes"]) + 1
+
+
+def build_model(z, meta) -> orc.Model:
+    nl = n_layers(meta)
+    weights = [np.array(z["w0_%d" % i]) for i in range(nl)]
+    mode = meta["mode"]
+    labels = z["labels"].astype(np.int64) if mode == "classification" else z["labels"].astype(np.float64)
+    lt = z["labels_test"]
+    labels_test = lt.astype(np.int64) if mode == "classification" else lt.astype(np.float64)
+    mask = [np.array(z["mask_%d" % i]) for i in range(nl)] if "mask_0" in z.files else None
+    return orc.Model(
+        x=np.array(z["x"]), labels=labels, weights=weights, act=meta["act"],
+        alphas=np.array(meta["alphas"]) if meta.get("alphas") else None, mode=mode, prior=meta["prior"],
+        prior_scale=np.ones(nl) * meta["p_scale"], w_bound=meta["w_bound"], mask=mask,
+        class_w=np.array(z["class_w"]) if "class_w" in z.files else None,
+        inst_w=np.array(z["inst_w"]) if "inst_w" in z.files else None,
+        empirical_error=bool(meta.get("empirical_error", False)),
+        error_prm=np.ones(labels.shape[1]) if mode == "regression" else 1.0,
+        x_test=np.array(z["x_test"]) if len(z["x_test"]) else None,
+        labels_test=labels_test if len(z["x_test"]) else None)
+
+
+def build_sampler(m, meta) -> orc.Sampler:
+    return orc.make_sampler(m, update_f=meta["update_f"], update_ws=meta["update_ws"],
+                            temperature=meta["temperature"], n_iteration=meta["n_iteration"],
+                            lik_temp=meta["lik_temp"], adapt_f=meta["adapt_f"], adapt_fM=meta["adapt_fM"],
+                            adapt_freq=meta["adapt_freq"])
+
+
+def injection(z, meta, t) -> orc.StepInjection:
+    nl = n_layers(meta)
+    layers = []
+    for i in range(nl):
+        off = z["prop_l%d_off" % i]
+        a, b = int(off[t]), int(off[t + 1])
+        if z["steps_proposed"][t][i]:
+            layers.append((z["prop_l%d_ix" % i][a:b].astype(np.int64), z["prop_l%d_iy" % i][a:b].astype(np.int64),
+                           z["prop_l%d_dz" % i][a:b]))
+        else:
+            layers.append(None)
+    return orc.StepInjection(rr=z["steps_rr"][t], layers=layers, log_u=float(z["steps_log_u"][t]))

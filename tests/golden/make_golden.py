@@ -1,0 +1,406 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONPATH=/root/reference PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference has no tests of its own, so parity is pinned to what
+the reference code itself computes here.  Randomness is recorded, not re-derived: the MCMC
+object's generator (`mcmc._rs`, BNN_env.py:362) is wrapped by a proxy that logs every
+integers()/normal()/random() call, so each MH iteration's proposal indices, increments and
+accept uniform can be replayed into the oracle and the CUDA path ("identical injected
+weights and proposals", BASELINE.json north_star).
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, "/root/reference")
+import np_bnn as bn  # noqa: E402  (the reference)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+EX = "/root/reference/example_files"
+
+
+class RecRNG:
+    """Recording proxy around numpy Generator (only the methods mh_step/UpdateNormal call)."""
+
+    def __init__(self, rng):
+        self._rng = rng
+        self.log = []
+
+    def integers(self, *a, **k):
+        v = self._rng.integers(*a, **k)
+        self.log.append(("integers", np.array(v)))
+        return v
+
+    def normal(self, *a, **k):
+        v = self._rng.normal(*a, **k)
+        self.log.append(("normal", np.array(v)))
+        return v
+
+    def random(self, *a, **k):
+        v = self._rng.random(*a, **k)
+        self.log.append(("random", np.array(v)))
+        return v
+
+
+def quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+def record_chain(bnn, mcmc, n_steps, out, prefix=""):
+    """Run n_steps of the reference's mh_step, recording injections and outcomes."""
+    rec = RecRNG(mcmc._rs)
+    mcmc._rs = rec
+    lik_log, prior_log = [], []
+    lik_f = mcmc._likelihood_f
+
+    def lik_wrap(*a, **k):
+        v = lik_f(*a, **k)
+        lik_log.append(v)
+        return v
+
+    mcmc._likelihood_f = lik_wrap
+    prior_f = bnn.calc_prior
+
+    def prior_wrap(*a, **k):
+        v = prior_f(*a, **k)
+        prior_log.append(v)
+        return v
+
+    bnn.calc_prior = prior_wrap
+    nl = bnn._n_layers
+    out[prefix + "n_steps"] = n_steps
+    out[prefix + "init_logLik"] = mcmc._logLik
+    out[prefix + "init_logPrior"] = mcmc._logPrior
+    out[prefix + "init_accuracy"] = mcmc._accuracy
+    out[prefix + "init_test_accuracy"] = mcmc._test_accuracy
+    out[prefix + "init_label_acc"] = np.asarray(mcmc._label_acc, dtype=np.float64)
+    out[prefix + "init_label_freq"] = np.asarray(mcmc._label_freq, dtype=np.float64)
+    out[prefix + "init_update_n"] = np.asarray(mcmc._update_n)
+    for i in range(nl):
+        out[prefix + "w0_%d" % i] = np.array(bnn._w_layers[i])
+    per_step = {}      # key -> list over steps (stacked at the end)
+    ragged = {i: {"ix": [], "iy": [], "dz": [], "off": [0]} for i in range(nl)}
+
+    def put(key, v):
+        per_step.setdefault(key, []).append(np.asarray(v))
+
+    for t in range(n_steps):
+        rec.log.clear(); lik_log.clear(); prior_log.clear()
+        quiet(mcmc.mh_step, bnn)
+        log = list(rec.log)
+        assert log[0][0] == "random" and log[0][1].shape == (nl,), log[0]
+        assert log[-1][0] == "random" and log[-1][1].shape == ()
+        rr = log[0][1]
+        body = log[1:-1]
+        assert len(body) % 3 == 0
+        # which layers were proposed: same rule as BNN_env.py:446-457 (freq_indicator == 0 here)
+        r2 = rr.copy(); r2[np.argmin(r2)] = 0
+        proposed = []
+        bi = 0
+        # the freq_layer_update used in THIS step is the post-adaptation one, which equals the
+        # value stored on the object after the step
+        flu = np.asarray(mcmc._freq_layer_update)
+        for i in range(nl):
+            if r2[i] < flu[i]:
+                ix, iy, dz = body[bi][1], body[bi + 1][1], body[bi + 2][1]
+                assert body[bi][0] == "integers" and body[bi + 2][0] == "normal"
+                ragged[i]["ix"].append(ix.astype(np.int32))
+                ragged[i]["iy"].append(iy.astype(np.int32))
+                ragged[i]["dz"].append(dz)
+                proposed.append(1)
+                bi += 3
+            else:
+                proposed.append(0)
+            ragged[i]["off"].append(ragged[i]["off"][-1] + (len(ragged[i]["ix"][-1]) if proposed[-1] else 0))
+        assert bi == len(body), (bi, len(body))
+        put("rr", rr)
+        put("proposed", np.array(proposed, dtype=np.int32))
+        put("log_u", np.log(log[-1][1]))
+        put("logLik_prime", lik_log[-1] if lik_log else 0.0)
+        put("logPrior_prime", prior_log[-1])
+        put("accepted", mcmc._last_accepted)
+        put("logLik", mcmc._logLik)
+        put("logPrior", mcmc._logPrior)
+        put("logPost", mcmc._logPost)
+        put("accuracy", mcmc._accuracy)
+        put("test_accuracy", mcmc._test_accuracy)
+        put("label_acc", np.asarray(mcmc._label_acc, dtype=np.float64))
+        put("label_freq", np.asarray(mcmc._label_freq, dtype=np.float64))
+        put("acceptance_rate", mcmc._acceptance_rate)
+        put("update_n", np.asarray(mcmc._update_n))
+        put("update_f", np.asarray(mcmc._update_f, dtype=np.float64))
+        put("update_ws", np.array([w.flat[0] for w in mcmc._update_ws]))
+        put("freq_layer_update", flu)
+        if bnn._estimation_mode == "regression":
+            put("error_prm", np.asarray(bnn._error_prm, dtype=np.float64) * np.ones(bnn._size_output))
+    for k, v in per_step.items():
+        out[prefix + "steps_" + k] = np.stack(v)
+    for i in range(nl):
+        r = ragged[i]
+        out[prefix + "prop_l%d_off" % i] = np.array(r["off"], dtype=np.int64)
+        out[prefix + "prop_l%d_ix" % i] = np.concatenate(r["ix"]) if r["ix"] else np.zeros(0, np.int32)
+        out[prefix + "prop_l%d_iy" % i] = np.concatenate(r["iy"]) if r["iy"] else np.zeros(0, np.int32)
+        out[prefix + "prop_l%d_dz" % i] = np.concatenate(r["dz"]) if r["dz"] else np.zeros(0)
+        out[prefix + "wN_%d" % i] = np.array(bnn._w_layers[i])
+    out[prefix + "yN"] = np.array(mcmc._y)
+
+
+def save(name, out, meta):
+    out = dict(out)
+    out["meta"] = np.array(json.dumps(meta))
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%.1f kB, %d arrays)" % (path, os.path.getsize(path) / 1e3, len(out)))
+
+
+def store_data(out, dat):
+    out["x"] = np.asarray(dat["data"], dtype=np.float64)
+    out["labels"] = np.asarray(dat["labels"])
+    out["x_test"] = np.asarray(dat["test_data"], dtype=np.float64) if len(dat["test_data"]) else np.zeros((0, out["x"].shape[1]))
+    out["labels_test"] = np.asarray(dat["test_labels"]) if len(dat["test_labels"]) else np.zeros((0,))
+
+
+# ---------------------------------------------------------------------------------------
+def case_c1(n_steps=120):
+    """BASELINE config 1: bnn_classify.py:15-70 on the shipped example files."""
+    dat = quiet(bn.get_data, EX + "/data_features.txt", EX + "/data_labels.txt", seed=1234, testsize=0.1,
+                all_class_in_testset=1, header=1, cv=0, instance_id=1)
+    np.random.seed(1234)
+    bnn = quiet(bn.npBNN, dat, n_nodes=[5, 5], use_class_weights=0, actFun=bn.ActFun(fun="tanh"),
+                use_bias_node=2, prior_f=1, p_scale=1, seed=1234, init_std=0.1, instance_weights=None)
+    mcmc = bn.MCMC(bnn, update_f=[0.05, 0.05, 0.07], update_ws=[0.075, 0.075, 0.075], n_iteration=10000,
+                   sampling_f=10, print_f=1000, n_post_samples=100, sample_from_prior=0, adapt_f=0.3, adapt_fM=0.6)
+    out = {}
+    store_data(out, dat)
+    out["x"] = out["x"].astype(np.float64)
+    record_chain(bnn, mcmc, n_steps, out)
+    meta = dict(act="tanh", mode="classification", prior=1, p_scale=1.0, use_bias_node=2, n_nodes=[5, 5],
+                update_f=[0.05, 0.05, 0.07], update_ws=[0.075] * 3, n_iteration=10000, adapt_f=0.3, adapt_fM=0.6,
+                adapt_freq=1000, temperature=1.0, lik_temp=1.0, w_bound=float("inf"))
+    save("c1_classify", out, meta)
+
+
+def case_c2(empirical, n_steps=120):
+    """BASELINE config 2: bnn_regress.py:19-52 data handling, [10,5] ReLU, Gaussian likelihood."""
+    dat = quiet(bn.get_data, EX + "/data_features_reg.txt", EX + "/data_lab_reg.txt", seed=1234, testsize=0.1,
+                all_class_in_testset=0, cv=0, header=True, from_file=True, instance_id=0, randomize_order=True,
+                label_mode="regression")
+    np.random.seed(1234)
+    bnn = quiet(bn.npBNN, dat, n_nodes=[10, 5], estimation_mode="regression", actFun=bn.ActFun(fun="ReLU"),
+                p_scale=1, use_bias_node=2, empirical_error=empirical)
+    mcmc = bn.MCMC(bnn, update_ws=[0.025, 0.025, 0.05], update_f=[0.005, 0.005, 0.05], n_iteration=20000,
+                   sampling_f=100, print_f=1000, n_post_samples=100, likelihood_tempering=1, adapt_f=0.3,
+                   estimate_error=False)
+    out = {}
+    store_data(out, dat)
+    record_chain(bnn, mcmc, n_steps, out)
+    meta = dict(act="ReLU", mode="regression", prior=1, p_scale=1.0, use_bias_node=2, n_nodes=[10, 5],
+                update_f=[0.005, 0.005, 0.05], update_ws=[0.025, 0.025, 0.05], n_iteration=20000, adapt_f=0.3,
+                adapt_fM=1.0, adapt_freq=1000, temperature=1.0, lik_temp=1.0, w_bound=float("inf"),
+                empirical_error=bool(empirical))
+    save("c2_regress_emp%d" % int(empirical), out, meta)
+
+
+def synth_class(n, f, k, seed, n_test=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n + n_test, f))
+    wt = rng.normal(0, 1.0, (k, f))
+    lab = np.argmax(x @ wt.T + rng.gumbel(size=(n + n_test, k)), axis=1)
+    lab[:k] = np.arange(k)  # every class present in train
+    if n_test:
+        lab[n:n + k] = np.arange(k)
+    return {"data": x[:n], "labels": lab[:n], "test_data": x[n:] if n_test else [],
+            "test_labels": lab[n:] if n_test else []}
+
+
+def case_synth(name, n=500, f=6, k=3, n_nodes=(4, 3), act="swish", alphas=None, prior=1, p_scale=1.0,
+               bias=2, class_w=0, inst_w=False, temperature=1.0, lik_temp=1.0, n_test=64, mask_spec=None,
+               n_steps=60, seed=7, adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, update_f=None, update_ws=None,
+               n_iteration=1000, w_bound=np.inf):
+    dat = synth_class(n, f, k, seed, n_test)
+    iw = None
+    if inst_w:
+        iw = np.random.default_rng(seed + 1).uniform(0.2, 1.5, n)
+    np.random.seed(seed)
+    af = bn.ActFun(fun=act, prm=np.array(alphas) if alphas is not None else np.zeros(1))
+    bnn = quiet(bn.npBNN, dat, n_nodes=list(n_nodes), use_class_weights=class_w, actFun=af, use_bias_node=bias,
+                prior_f=prior, p_scale=p_scale, seed=seed, instance_weights=iw, w_bound=w_bound)
+    out = {}
+    if mask_spec is not None:
+        m = bn.create_mask(bnn._w_layers, indx_input_list=mask_spec[0], nodes_per_feature_list=mask_spec[1])
+        quiet(bnn.apply_mask, m)
+        for i, mm in enumerate(m):
+            out["mask_%d" % i] = mm
+    mcmc = bn.MCMC(bnn, update_f=update_f, update_ws=update_ws, temperature=temperature, n_iteration=n_iteration,
+                   likelihood_tempering=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq)
+    store_data(out, dat)
+    if iw is not None:
+        out["inst_w"] = iw
+    if class_w:
+        out["class_w"] = np.asarray(bnn._class_w)
+    record_chain(bnn, mcmc, n_steps, out)
+    nl = len(n_nodes) + 1
+    meta = dict(act=act, alphas=list(alphas) if alphas is not None else None, mode="classification", prior=prior,
+                p_scale=p_scale, use_bias_node=bias, n_nodes=list(n_nodes),
+                update_f=list(update_f) if update_f else [0.05] * nl,
+                update_ws=list(update_ws) if update_ws else [0.075] * nl, n_iteration=n_iteration, adapt_f=adapt_f,
+                adapt_fM=adapt_fM, adapt_freq=adapt_freq, temperature=temperature, lik_temp=lik_temp,
+                w_bound=float(bnn._w_bound))
+    save(name, out, meta)
+
+
+def case_regerr(n_steps=60):
+    rng = np.random.default_rng(11)
+    n, f, o = 400, 5, 2
+    x = rng.standard_normal((n + 50, f))
+    yv = np.stack([x[:, 0] - 0.5 * x[:, 1], np.sin(x[:, 2])], axis=1) + 0.1 * rng.standard_normal((n + 50, o))
+    dat = {"data": x[:n], "labels": yv[:n], "test_data": x[n:], "test_labels": yv[n:]}
+    np.random.seed(11)
+    bnn = quiet(bn.npBNN, dat, n_nodes=[6, 4], estimation_mode="regression-error", actFun=bn.ActFun(fun="tanh"),
+                use_bias_node=3, output_act_fun=bn.RegressTransformError)
+    mcmc = bn.MCMC(bnn, n_iteration=1000)
+    out = {}
+    store_data(out, dat)
+    record_chain(bnn, mcmc, n_steps, out)
+    meta = dict(act="tanh", mode="regression-error", prior=1, p_scale=1.0, use_bias_node=3, n_nodes=[6, 4],
+                update_f=[0.05] * 3, update_ws=[0.075] * 3, n_iteration=1000, adapt_f=0.0, adapt_fM=1.0,
+                adapt_freq=1000, temperature=1.0, lik_temp=1.0, w_bound=float("inf"))
+    save("syn_regress_error", out, meta)
+
+
+def case_masks():
+    """The three block_bnns.py examples (block_bnns.py:39-41,57-59,79-81) + a 40-feature c3-style one."""
+    out = {}
+    specs = [
+        ([(6, 3), (2, 6), (2, 3)], [[0, 1, 2], [], []], [[2, 2, 2], [], []]),
+        ([(9, 3), (6, 9), (2, 7)], [[0, 1, 2], [0, 0, 0, 1, 1, 1, 2, 2, 2], []], [[3, 3, 3], [2, 2, 2], []]),
+        ([(9, 3), (5, 9), (2, 6)], [[0, 1, 1], [0, 0, 0, 1, 1, 1, 1, 1, 1], []], [[3, 6], [2, 3], []]),
+        ([(24, 8), (16, 24), (5, 17)], [list(range(8)), sum(([g] * 3 for g in range(8)), []), []],
+         [[3] * 8, [2] * 8, []]),
+    ]
+    meta = {"specs": []}
+    for si, (shapes, idx, npf) in enumerate(specs):
+        w = [np.ones(s) for s in shapes]
+        m = bn.create_mask(w, indx_input_list=idx, nodes_per_feature_list=npf)
+        for li, mm in enumerate(m):
+            out["m%d_%d" % (si, li)] = mm
+        meta["specs"].append({"shapes": shapes, "indx_input_list": idx, "nodes_per_feature_list": npf})
+    save("masks", out, meta)
+
+
+def case_predict():
+    """get_posterior_cat_prob modes 0 and 1 (BNN_lib.py:352-397) and one get_pdp call (BNN_pdp.py:48-84)."""
+    rng = np.random.default_rng(5)
+    n, f, k, s = 300, 7, 4, 9
+    x = rng.standard_normal((n, f))
+    x[:, 3] = rng.integers(0, 3, n)   # an ordinal feature for the PDP grid
+    out = {"x": x}
+    meta = {"S": s, "cases": []}
+    for ci, (act, bias, alphas) in enumerate([("swish", -1, None), ("tanh", 2, None), ("genReLU", 3, [0.01, 0.2])]):
+        post = []
+        for j in range(s):
+            np.random.seed(100 * ci + j)
+            w = bn.init_weight_prm([6, 5], f, k, init_std=0.1, bias_node=bias)
+            w = [wi + rng.normal(0, 0.6, wi.shape) for wi in w]
+            post.append({"weights": w, "alphas": list(alphas) if alphas else [0.0]})
+            for li, wi in enumerate(w):
+                out["p%d_s%d_w%d" % (ci, j, li)] = wi
+        af = bn.ActFun(fun=act, prm=np.array(alphas) if alphas else np.zeros(1))
+        for mode in (0, 1):
+            dense_out, summ = bn.get_posterior_cat_prob(x, post, post_summary_mode=mode, actFun=af,
+                                                        output_act_fun=bn.SoftMax)
+            out["p%d_mode%d" % (ci, mode)] = summ
+        out["p%d_dense" % ci] = dense_out
+        # PDP on one continuous and one ordinal feature
+        for focal in ([1], [3]):
+            res = bn.get_pdp(x, focal, "classification", k, af, bn.SoftMax, [p["weights"] for p in post],
+                             [p["alphas"] for p in post], None)
+            out["p%d_pdp%d_feature" % (ci, focal[0])] = res["feature"]
+            out["p%d_pdp%d" % (ci, focal[0])] = res["pdp"]
+        meta["cases"].append({"act": act, "use_bias_node": bias, "alphas": alphas})
+    save("predict", out, meta)
+
+
+def case_mc3():
+    """Reference MC3.run_mcmc (BNN_mc3.py:87-126) on a toy problem: 3 chains, swap every 5 steps.
+    The swap RNG (global np.random, BNN_mc3.py:99,109) is recorded by monkeypatching."""
+    dat = synth_class(200, 5, 3, 21)
+    np.random.seed(21)
+    bnn = quiet(bn.npBNN, dat, n_nodes=[4, 3], use_bias_node=-1, seed=1, actFun=bn.ActFun(fun="swish"))
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+    try:
+        logger = bn.postLogger(bnn, filename="mc3gold", log_all_weights=0)
+        np.random.seed(77)
+        mc3 = quiet(bn.MC3, bnn, logger=logger, n_post_samples=10, sampling_f=5, n_iteration=40, n_chains=3,
+                    swap_frequency=5, verbose=0, adapt_freq=50, adapt_f=0.1, adapt_fM=0.6, adapt_stop=1000)
+        out = {}
+        store_data(out, dat)
+        for i in range(3):
+            out["w0_%d" % i] = np.array(bnn._w_layers[i])
+        out["temps0"] = np.array(mc3.temperatures, dtype=np.float64)
+        # drive the reference's outer loop one swap period at a time so the state can be recorded
+        rec = {"choice": [], "random": []}
+        real_choice, real_random = np.random.choice, np.random.random
+
+        def choice(*a, **k):
+            v = real_choice(*a, **k); rec["choice"].append(np.array(v)); return v
+
+        def rnd(*a, **k):
+            v = real_random(*a, **k); rec["random"].append(v); return v
+
+        n_it = mc3.n_mc3_iteration
+        mc3.n_mc3_iteration = 1
+        np.random.choice, np.random.random = choice, rnd
+        try:
+            for it in range(n_it):
+                rec["choice"].clear(); rec["random"].clear()
+                temps_before = np.array([a[1]._temperature for a in mc3.singleChainArgs], dtype=np.float64)
+                quiet(mc3.run_mcmc)
+                out["it%d_logPost" % it] = np.array([a[1]._logPost for a in mc3.singleChainArgs])
+                out["it%d_logLik" % it] = np.array([a[1]._logLik for a in mc3.singleChainArgs])
+                out["it%d_temps_before" % it] = temps_before
+                out["it%d_temps_after" % it] = np.array([a[1]._temperature for a in mc3.singleChainArgs], dtype=np.float64)
+                out["it%d_pair" % it] = rec["choice"][0].astype(np.int32)
+                out["it%d_log_u" % it] = np.log(rec["random"][0])
+                out["it%d_iteration" % it] = np.array([a[1]._current_iteration for a in mc3.singleChainArgs])
+                for c in range(3):
+                    for li in range(3):
+                        out["it%d_c%d_w%d" % (it, c, li)] = np.array(mc3.singleChainArgs[c][0]._w_layers[li])
+        finally:
+            np.random.choice, np.random.random = real_choice, real_random
+    finally:
+        os.chdir(cwd)
+    meta = dict(act="swish", mode="classification", prior=1, p_scale=1.0, use_bias_node=-1, n_nodes=[4, 3],
+                n_chains=3, swap_frequency=5, n_mc3_iterations=int(n_it), adapt_freq=50, adapt_f=0.1, adapt_fM=0.6,
+                adapt_stop=1000, update_f=[0.05] * 3, update_ws=[0.075] * 3, min_temperature=0.8)
+    save("mc3", out, meta)
+
+
+if __name__ == "__main__":
+    case_c1()
+    case_c2(True)
+    case_c2(False)
+    case_synth("syn_swish_cauchy", act="swish", prior=2, p_scale=0.7, bias=2)
+    case_synth("syn_genrelu_laplace", act="genReLU", alphas=[0.01, 0.3], prior=3, p_scale=1.3, bias=1)
+    case_synth("syn_uniform_bound", act="tanh", prior=0, p_scale=0.25, bias=3, update_ws=[0.2, 0.2, 0.2])
+    case_synth("syn_classw_temp", act="ReLU", class_w=1, temperature=0.8, lik_temp=0.9, bias=-1)
+    case_synth("syn_instw", act="swish", inst_w=True, bias=0)
+    case_synth("syn_adapt", act="tanh", adapt_f=0.3, adapt_fM=0.6, adapt_freq=10, n_iteration=1000, n_steps=80,
+               update_f=[0.3, 0.3, 0.3])
+    case_synth("syn_block_mask", f=8, k=5, n_nodes=(24, 16), act="tanh", bias=-1,
+               mask_spec=([list(range(8)), sum(([g] * 3 for g in range(8)), []), []], [[3] * 8, [2] * 8, []]))
+    case_regerr()
+    case_masks()
+    case_predict()
+    case_mc3()

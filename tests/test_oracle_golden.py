@@ -1,0 +1,127 @@
+"""CPU: pin the oracle (oracle/npbnn_oracle.py) to the reference's own outputs (tests/golden/)."""
+import numpy as np
+import pytest
+
+from oracle import npbnn_oracle as orc
+from tests import _golden as G
+
+RTOL = 1e-12   # same FP64 arithmetic, different summation order only
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    return np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", G.CHAIN_CASES)
+def test_chain_replay_matches_reference(name):
+    z, meta = G.load(name)
+    m = G.build_model(z, meta)
+    s = G.build_sampler(m, meta)
+    assert close(s.logLik, z["init_logLik"]), (s.logLik, float(z["init_logLik"]))
+    assert close(s.logPrior, z["init_logPrior"])
+    assert close(s.accuracy, z["init_accuracy"])
+    assert close(s.test_accuracy, z["init_test_accuracy"])
+    assert close(s.label_acc, z["init_label_acc"])
+    assert np.array_equal(s.update_n, z["init_update_n"])
+    n_steps = int(z["n_steps"])
+    near_ties = 0
+    for t in range(n_steps):
+        inj = G.injection(z, meta, t)
+        # the proposed-layer rule must reproduce what the reference did
+        d = orc.mh_step(m, s, inj)
+        ok = orc.layer_is_proposed(inj.rr, z["steps_freq_layer_update"][t])
+        assert np.array_equal(ok.astype(np.int32), z["steps_proposed"][t]), t
+        assert close(d["logLik_prime"], z["steps_logLik_prime"][t]), (t, d["logLik_prime"], float(z["steps_logLik_prime"][t]))
+        assert close(d["logPrior_prime"], z["steps_logPrior_prime"][t]), t
+        assert d["accepted"] == int(z["steps_accepted"][t]), t
+        assert close(s.logLik, z["steps_logLik"][t]) and close(s.logPrior, z["steps_logPrior"][t])
+        assert close(s.logPost, z["steps_logPost"][t])
+        assert close(s.accuracy, z["steps_accuracy"][t]) and close(s.test_accuracy, z["steps_test_accuracy"][t])
+        assert close(s.label_acc, z["steps_label_acc"][t])
+        if meta["mode"] == "classification":
+            assert close(s.label_freq, z["steps_label_freq"][t])
+        assert close(s.acceptance_rate, z["steps_acceptance_rate"][t], rtol=1e-15)
+        assert np.array_equal(s.update_n, z["steps_update_n"][t]), t
+        assert close(s.update_f, z["steps_update_f"][t], rtol=1e-15)
+        assert close(s.update_ws, z["steps_update_ws"][t], rtol=1e-15)
+        assert close(s.freq_layer_update, z["steps_freq_layer_update"][t], rtol=1e-15)
+        if meta["mode"] == "regression":
+            assert close(np.asarray(m.error_prm) * np.ones(m.labels.shape[1]), z["steps_error_prm"][t])
+    for i, w in enumerate(m.weights):
+        assert np.array_equal(w, z["wN_%d" % i]), "final weights layer %d" % i
+    y = orc.forward(m.x, m.weights, m.act, m.alphas, m.out_kind)
+    assert close(y, z["yN"], rtol=1e-11, atol=1e-300)
+    assert near_ties == 0
+
+
+def test_survey_anchor_values():
+    """SURVEY.md section 8c anchors for BASELINE config 1 and 2 (measured by the survey on the reference)."""
+    z, meta = G.load("c1_classify")
+    assert abs(float(z["init_logLik"]) - (-3621.998513641989)) < 1e-9
+    assert abs(float(z["init_logPrior"]) - (-646.541793988718)) < 1e-9
+    assert abs(float(z["steps_logLik"][99]) - (-3623.157147588077)) < 1e-9
+    assert abs(float(z["steps_logPrior"][99]) - (-650.529100740772)) < 1e-9
+    assert int(np.sum(z["steps_accepted"][:100])) == 89
+    assert list(z["steps_update_n"][99]) == [27, 1, 1]
+    z, meta = G.load("c2_regress_emp1")
+    assert abs(float(z["init_logLik"]) - (-16509.872057635934)) < 1e-8
+    assert abs(float(z["init_logPrior"]) - (-96.989733054569)) < 1e-9
+
+
+def test_masks_match_create_mask():
+    z, meta = G.load("masks")
+    for si, spec in enumerate(meta["specs"]):
+        for li, shape in enumerate(spec["shapes"]):
+            got = orc.block_mask(tuple(shape), spec["indx_input_list"][li], spec["nodes_per_feature_list"][li])
+            assert np.array_equal(got, z["m%d_%d" % (si, li)]), (si, li)
+
+
+def test_posterior_predict_and_pdp():
+    z, meta = G.load("predict")
+    x = z["x"]
+    for ci, case in enumerate(meta["cases"]):
+        post = [[z["p%d_s%d_w%d" % (ci, j, li)] for li in range(3)] for j in range(meta["S"])]
+        alphas = [case["alphas"]] * meta["S"] if case["alphas"] else None
+        dense0, votes = orc.posterior_predict(x, post, case["act"], alphas, "softmax", 0)
+        _, mean = orc.posterior_predict(x, post, case["act"], alphas, "softmax", 1)
+        assert close(dense0, z["p%d_dense" % ci], rtol=1e-12, atol=1e-300)
+        assert np.array_equal(votes, z["p%d_mode0" % ci])
+        assert close(mean, z["p%d_mode1" % ci], rtol=1e-13)
+        for focal in (1, 3):
+            feats = z["p%d_pdp%d_feature" % (ci, focal)]
+            gold = z["p%d_pdp%d" % (ci, focal)]
+            for n in range(feats.shape[0]):
+                mean_, lo, hi = orc.pdp_step(x, [focal], feats[n, :], post, case["act"], alphas)
+                assert close(mean_, gold[n, :, 0], rtol=1e-12)
+                assert close(lo, gold[n, :, 1], rtol=1e-12) and close(hi, gold[n, :, 2], rtol=1e-12)
+
+
+def test_mc3_swaps_and_chain_states():
+    """Replay the reference MC3 run: per-chain steps reseed default_rng(it + id) every step
+    (BNN_env.py:383-384); swap rule BNN_mc3.py:98-112."""
+    z, meta = G.load("mc3")
+    nc, sf = meta["n_chains"], meta["swap_frequency"]
+    labels = z["labels"].astype(np.int64)
+    temps = np.array(z["temps0"])
+    models, samplers = [], []
+    for c in range(nc):
+        m = orc.Model(x=np.array(z["x"]), labels=labels, weights=[np.array(z["w0_%d" % i]) for i in range(3)],
+                      act=meta["act"], mode="classification", prior=1, prior_scale=np.ones(3))
+        s = orc.make_sampler(m, temperature=temps[c], n_iteration=sf, adapt_f=meta["adapt_f"],
+                             adapt_fM=meta["adapt_fM"], adapt_freq=meta["adapt_freq"], adapt_stop=meta["adapt_stop"])
+        models.append(m); samplers.append(s)
+    for it in range(meta["n_mc3_iterations"]):
+        assert close(temps, z["it%d_temps_before" % it], rtol=0)
+        for c in range(nc):
+            m, s = models[c], samplers[c]
+            s.temperature = temps[c]
+            for _ in range(sf):
+                rs = np.random.default_rng(s.it + c)
+                orc.mh_step(m, s, rs=rs)
+            for li in range(3):
+                assert np.array_equal(m.weights[li], z["it%d_c%d_w%d" % (it, c, li)]), (it, c, li)
+        lp = np.array([s.logPost for s in samplers])
+        assert close(lp, z["it%d_logPost" % it])
+        j, k = [int(v) for v in z["it%d_pair" % it]]
+        temps, swapped, r = orc.mc3_swap(lp, temps, j, k, float(z["it%d_log_u" % it]))
+        assert close(temps, z["it%d_temps_after" % it], rtol=0), it
