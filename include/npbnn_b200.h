@@ -1,0 +1,204 @@
+/* npbnn_b200 -- C ABI of the B200-native npBNN Metropolis-Hastings hot path.
+ *
+ * The reference (dsilvestro/npBNN) is pure Python and has no FFI layer; its boundary is the
+ * Python call surface of np_bnn/__init__.py:6-25.  The entry points below are what a ctypes
+ * binding inside the reference would call in place of its numpy code (INTEGRATION.md shows
+ * the stub).  Each entry point names the reference code it replaces (file:line into the
+ * reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; bnn_last_error() gives the text
+ *   - `*_dev` pointers are CUDA device pointers (e.g. torch.Tensor.data_ptr()); `*_host`
+ *     pointers are host pointers (pinned memory gives asynchronous copies)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - no ownership transfer: the context owns only its internal workspace
+ *   - weights use the reference's canonical layout: layer l is a row-major
+ *     [out_l, in_l + has_bias_l] float64 matrix, bias in column 0 (BNN_lib.py:154-162);
+ *     a weight set is the concatenation of its layers (`n_params` doubles)
+ */
+#ifndef NPBNN_B200_H
+#define NPBNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_ABI_VERSION 1
+#define BNN_MAX_LAYERS 8
+#define BNN_MAX_OUT 32          /* max width of the output layer (classes, or 2*O for the sigma head) */
+
+/* activation of the hidden layers: relu_f / leaky_relu_f / swish_f / tanh_f, BNN_lib.py:50-66 */
+enum { BNN_ACT_RELU = 0, BNN_ACT_LEAKY = 1, BNN_ACT_SWISH = 2, BNN_ACT_TANH = 3 };
+/* output transform + likelihood:
+ *   CATEGORICAL   SoftMax (BNN_lib.py:166-168) + calc_likelihood (BNN_lib.py:100-121)
+ *   GAUSSIAN      RegressTransform (BNN_lib.py:174) + calc_likelihood_regression (BNN_lib.py:123-131)
+ *   GAUSSIAN_HEAD RegressTransformError (BNN_lib.py:177-182) + calc_likelihood_regression_error (:134-143) */
+enum { BNN_LIK_CATEGORICAL = 0, BNN_LIK_GAUSSIAN = 1, BNN_LIK_GAUSSIAN_HEAD = 2 };
+/* npBNN prior_f, BNN_env.py:135-150 */
+enum { BNN_PRIOR_UNIFORM = 0, BNN_PRIOR_NORMAL = 1, BNN_PRIOR_CAUCHY = 2, BNN_PRIOR_LAPLACE = 3 };
+/* error parameter of the Gaussian likelihood: fixed sigma[O] per chain, or the population std of the
+ * residuals recomputed for every proposal (empirical_error, BNN_env.py:475-476) */
+enum { BNN_SIGMA_FIXED = 0, BNN_SIGMA_EMPIRICAL = 1 };
+/* posterior summary of bnn_predict: argmax vote share / mean (get_posterior_cat_prob modes 0 / 1,
+ * BNN_lib.py:382-392) */
+enum { BNN_SUMMARY_VOTES = 1, BNN_SUMMARY_MEAN = 2, BNN_SUMMARY_DENSE = 4 };
+
+typedef struct bnn_ctx bnn_ctx;
+
+/* Network shape: what init_weight_prm (BNN_mcmc.py:9-25) and ActFun (BNN_lib.py:68-94) fix. */
+typedef struct {
+  int32_t n_layers;                    /* hidden layers + 1 */
+  int32_t n_features;
+  int32_t out_dim[BNN_MAX_LAYERS];     /* rows of each weight matrix */
+  int32_t has_bias[BNN_MAX_LAYERS];    /* 1 if column 0 of that matrix is a bias */
+  int32_t act;                         /* BNN_ACT_* */
+  int32_t lik;                         /* BNN_LIK_* */
+} bnn_net_spec;
+
+/* Sampler configuration shared by all chains of a context: the constructor arguments of MCMC
+ * (BNN_env.py:274-281) and the prior fields of npBNN (BNN_env.py:85-154). */
+typedef struct {
+  int32_t prior;                       /* BNN_PRIOR_* */
+  int32_t sigma_mode;                  /* BNN_SIGMA_* (Gaussian likelihood only) */
+  int32_t sample_from_prior;           /* MCMC(sample_from_prior=) : likelihood forced to 0 */
+  int32_t adapt_freq;                  /* MCMC(adapt_freq=) */
+  int32_t adapt_stop;                  /* MCMC(adapt_stop=), already resolved (int(0.05 n_iter) default) */
+  int32_t use_mask;                    /* mask_dev given to bnn_chains_init */
+  double adapt_f, adapt_fM;            /* MCMC(adapt_f=, adapt_fM=) */
+  double lik_temp;                     /* MCMC(likelihood_tempering=) */
+  double w_bound;                      /* npBNN._w_bound (inf = no reflection) */
+  double prior_scale[BNN_MAX_LAYERS];  /* npBNN._prior_scale (one scalar per layer) */
+  uint64_t seed;                       /* Philox key for free-running proposals */
+} bnn_sampler_config;
+
+/* Random draws of `n_steps` MH iterations for every chain, recorded from (or generated like) the
+ * reference's generator calls in BNN_env.py:446-453,493 and BNN_mcmc.py:62-65.  All host pointers.
+ *   proposed [n_steps, C, L]        1 if the layer is proposed in that step
+ *   count    [n_steps, C, L]        number of (ix, iy, dz) triples of that layer (= update_n)
+ *   ix, iy   [n_steps, C, cap]      row / column indices, layers concatenated in order
+ *   dz       [n_steps, C, cap]      the normal increments (already scaled by update_ws)
+ *   log_u    [n_steps, C]           log of the accept uniform */
+typedef struct {
+  int32_t n_steps;
+  int32_t cap;
+  const int32_t* proposed;
+  const int32_t* count;
+  const int32_t* ix;
+  const int32_t* iy;
+  const double* dz;
+  const double* log_u;
+} bnn_injection;
+
+/* ---- per-chain state export (bnn_chains_read): slot indices ------------------------------------ */
+enum {
+  BNN_F_LOGLIK = 0, BNN_F_LOGPRIOR = 1, BNN_F_LOGPOST = 2, BNN_F_TEMPERATURE = 3, BNN_F_ACC_RATE = 4,
+  BNN_F_LOGLIK_PROP = 5, BNN_F_LOGPRIOR_PROP = 6, BNN_F_LOG_U = 7,
+  BNN_F_UPDATE_F = 16,           /* [BNN_MAX_LAYERS] */
+  BNN_F_UPDATE_WS = 24,          /* [BNN_MAX_LAYERS] */
+  BNN_F_FREQ_LAYER = 32,         /* [BNN_MAX_LAYERS] */
+  BNN_F_ALPHA = 40,              /* [BNN_MAX_LAYERS] genReLU slopes */
+  BNN_F_SIGMA = 48,              /* [BNN_MAX_OUT] current error_prm */
+  BNN_F_SUM_R = 80,              /* [BNN_MAX_OUT] current sum of residuals (train) */
+  BNN_F_SUM_R2 = 112,            /* [BNN_MAX_OUT] current sum of squared residuals (train) */
+  BNN_F_SUM_R2_TEST = 144,       /* [BNN_MAX_OUT] current sum of squared residuals (test) */
+  BNN_F_STRIDE = 192
+};
+enum {
+  BNN_I_ITERATION = 0, BNN_I_LAST_ACCEPTED = 1, BNN_I_N_ACCEPTED = 2, BNN_I_RING_LEN = 3, BNN_I_RING_HEAD = 4,
+  BNN_I_RING_SUM = 5,
+  BNN_I_UPDATE_N = 8,            /* [BNN_MAX_LAYERS] */
+  BNN_I_MAX_N = 16,              /* [BNN_MAX_LAYERS] */
+  BNN_I_PROPOSED = 24,           /* [BNN_MAX_LAYERS] layers proposed in the last step */
+  BNN_I_N_CORRECT = 32, BNN_I_N_CORRECT_TEST = 33,
+  BNN_I_CLASS_CORRECT = 34,      /* [BNN_MAX_OUT] */
+  BNN_I_PRED_HIST = 66,          /* [BNN_MAX_OUT] */
+  BNN_I_RING = 98,               /* [100] last outcomes */
+  BNN_I_STRIDE = 200
+};
+
+const char* bnn_last_error(void);
+int bnn_abi_version(void);
+
+int bnn_ctx_create(bnn_ctx** ctx, int device);
+int bnn_ctx_destroy(bnn_ctx* ctx);
+
+/* Fix the network shape.  Replaces the shape bookkeeping of npBNN.__init__ (BNN_env.py:79-124). */
+int bnn_set_net(bnn_ctx* ctx, const bnn_net_spec* spec);
+int64_t bnn_n_params(const bnn_ctx* ctx);
+
+/* Stage the data set once (npBNN._data/_labels/_test_data/_test_labels, BNN_env.py:35-49; the
+ * reference re-copies X every step, BNN_env.py:388).  x_dev is [n_train + n_test, F] row-major,
+ * training rows first.  labels_dev (int32 [n]) for CATEGORICAL, targets_dev (f64 [n, O]) for the
+ * Gaussian likelihoods.  inst_w_dev [n_train] and class_w_dev [K] may be NULL
+ * (calc_likelihood's instance_weight / class_weight, BNN_lib.py:100-121). */
+int bnn_set_data(bnn_ctx* ctx, const double* x_dev, int64_t n_train, int64_t n_test,
+                 const int32_t* labels_dev, const double* targets_dev,
+                 const double* inst_w_dev, const double* class_w_dev, void* stream);
+
+/* Score n_sets weight sets against the staged data in one pass over X.
+ * Replaces, per weight set: RunPredict (BNN_lib.py:245-256) + likelihood_f (BNN_lib.py:100-143) +
+ * CalcAccuracy / CalcLabelAccuracy / CalcLabelFreq (BNN_lib.py:195-233) on train and test rows.
+ *   w_dev      [n_sets, n_params] canonical weights
+ *   alpha_dev  [n_sets, n_layers] genReLU slopes or NULL
+ *   sigma_dev  [n_sets, O] error_prm or NULL (= 1); ignored when sigma_mode == BNN_SIGMA_EMPIRICAL
+ *   loglik_dev [n_sets]
+ *   sums_dev   [n_sets, 3, O]  sum r, sum r^2 (train), sum r^2 (test)   (Gaussian; may be NULL)
+ *   counts_dev [n_sets, 2 + 2K] n_correct, n_correct_test, class_correct[K], pred_hist[K] (may be NULL) */
+int bnn_forward_lik(bnn_ctx* ctx, const double* w_dev, int32_t n_sets, const double* alpha_dev,
+                    const double* sigma_dev, int32_t sigma_mode, double lik_temp,
+                    double* loglik_dev, double* sums_dev, int32_t* counts_dev, void* stream);
+/* Same call with host buffers: copies w_host to the device, runs, copies loglik back and synchronises. */
+int bnn_forward_lik_host(bnn_ctx* ctx, const double* w_host, int32_t n_sets, const double* alpha_host,
+                         const double* sigma_host, int32_t sigma_mode, double lik_temp,
+                         double* loglik_host, double* sums_host, int32_t* counts_host, void* stream);
+
+/* Log-prior of n_sets weight sets: npBNN.calc_prior (BNN_env.py:180-194) without indicators. */
+int bnn_log_prior(bnn_ctx* ctx, const double* w_dev, int32_t n_sets, int32_t prior,
+                  const double* prior_scale /* host [n_layers] */, double* logprior_dev, void* stream);
+
+/* Create n_chains chains resident on the device.  Replaces MCMC.__init__ (BNN_env.py:274-379) for
+ * every chain: initial forward, likelihood, prior and accuracy counters are computed here.
+ *   w0_host     [C, n_params]
+ *   mask_host   [n_params] 0/1 (npBNN._mask, BNN_env.py:259-267) or NULL
+ *   temperature [C]; update_f, update_ws [C, n_layers]; alpha [C, n_layers] or NULL; sigma0 [C, O] or NULL */
+int bnn_chains_init(bnn_ctx* ctx, int32_t n_chains, const bnn_sampler_config* cfg, const double* w0_host,
+                    const double* mask_host, const double* temperature, const double* update_f,
+                    const double* update_ws, const double* alpha, const double* sigma0, void* stream);
+
+/* Run n_steps MH iterations of every chain without leaving the device.  One iteration replaces
+ * MCMC.mh_step (BNN_env.py:381-532) with update_function = UpdateNormal (BNN_mcmc.py:57-69).
+ * inj == NULL: free-running Philox proposals; otherwise the recorded draws are replayed. */
+int bnn_mh_steps(bnn_ctx* ctx, int32_t n_steps, const bnn_injection* inj, void* stream);
+
+/* Export chain state (synchronises the stream).  Any pointer may be NULL.
+ *   f64_host [C, BNN_F_STRIDE], i32_host [C, BNN_I_STRIDE], w_host [C, n_params] */
+int bnn_chains_read(bnn_ctx* ctx, double* f64_host, int32_t* i32_host, double* w_host, void* stream);
+/* Device pointers to the live chain state (same layout as bnn_chains_read; e.g. the log-posteriors for
+ * the MC3 all-gather are f64_dev[c * BNN_F_STRIDE + BNN_F_LOGPOST]).  Any pointer may be NULL. */
+int bnn_chains_state_dev(bnn_ctx* ctx, double** f64_dev, int32_t** i32_dev, double** w_dev);
+/* Temperature update after an MC3 swap (BNN_mc3.py:98-112; reset_temperature, BNN_env.py:549-550). */
+int bnn_chains_set_temperature(bnn_ctx* ctx, const double* temperature_host, void* stream);
+
+/* Posterior prediction for n_sets weight sets over rows of x_dev [n, F] (not the staged data):
+ * replaces the loop `for i in range(S): RunPredict(...)` of get_posterior_cat_prob (BNN_lib.py:376-397),
+ * get_posterior_est (BNN_lib.py:731-737) and get_pdp (BNN_pdp.py:63-73).
+ *   override_cols [n_override] / override_vals [n_override]: PDP column overwrite (BNN_pdp.py:65), host, may be NULL
+ *   mean_dev [n, K] mean of the transformed outputs; votes_dev [n, K] argmax vote share;
+ *   dense_dev [n_sets, n, K] every prediction (only for small problems); any may be NULL */
+int bnn_predict(bnn_ctx* ctx, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
+                int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, void* stream);
+
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+int64_t bnn_launch_count(const bnn_ctx* ctx);
+/* Name of the forward kernel variant used by the last call ("k_fwd3<...>" or "k_fwd_generic"). */
+const char* bnn_last_kernel(const bnn_ctx* ctx);
+/* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests). */
+int bnn_set_option(bnn_ctx* ctx, const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPBNN_B200_H */

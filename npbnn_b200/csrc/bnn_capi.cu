@@ -1,0 +1,584 @@
+// C-ABI layer of npbnn_b200 (include/npbnn_b200.h): context, workspace management, launch sequencing.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bnn_kernels.h"
+
+static thread_local std::string g_last_error;
+
+static int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                             \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(msg); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  // grow-only; newly allocated memory is zero-filled when `zero`
+  cudaError_t ensure(size_t n, bool zero, cudaStream_t st, bool* grew = nullptr) {
+    if (grew) *grew = false;
+    if (n <= bytes) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaFree(p);
+      p = nullptr; bytes = 0;
+      if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return e;
+    bytes = n;
+    if (grew) *grew = true;
+    if (zero) return cudaMemsetAsync(p, 0, n, st);
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct bnn_ctx {
+  int device = 0, n_sms = 0;
+  bool have_net = false, have_data = false, have_chains = false;
+  int force_generic = 0;
+  long long launches = 0;
+  NetGeom g{};
+  // staged data
+  DevBuf xs, labels, targets, inst_w, class_w;
+  bool has_iw = false, has_cw = false;
+  long long n_train = 0, n_test = 0, n_total = 0, n_pad = 0, n_tiles16 = 0;
+  // workspaces
+  DevBuf exp_tab, wp_scratch, part, counts_scratch, xs_pred, ov_cols, ov_vals;
+  DevBuf h_w, h_alpha, h_sigma, h_loglik, h_sums, h_counts;    // device staging of the *_host entry points
+  // chains
+  int C = 0;
+  bnn_sampler_config cfg{};
+  PriorScales ps{};
+  DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
+  DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
+  const char* last_kernel = "";
+};
+
+static int sets_per_pass(const NetGeom& g) {
+  int nc = 2 + 2 * g.K;
+  int byc = 16384 / (nc * 4);
+  int v = byc < BNN_MAX_SETS_PER_PASS ? byc : BNN_MAX_SETS_PER_PASS;
+  return v < 1 ? 1 : v;
+}
+static int n_slots(const NetGeom& g) { return g.lik == BNN_LIK_CATEGORICAL ? 1 : 1 + 3 * g.K; }
+
+static FwdParams base_params(const bnn_ctx* c) {
+  FwdParams p{};
+  p.g = c->g;
+  p.x = c->xs.as<double>();
+  p.n_train = c->n_train;
+  p.n_total = c->n_total;
+  p.n_tiles16 = c->n_tiles16;
+  p.labels = c->labels.as<int>();
+  p.targets = c->targets.as<double>();
+  p.inst_w = c->has_iw ? c->inst_w.as<double>() : nullptr;
+  p.class_w = c->has_cw ? c->class_w.as<double>() : nullptr;
+  p.exp_tab = c->exp_tab.as<double>();
+  p.NF = n_slots(c->g);
+  p.inv_sets = 1.0;
+  return p;
+}
+
+template <typename T>
+static int upload(DevBuf& b, const T* src, size_t n, cudaStream_t st) {
+  CUDA_TRY(b.ensure(sizeof(T) * n, false, st));
+  CUDA_TRY(cudaMemcpyAsync(b.p, src, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+extern "C" {
+
+const char* bnn_last_error(void) { return g_last_error.c_str(); }
+int bnn_abi_version(void) { return BNN_ABI_VERSION; }
+
+int bnn_ctx_create(bnn_ctx** out, int device) {
+  REQUIRE(out != nullptr, "bnn_ctx_create: null output pointer");
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  REQUIRE(device >= 0 && device < n, "bnn_ctx_create: no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major == 10, "npbnn_b200 kernels are built for sm_100a (Blackwell B200) only; found sm_" +
+                                std::to_string(prop.major) + std::to_string(prop.minor));
+  bnn_ctx* c = new bnn_ctx();
+  c->device = device;
+  c->n_sms = prop.multiProcessorCount;
+  const char* fg = getenv("NPBNN_FORCE_GENERIC");
+  c->force_generic = (fg && fg[0] == '1') ? 1 : 0;
+  std::vector<double> tab(BNN_EXP_TAB_SIZE);
+  for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = exp2((double)j / BNN_EXP_TAB_SIZE);
+  cudaError_t e = c->exp_tab.ensure(sizeof(double) * BNN_EXP_TAB_SIZE, false, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(c->exp_tab.p, tab.data(), sizeof(double) * BNN_EXP_TAB_SIZE, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(std::string("bnn_ctx_create: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return 0;
+}
+
+int bnn_ctx_destroy(bnn_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&c->xs, &c->labels, &c->targets, &c->inst_w, &c->class_w, &c->exp_tab, &c->wp_scratch, &c->part,
+                    &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
+                    &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
+                    &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu};
+  for (DevBuf* b : bufs) b->release();
+  delete c;
+  return 0;
+}
+
+int bnn_set_option(bnn_ctx* c, const char* name, int value) {
+  REQUIRE(c && name, "bnn_set_option: null argument");
+  if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
+  return fail(std::string("bnn_set_option: unknown option ") + name);
+}
+
+const char* bnn_last_kernel(const bnn_ctx* c) { return c ? c->last_kernel : ""; }
+
+int bnn_set_net(bnn_ctx* c, const bnn_net_spec* s) {
+  REQUIRE(c && s, "bnn_set_net: null argument");
+  REQUIRE(s->n_layers >= 1 && s->n_layers <= BNN_MAX_LAYERS, "bnn_set_net: n_layers must be in [1, 8]");
+  REQUIRE(s->n_features >= 1, "bnn_set_net: n_features must be positive");
+  REQUIRE(s->act >= BNN_ACT_RELU && s->act <= BNN_ACT_TANH, "bnn_set_net: unknown activation");
+  REQUIRE(s->lik >= BNN_LIK_CATEGORICAL && s->lik <= BNN_LIK_GAUSSIAN_HEAD, "bnn_set_net: unknown likelihood");
+  NetGeom g{};
+  g.L = s->n_layers;
+  g.F = s->n_features;
+  g.act = s->act;
+  g.lik = s->lik;
+  int in = s->n_features, off = 0, coff = 0;
+  g.max_w = 8;
+  for (int l = 0; l < g.L; ++l) {
+    LayerGeom& lg = g.l[l];
+    REQUIRE(s->out_dim[l] >= 1, "bnn_set_net: layer width must be positive");
+    lg.in = in;
+    lg.out = s->out_dim[l];
+    lg.bias = s->has_bias[l] ? 1 : 0;
+    lg.in_pad = bnn_round_up(in, 8);
+    lg.out_pad = bnn_round_up(lg.out, 8);
+    lg.stride = lg.in_pad;
+    lg.swz = bnn_swz_for(lg.stride);
+    lg.w_off = off;
+    off += lg.out_pad * lg.stride;
+    lg.b_off = off;
+    off += lg.out_pad;
+    lg.c_off = coff;
+    coff += lg.out * (lg.in + lg.bias);
+    if (l >= 1 && lg.in_pad > g.max_w) g.max_w = lg.in_pad;
+    in = lg.out;
+  }
+  g.F_pad = g.l[0].in_pad;
+  g.x_swz = g.l[0].swz;
+  g.P = coff;
+  g.PB = off;
+  g.O = g.l[g.L - 1].out;
+  REQUIRE(g.O <= BNN_MAX_OUT, "bnn_set_net: output layer wider than BNN_MAX_OUT (32)");
+  if (g.lik == BNN_LIK_GAUSSIAN_HEAD) {
+    REQUIRE(g.O % 2 == 0, "bnn_set_net: the sigma-head likelihood needs an even output width");
+    g.K = g.O / 2;
+  } else {
+    g.K = g.O;
+  }
+  c->g = g;
+  c->wp_scratch.release();   // packed layout changed: padding entries must be re-zeroed
+  c->have_net = true;
+  c->have_data = false;
+  c->have_chains = false;
+  return 0;
+}
+
+int64_t bnn_n_params(const bnn_ctx* c) { return (c && c->have_net) ? c->g.P : -1; }
+int64_t bnn_launch_count(const bnn_ctx* c) { return c ? c->launches : -1; }
+
+int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_test, const int32_t* labels_dev,
+                 const double* targets_dev, const double* inst_w_dev, const double* class_w_dev, void* stream) {
+  REQUIRE(c && c->have_net, "bnn_set_data: call bnn_set_net first");
+  REQUIRE(x_dev != nullptr && n_train >= 1 && n_test >= 0, "bnn_set_data: bad arguments");
+  const NetGeom& g = c->g;
+  if (g.lik == BNN_LIK_CATEGORICAL) REQUIRE(labels_dev != nullptr, "bnn_set_data: labels_dev required for the categorical likelihood");
+  else REQUIRE(targets_dev != nullptr, "bnn_set_data: targets_dev required for the Gaussian likelihoods");
+  if (g.lik != BNN_LIK_CATEGORICAL) REQUIRE(inst_w_dev == nullptr, "instance_weight not implemented for regression (BNN_lib.py:129-130)");
+  REQUIRE(!(inst_w_dev && class_w_dev), "class_weight together with instance_weight is an AxisError in the reference (BNN_lib.py:105)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  c->n_train = n_train; c->n_test = n_test; c->n_total = n_train + n_test;
+  c->n_pad = (c->n_total + 15) / 16 * 16;
+  c->n_tiles16 = c->n_pad / 16;
+  CUDA_TRY(c->xs.ensure(sizeof(double) * c->n_pad * g.F_pad, false, st));
+  CUDA_TRY(bnn_launch_pack_x(x_dev, c->xs.as<double>(), c->n_total, c->n_pad, g.F, g.F_pad, g.x_swz, nullptr, nullptr, 0, st));
+  c->launches++;
+  if (g.lik == BNN_LIK_CATEGORICAL) {
+    CUDA_TRY(c->labels.ensure(sizeof(int) * c->n_total, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->labels.p, labels_dev, sizeof(int) * c->n_total, cudaMemcpyDeviceToDevice, st));
+  } else {
+    CUDA_TRY(c->targets.ensure(sizeof(double) * c->n_total * g.K, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->targets.p, targets_dev, sizeof(double) * c->n_total * g.K, cudaMemcpyDeviceToDevice, st));
+  }
+  c->has_iw = inst_w_dev != nullptr;
+  if (c->has_iw) {
+    CUDA_TRY(c->inst_w.ensure(sizeof(double) * n_train, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->inst_w.p, inst_w_dev, sizeof(double) * n_train, cudaMemcpyDeviceToDevice, st));
+  }
+  c->has_cw = class_w_dev != nullptr;
+  if (c->has_cw) {
+    CUDA_TRY(c->class_w.ensure(sizeof(double) * g.K, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->class_w.p, class_w_dev, sizeof(double) * g.K, cudaMemcpyDeviceToDevice, st));
+  }
+  c->have_data = true;
+  c->have_chains = false;
+  return 0;
+}
+
+int bnn_forward_lik(bnn_ctx* c, const double* w_dev, int32_t n_sets, const double* alpha_dev, const double* sigma_dev,
+                    int32_t sigma_mode, double lik_temp, double* loglik_dev, double* sums_dev, int32_t* counts_dev,
+                    void* stream) {
+  REQUIRE(c && c->have_data, "bnn_forward_lik: call bnn_set_net and bnn_set_data first");
+  REQUIRE(w_dev && loglik_dev && n_sets >= 1, "bnn_forward_lik: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetGeom& g = c->g;
+  const int NC = 2 + 2 * g.K;
+  CUDA_TRY(c->wp_scratch.ensure(sizeof(double) * (size_t)n_sets * g.PB, true, st));
+  CUDA_TRY(bnn_launch_pack_w(g, w_dev, c->wp_scratch.as<double>(), n_sets, st));
+  c->launches++;
+  int* counts = counts_dev;
+  if (g.lik == BNN_LIK_CATEGORICAL) {
+    if (!counts) {
+      CUDA_TRY(c->counts_scratch.ensure(sizeof(int) * (size_t)n_sets * NC, false, st));
+      counts = c->counts_scratch.as<int>();
+    }
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n_sets * NC, st));
+  }
+  const int per = sets_per_pass(g);
+  FwdParams p = base_params(c);
+  CUDA_TRY(c->part.ensure(sizeof(double) * (size_t)p.NF * per * c->n_tiles16, false, st));
+  p.part = c->part.as<double>();
+  for (int s0 = 0; s0 < n_sets; s0 += per) {
+    const int n = (n_sets - s0 < per) ? n_sets - s0 : per;
+    p.wp = c->wp_scratch.as<double>() + (size_t)s0 * g.PB;
+    p.alpha = alpha_dev ? alpha_dev + (size_t)s0 * g.L : nullptr;
+    p.C = n;
+    p.counts = counts ? counts + (size_t)s0 * NC : nullptr;
+    CUDA_TRY(bnn_launch_forward(p, false, c->n_sms, c->force_generic, st, &c->last_kernel));
+    CUDA_TRY(bnn_launch_finalize_lik(g, p.part, p.NF, c->n_tiles16, c->n_train, lik_temp, sigma_mode, sigma_dev,
+                                     loglik_dev, sums_dev, s0, n, st));
+    c->launches += 2;
+  }
+  return 0;
+}
+
+int bnn_forward_lik_host(bnn_ctx* c, const double* w_host, int32_t n_sets, const double* alpha_host,
+                         const double* sigma_host, int32_t sigma_mode, double lik_temp, double* loglik_host,
+                         double* sums_host, int32_t* counts_host, void* stream) {
+  REQUIRE(c && c->have_data, "bnn_forward_lik_host: call bnn_set_net and bnn_set_data first");
+  REQUIRE(w_host && loglik_host && n_sets >= 1, "bnn_forward_lik_host: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetGeom& g = c->g;
+  const int NC = 2 + 2 * g.K;
+  CUDA_TRY(c->h_w.ensure(sizeof(double) * (size_t)n_sets * g.P, false, st));
+  CUDA_TRY(cudaMemcpyAsync(c->h_w.p, w_host, sizeof(double) * (size_t)n_sets * g.P, cudaMemcpyHostToDevice, st));
+  if (alpha_host) {
+    CUDA_TRY(c->h_alpha.ensure(sizeof(double) * (size_t)n_sets * g.L, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_alpha.p, alpha_host, sizeof(double) * (size_t)n_sets * g.L, cudaMemcpyHostToDevice, st));
+  }
+  if (sigma_host) {
+    CUDA_TRY(c->h_sigma.ensure(sizeof(double) * (size_t)n_sets * g.K, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_sigma.p, sigma_host, sizeof(double) * (size_t)n_sets * g.K, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(c->h_loglik.ensure(sizeof(double) * n_sets, false, st));
+  CUDA_TRY(c->h_sums.ensure(sizeof(double) * (size_t)n_sets * 3 * g.K, false, st));
+  CUDA_TRY(c->h_counts.ensure(sizeof(int) * (size_t)n_sets * NC, false, st));
+  int rc = bnn_forward_lik(c, c->h_w.as<double>(), n_sets, alpha_host ? c->h_alpha.as<double>() : nullptr,
+                           sigma_host ? c->h_sigma.as<double>() : nullptr, sigma_mode, lik_temp,
+                           c->h_loglik.as<double>(), c->h_sums.as<double>(), c->h_counts.as<int>(), stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(loglik_host, c->h_loglik.p, sizeof(double) * n_sets, cudaMemcpyDeviceToHost, st));
+  if (sums_host && g.lik != BNN_LIK_CATEGORICAL)
+    CUDA_TRY(cudaMemcpyAsync(sums_host, c->h_sums.p, sizeof(double) * (size_t)n_sets * 3 * g.K, cudaMemcpyDeviceToHost, st));
+  if (counts_host && g.lik == BNN_LIK_CATEGORICAL)
+    CUDA_TRY(cudaMemcpyAsync(counts_host, c->h_counts.p, sizeof(int) * (size_t)n_sets * NC, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static void fill_prior_scales(PriorScales& ps, const double* s, int L) {
+  for (int l = 0; l < BNN_MAX_LAYERS; ++l) {
+    ps.s[l] = (l < L) ? s[l] : 1.0;
+    ps.ls[l] = log(ps.s[l]);
+  }
+}
+
+int bnn_log_prior(bnn_ctx* c, const double* w_dev, int32_t n_sets, int32_t prior, const double* prior_scale,
+                  double* logprior_dev, void* stream) {
+  REQUIRE(c && c->have_net, "bnn_log_prior: call bnn_set_net first");
+  REQUIRE(w_dev && logprior_dev && prior_scale && n_sets >= 1, "bnn_log_prior: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  PriorScales ps;
+  fill_prior_scales(ps, prior_scale, c->g.L);
+  CUDA_TRY(bnn_launch_log_prior(c->g, w_dev, n_sets, prior, ps, logprior_dev, (cudaStream_t)stream));
+  c->launches++;
+  return 0;
+}
+
+static ChainDev chain_dev(bnn_ctx* c) {
+  ChainDev d{};
+  d.g = c->g;
+  d.cfg = c->cfg;
+  d.ps = c->ps;
+  d.C = c->C;
+  d.n_train = c->n_train;
+  d.n_tiles16 = c->n_tiles16;
+  d.w_cur = c->w_cur.as<double>();
+  d.w_prop = c->w_prop.as<double>();
+  d.wp_prop = c->wp_prop.as<double>();
+  d.mask = c->cfg.use_mask ? c->mask.as<double>() : nullptr;
+  d.owner = c->owner.as<int>();
+  d.sf = c->sf.as<double>();
+  d.si = c->si.as<int>();
+  d.part = c->part.as<double>();
+  d.NF = n_slots(c->g);
+  d.counts_prop = c->counts_prop.as<int>();
+  return d;
+}
+
+// forward pass of every chain's packed proposal -> partials + proposal counters
+static int chains_forward(bnn_ctx* c, cudaStream_t st) {
+  const NetGeom& g = c->g;
+  const int NC = 2 + 2 * g.K;
+  const int per = sets_per_pass(g);
+  FwdParams p = base_params(c);
+  for (int s0 = 0; s0 < c->C; s0 += per) {
+    const int n = (c->C - s0 < per) ? c->C - s0 : per;
+    p.wp = c->wp_prop.as<double>() + (size_t)s0 * g.PB;
+    p.alpha = c->alpha_chain.as<double>() + (size_t)s0 * g.L;
+    p.C = n;
+    p.part = c->part.as<double>() + (size_t)s0 * p.NF * c->n_tiles16;
+    p.counts = c->counts_prop.as<int>() + (size_t)s0 * NC;
+    CUDA_TRY(bnn_launch_forward(p, false, c->n_sms, c->force_generic, st, &c->last_kernel));
+    c->launches++;
+  }
+  return 0;
+}
+
+int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg, const double* w0_host,
+                    const double* mask_host, const double* temperature, const double* update_f,
+                    const double* update_ws, const double* alpha, const double* sigma0, void* stream) {
+  REQUIRE(c && c->have_data, "bnn_chains_init: call bnn_set_net and bnn_set_data first");
+  REQUIRE(cfg && w0_host && temperature && update_f && update_ws && n_chains >= 1, "bnn_chains_init: bad arguments");
+  REQUIRE(cfg->adapt_freq >= 1, "bnn_chains_init: adapt_freq must be >= 1");
+  REQUIRE(!cfg->use_mask || mask_host, "bnn_chains_init: use_mask set but mask_host is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetGeom& g = c->g;
+  const int C = n_chains, NC = 2 + 2 * g.K;
+  c->C = C;
+  c->cfg = *cfg;
+  fill_prior_scales(c->ps, cfg->prior_scale, g.L);
+  CUDA_TRY(c->w_cur.ensure(sizeof(double) * (size_t)C * g.P, false, st));
+  CUDA_TRY(c->w_prop.ensure(sizeof(double) * (size_t)C * g.P, false, st));
+  CUDA_TRY(c->wp_prop.ensure(sizeof(double) * (size_t)C * g.PB, false, st));
+  CUDA_TRY(cudaMemsetAsync(c->wp_prop.p, 0, sizeof(double) * (size_t)C * g.PB, st));
+  CUDA_TRY(c->owner.ensure(sizeof(int) * (size_t)C * g.P, false, st));
+  CUDA_TRY(cudaMemsetAsync(c->owner.p, 0xff, sizeof(int) * (size_t)C * g.P, st));
+  CUDA_TRY(c->sf.ensure(sizeof(double) * (size_t)C * BNN_F_STRIDE, false, st));
+  CUDA_TRY(c->si.ensure(sizeof(int) * (size_t)C * BNN_I_STRIDE, false, st));
+  CUDA_TRY(c->counts_prop.ensure(sizeof(int) * (size_t)C * NC, false, st));
+  CUDA_TRY(c->alpha_chain.ensure(sizeof(double) * (size_t)C * g.L, false, st));
+  CUDA_TRY(c->part.ensure(sizeof(double) * (size_t)n_slots(g) * C * c->n_tiles16, false, st));
+  if (cfg->use_mask) {
+    CUDA_TRY(c->mask.ensure(sizeof(double) * g.P, false, st));
+    CUDA_TRY(cudaMemcpyAsync(c->mask.p, mask_host, sizeof(double) * g.P, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->w_cur.p, w0_host, sizeof(double) * (size_t)C * g.P, cudaMemcpyHostToDevice, st));
+
+  std::vector<double> sf((size_t)C * BNN_F_STRIDE, 0.0), al((size_t)C * g.L, 0.0);
+  std::vector<int> si((size_t)C * BNN_I_STRIDE, 0);
+  for (int ch = 0; ch < C; ++ch) {
+    double* f = sf.data() + (size_t)ch * BNN_F_STRIDE;
+    int* i = si.data() + (size_t)ch * BNN_I_STRIDE;
+    f[BNN_F_TEMPERATURE] = temperature[ch];
+    for (int l = 0; l < g.L; ++l) {
+      const int size = g.l[l].out * (g.l[l].in + g.l[l].bias);
+      f[BNN_F_UPDATE_F + l] = update_f[ch * g.L + l];
+      f[BNN_F_UPDATE_WS + l] = update_ws[ch * g.L + l];
+      f[BNN_F_FREQ_LAYER + l] = 1.0;
+      f[BNN_F_ALPHA + l] = alpha ? alpha[ch * g.L + l] : 0.0;
+      al[(size_t)ch * g.L + l] = f[BNN_F_ALPHA + l];
+      // update_n = max(1, round(size * update_f)) with numpy's half-to-even rounding (BNN_env.py:292-293)
+      int n = (int)nearbyint((double)size * update_f[ch * g.L + l]);
+      i[BNN_I_UPDATE_N + l] = n < 1 ? 1 : n;
+      i[BNN_I_MAX_N + l] = size;
+    }
+    for (int j = 0; j < g.K; ++j) f[BNN_F_SIGMA + j] = sigma0 ? sigma0[ch * g.K + j] : 1.0;
+    // _last_accepted = 1, _last_accepted_mem = [1], _acceptance_rate = 0 (BNN_env.py:356-358)
+    i[BNN_I_LAST_ACCEPTED] = 1;
+    i[BNN_I_RING_LEN] = 1; i[BNN_I_RING_SUM] = 1; i[BNN_I_RING + 0] = 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->sf.p, sf.data(), sizeof(double) * sf.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->si.p, si.data(), sizeof(int) * si.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->alpha_chain.p, al.data(), sizeof(double) * al.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // host staging vectors go out of scope
+
+  // initial state: forward + likelihood + prior + counters of w0 (MCMC.__init__, BNN_env.py:299-353)
+  ChainDev d = chain_dev(c);
+  CUDA_TRY(bnn_launch_mh_update(d, 0, 2, 0, st));
+  c->launches++;
+  int rc = chains_forward(c, st);
+  if (rc) return rc;
+  CUDA_TRY(bnn_launch_mh_update(d, 2, 0, 0, st));
+  c->launches++;
+  c->have_chains = true;
+  return 0;
+}
+
+int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_mh_steps: call bnn_chains_init first");
+  REQUIRE(n_steps >= 1, "bnn_mh_steps: n_steps must be >= 1");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetGeom& g = c->g;
+  ChainDev d = chain_dev(c);
+  if (inj) {
+    REQUIRE(inj->n_steps >= n_steps && inj->cap >= 1, "bnn_mh_steps: injection shorter than n_steps");
+    REQUIRE(inj->proposed && inj->count && inj->ix && inj->iy && inj->dz && inj->log_u, "bnn_mh_steps: null injection array");
+    const size_t nl = (size_t)n_steps * c->C * g.L, nc = (size_t)n_steps * c->C * inj->cap;
+    // bounds check on the host: indices address the canonical matrices directly
+    for (size_t s = 0; s < (size_t)n_steps * c->C; ++s) {
+      size_t off = 0;
+      for (int l = 0; l < g.L; ++l) {
+        if (!inj->proposed[s * g.L + l]) continue;
+        const int cnt = inj->count[s * g.L + l];
+        REQUIRE(cnt >= 0 && off + cnt <= (size_t)inj->cap, "bnn_mh_steps: injection count exceeds cap");
+        for (int k = 0; k < cnt; ++k) {
+          const int ix = inj->ix[s * inj->cap + off + k], iy = inj->iy[s * inj->cap + off + k];
+          REQUIRE(ix >= 0 && ix < g.l[l].out && iy >= 0 && iy < g.l[l].in + g.l[l].bias, "bnn_mh_steps: injected index out of range");
+        }
+        off += cnt;
+      }
+    }
+    int rc = 0;
+    rc |= upload(c->inj_proposed, inj->proposed, nl, st);
+    rc |= upload(c->inj_count, inj->count, nl, st);
+    rc |= upload(c->inj_ix, inj->ix, nc, st);
+    rc |= upload(c->inj_iy, inj->iy, nc, st);
+    rc |= upload(c->inj_dz, inj->dz, nc, st);
+    rc |= upload(c->inj_logu, inj->log_u, (size_t)n_steps * c->C, st);
+    if (rc) return rc;
+    d.inj_proposed = c->inj_proposed.as<int>();
+    d.inj_count = c->inj_count.as<int>();
+    d.inj_ix = c->inj_ix.as<int>();
+    d.inj_iy = c->inj_iy.as<int>();
+    d.inj_dz = c->inj_dz.as<double>();
+    d.inj_logu = c->inj_logu.as<double>();
+    d.inj_cap = inj->cap;
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    CUDA_TRY(bnn_launch_mh_update(d, s > 0 ? 1 : 0, 1, s, st));
+    c->launches++;
+    int rc = chains_forward(c, st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(bnn_launch_mh_update(d, 1, 0, n_steps, st));
+  c->launches++;
+  if (inj) CUDA_TRY(cudaStreamSynchronize(st));   // the caller may free the host arrays after return
+  return 0;
+}
+
+int bnn_chains_read(bnn_ctx* c, double* f64_host, int32_t* i32_host, double* w_host, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_chains_read: call bnn_chains_init first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f64_host) CUDA_TRY(cudaMemcpyAsync(f64_host, c->sf.p, sizeof(double) * (size_t)c->C * BNN_F_STRIDE, cudaMemcpyDeviceToHost, st));
+  if (i32_host) CUDA_TRY(cudaMemcpyAsync(i32_host, c->si.p, sizeof(int) * (size_t)c->C * BNN_I_STRIDE, cudaMemcpyDeviceToHost, st));
+  if (w_host) CUDA_TRY(cudaMemcpyAsync(w_host, c->w_cur.p, sizeof(double) * (size_t)c->C * c->g.P, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bnn_chains_state_dev(bnn_ctx* c, double** f64_dev, int32_t** i32_dev, double** w_dev) {
+  REQUIRE(c && c->have_chains, "bnn_chains_state_dev: call bnn_chains_init first");
+  if (f64_dev) *f64_dev = c->sf.as<double>();
+  if (i32_dev) *i32_dev = c->si.as<int>();
+  if (w_dev) *w_dev = c->w_cur.as<double>();
+  return 0;
+}
+
+int bnn_chains_set_temperature(bnn_ctx* c, const double* temperature_host, void* stream) {
+  REQUIRE(c && c->have_chains && temperature_host, "bnn_chains_set_temperature: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpy2DAsync(c->sf.as<double>() + BNN_F_TEMPERATURE, sizeof(double) * BNN_F_STRIDE, temperature_host,
+                             sizeof(double), sizeof(double), c->C, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
+                int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, void* stream) {
+  REQUIRE(c && c->have_net, "bnn_predict: call bnn_set_net first");
+  REQUIRE(x_dev && w_dev && n >= 1 && n_sets >= 1, "bnn_predict: bad arguments");
+  REQUIRE(mean_dev || votes_dev || dense_dev, "bnn_predict: no output requested");
+  REQUIRE(n_override >= 0 && (n_override == 0 || (override_cols && override_vals)), "bnn_predict: bad override arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetGeom& g = c->g;
+  REQUIRE(!(votes_dev && g.lik != BNN_LIK_CATEGORICAL), "bnn_predict: vote summary needs the categorical likelihood");
+  const long long n_pad = (n + 15) / 16 * 16;
+  CUDA_TRY(c->xs_pred.ensure(sizeof(double) * (size_t)n_pad * g.F_pad, false, st));
+  const int* ovc = nullptr;
+  const double* ovv = nullptr;
+  if (n_override > 0) {
+    for (int k = 0; k < n_override; ++k) REQUIRE(override_cols[k] >= 0 && override_cols[k] < g.F, "bnn_predict: override column out of range");
+    if (upload(c->ov_cols, override_cols, n_override, st)) return 1;
+    if (upload(c->ov_vals, override_vals, n_override, st)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ovc = c->ov_cols.as<int>();
+    ovv = c->ov_vals.as<double>();
+  }
+  CUDA_TRY(bnn_launch_pack_x(x_dev, c->xs_pred.as<double>(), n, n_pad, g.F, g.F_pad, g.x_swz, ovc, ovv, n_override, st));
+  CUDA_TRY(c->wp_scratch.ensure(sizeof(double) * (size_t)n_sets * g.PB, true, st));
+  CUDA_TRY(bnn_launch_pack_w(g, w_dev, c->wp_scratch.as<double>(), n_sets, st));
+  FwdParams p{};
+  p.g = g;
+  p.x = c->xs_pred.as<double>();
+  p.n_train = n; p.n_total = n; p.n_tiles16 = n_pad / 16;
+  p.wp = c->wp_scratch.as<double>();
+  p.alpha = alpha_dev;
+  p.C = n_sets;
+  p.NF = n_slots(g);
+  p.mean_out = mean_dev; p.votes_out = votes_dev; p.dense_out = dense_dev;
+  p.inv_sets = (double)n_sets;   // divisor (np.mean and the vote share divide, BNN_lib.py:390-392)
+  p.exp_tab = c->exp_tab.as<double>();
+  CUDA_TRY(bnn_launch_forward(p, true, c->n_sms, c->force_generic, st, &c->last_kernel));
+  c->launches += 3;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// Shared device/host definitions for the npbnn_b200 kernels (sm_100a).
+//
+// Data layout in HBM:
+//   X     "swizzled rows": [n_pad16, F_pad] f64, element (r, c) at r*F_pad + (c ^ ((r&1)*x_swz)).
+//         F_pad = F rounded up to 8, rows rounded up to 16, zero filled.  The XOR swaps the two
+//         64-byte halves of each 128-byte group on odd rows so that the 16-byte fragment loads of a
+//         quarter-warp (2 rows x 4 chunks) hit 8 different 16-byte bank groups.
+//   W     "packed weight set": per layer a [out_pad, stride] matrix in the same swizzled-row form
+//         (bias column removed) followed by bias[out_pad]; padding is zero and never written.
+//   both are moved to shared memory verbatim (cp.async.bulk), so global layout == smem layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/npbnn_b200.h"
+
+#define BNN_EXP_TAB_BITS 8
+#define BNN_EXP_TAB_SIZE (1 << BNN_EXP_TAB_BITS)
+
+struct LayerGeom {
+  int in, out, bias;        // canonical: W is [out, in + bias]
+  int in_pad, out_pad;      // rounded up to 8
+  int stride, swz;          // packed row stride (= in_pad) and XOR constant (8 or 0)
+  int w_off, b_off;         // offsets (doubles) of matrix / bias inside a packed weight set
+  int c_off;                // offset (doubles) of the layer inside a canonical weight set
+};
+
+struct NetGeom {
+  int L;
+  int F, F_pad, x_swz;
+  int act, lik;
+  int O;                    // width of the output layer
+  int K;                    // classes (CATEGORICAL) or number of modelled outputs (Gaussian)
+  int P;                    // canonical parameters per weight set
+  int PB;                   // packed doubles per weight set
+  int max_w;                // widest padded activation (for smem staging)
+  LayerGeom l[BNN_MAX_LAYERS];
+};
+
+__host__ __device__ inline int bnn_round_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ inline int bnn_swz_for(int stride) { return (stride % 16 == 0) ? 8 : 0; }
+
+// canonical (layer, r, cc) -> offset inside a packed weight set
+__host__ __device__ inline int bnn_packed_index(const LayerGeom& g, int r, int cc) {
+  if (g.bias) {
+    if (cc == 0) return g.b_off + r;
+    cc -= 1;
+  }
+  return g.w_off + r * g.stride + (cc ^ ((r & 1) * g.swz));
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 tensor-core MMA (DMMA).  Fragment <-> matrix mapping (g = lane>>2, t = lane&3), with the K
+// index permuted inside each group of 8 columns (k-slot t <-> column 2t, k-slot t+4 <-> column 2t+1;
+// a sum over k is order-free) so that one 16-byte load feeds both k-slots and the accumulator of
+// one layer IS the A operand of the next:
+//   a0=A[g][8j+2t] a1=A[g+8][8j+2t] a2=A[g][8j+2t+1] a3=A[g+8][8j+2t+1]
+//   b0=W[n0+g][8j+2t] b1=W[n0+g][8j+2t+1]
+//   c0=C[g][n0+2t] c1=C[g][n0+2t+1] c2=C[g+8][n0+2t] c3=C[g+8][n0+2t+1]
+// Verified on a B200 by tools/peak_fp64.cu (layout probe, profiles/r01_fp64_peaks.log).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1, double a2, double a3,
+                                           double b0, double b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 transcendentals tuned for the shared FP64 pipe (DMMA and DFMA issue to the same pipe on B200,
+// profiles/r01_fp64_peaks.log), i.e. as few FP64 instructions as possible:
+//   exp : 256-entry table of 2^(j/256) + degree-4 polynomial, 9 FP64 instructions, |rel err| < 3e-16
+//   rcp : MUFU.RCP64H seed + 2 Newton steps, 4 FP64 instructions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bnn_exp_core(double x, const double* __restrict__ tab) {
+  const double INV = 369.3299304675746271;           // 256 / ln 2
+  const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest-integer trick
+  const double C_HI = 0.00270760617331689;           // ln2/256, low 21 mantissa bits zero (0x1.62e42fee00000p-9)
+  const double C_LO = 7.453964567463233e-13;         // ln2/256 - C_HI
+  double t = fma(x, INV, MAGIC);
+  int k = __double2loint(t);
+  double kd = t - MAGIC;
+  double r = fma(kd, -C_HI, x);
+  r = fma(kd, -C_LO, r);
+  double q = fma(r, 4.16666666666666644e-02, 1.66666666666666657e-01);
+  q = fma(r, q, 0.5);
+  double r2 = r * r;
+  double p = fma(r2, q, r);
+  double T = tab[k & (BNN_EXP_TAB_SIZE - 1)];
+  double res = fma(T, p, T);
+  int n = k >> BNN_EXP_TAB_BITS;
+  return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
+}
+
+// exp with results below 2^-1022 flushed to 0 and overflow to +inf (NaN propagates).
+__device__ __forceinline__ double bnn_exp(double x, const double* __restrict__ tab) {
+  int hx = __double2hiint(x);
+  int ax = hx & 0x7fffffff;
+  double res = bnn_exp_core(x, tab);
+  if (ax >= 0x40862278) {                   // |x| >= ~708.27: slow path
+    if (ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0)) return x + x;   // NaN
+    if (hx < 0) return (x < -708.3964185322641) ? 0.0 : res;
+    return (x > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000LL) : res;
+  }
+  return res;
+}
+
+// exp for activations: saturates at 2^1023 instead of +inf so that 1/(1+e) stays NaN-free.
+__device__ __forceinline__ double bnn_exp_sat(double x, const double* __restrict__ tab) {
+  int hx = __double2hiint(x);
+  int ax = hx & 0x7fffffff;
+  double res = bnn_exp_core(x, tab);
+  if (ax >= 0x40862278) {
+    if (ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0)) return x + x;
+    if (hx < 0) return (x < -708.3964185322641) ? 0.0 : res;
+    return (x > 709.08) ? 8.98846567431158e307 : res;
+  }
+  return res;
+}
+
+// 1/d for d >= 1 (finite).  rcp.approx.ftz.f64 = MUFU.RCP64H (about 20 good bits).
+__device__ __forceinline__ double bnn_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// Hidden-layer activation, matching the reference formulas (BNN_lib.py:50-66):
+//   swish z*(1+exp(-z))^-1 ; tanh 1 - 2/(exp(2z)+1) ; ReLU ; leaky (alpha*z for z<0)
+template <int ACT>
+__device__ __forceinline__ double bnn_act(double z, double alpha, const double* __restrict__ tab) {
+  if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
+  if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
+  if (ACT == BNN_ACT_SWISH) {
+    double e = bnn_exp_sat(-z, tab);
+    return z * bnn_rcp(1.0 + e);
+  }
+  double e = bnn_exp_sat(2.0 * z, tab);
+  return fma(-2.0, bnn_rcp(e + 1.0), 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D) helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / likelihood kernel parameters
+// ---------------------------------------------------------------------------------------------
+#define BNN_MAX_SETS_PER_PASS 64
+
+struct FwdParams {
+  NetGeom g;
+  const double* x;          // swizzled rows
+  long long n_train, n_total, n_tiles16;
+  const int* labels;        // [n_total] (categorical)
+  const double* targets;    // [n_total, K] (Gaussian)
+  const double* inst_w;     // [n_train] or null
+  const double* class_w;    // [K] or null
+  const double* wp;         // packed weight sets [C, PB]
+  const double* alpha;      // [C, L] or null
+  int C;
+  // likelihood mode outputs
+  double* part;             // [n_part, C, NF] per-warp partial sums (fixed order -> deterministic)
+  int NF;                   // 1 (categorical / head: loglik) + Gaussian: 3*K (sum r, sum r^2, sum r^2 test)
+  int* counts;              // [C, 2 + 2K] (atomics on integers: order independent)
+  // prediction mode outputs
+  double* mean_out;         // [n, K] or null
+  double* votes_out;        // [n, K] or null
+  double* dense_out;        // [C, n, K] or null
+  double inv_sets;         // number of weight sets as a double: summaries are divided by it
+  const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j/256)
+};

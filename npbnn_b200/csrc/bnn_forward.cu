@@ -1,0 +1,552 @@
+// K1 / K3: chain-batched forward pass fused with likelihood, accuracy counters or posterior summaries.
+//
+// Replaces (reference file:line): RunHiddenLayer / MatrixMultiplicationD / ActFun.eval
+// (BNN_lib.py:184-193, 154-162, 83-87), SoftMax / RegressTransform(Error) (BNN_lib.py:166-182),
+// calc_likelihood* (BNN_lib.py:100-143), CalcAccuracy / CalcLabelAccuracy / CalcLabelFreq
+// (BNN_lib.py:195-233) as called from MCMC.mh_step (BNN_env.py:449-518), and the RunPredict loops of
+// get_posterior_cat_prob / get_posterior_est / get_pdp (BNN_lib.py:376-392, 731-737, BNN_pdp.py:63-73).
+//
+// Work decomposition: a warp owns 16 rows of X ("warp tile") and runs every weight set of the pass
+// over them, so X is read from HBM exactly once per pass.  Each layer is a chain of FP64 tensor-core
+// MMAs (m16n8k8, bnn_common.cuh) whose accumulators are the next layer's A operand.
+//   k_fwd3        3-layer nets with compile-time padded widths: X warp tile in shared memory (bulk
+//                 async copy), weight sets streamed through a 2-deep shared-memory ring by bulk async
+//                 copies + mbarriers, hidden activations never leave registers.
+//   k_fwd_generic any depth/width: hidden activations staged in per-warp shared memory, weights read
+//                 through L1/L2.
+#include "bnn_common.cuh"
+
+#define FULL_MASK 0xffffffffu
+static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
+
+__device__ __forceinline__ double warp16_sum(double v) {
+  // lanes 0..15 hold values; fixed xor tree => deterministic
+  v += __shfl_xor_sync(FULL_MASK, v, 8);
+  v += __shfl_xor_sync(FULL_MASK, v, 4);
+  v += __shfl_xor_sync(FULL_MASK, v, 2);
+  v += __shfl_xor_sync(FULL_MASK, v, 1);
+  return v;
+}
+
+__device__ __forceinline__ double softplus_ref(double z) {
+  // np.logaddexp(0, z) (BNN_lib.py:170-172)
+  return fmax(z, 0.0) + log1p(exp(-fabs(z)));
+}
+
+// Per-warp epilogue on the staged outputs of one (warp tile, weight set).
+//   zs  : [16][ZS] pre-transform outputs of the last layer (row-major, per warp)
+//   lane r < 16 owns row r of the tile.
+// Likelihood mode (PREDICT=false): writes part[(c*NF+slot)*n_tiles16 + wt] and bumps the CTA counters.
+// Prediction mode: accumulates transformed outputs into pacc/pvote (per warp, [16][K_out]) and
+// optionally writes the dense tensor.
+template <bool PREDICT>
+__device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long long wt, int lane, const double* zs,
+                                             int ZS, const double* tab, int* cnt_smem, double* pacc, int* pvote) {
+  const NetGeom& g = p.g;
+  const long long row = wt * 16 + (lane & 15);
+  const bool active = lane < 16 && row < p.n_total;
+  const bool is_train = active && row < p.n_train;
+  const bool is_test = active && !is_train;
+  const double* z = zs + (lane & 15) * ZS;
+  const long long nt = p.n_tiles16;
+
+  if (g.lik == BNN_LIK_CATEGORICAL) {
+    const int K = g.K;
+    double m = -INFINITY;
+    int arg = 0;
+    double S = 0.0, ll = 0.0;
+    if (active) {
+      m = z[0];
+      for (int k = 1; k < K; ++k) {
+        double v = z[k];
+        if (v > m) { m = v; arg = k; }   // first maximum wins, as np.argmax
+      }
+      if (!PREDICT && is_train) {
+        for (int k = 0; k < K; ++k) S += bnn_exp(z[k] - m, tab);
+      }
+    }
+    if (!PREDICT) {
+      int y = 0;
+      if (active) {
+        y = p.labels[row];
+        bool ok = (arg == y);
+        if (is_train) {
+          double d = z[y] - m;
+          // log(softmax) of the reference is -inf once exp(d) underflows to 0 (BNN_lib.py:121,168)
+          ll = (d < -745.1332191019412) ? -INFINITY : d - log(S);
+          if (p.class_w) ll *= p.class_w[y];
+          if (p.inst_w) ll *= p.inst_w[row];
+          int* cc = cnt_smem + c * (2 + 2 * K);
+          if (ok) atomicAdd(&cc[2 + y], 1);
+          atomicAdd(&cc[2 + K + arg], 1);
+          if (ok) atomicAdd(&cc[0], 1);
+        } else if (ok) {
+          atomicAdd(&cnt_smem[c * (2 + 2 * K) + 1], 1);
+        }
+      }
+      double s = warp16_sum(is_train ? ll : 0.0);
+      if (lane == 0) p.part[((long long)c * p.NF) * nt + wt] = s;
+    } else {
+      if (active) {
+        double* zw = const_cast<double*>(z);     // the staged row is private to this lane: reuse as scratch
+        for (int k = 0; k < K; ++k) { double e = bnn_exp(z[k] - m, tab); zw[k] = e; S += e; }
+        double inv = 1.0 / S;
+        double* pa = pacc + (lane & 15) * K;
+        for (int k = 0; k < K; ++k) {
+          double pk = zw[k] * inv;
+          pa[k] += pk;
+          if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + k] = pk;
+        }
+        pvote[(lane & 15) * K + arg] += 1;
+      }
+    }
+    return;
+  }
+
+  // Gaussian likelihoods: K modelled outputs, targets [n_total, K]
+  const int K = g.K;
+  const bool head = (g.lik == BNN_LIK_GAUSSIAN_HEAD);
+  if (!PREDICT) {
+    double ll = 0.0;
+    for (int j = 0; j < K; ++j) {
+      double r = 0.0;
+      if (active) {
+        double t = p.targets[row * K + j];
+        r = z[j] - t;
+        if (head && is_train) {
+          double s = softplus_ref(z[K + j]);
+          double u = (t - z[j]) / s;
+          ll += -0.5 * u * u - kLogSqrt2Pi - log(s);
+        }
+      }
+      double sr = warp16_sum(is_train ? r : 0.0);
+      double sr2 = warp16_sum(is_train ? r * r : 0.0);
+      double st2 = warp16_sum(is_test ? r * r : 0.0);
+      if (lane == 0) {
+        p.part[((long long)c * p.NF + 1 + j) * nt + wt] = sr;
+        p.part[((long long)c * p.NF + 1 + K + j) * nt + wt] = sr2;
+        p.part[((long long)c * p.NF + 1 + 2 * K + j) * nt + wt] = st2;
+      }
+    }
+    double s = warp16_sum(ll);
+    if (lane == 0) p.part[((long long)c * p.NF) * nt + wt] = s;
+  } else {
+    if (active) {
+      const int O = g.O;
+      double* pa = pacc + (lane & 15) * O;
+      for (int j = 0; j < O; ++j) {
+        double v = z[j];
+        if (head && j >= K) v = softplus_ref(v);
+        pa[j] += v;
+        if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * O + j] = v;
+      }
+    }
+  }
+}
+
+// number of output columns per row in prediction mode
+__device__ __forceinline__ int bnn_pred_width(const NetGeom& g) { return g.lik == BNN_LIK_CATEGORICAL ? g.K : g.O; }
+
+template <bool PREDICT>
+__device__ __forceinline__ void bnn_pred_flush(const FwdParams& p, long long wt, int lane, double* pacc, int* pvote) {
+  if (!PREDICT) return;
+  const int W = bnn_pred_width(p.g);
+  for (int i = lane; i < 16 * W; i += 32) {
+    long long row = wt * 16 + i / W;
+    if (row < p.n_total) {
+      if (p.mean_out) p.mean_out[row * W + (i % W)] = pacc[i] / p.inv_sets;
+      if (p.votes_out) p.votes_out[row * W + (i % W)] = (double)pvote[i] / p.inv_sets;
+    }
+  }
+}
+
+// =============================================================================================
+// generic kernel
+// =============================================================================================
+constexpr int GEN_WARPS = 4;
+
+template <int ACT, bool PREDICT>
+__global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const NetGeom& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int ZS = bnn_round_up(g.O, 8) + 1;
+  const int PW = bnn_pred_width(g);
+
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  double* hbase = tab + BNN_EXP_TAB_SIZE;
+  const int per_warp = 2 * 16 * g.max_w + 16 * ZS + (PREDICT ? 16 * PW : 0);
+  double* h0 = hbase + warp * per_warp;
+  double* h1 = h0 + 16 * g.max_w;
+  double* zs = h1 + 16 * g.max_w;
+  double* pacc = zs + 16 * ZS;
+  int* ibase = reinterpret_cast<int*>(hbase + GEN_WARPS * per_warp);
+  int* pvote = ibase + warp * (PREDICT ? 16 * PW : 0);
+  int* cnt = ibase;   // likelihood mode: [C][2+2K]
+  const int n_cnt = (!PREDICT && g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+
+  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+
+  const long long total_warps = (long long)gridDim.x * GEN_WARPS;
+  for (long long wt = (long long)blockIdx.x * GEN_WARPS + warp; wt < p.n_tiles16; wt += total_warps) {
+    if (PREDICT) {
+      for (int i = lane; i < 16 * PW; i += 32) { pacc[i] = 0.0; pvote[i] = 0; }
+      __syncwarp();
+    }
+    const double* xrow0 = p.x + (wt * 16 + gq) * (long long)g.F_pad;
+    const double* xrow1 = xrow0 + 8LL * g.F_pad;
+    for (int c = 0; c < p.C; ++c) {
+      const double* W = p.wp + (long long)c * g.PB;
+      const double* src = nullptr;
+      double* dst = h0;
+      for (int l = 0; l < g.L; ++l) {
+        const LayerGeom& lg = g.l[l];
+        const bool last = (l == g.L - 1);
+        const double alpha = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * g.L + l] : 0.0;
+        const int sw = (gq & 1) * lg.swz;
+        const int nkg = lg.in_pad >> 3;
+        // destination geometry = next layer's A operand
+        const int dstride = last ? ZS : g.l[l + 1].stride;
+        const int dsw = last ? 0 : (gq & 1) * g.l[l + 1].swz;
+        for (int n0 = 0; n0 < lg.out_pad; n0 += 32) {
+          const int ntile = min(4, (lg.out_pad - n0) >> 3);
+          double acc[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double b0 = 0.0, b1 = 0.0;
+            if (j < ntile) {
+              const double2 bb = *reinterpret_cast<const double2*>(W + lg.b_off + n0 + 8 * j + 2 * t);
+              b0 = bb.x; b1 = bb.y;
+            }
+            acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
+          }
+          for (int kg = 0; kg < nkg; ++kg) {
+            const int col = (8 * kg + 2 * t) ^ sw;
+            double2 a_lo, a_hi;
+            if (l == 0) {
+              a_lo = __ldg(reinterpret_cast<const double2*>(xrow0 + col));
+              a_hi = __ldg(reinterpret_cast<const double2*>(xrow1 + col));
+            } else {
+              a_lo = *reinterpret_cast<const double2*>(src + gq * lg.stride + col);
+              a_hi = *reinterpret_cast<const double2*>(src + (gq + 8) * lg.stride + col);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < ntile) {
+                const double2 bb =
+                    __ldg(reinterpret_cast<const double2*>(W + lg.w_off + (long long)(n0 + 8 * j + gq) * lg.stride + col));
+                dmma16x8x8(acc[j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bb.x, bb.y);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < ntile) {
+              const int cn = n0 + 8 * j + 2 * t;
+              if (!last) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[j][e] = bnn_act<ACT>(acc[j][e], alpha, tab);
+                *reinterpret_cast<double2*>(dst + gq * dstride + (cn ^ dsw)) = make_double2(acc[j][0], acc[j][1]);
+                *reinterpret_cast<double2*>(dst + (gq + 8) * dstride + (cn ^ dsw)) = make_double2(acc[j][2], acc[j][3]);
+              } else {
+                zs[gq * ZS + cn] = acc[j][0]; zs[gq * ZS + cn + 1] = acc[j][1];
+                zs[(gq + 8) * ZS + cn] = acc[j][2]; zs[(gq + 8) * ZS + cn + 1] = acc[j][3];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        src = dst;
+        dst = (dst == h0) ? h1 : h0;
+      }
+      bnn_epilogue<PREDICT>(p, c, wt, lane, zs, ZS, tab, cnt, pacc, pvote);
+      __syncwarp();
+    }
+    bnn_pred_flush<PREDICT>(p, wt, lane, pacc, pvote);
+  }
+  if (n_cnt) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
+      if (cnt[i]) atomicAdd(&p.counts[i], cnt[i]);
+  }
+}
+
+// =============================================================================================
+// specialised 3-layer kernel (compile-time padded widths KP0 -> N1 -> N2 -> N3)
+// =============================================================================================
+template <int KP0, int N1, int N2, int N3>
+struct Fwd3Geom {
+  static constexpr int SW0 = (KP0 % 16 == 0) ? 8 : 0;
+  static constexpr int SW1 = (N1 % 16 == 0) ? 8 : 0;
+  static constexpr int SW2 = (N2 % 16 == 0) ? 8 : 0;
+  static constexpr int W1_OFF = 0, B1_OFF = N1 * KP0;
+  static constexpr int W2_OFF = B1_OFF + N1, B2_OFF = W2_OFF + N2 * N1;
+  static constexpr int W3_OFF = B2_OFF + N2, B3_OFF = W3_OFF + N3 * N2;
+  static constexpr int PB = B3_OFF + N3;
+  static constexpr int ZS = N3 + 1;
+};
+
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+__global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__ FwdParams p) {
+  using G3 = Fwd3Geom<KP0, N1, N2, N3>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const NetGeom& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int PW = bnn_pred_width(g);
+
+  // ---- shared memory carve-up
+  double* wbuf = reinterpret_cast<double*>(smem_raw);                  // [2][PB]
+  double* xs = wbuf + 2 * G3::PB + warp * 16 * KP0;                     // [NWARPS][16*KP0]
+  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // [256]
+  double* zs = tab + BNN_EXP_TAB_SIZE + warp * 16 * G3::ZS;             // [NWARPS][16*ZS]
+  double* pacc_base = tab + BNN_EXP_TAB_SIZE + NWARPS * 16 * G3::ZS;
+  double* pacc = pacc_base + warp * (PREDICT ? 16 * PW : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pacc_base + NWARPS * (PREDICT ? 16 * PW : 0));
+  uint64_t* full = bars;            // [2]
+  uint64_t* empty = bars + 2;       // [2]
+  uint64_t* xbar = bars + 4 + warp; // [NWARPS]
+  int* ibase = reinterpret_cast<int*>(bars + 4 + NWARPS);
+  int* pvote = ibase + warp * (PREDICT ? 16 * PW : 0);
+  int* cnt = ibase;
+  const int n_cnt = (!PREDICT && g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+
+  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], NWARPS); mbar_init(&empty[1], NWARPS);
+    for (int w = 0; w < NWARPS; ++w) mbar_init(&bars[4 + w], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long total_warps = (long long)gridDim.x * NWARPS;
+  const long long n_iter = (p.n_tiles16 + total_warps - 1) / total_warps;
+  const long long total_q = n_iter * p.C;     // weight-set uses, identical for every warp of the CTA
+  constexpr uint32_t W_BYTES = G3::PB * sizeof(double);
+  constexpr uint32_t X_BYTES = 16 * KP0 * sizeof(double);
+
+  const bool producer = (threadIdx.x == 0);
+  if (producer) {
+    for (int q = 0; q < 2 && q < total_q; ++q) {
+      mbar_arrive_expect_tx(&full[q], W_BYTES);
+      bulk_g2s(wbuf + q * G3::PB, p.wp + (long long)(q % p.C) * G3::PB, W_BYTES, &full[q]);
+    }
+  }
+
+  long long q = 0;
+  for (long long it = 0; it < n_iter; ++it) {
+    const long long wt = it * total_warps + (long long)blockIdx.x * NWARPS + warp;
+    const bool have_tile = wt < p.n_tiles16;
+    if (have_tile) {
+      if (lane == 0) {
+        // order this warp's earlier generic-proxy reads of xs before the async-proxy overwrite
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(xbar, X_BYTES);
+        bulk_g2s(xs, p.x + wt * 16 * KP0, X_BYTES, xbar);
+      }
+      if (PREDICT) {
+        for (int i = lane; i < 16 * PW; i += 32) { pacc[i] = 0.0; pvote[i] = 0; }
+      }
+      mbar_wait(xbar, (uint32_t)(it & 1));
+    }
+    for (int c = 0; c < p.C; ++c, ++q) {
+      const int b = (int)(q & 1);
+      // producer: refill the other buffer (use q+1) once every warp has released use q-1
+      if (producer && q >= 1 && q + 1 < total_q) {
+        const int nb = b ^ 1;
+        mbar_wait(&empty[nb], (uint32_t)(((q - 1) >> 1) & 1));
+        mbar_arrive_expect_tx(&full[nb], W_BYTES);
+        bulk_g2s(wbuf + nb * G3::PB, p.wp + (long long)((q + 1) % p.C) * G3::PB, W_BYTES, &full[nb]);
+      }
+      __syncwarp();
+      mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
+      if (have_tile) {
+        const double* W = wbuf + b * G3::PB;
+        const double a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
+        const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
+        // ---------------- layer 1: [16 x KP0] x [KP0 x N1]
+        double acc1[N1 / 8][4];
+#pragma unroll
+        for (int j = 0; j < N1 / 8; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B1_OFF + 8 * j + 2 * t);
+          acc1[j][0] = bb.x; acc1[j][1] = bb.y; acc1[j][2] = bb.x; acc1[j][3] = bb.y;
+        }
+        {
+          const double* xr0 = xs + gq * KP0;
+          const double* xr1 = xs + (gq + 8) * KP0;
+          const double* wr = W + G3::W1_OFF + gq * KP0;
+          const int sw = (gq & 1) * G3::SW0;
+#pragma unroll 2
+          for (int kg = 0; kg < KP0 / 8; ++kg) {
+            const int col = (8 * kg + 2 * t) ^ sw;
+            const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
+            const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
+#pragma unroll
+            for (int j = 0; j < N1 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
+              dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < N1 / 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc1[j][e] = bnn_act<ACT>(acc1[j][e], a1, tab);
+        // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = acc1, no data movement)
+        double acc2[N2 / 8][4];
+#pragma unroll
+        for (int j = 0; j < N2 / 8; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B2_OFF + 8 * j + 2 * t);
+          acc2[j][0] = bb.x; acc2[j][1] = bb.y; acc2[j][2] = bb.x; acc2[j][3] = bb.y;
+        }
+        {
+          const double* wr = W + G3::W2_OFF + gq * N1;
+          const int sw = (gq & 1) * G3::SW1;
+#pragma unroll
+          for (int kg = 0; kg < N1 / 8; ++kg) {
+            const int col = (8 * kg + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N2 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + col);
+              dmma16x8x8(acc2[j], acc1[kg][0], acc1[kg][2], acc1[kg][1], acc1[kg][3], bb.x, bb.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < N2 / 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc2[j][e] = bnn_act<ACT>(acc2[j][e], a2, tab);
+        // ---------------- layer 3: [16 x N2] x [N2 x N3]
+        double acc3[N3 / 8][4];
+#pragma unroll
+        for (int j = 0; j < N3 / 8; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
+          acc3[j][0] = bb.x; acc3[j][1] = bb.y; acc3[j][2] = bb.x; acc3[j][3] = bb.y;
+        }
+        {
+          const double* wr = W + G3::W3_OFF + gq * N2;
+          const int sw = (gq & 1) * G3::SW2;
+#pragma unroll
+          for (int kg = 0; kg < N2 / 8; ++kg) {
+            const int col = (8 * kg + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N3 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N2 + col);
+              dmma16x8x8(acc3[j], acc2[kg][0], acc2[kg][2], acc2[kg][1], acc2[kg][3], bb.x, bb.y);
+            }
+          }
+        }
+        // weights of this use are no longer needed by this warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[b]);
+#pragma unroll
+        for (int j = 0; j < N3 / 8; ++j) {
+          const int cn = 8 * j + 2 * t;
+          zs[gq * G3::ZS + cn] = acc3[j][0]; zs[gq * G3::ZS + cn + 1] = acc3[j][1];
+          zs[(gq + 8) * G3::ZS + cn] = acc3[j][2]; zs[(gq + 8) * G3::ZS + cn + 1] = acc3[j][3];
+        }
+        __syncwarp();
+        bnn_epilogue<PREDICT>(p, c, wt, lane, zs, G3::ZS, tab, cnt, pacc, pvote);
+        __syncwarp();
+      } else {
+        if (lane == 0) mbar_arrive(&empty[b]);
+      }
+    }
+    if (have_tile) bnn_pred_flush<PREDICT>(p, wt, lane, pacc, pvote);
+  }
+  if (n_cnt) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
+      if (cnt[i]) atomicAdd(&p.counts[i], cnt[i]);
+  }
+}
+
+// =============================================================================================
+// host-side launchers
+// =============================================================================================
+template <int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+static size_t fwd3_smem_bytes(const FwdParams& p) {
+  using G3 = Fwd3Geom<KP0, N1, N2, N3>;
+  const int PW = (p.g.lik == BNN_LIK_CATEGORICAL) ? p.g.K : p.g.O;
+  size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE + (size_t)NWARPS * 16 * G3::ZS +
+             (PREDICT ? (size_t)NWARPS * 16 * PW : 0);
+  size_t bytes = d * sizeof(double) + (4 + NWARPS) * sizeof(uint64_t);
+  size_t ints = PREDICT ? (size_t)NWARPS * 16 * PW
+                        : (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) : 0);
+  return bytes + ints * sizeof(int);
+}
+
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+static cudaError_t launch_fwd3(const FwdParams& p, int n_sms, cudaStream_t st) {
+  auto kern = k_fwd3<ACT, KP0, N1, N2, N3, NWARPS, PREDICT>;
+  size_t smem = fwd3_smem_bytes<KP0, N1, N2, N3, NWARPS, PREDICT>(p);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (smem > 232448) return cudaErrorInvalidConfiguration;
+  long long ctas = (p.n_tiles16 + NWARPS - 1) / NWARPS;
+  int grid = (int)(ctas < n_sms ? ctas : n_sms);
+  kern<<<grid, NWARPS * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int ACT, bool PREDICT>
+static cudaError_t launch_generic_t(const FwdParams& p, int n_sms, cudaStream_t st) {
+  auto kern = k_fwd_generic<ACT, PREDICT>;
+  const int ZS = bnn_round_up(p.g.O, 8) + 1;
+  const int PW = (p.g.lik == BNN_LIK_CATEGORICAL) ? p.g.K : p.g.O;
+  size_t per_warp = 2 * 16 * (size_t)p.g.max_w + 16 * ZS + (PREDICT ? 16 * PW : 0);
+  size_t bytes = (BNN_EXP_TAB_SIZE + GEN_WARPS * per_warp) * sizeof(double);
+  size_t ints = PREDICT ? (size_t)GEN_WARPS * 16 * PW
+                        : (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) : 0);
+  bytes += ints * sizeof(int);
+  if (bytes > 232448) return cudaErrorInvalidConfiguration;
+  static size_t attr_bytes = 0;
+  if (bytes > 48 * 1024 && bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_bytes = 232448;
+  }
+  long long ctas = (p.n_tiles16 + GEN_WARPS - 1) / GEN_WARPS;
+  // resident CTAs per SM limited by shared memory; cap the grid at a few waves of resident CTAs
+  long long max_grid = (long long)n_sms * 8;
+  int grid = (int)(ctas < max_grid ? ctas : max_grid);
+  kern<<<grid, GEN_WARPS * 32, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool PREDICT>
+static cudaError_t launch_generic(const FwdParams& p, int n_sms, cudaStream_t st) {
+  switch (p.g.act) {
+    case BNN_ACT_RELU: return launch_generic_t<BNN_ACT_RELU, PREDICT>(p, n_sms, st);
+    case BNN_ACT_LEAKY: return launch_generic_t<BNN_ACT_LEAKY, PREDICT>(p, n_sms, st);
+    case BNN_ACT_SWISH: return launch_generic_t<BNN_ACT_SWISH, PREDICT>(p, n_sms, st);
+    default: return launch_generic_t<BNN_ACT_TANH, PREDICT>(p, n_sms, st);
+  }
+}
+
+// Dispatch: specialised kernel when the padded shape is one of the compiled instantiations.
+// force_generic != 0 disables the specialised path (used by the tests to cross-check both kernels).
+cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
+                               const char** which) {
+  const NetGeom& g = p.g;
+  if (!force_generic && g.L == 3) {
+    const int k0 = g.F_pad, n1 = g.l[0].out_pad, n2 = g.l[1].out_pad, n3 = g.l[2].out_pad;
+    // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
+    if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH) {
+      if (which) *which = "k_fwd3<swish,64,64,32,16>";
+      return predict ? launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, true>(p, n_sms, st)
+                     : launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, false>(p, n_sms, st);
+    }
+  }
+  if (which) *which = "k_fwd_generic";
+  return predict ? launch_generic<true>(p, n_sms, st) : launch_generic<false>(p, n_sms, st);
+}

@@ -1,0 +1,47 @@
+// Internal interface between the kernel translation units and the C-ABI layer (bnn_capi.cu).
+#pragma once
+#include "bnn_common.cuh"
+
+struct PriorScales {
+  double s[BNN_MAX_LAYERS];    // npBNN._prior_scale
+  double ls[BNN_MAX_LAYERS];   // log of it
+};
+
+// Device-resident state of C chains.
+struct ChainDev {
+  NetGeom g;
+  bnn_sampler_config cfg;
+  PriorScales ps;
+  int C;
+  long long n_train, n_tiles16;
+  double* w_cur;        // [C, P] canonical current weights
+  double* w_prop;       // [C, P] canonical proposal
+  double* wp_prop;      // [C, PB] packed proposal (input of the forward kernel)
+  const double* mask;   // [P] or null
+  int* owner;           // [C, P] scratch for last-write-wins, all -1 between launches
+  double* sf;           // [C, BNN_F_STRIDE]
+  int* si;              // [C, BNN_I_STRIDE]
+  const double* part;   // forward partials [C, NF, n_tiles16]
+  int NF;
+  int* counts_prop;     // [C, 2 + 2K]
+  // injected draws of the current bnn_mh_steps call (device copies) or null
+  const int* inj_proposed;
+  const int* inj_count;
+  const int* inj_ix;
+  const int* inj_iy;
+  const double* inj_dz;
+  const double* inj_logu;
+  int inj_cap;
+};
+
+cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
+                               const char** which);
+cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
+                              const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st);
+cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st);
+cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF, long long nt, long long n_train,
+                                    double lik_temp, int sigma_mode, const double* sigma, double* loglik, double* sums,
+                                    int set0, int n_sets, cudaStream_t st);
+cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
+                                 double* out, cudaStream_t st);
+cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);

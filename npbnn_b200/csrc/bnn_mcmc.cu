@@ -1,0 +1,407 @@
+// K2: proposal generation, log-prior, Metropolis-Hastings accept/reject and state commit, plus the
+// small layout kernels (X / weight packing) and the deterministic reduction of the forward partials.
+//
+// Replaces (reference file:line): UpdateNormal (BNN_mcmc.py:57-69), the proposal / mask / prior /
+// accept / adaptation / acceptance-window parts of MCMC.mh_step (BNN_env.py:392-413, 446-466, 481,
+// 492-530) and npBNN.calc_prior (BNN_env.py:180-194).
+#include "bnn_common.cuh"
+#include "bnn_kernels.h"
+
+static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
+static constexpr double kLogPi = 1.14472988584940017414;
+static constexpr double kLog2 = 0.69314718055994530942;
+#define UPD_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------------
+// canonical X [n, F] -> swizzled, padded rows [n_pad16, F_pad]; optional column override (PDP)
+__global__ void k_pack_x(const double* __restrict__ x, double* __restrict__ xs, long long n, long long n_pad, int F,
+                         int F_pad, int swz, const int* __restrict__ ov_cols, const double* __restrict__ ov_vals,
+                         int n_ov) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = n_pad * F_pad;
+  if (i >= total) return;
+  long long r = i / F_pad;
+  int c = (int)(i % F_pad);
+  double v = 0.0;
+  if (r < n && c < F) {
+    v = x[r * F + c];
+    for (int k = 0; k < n_ov; ++k)
+      if (ov_cols[k] == c) v = ov_vals[k];
+  }
+  xs[r * F_pad + (c ^ ((int)(r & 1) * swz))] = v;
+}
+
+__device__ __forceinline__ int layer_of(const NetGeom& g, int i) {
+  int l = 0;
+#pragma unroll 1
+  for (int k = 1; k < g.L; ++k)
+    if (i >= g.l[k].c_off) l = k;
+  return l;
+}
+
+// canonical weight sets [n_sets, P] -> packed [n_sets, PB] (padding entries are pre-zeroed, never written)
+__global__ void k_pack_w(const __grid_constant__ NetGeom g, const double* __restrict__ w, double* __restrict__ wp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.P) return;
+  int l = layer_of(g, i);
+  const LayerGeom& lg = g.l[l];
+  int cols = lg.in + lg.bias;
+  int r = (i - lg.c_off) / cols, cc = (i - lg.c_off) % cols;
+  wp[(long long)blockIdx.y * g.PB + bnn_packed_index(lg, r, cc)] = w[(long long)blockIdx.y * g.P + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic block reductions (fixed order: per-thread strided sum -> xor tree -> warps in order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_fixed(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+  return s;
+}
+
+__device__ __forceinline__ double logpdf_prior(double w, int kind, double scale, double log_scale) {
+  // closed forms of scipy.stats.{norm,cauchy,laplace}.logpdf(w, 0, scale) (BNN_env.py:139-150)
+  double x = w / scale;
+  if (kind == BNN_PRIOR_CAUCHY) return -kLogPi - log1p(x * x) - log_scale;
+  if (kind == BNN_PRIOR_LAPLACE) return -kLog2 - fabs(x) - log_scale;
+  return -0.5 * x * x - kLogSqrt2Pi - log_scale;
+}
+
+// Reduce the per-warp-tile partials of chain `c` and turn them into the log-likelihood.
+//   red : shared [1 + 3*BNN_MAX_OUT] receives the reduced slots; sig_out [K] the sigma that was used
+__device__ double finalize_loglik(const NetGeom& g, const double* __restrict__ part, int NF, long long nt, int c,
+                                  long long n_train, double lik_temp, int sigma_mode,
+                                  const double* __restrict__ sigma_in, double* red, double* sig_out, double* sh) {
+  for (int slot = 0; slot < NF; ++slot) {
+    const double* src = part + ((long long)c * NF + slot) * nt;
+    double v = 0.0;
+    for (long long i = threadIdx.x; i < nt; i += blockDim.x) v += src[i];
+    double s = block_sum_fixed(v, sh);
+    if (threadIdx.x == 0) red[slot] = s;
+  }
+  __syncthreads();
+  double ll = red[0];
+  if (g.lik == BNN_LIK_GAUSSIAN) {
+    // calc_likelihood_regression (BNN_lib.py:123-131) from sum r, sum r^2:
+    //   sum_i logN(y_i; mu_i, s) = -SSR/(2 s^2) - N log s - N log sqrt(2 pi)
+    ll = 0.0;
+    const double N = (double)n_train;
+    for (int j = 0; j < g.K; ++j) {
+      double sr = red[1 + j], ssr = red[1 + g.K + j];
+      double s;
+      if (sigma_mode == BNN_SIGMA_EMPIRICAL) {
+        double mu = sr / N;                       // np.std(y' - labels, axis=0) (BNN_env.py:475-476)
+        s = sqrt(fmax(ssr / N - mu * mu, 0.0));
+      } else {
+        s = sigma_in ? sigma_in[j] : 1.0;
+      }
+      if (threadIdx.x == 0) sig_out[j] = s;
+      ll += -ssr / (2.0 * s * s) - N * log(s) - N * kLogSqrt2Pi;
+    }
+  }
+  __syncthreads();
+  return lik_temp * ll;
+}
+
+// stateless scoring: loglik / sums for bnn_forward_lik
+__global__ void __launch_bounds__(UPD_THREADS) k_finalize_lik(const __grid_constant__ NetGeom g, const double* part,
+                                                               int NF, long long nt, long long n_train,
+                                                               double lik_temp, int sigma_mode, const double* sigma,
+                                                               double* loglik, double* sums, int set0) {
+  __shared__ double red[1 + 3 * BNN_MAX_OUT];
+  __shared__ double sig[BNN_MAX_OUT];
+  __shared__ double sh[32];
+  const int c = blockIdx.x;
+  const double* sg = sigma ? sigma + (long long)(set0 + c) * g.K : nullptr;
+  double ll = finalize_loglik(g, part, NF, nt, c, n_train, lik_temp, sigma_mode, sg, red, sig, sh);
+  if (threadIdx.x == 0) loglik[set0 + c] = ll;
+  if (sums && g.lik != BNN_LIK_CATEGORICAL)
+    for (int i = threadIdx.x; i < 3 * g.K; i += blockDim.x) sums[(long long)(set0 + c) * 3 * g.K + i] = red[1 + i];
+}
+
+__global__ void __launch_bounds__(UPD_THREADS) k_log_prior(const __grid_constant__ NetGeom g, const double* w, int prior,
+                                                            PriorScales ps, double* out) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x;
+  double v = 0.0;
+  if (prior != BNN_PRIOR_UNIFORM)
+    for (int i = threadIdx.x; i < g.P; i += blockDim.x) {
+      int l = layer_of(g, i);
+      v += logpdf_prior(w[(long long)c * g.P + i], prior, ps.s[l], ps.ls[l]);
+    }
+  double s = block_sum_fixed(v, sh);
+  if (threadIdx.x == 0) out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (free-running proposals)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // [0,1)
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+struct Draw { int ix, iy; double dz; };
+// k-th proposal of layer l of chain c at iteration it
+__device__ __forceinline__ Draw philox_draw(uint64_t seed, int c, int it, int l, int k, int rows, int cols, double ws) {
+  uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)c, (uint32_t)(seed >> 32));
+  uint4 a = philox4x32(make_uint4((uint32_t)it, (uint32_t)k, (uint32_t)l, 0u), key);
+  uint4 b = philox4x32(make_uint4((uint32_t)it, (uint32_t)k, (uint32_t)l, 1u), key);
+  Draw d;
+  d.ix = (int)__umulhi(a.x, (uint32_t)rows);
+  d.iy = (int)__umulhi(a.y, (uint32_t)cols);
+  double u1 = 1.0 - u53(a.z, a.w);            // (0,1]
+  double u2 = u53(b.x, b.y);
+  double s, co;
+  sincospi(2.0 * u2, &s, &co);
+  d.dz = ws * sqrt(-2.0 * log(u1)) * co;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per chain: [accept previous proposal] + [adapt, propose, prior, pack]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant__ ChainDev d, int accept_mode,
+                                                            int propose_mode, int step) {
+  __shared__ double red[1 + 3 * BNN_MAX_OUT];
+  __shared__ double sig[BNN_MAX_OUT];
+  __shared__ double sh[32];
+  __shared__ int s_flag;
+  __shared__ int s_prop[BNN_MAX_LAYERS], s_cnt[BNN_MAX_LAYERS], s_off[BNN_MAX_LAYERS];
+  const NetGeom& g = d.g;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double* sf = d.sf + (long long)c * BNN_F_STRIDE;
+  int* si = d.si + (long long)c * BNN_I_STRIDE;
+  double* wc = d.w_cur + (long long)c * g.P;
+  double* wn = d.w_prop + (long long)c * g.P;
+  const int NC = 2 + 2 * g.K;
+
+  // ------------------------------------------------------------------ accept / reject
+  if (accept_mode) {
+    const bool smode_is_empirical = (accept_mode != 2) && d.cfg.sigma_mode == BNN_SIGMA_EMPIRICAL;
+    // the initial likelihood of MCMC.__init__ always uses the stored error_prm (ones), even with
+    // empirical_error=True (BNN_env.py:313-319); the empirical std only enters in mh_step (:475-476)
+    const int smode = (accept_mode == 2) ? BNN_SIGMA_FIXED : d.cfg.sigma_mode;
+    const double* sg_in = (g.lik == BNN_LIK_GAUSSIAN && smode == BNN_SIGMA_FIXED) ? sf + BNN_F_SIGMA : nullptr;
+    double ll = finalize_loglik(g, d.part, d.NF, d.n_tiles16, c, d.n_train, d.cfg.lik_temp, smode, sg_in, red, sig, sh);
+    if (d.cfg.sample_from_prior) ll = 0.0;
+    if (tid == 0) {
+      double lp = sf[BNN_F_LOGPRIOR_PROP];
+      double post = ll + lp;
+      sf[BNN_F_LOGLIK_PROP] = ll;
+      // accept iff (logPost' - logPost) * T + hastings >= log u   (BNN_env.py:493-494); NaN compares false
+      int acc = (accept_mode == 2) ? 1 : (((post - sf[BNN_F_LOGPOST]) * sf[BNN_F_TEMPERATURE] + 0.0 >= sf[BNN_F_LOG_U]) ? 1 : 0);
+      s_flag = acc;
+      if (acc) {
+        sf[BNN_F_LOGLIK] = ll; sf[BNN_F_LOGPRIOR] = lp; sf[BNN_F_LOGPOST] = post;
+      }
+      if (accept_mode == 1) {
+        si[BNN_I_LAST_ACCEPTED] = acc;
+        si[BNN_I_N_ACCEPTED] += acc;
+        // acceptance window (BNN_env.py:523-529): mean over the stored outcomes + the new one, then keep 100
+        int len = si[BNN_I_RING_LEN], head = si[BNN_I_RING_HEAD], sum = si[BNN_I_RING_SUM];
+        sf[BNN_F_ACC_RATE] = (double)(sum + acc) / (double)(len + 1);
+        if (len < 100) {
+          si[BNN_I_RING + (head + len) % 100] = acc;
+          si[BNN_I_RING_LEN] = len + 1;
+          si[BNN_I_RING_SUM] = sum + acc;
+        } else {
+          si[BNN_I_RING_SUM] = sum + acc - si[BNN_I_RING + head];
+          si[BNN_I_RING + head] = acc;
+          si[BNN_I_RING_HEAD] = (head + 1) % 100;
+        }
+        si[BNN_I_ITERATION] += 1;
+      }
+    }
+    __syncthreads();
+    if (s_flag) {
+      for (int i = tid; i < g.P; i += UPD_THREADS) wc[i] = wn[i];
+      if (g.lik == BNN_LIK_CATEGORICAL) {
+        const int* cp = d.counts_prop + (long long)c * NC;
+        if (tid < 2) si[BNN_I_N_CORRECT + tid] = cp[tid];
+        for (int i = tid; i < g.K; i += UPD_THREADS) {
+          si[BNN_I_CLASS_CORRECT + i] = cp[2 + i];
+          si[BNN_I_PRED_HIST + i] = cp[2 + g.K + i];
+        }
+      } else {
+        for (int i = tid; i < g.K; i += UPD_THREADS) {
+          sf[BNN_F_SUM_R + i] = red[1 + i];
+          sf[BNN_F_SUM_R2 + i] = red[1 + g.K + i];
+          sf[BNN_F_SUM_R2_TEST + i] = red[1 + 2 * g.K + i];
+          // reset_error_prm on accept, regression mode only (BNN_env.py:500-501)
+          if (g.lik == BNN_LIK_GAUSSIAN && smode_is_empirical) sf[BNN_F_SIGMA + i] = sig[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!propose_mode) return;
+
+  // ------------------------------------------------------------------ adaptation + which layers
+  const int it = si[BNN_I_ITERATION];
+  if (tid == 0) {
+    if (propose_mode == 1) {
+      // BNN_env.py:392-413
+      if (it % d.cfg.adapt_freq == 0 && it < d.cfg.adapt_stop) {
+        double ar = sf[BNN_F_ACC_RATE];
+        if (ar < d.cfg.adapt_f) {
+          for (int l = 0; l < g.L; ++l) {
+            sf[BNN_F_FREQ_LAYER + l] *= 0.8;
+            sf[BNN_F_UPDATE_F + l] *= 0.85;
+            int n = (int)((double)si[BNN_I_MAX_N + l] * sf[BNN_F_UPDATE_F + l]);
+            si[BNN_I_UPDATE_N + l] = n < 1 ? 1 : n;
+            sf[BNN_F_UPDATE_WS + l] *= 0.9;
+          }
+        }
+        int tot = 0;
+        for (int l = 0; l < g.L; ++l) tot += si[BNN_I_UPDATE_N + l];
+        if (ar > d.cfg.adapt_fM && tot < g.P) {
+          for (int l = 0; l < g.L; ++l) {
+            sf[BNN_F_UPDATE_F + l] = exp(log(sf[BNN_F_UPDATE_F + l]) * 0.85);
+            int n = (int)((double)si[BNN_I_MAX_N + l] * sf[BNN_F_UPDATE_F + l]);
+            si[BNN_I_UPDATE_N + l] = n < 1 ? 1 : n;
+            sf[BNN_F_UPDATE_WS + l] *= 1.2;
+          }
+        }
+      }
+      int off = 0;
+      if (d.inj_proposed) {
+        const long long base = ((long long)step * d.C + c) * g.L;
+        for (int l = 0; l < g.L; ++l) {
+          s_prop[l] = d.inj_proposed[base + l];
+          s_cnt[l] = s_prop[l] ? d.inj_count[base + l] : 0;
+          s_off[l] = off;
+          off += s_cnt[l];
+        }
+        sf[BNN_F_LOG_U] = d.inj_logu[(long long)step * d.C + c];
+      } else {
+        // rr = rs.random(L); rr[argmin] = 0; layer proposed iff rr < freq_layer_update (BNN_env.py:446-451)
+        uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)c, (uint32_t)(d.cfg.seed >> 32));
+        double rr[BNN_MAX_LAYERS];
+        int amin = 0;
+        for (int l = 0; l < g.L; ++l) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFFu, (uint32_t)l, 2u), key);
+          rr[l] = u53(r.x, r.y);
+          if (rr[l] < rr[amin]) amin = l;
+        }
+        rr[amin] = 0.0;
+        for (int l = 0; l < g.L; ++l) {
+          s_prop[l] = rr[l] < sf[BNN_F_FREQ_LAYER + l];
+          s_cnt[l] = s_prop[l] ? si[BNN_I_UPDATE_N + l] : 0;
+          s_off[l] = off;
+          off += s_cnt[l];
+        }
+        uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFEu, 0u, 3u), key);
+        sf[BNN_F_LOG_U] = log(u53(r.x, r.y));
+      }
+      for (int l = 0; l < g.L; ++l) si[BNN_I_PROPOSED + l] = s_prop[l];
+    } else {
+      for (int l = 0; l < g.L; ++l) { s_prop[l] = 0; s_cnt[l] = 0; s_off[l] = 0; }
+    }
+  }
+  // zero the proposal's counters (the forward kernel accumulates into them)
+  if (g.lik == BNN_LIK_CATEGORICAL)
+    for (int i = tid; i < NC; i += UPD_THREADS) d.counts_prop[(long long)c * NC + i] = 0;
+  for (int i = tid; i < g.P; i += UPD_THREADS) wn[i] = wc[i];
+  __syncthreads();
+
+  // ------------------------------------------------------------------ UpdateNormal (BNN_mcmc.py:57-69)
+  // z[Ix,Iy] = z[Ix,Iy] + N(0, d): fancy assignment => for duplicate (ix,iy) the LAST draw wins and
+  // increments are not accumulated.  owner[idx] = largest draw index touching idx.
+  int* owner = d.owner + (long long)c * g.P;
+  const long long inj_base = ((long long)step * d.C + c) * d.inj_cap;
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int l = 0; l < g.L; ++l) {
+      if (!s_prop[l]) continue;
+      const LayerGeom& lg = g.l[l];
+      const int cols = lg.in + lg.bias;
+      const double ws = sf[BNN_F_UPDATE_WS + l];
+      for (int k = tid; k < s_cnt[l]; k += UPD_THREADS) {
+        Draw dr;
+        if (d.inj_proposed) {
+          dr.ix = d.inj_ix[inj_base + s_off[l] + k];
+          dr.iy = d.inj_iy[inj_base + s_off[l] + k];
+          dr.dz = d.inj_dz[inj_base + s_off[l] + k];
+        } else {
+          dr = philox_draw(d.cfg.seed, c, it, l, k, lg.out, cols, ws);
+        }
+        const int idx = lg.c_off + dr.ix * cols + dr.iy;
+        if (pass == 0) atomicMax(&owner[idx], k);
+        else if (pass == 1) { if (owner[idx] == k) wn[idx] = wc[idx] + dr.dz; }
+        else owner[idx] = -1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ reflect, mask, prior, pack
+  const double hi = d.cfg.w_bound, lo = -d.cfg.w_bound;
+  double lp = 0.0;
+  double* wpk = d.wp_prop + (long long)c * g.PB;
+  for (int i = tid; i < g.P; i += UPD_THREADS) {
+    const int l = layer_of(g, i);
+    const LayerGeom& lg = g.l[l];
+    double z = wn[i];
+    if (propose_mode == 1) {
+      if (s_prop[l]) {                 // single reflection at the bounds (BNN_mcmc.py:66-67)
+        if (z > hi) z = hi - (z - hi);
+        if (z < lo) z = lo + (lo - z);
+      }
+      if (d.mask) z *= d.mask[i];      // w' *= mask for every layer (BNN_env.py:461-462)
+      wn[i] = z;
+    }
+    if (d.cfg.prior != BNN_PRIOR_UNIFORM) lp += logpdf_prior(z, d.cfg.prior, d.ps.s[l], d.ps.ls[l]);
+    const int cols = lg.in + lg.bias;
+    const int r = (i - lg.c_off) / cols, cc = (i - lg.c_off) % cols;
+    wpk[bnn_packed_index(lg, r, cc)] = z;
+  }
+  double s = block_sum_fixed(lp, sh);
+  if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers (called from bnn_capi.cu)
+// ------------------------------------------------------------------------------------------------
+cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
+                              const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st) {
+  long long total = n_pad * F_pad;
+  if (total == 0) return cudaSuccess;
+  k_pack_x<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, xs, n, n_pad, F, F_pad, swz, ov_cols, ov_vals, n_ov);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st) {
+  dim3 grid((g.P + 255) / 256, n_sets);
+  k_pack_w<<<grid, 256, 0, st>>>(g, w, wp);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF, long long nt, long long n_train,
+                                    double lik_temp, int sigma_mode, const double* sigma, double* loglik, double* sums,
+                                    int set0, int n_sets, cudaStream_t st) {
+  k_finalize_lik<<<n_sets, UPD_THREADS, 0, st>>>(g, part, NF, nt, n_train, lik_temp, sigma_mode, sigma, loglik, sums, set0);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
+                                 double* out, cudaStream_t st) {
+  k_log_prior<<<n_sets, UPD_THREADS, 0, st>>>(g, w, prior, ps, out);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st) {
+  k_mh_update<<<d.C, UPD_THREADS, 0, st>>>(d, accept_mode, propose_mode, step);
+  return cudaGetLastError();
+}

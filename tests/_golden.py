@@ -63,3 +63,32 @@ def injection(z, meta, t) -> orc.StepInjection:
         else:
             layers.append(None)
     return orc.StepInjection(rr=z["steps_rr"][t], layers=layers, log_u=float(z["steps_log_u"][t]))
+
+
+def injection_arrays(z, meta, t0, t1, n_chains=1):
+    """Pack steps [t0, t1) of a golden case into the arrays bnn_mh_steps expects (same draws for every chain)."""
+    nl = n_layers(meta)
+    T = t1 - t0
+    cap = 1
+    for t in range(t0, t1):
+        tot = sum(int(z["prop_l%d_off" % i][t + 1] - z["prop_l%d_off" % i][t]) for i in range(nl))
+        cap = max(cap, tot)
+    proposed = np.zeros((T, n_chains, nl), np.int32)
+    count = np.zeros((T, n_chains, nl), np.int32)
+    ix = np.zeros((T, n_chains, cap), np.int32)
+    iy = np.zeros((T, n_chains, cap), np.int32)
+    dz = np.zeros((T, n_chains, cap))
+    log_u = np.zeros((T, n_chains))
+    for t in range(t0, t1):
+        o = 0
+        for i in range(nl):
+            off = z["prop_l%d_off" % i]
+            a, b = int(off[t]), int(off[t + 1])
+            proposed[t - t0, :, i] = int(z["steps_proposed"][t][i])
+            count[t - t0, :, i] = b - a
+            ix[t - t0, :, o:o + b - a] = z["prop_l%d_ix" % i][a:b]
+            iy[t - t0, :, o:o + b - a] = z["prop_l%d_iy" % i][a:b]
+            dz[t - t0, :, o:o + b - a] = z["prop_l%d_dz" % i][a:b]
+            o += b - a
+        log_u[t - t0, :] = float(z["steps_log_u"][t])
+    return dict(proposed=proposed, count=count, ix=ix, iy=iy, dz=dz, log_u=log_u)

@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Tolerances: FP64 mode, log-likelihood / log-prior within 1e-9 relative (BASELINE.json north_star);
+integer counters, accept decisions and weights bit-exact on injected proposals."""
+import numpy as np
+import pytest
+
+from oracle import npbnn_oracle as orc
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+LIK = {"classification": 0, "regression": 1, "regression-error": 2}
+
+
+def rel_close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.allclose(a, b, rtol=rtol, atol=rtol * 1e-3)
+
+
+def make_engine(m, meta=None):
+    from npbnn_b200.engine import Engine, NetShape
+    net = NetShape.from_weights(m.weights, m.x.shape[1], act=m.act, lik=LIK[m.mode])
+    eng = Engine(net)
+    eng.set_data(m.x, m.labels, m.x_test, m.labels_test, inst_w=m.inst_w, class_w=m.class_w)
+    return eng
+
+
+def oracle_score(m, weights, sig=None, lik_temp=1.0):
+    y = orc.forward(m.x, weights, m.act, m.alphas, m.out_kind)
+    out = {}
+    if m.mode == "classification":
+        out["loglik"] = orc.loglik_categorical(y, m.labels, m.class_w, m.inst_w, lik_temp)
+        nc, ck, tk, hist = orc.class_counters(y, m.labels)
+        out["n_correct"], out["class_correct"], out["pred_hist"] = nc, ck, hist
+        if m.x_test is not None:
+            yt = orc.forward(m.x_test, weights, m.act, m.alphas, m.out_kind)
+            out["n_correct_test"] = orc.class_counters(yt, m.labels_test)[0]
+    else:
+        sr, sr2 = orc.regression_sums(y, m.labels)
+        out["sum_r"], out["sum_r2"] = sr, sr2
+        if m.mode == "regression":
+            s = np.std(y - m.labels, axis=0) if sig == "empirical" else (1.0 if sig is None else sig)
+            out["loglik"] = orc.loglik_regression(y, m.labels, s, lik_temp)
+        else:
+            out["loglik"] = orc.loglik_regression_error(y, m.labels, lik_temp)
+        if m.x_test is not None:
+            yt = orc.forward(m.x_test, weights, m.act, m.alphas, m.out_kind)
+            out["sum_r2_test"] = orc.regression_sums(yt, m.labels_test)[1]
+    return out
+
+
+@pytest.mark.parametrize("name", G.CHAIN_CASES)
+def test_forward_lik_matches_oracle(name):
+    """bnn_forward_lik on the golden data: initial weights, final weights and random jitter, batched."""
+    z, meta = G.load(name)
+    m = G.build_model(z, meta)
+    nl = G.n_layers(meta)
+    rng = np.random.default_rng(3)
+    sets = [m.weights, [np.array(z["wN_%d" % i]) for i in range(nl)]]
+    for s in range(5):
+        sets.append([w + rng.normal(0, 0.3, w.shape) for w in m.weights])
+    eng = make_engine(m)
+    al = None if m.alphas is None else np.tile(np.resize(m.alphas, nl), (len(sets), 1))
+    sig_mode = 1 if meta.get("empirical_error") else 0
+    for host in (False, True):
+        res = eng.forward_lik(sets, alphas=al, sigma_mode=sig_mode, lik_temp=meta["lik_temp"], host=host)
+        for i, w in enumerate(sets):
+            ref = oracle_score(m, w, "empirical" if sig_mode else None, meta["lik_temp"])
+            assert rel_close(res["loglik"][i], ref["loglik"]), (name, i, res["loglik"][i], ref["loglik"])
+            if m.mode == "classification":
+                K = eng.K
+                c = res["counts"][i]
+                assert c[0] == ref["n_correct"]
+                assert np.array_equal(c[2:2 + K], ref["class_correct"])
+                assert np.array_equal(c[2 + K:2 + 2 * K], ref["pred_hist"])
+                if m.x_test is not None:
+                    assert c[1] == ref["n_correct_test"]
+            else:
+                assert rel_close(res["sums"][i][0], ref["sum_r"], 1e-9) or np.allclose(res["sums"][i][0], ref["sum_r"], atol=1e-9)
+                assert rel_close(res["sums"][i][1], ref["sum_r2"])
+                if m.x_test is not None:
+                    assert rel_close(res["sums"][i][2], ref["sum_r2_test"])
+    # the -m gpu run must go through the CUDA library, never a fallback
+    assert eng.launch_count > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("prior,scale", [(1, 1.0), (2, 0.7), (3, 1.3), (0, 1.0), (1, [0.5, 1.0, 2.0])])
+def test_log_prior_matches_oracle(prior, scale):
+    z, meta = G.load("syn_swish_cauchy")
+    m = G.build_model(z, meta)
+    eng = make_engine(m)
+    rng = np.random.default_rng(1)
+    sets = [[w + rng.normal(0, 0.5, w.shape) for w in m.weights] for _ in range(4)]
+    got = eng.log_prior(sets, prior, scale)
+    sc = np.broadcast_to(np.asarray(scale, dtype=np.float64), (3,))
+    for i, w in enumerate(sets):
+        assert rel_close(got[i], orc.log_prior(w, prior, sc)), (prior, i)
+    eng.close()
+
+
+def _init_chains(eng, m, meta, n_chains):
+    w0 = [m.weights] * n_chains
+    nl = len(m.weights)
+    n_it = meta["n_iteration"]
+    eng.chains_init(w0, temperature=meta["temperature"], update_f=meta["update_f"][:nl], update_ws=meta["update_ws"][:nl],
+                    prior=meta["prior"], prior_scale=meta["p_scale"], w_bound=meta["w_bound"], mask=m.mask,
+                    alphas=None if m.alphas is None else np.resize(m.alphas, nl),
+                    sigma_mode=1 if meta.get("empirical_error") else 0, lik_temp=meta["lik_temp"],
+                    adapt_f=meta["adapt_f"], adapt_fM=meta["adapt_fM"], adapt_freq=meta["adapt_freq"],
+                    adapt_stop=int(n_it * 0.05))
+
+
+@pytest.mark.parametrize("name", G.CHAIN_CASES)
+def test_chain_replay_step_by_step(name):
+    """Replay the reference's recorded proposals one MH iteration at a time: proposal log-lik / log-prior
+    within 1e-9, identical accept decisions, identical adaptation state, bit-identical weights."""
+    z, meta = G.load(name)
+    m = G.build_model(z, meta)
+    eng = make_engine(m)
+    _init_chains(eng, m, meta, 2)
+    st = eng.read_state()
+    N = m.x.shape[0]
+    assert rel_close(st.logLik, float(z["init_logLik"])) and rel_close(st.logPrior, float(z["init_logPrior"]))
+    assert np.array_equal(st.update_n[0], z["init_update_n"])
+    n_steps = min(int(z["n_steps"]), 60)
+    near_tie = 0
+    for t in range(n_steps):
+        eng.mh_steps(1, G.injection_arrays(z, meta, t, t + 1, 2))
+        st = eng.read_state()
+        for c in range(2):
+            assert rel_close(st.logLik_prop[c], z["steps_logLik_prime"][t]), (t, st.logLik_prop[c], float(z["steps_logLik_prime"][t]))
+            assert rel_close(st.logPrior_prop[c], z["steps_logPrior_prime"][t]), t
+            margin = abs((float(z["steps_logLik_prime"][t]) + float(z["steps_logPrior_prime"][t]) - float(z["steps_logPost"][t - 1] if t else z["init_logLik"] + z["init_logPrior"])) * meta["temperature"] - float(z["steps_log_u"][t]))
+            if margin < 1e-8:
+                near_tie += 1       # decision inside the summation-order noise: reported, not asserted
+                continue
+            assert st.last_accepted[c] == int(z["steps_accepted"][t]), t
+            assert rel_close(st.logLik[c], z["steps_logLik"][t]) and rel_close(st.logPost[c], z["steps_logPost"][t])
+            assert st.iteration[c] == t + 1
+            assert abs(st.acceptance_rate[c] - float(z["steps_acceptance_rate"][t])) < 1e-15
+            assert np.array_equal(st.update_n[c], z["steps_update_n"][t]), t
+            assert np.allclose(st.update_f[c], z["steps_update_f"][t], rtol=1e-14)
+            assert np.allclose(st.update_ws[c], z["steps_update_ws"][t], rtol=1e-14)
+            assert np.allclose(st.freq_layer_update[c], z["steps_freq_layer_update"][t], rtol=1e-14)
+            if meta["mode"] == "classification":
+                assert st.n_correct[c] / N == float(z["steps_accuracy"][t])
+                assert np.array_equal(st.pred_hist[c] / N, z["steps_label_freq"][t])
+                if m.x_test is not None:
+                    assert st.n_correct_test[c] / m.x_test.shape[0] == float(z["steps_test_accuracy"][t])
+            else:
+                assert rel_close(np.sum(st.sum_r2[c]) / (N * eng.K), z["steps_accuracy"][t])
+                assert rel_close(st.sum_r2[c] / N, z["steps_label_acc"][t])
+                if meta["mode"] == "regression":
+                    assert rel_close(st.sigma[c], z["steps_error_prm"][t])
+    assert near_tie == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", G.CHAIN_CASES)
+def test_chain_replay_one_launch(name):
+    """All recorded iterations in ONE bnn_mh_steps call (no host round trips): final weights bit-identical
+    to the reference's, accept count identical."""
+    z, meta = G.load(name)
+    m = G.build_model(z, meta)
+    eng = make_engine(m)
+    _init_chains(eng, m, meta, 3)
+    T = int(z["n_steps"])
+    eng.mh_steps(T, G.injection_arrays(z, meta, 0, T, 3))
+    st = eng.read_state()
+    for c in range(3):
+        assert st.n_accepted[c] == int(np.sum(z["steps_accepted"]))
+        for i, w in enumerate(st.weights(c)):
+            assert np.array_equal(w, z["wN_%d" % i]), (name, c, i)
+        assert rel_close(st.logLik[c], z["steps_logLik"][T - 1])
+        assert rel_close(st.logPrior[c], z["steps_logPrior"][T - 1])
+    eng.close()
+
+
+def test_predict_matches_reference_goldens():
+    from npbnn_b200.engine import Engine, NetShape
+    z, meta = G.load("predict")
+    x = z["x"]
+    for ci, case in enumerate(meta["cases"]):
+        post = [[z["p%d_s%d_w%d" % (ci, j, li)] for li in range(3)] for j in range(meta["S"])]
+        net = NetShape.from_weights(post[0], x.shape[1], act=case["act"], lik=0)
+        eng = Engine(net)
+        al = None if not case["alphas"] else np.tile(np.resize(np.array(case["alphas"]), 3), (meta["S"], 1))
+        out = eng.predict(x, post, alphas=al, mean=True, votes=True, dense=True)
+        assert np.allclose(out["dense"], z["p%d_dense" % ci], rtol=1e-10, atol=1e-300)
+        assert np.allclose(out["mean"], z["p%d_mode1" % ci], rtol=1e-10, atol=1e-300)
+        assert np.array_equal(out["votes"], z["p%d_mode0" % ci])
+        # PDP grid steps (BNN_pdp.py:63-82): column overwrite fused into the X staging
+        for focal in (1, 3):
+            feats = z["p%d_pdp%d_feature" % (ci, focal)]
+            gold = z["p%d_pdp%d" % (ci, focal)]
+            for n in range(feats.shape[0]):
+                o = eng.predict(x, post, alphas=al, override=([focal], feats[n, :]), mean=True)
+                smean = np.cumsum(o["mean"], axis=1)       # cumsum commutes with the mean over samples
+                assert np.allclose(np.mean(smean, axis=0), gold[n, :, 0], rtol=1e-10)
+                q = np.quantile(smean, q=(0.025, 0.975), axis=0)
+                assert np.allclose(q[0], gold[n, :, 1], rtol=1e-9) and np.allclose(q[1], gold[n, :, 2], rtol=1e-9)
+        eng.close()
+
+
+def _c4_like(n, n_sets, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, 64))
+    shapes = [(64, 64), (32, 64), (10, 33)]
+    teacher = [rng.normal(0, 0.5, s) for s in shapes]
+    labels = np.argmax(orc.forward(x, teacher, "swish", None, "softmax"), axis=1)
+    sets = [[rng.normal(0, 0.3, s) for s in shapes] for _ in range(n_sets)]
+    return x, labels, sets
+
+
+@pytest.mark.parametrize("n", [16, 1000, 4099])
+def test_c4_shape_specialised_kernel(n):
+    """BASELINE config 4 shape (64 -> 64 -> 32 -> 10, swish, bias on the last layer) at small N: the
+    shape-specialised kernel against the oracle and against the generic kernel."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(n, 5)
+    m = orc.Model(x=x, labels=labels, weights=sets[0], act="swish", mode="classification")
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x, labels)
+    res = eng.forward_lik(sets)
+    assert eng.last_kernel.startswith("k_fwd3"), eng.last_kernel
+    eng.set_option("force_generic", 1)
+    gen = eng.forward_lik(sets)
+    assert eng.last_kernel == "k_fwd_generic"
+    for i, w in enumerate(sets):
+        ref = oracle_score(m, w)
+        assert rel_close(res["loglik"][i], ref["loglik"]), (i, res["loglik"][i], ref["loglik"])
+        assert rel_close(gen["loglik"][i], ref["loglik"])
+        K = 10
+        for r in (res, gen):
+            c = r["counts"][i]
+            assert c[0] == ref["n_correct"]
+            assert np.array_equal(c[2:2 + K], ref["class_correct"]) and np.array_equal(c[2 + K:2 + 2 * K], ref["pred_hist"])
+    # prediction through the specialised kernel
+    eng.set_option("force_generic", 0)
+    out = eng.predict(x, sets, mean=True, votes=True, dense=True)
+    assert eng.last_kernel.startswith("k_fwd3")
+    dense_ref, mean_ref = orc.posterior_predict(x, sets, "swish", None, "softmax", 1)
+    _, votes_ref = orc.posterior_predict(x, sets, "swish", None, "softmax", 0)
+    assert np.allclose(out["dense"], dense_ref, rtol=1e-10, atol=1e-300)
+    assert np.allclose(out["mean"], mean_ref, rtol=1e-10, atol=1e-300)
+    assert np.array_equal(out["votes"], votes_ref)
+    eng.close()
+
+
+def test_run_is_deterministic():
+    """Fixed-order reductions: two identical runs give bit-identical log-likelihoods."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(20000, 4, seed=5)
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x, labels)
+    a = eng.forward_lik(sets)["loglik"]
+    b = eng.forward_lik(sets)["loglik"]
+    assert np.array_equal(a, b)
+    eng.close()
+
+
+def test_philox_chains_run_and_agree_with_oracle_state():
+    """Free-running (Philox) proposals: the chain's own book-keeping stays consistent -- after T steps
+    the stored logLik / logPrior equal the oracle's evaluation of the stored weights."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(3000, 4, seed=9)
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x, labels)
+    eng.chains_init(sets, temperature=[1.0, 0.95, 0.9, 0.8], seed=42, adapt_f=0.1, adapt_fM=0.6, adapt_freq=10, adapt_stop=100)
+    eng.mh_steps(50)
+    st = eng.read_state()
+    assert np.all(st.iteration == 50)
+    assert np.all(st.n_accepted > 0)
+    for c in range(4):
+        w = st.weights(c)
+        m = orc.Model(x=x, labels=labels, weights=w, act="swish", mode="classification")
+        ref = oracle_score(m, w)
+        assert rel_close(st.logLik[c], ref["loglik"])
+        assert rel_close(st.logPrior[c], orc.log_prior(w, 1, np.ones(3)))
+        assert st.n_correct[c] == ref["n_correct"]
+    eng.close()
