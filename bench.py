@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the npBNN Metropolis-Hastings hot path on B200 (contract: task brief, section 4).
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "c4"): MC3 with 32 tempered chains on a synthetic
+1,000,000 x 64 float64 feature matrix, [64,32] swish hidden layers, 10 classes, bias on the last layer,
+Normal(0,1) prior, update_f 0.05, update_ws 0.075.  A "step" is one MH iteration of every chain.
+  value  = chains x steps / s with X resident in HBM, proposals generated on the device (Philox)
+  e2e    = the same metric through the C ABI with HOST buffers: X staged from pinned host memory, chains
+           initialised, per step host-generated proposals copied in and the chain state copied back
+Chains are sharded over ranks (32 / N per GPU, strong scaling); the only exchange is the MC3 swap
+(all-gather of 32 log-posteriors every swap_frequency steps).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (numpy oracle port) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS = 1_000_000
+N_CHAINS = 32
+SWAP_FREQUENCY = 100
+CPU_SAMPLE_ROWS = 100_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--chains", type=int, default=N_CHAINS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mxv = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxv
+            if t0 <= t <= t1:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's algorithm on the host cores (numpy oracle port): bounded sample per step."""
+    if rank != 0:
+        return
+    from npbnn_b200 import workloads as wl
+    from oracle import cpu_baseline
+    x, labels = wl.c4_data(min(args.rows, CPU_SAMPLE_ROWS), seed=0)
+    K = max(1, args.steps)
+    t0 = time.perf_counter()
+    # each "step" = one MH iteration of min(32, cores) chains on the row sample
+    res = cpu_baseline.mh_rate(x, labels.astype(np.int64), wl.C4_SHAPES, "swish", args.rows,
+                               steps_per_proc=K, seconds=30.0 + 5.0 * K)
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": "MH iterations/sec (chains x steps / s)", "value": res["value"],
+            "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+            "ms_per_step": 1e3 * res["cores"] / res["value"] if res["value"] else None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": res["value"], "unit": "chain-steps/s", "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "c4: MC3 %d tempered chains, synthetic %dx64 f64, [64,32] swish, 10 classes, bias on last layer"
+                        % (args.chains, args.rows),
+            "rows": args.rows, "features": 64, "chains": args.chains, "swap_frequency": SWAP_FREQUENCY,
+            "update_f": 0.05, "update_ws": 0.075, "prior": "Normal(0,1)", "parallelism": "chains sharded over GPUs",
+            "l2": "inputs larger than L2 (X = %.0f MB streamed once per step)" % (args.rows * 64 * 8 / 1e6)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from npbnn_b200 import _lib as L
+    from npbnn_b200 import mc3, workloads as wl
+    from npbnn_b200.engine import Engine, NetShape, flatten_weights
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ workload (host, pinned)
+    x_np, y_np = wl.c4_data(args.rows, seed=0)
+    x_pin = torch.from_numpy(x_np).pin_memory()
+    y_pin = torch.from_numpy(y_np).pin_memory()
+    start, n_local = mc3.chain_partition(args.chains, world, rank)
+    temps_all = mc3.default_temperatures(args.chains, 0.8)
+    w0 = np.stack([flatten_weights(w) for w in wl.c4_init_weights(n_local, start)])
+    net = NetShape(64, list(wl.C4_SHAPES), act="swish", lik=L.LIK_CATEGORICAL)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ------------------------------------------------------------------ device-resident leg (value)
+    eng = Engine(net, device=local_rank)
+    eng.set_data(x_pin.to(dev), y_pin.to(dev))
+    eng.chains_init(w0, temperature=temps_all[start:start + n_local], seed=1234 + rank)
+    rng = mc3.SwapRNG(4321)
+    step_ctr = [0]
+
+    def run_steps(n, temps):
+        """n MH iterations of every chain with the MC3 swap every SWAP_FREQUENCY steps."""
+        done = 0
+        while done < n:
+            chunk = min(n - done, SWAP_FREQUENCY - step_ctr[0] % SWAP_FREQUENCY)
+            eng.mh_steps(chunk)
+            done += chunk
+            step_ctr[0] += chunk
+            if step_ctr[0] % SWAP_FREQUENCY == 0 and args.chains > 1:
+                temps, _, _, _ = mc3.exchange(eng.gather(L.F_LOGPOST), temps, rng, None, world)
+                eng.set_temperature(temps[start:start + n_local])
+        return temps
+
+    peak_tf = eng.measure_fp64_peak()
+    temps_all = run_steps(W, temps_all)
+    barrier()
+    eng.set_option("time_forward", 1)
+    eng.forward_time(reset=True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.25)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    temps_all = run_steps(K, temps_all)
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop(t_wall0, t_wall1)
+    fwd_ms, fwd_n = eng.forward_time(reset=True)
+    eng.set_option("time_forward", 0)
+    launches = eng.launch_count - launches0
+    value = args.chains * K / (ms * 1e-3)
+    st = eng.read_state(weights=False)
+    kernel_name = eng.last_kernel
+
+    # roofline of the dominant kernel (forward + likelihood): algorithmic FLOPs per launch / its mean duration
+    flop_per_launch = float(n_local) * args.rows * wl.C4_FLOP_PER_ROW
+    fwd_avg_ms = fwd_ms / max(fwd_n, 1)
+    achieved_tf = flop_per_launch / (fwd_avg_ms * 1e-3) / 1e12 if fwd_n else None
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "pipe": "fp64 (DMMA and DFMA share one pipe on B200)", "kernel": kernel_name,
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (achieved_tf / peak_tf) if achieved_tf else None,
+                "peak_source": "measured live on this GPU: back-to-back FP64 DMMA (bnn_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "flop_per_launch": flop_per_launch, "launch_ms": fwd_avg_ms, "launches_timed": int(fwd_n),
+                "kernel_share_of_step": fwd_ms / (ev0.elapsed_time(ev1)) if fwd_n else None,
+                "traffic": ncu.get("dram_bytes_per_launch"),
+                "hbm": {"algorithmic_bytes_per_launch": args.rows * (64 * 8 + 4),
+                        "achieved_gbs": args.rows * (64 * 8 + 4) / (fwd_avg_ms * 1e-3) / 1e9 if fwd_n else None}}
+
+    # ------------------------------------------------------------------ end-to-end leg (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        host_rng = np.random.default_rng(99 + rank)
+        sizes = [r * c for r, c in wl.C4_SHAPES]
+        upd_n = [max(1, int(round(s * 0.05))) for s in sizes]
+        cap = sum(upd_n)
+        barrier()
+        t0 = time.perf_counter()
+        eng2 = Engine(net, device=local_rank)
+        eng2.set_data(x_pin, y_pin)                       # H2D from pinned host memory inside the timed region
+        eng2.chains_init(w0, temperature=temps_all[start:start + n_local], seed=1)
+        h2d = x_pin.numel() * 8 + y_pin.numel() * 4 + w0.nbytes
+        d2h = 0
+        for s in range(K):
+            inj = {"proposed": np.ones((1, n_local, 3), np.int32),
+                   "count": np.tile(np.array(upd_n, np.int32), (1, n_local, 1)),
+                   "ix": np.zeros((1, n_local, cap), np.int32), "iy": np.zeros((1, n_local, cap), np.int32),
+                   "dz": host_rng.normal(0, 0.075, (1, n_local, cap)),
+                   "log_u": np.log(host_rng.random((1, n_local)))}
+            o = 0
+            for l, (r, c) in enumerate(wl.C4_SHAPES):
+                inj["ix"][0, :, o:o + upd_n[l]] = host_rng.integers(0, r, (n_local, upd_n[l]))
+                inj["iy"][0, :, o:o + upd_n[l]] = host_rng.integers(0, c, (n_local, upd_n[l]))
+                o += upd_n[l]
+            eng2.mh_steps(1, inj)
+            st2 = eng2.read_state(weights=False)          # D2H of the step's result (logLik, counters, ...)
+            h2d += sum(a.nbytes for a in inj.values())
+            d2h += st2.f64.nbytes + st2.i32.nbytes
+        barrier()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": args.chains * K / t_e2e, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d / K,
+               "d2h_bytes_per_step": d2h / K,
+               "includes": "per rank: X+labels staged from pinned host memory (once), chain init (one extra forward), "
+                           "per step: host-generated proposals H2D, bnn_mh_steps(1), state D2H",
+               "seconds": t_e2e, "finite_logLik": bool(np.all(np.isfinite(st2.logLik)))}
+        eng2.close()
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        ns = min(args.rows, CPU_SAMPLE_ROWS)
+        cpu = cpu_baseline.mh_rate(x_np[:ns], y_np[:ns].astype(np.int64), wl.C4_SHAPES, "swish", args.rows,
+                                   steps_per_proc=3, seconds=20.0)
+        cpu = {"value": cpu["value"], "unit": "chain-steps/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+
+    if rank == 0:
+        line = {"metric": "MH iterations/sec (chains x steps / s)", "value": value, "unit": "chain-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clk,
+                "check": {"logLik_finite": bool(np.all(np.isfinite(st.logLik))),
+                          "mean_acceptance": float(np.mean(st.n_accepted / np.maximum(st.iteration, 1)))}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

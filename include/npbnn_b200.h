@@ -178,6 +178,9 @@ int bnn_chains_read(bnn_ctx* ctx, double* f64_host, int32_t* i32_host, double* w
 /* Device pointers to the live chain state (same layout as bnn_chains_read; e.g. the log-posteriors for
  * the MC3 all-gather are f64_dev[c * BNN_F_STRIDE + BNN_F_LOGPOST]).  Any pointer may be NULL. */
 int bnn_chains_state_dev(bnn_ctx* ctx, double** f64_dev, int32_t** i32_dev, double** w_dev);
+/* Copy one f64 state slot of every chain (e.g. BNN_F_LOGPOST) into out_dev [C] on the stream: the send
+ * buffer of the MC3 all-gather that replaces the pickling of whole chains in BNN_mc3.py:96. */
+int bnn_chains_gather(bnn_ctx* ctx, int32_t slot, double* out_dev, void* stream);
 /* Temperature update after an MC3 swap (BNN_mc3.py:98-112; reset_temperature, BNN_env.py:549-550). */
 int bnn_chains_set_temperature(bnn_ctx* ctx, const double* temperature_host, void* stream);
 
@@ -193,9 +196,15 @@ int bnn_predict(bnn_ctx* ctx, const double* x_dev, int64_t n, const double* w_de
 
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bnn_launch_count(const bnn_ctx* ctx);
+/* With option "time_forward" = 1 every forward launch is bracketed by CUDA events on its stream; this
+ * returns the accumulated device time and launch count (and optionally resets them). */
+int bnn_forward_time(bnn_ctx* ctx, double* total_ms, int64_t* n_launches, int32_t reset);
+/* Measured FP64 tensor-pipe peak of this GPU in TFLOP/s (back-to-back DMMA): roofline denominator. */
+int bnn_measure_fp64_peak(bnn_ctx* ctx, double* tflops);
 /* Name of the forward kernel variant used by the last call ("k_fwd3<...>" or "k_fwd_generic"). */
 const char* bnn_last_kernel(const bnn_ctx* ctx);
-/* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests). */
+/* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests);
+ * "time_forward" = 1 enables bnn_forward_time. */
 int bnn_set_option(bnn_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus

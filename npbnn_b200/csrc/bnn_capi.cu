@@ -72,7 +72,32 @@ struct bnn_ctx {
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
   const char* last_kernel = "";
+  // optional per-launch timing of the forward kernel (bench.py roofline): event pairs on the launch stream
+  int time_forward = 0;
+  std::vector<cudaEvent_t> ev;      // start/stop pairs, recorded but not yet read
+  size_t ev_used = 0;
+  double fwd_ms_sum = 0.0;
+  long long fwd_count = 0;
 };
+
+static cudaError_t timed_forward(bnn_ctx* c, const FwdParams& p, bool predict, cudaStream_t st) {
+  if (!c->time_forward) return bnn_launch_forward(p, predict, c->n_sms, c->force_generic, st, &c->last_kernel);
+  if (c->ev_used + 2 > c->ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaError_t r = cudaEventCreate(&e);
+      if (r != cudaSuccess) return r;
+      c->ev.push_back(e);
+    }
+  }
+  cudaError_t r = cudaEventRecord(c->ev[c->ev_used], st);
+  if (r != cudaSuccess) return r;
+  r = bnn_launch_forward(p, predict, c->n_sms, c->force_generic, st, &c->last_kernel);
+  if (r != cudaSuccess) return r;
+  r = cudaEventRecord(c->ev[c->ev_used + 1], st);
+  c->ev_used += 2;
+  return r;
+}
 
 static int sets_per_pass(const NetGeom& g) {
   int nc = 2 + 2 * g.K;
@@ -148,6 +173,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
                     &c->inj_iy, &c->inj_dz, &c->inj_logu};
   for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -155,6 +181,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
 int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   REQUIRE(c && name, "bnn_set_option: null argument");
   if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
+  if (strcmp(name, "time_forward") == 0) { c->time_forward = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
 
@@ -284,7 +311,7 @@ int bnn_forward_lik(bnn_ctx* c, const double* w_dev, int32_t n_sets, const doubl
     p.alpha = alpha_dev ? alpha_dev + (size_t)s0 * g.L : nullptr;
     p.C = n;
     p.counts = counts ? counts + (size_t)s0 * NC : nullptr;
-    CUDA_TRY(bnn_launch_forward(p, false, c->n_sms, c->force_generic, st, &c->last_kernel));
+    CUDA_TRY(timed_forward(c, p, false, st));
     CUDA_TRY(bnn_launch_finalize_lik(g, p.part, p.NF, c->n_tiles16, c->n_train, lik_temp, sigma_mode, sigma_dev,
                                      loglik_dev, sums_dev, s0, n, st));
     c->launches += 2;
@@ -380,7 +407,7 @@ static int chains_forward(bnn_ctx* c, cudaStream_t st) {
     p.C = n;
     p.part = c->part.as<double>() + (size_t)s0 * p.NF * c->n_tiles16;
     p.counts = c->counts_prop.as<int>() + (size_t)s0 * NC;
-    CUDA_TRY(bnn_launch_forward(p, false, c->n_sms, c->force_generic, st, &c->last_kernel));
+    CUDA_TRY(timed_forward(c, p, false, st));
     c->launches++;
   }
   return 0;
@@ -529,6 +556,39 @@ int bnn_chains_state_dev(bnn_ctx* c, double** f64_dev, int32_t** i32_dev, double
   return 0;
 }
 
+int bnn_chains_gather(bnn_ctx* c, int32_t slot, double* out_dev, void* stream) {
+  REQUIRE(c && c->have_chains && out_dev, "bnn_chains_gather: bad arguments");
+  REQUIRE(slot >= 0 && slot < BNN_F_STRIDE, "bnn_chains_gather: slot out of range");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpy2DAsync(out_dev, sizeof(double), c->sf.as<double>() + slot, sizeof(double) * BNN_F_STRIDE,
+                             sizeof(double), c->C, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int bnn_forward_time(bnn_ctx* c, double* total_ms, int64_t* n_launches, int32_t reset) {
+  REQUIRE(c, "bnn_forward_time: null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(c->ev[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+    c->fwd_ms_sum += ms;
+    c->fwd_count++;
+  }
+  c->ev_used = 0;
+  if (total_ms) *total_ms = c->fwd_ms_sum;
+  if (n_launches) *n_launches = c->fwd_count;
+  if (reset) { c->fwd_ms_sum = 0.0; c->fwd_count = 0; }
+  return 0;
+}
+
+int bnn_measure_fp64_peak(bnn_ctx* c, double* tflops) {
+  REQUIRE(c && tflops, "bnn_measure_fp64_peak: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(bnn_measure_dmma_peak(c->n_sms, tflops));
+  return 0;
+}
+
 int bnn_chains_set_temperature(bnn_ctx* c, const double* temperature_host, void* stream) {
   REQUIRE(c && c->have_chains && temperature_host, "bnn_chains_set_temperature: bad arguments");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -576,7 +636,7 @@ int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev,
   p.mean_out = mean_dev; p.votes_out = votes_dev; p.dense_out = dense_dev;
   p.inv_sets = (double)n_sets;   // divisor (np.mean and the vote share divide, BNN_lib.py:390-392)
   p.exp_tab = c->exp_tab.as<double>();
-  CUDA_TRY(bnn_launch_forward(p, true, c->n_sms, c->force_generic, st, &c->last_kernel));
+  CUDA_TRY(timed_forward(c, p, true, st));
   c->launches += 3;
   return 0;
 }

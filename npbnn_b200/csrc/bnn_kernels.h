@@ -45,3 +45,5 @@ cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF
 cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
                                  double* out, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
+// FP64 tensor-pipe peak (back-to-back DMMA, no memory traffic): the roofline denominator of the forward kernel
+cudaError_t bnn_measure_dmma_peak(int n_sms, double* tflops);

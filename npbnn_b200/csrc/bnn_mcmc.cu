@@ -405,3 +405,51 @@ cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose
   k_mh_update<<<d.C, UPD_THREADS, 0, st>>>(d, accept_mode, propose_mode, step);
   return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probe (same loop as tools/peak_fp64.cu, m16n8k8): 8 independent accumulators per warp
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters) {
+  double c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.0;
+  const double a0 = 1.0 + threadIdx.x * 1e-6, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  const double b0 = 1e-9 + threadIdx.x * 1e-12, b1 = b0 * 2;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmma16x8x8(c[i], a0, a1, a2, a3, b0, b1);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t bnn_measure_dmma_peak(int n_sms, double* tflops) {
+  const int grid = n_sms * 2, threads = 256, iters = 2048;
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * grid * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int w = 0; w < 3; ++w) k_dmma_peak<<<grid, threads>>>(out, iters);
+  double best = 1e30;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<grid, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess) return e;
+  const double flops = 2.0 * 16 * 8 * 8 * (double)iters * 4 * 8 * (grid * threads / 32);
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return cudaSuccess;
+}

@@ -305,6 +305,23 @@ class Engine:
         assert t.shape == (self.n_chains,)
         L.check(self.lib.bnn_chains_set_temperature(self._h, _np_ptr(t), self._stream()))
 
+    def gather(self, slot: int = L.F_LOGPOST) -> torch.Tensor:
+        """One f64 state slot of every local chain as a device tensor [C] (send buffer of the MC3 all-gather)."""
+        out = torch.empty(self.n_chains, dtype=torch.float64, device=self.device)
+        L.check(self.lib.bnn_chains_gather(self._h, int(slot), _ptr(out), self._stream()))
+        return out
+
+    def forward_time(self, reset=True):
+        """(total device ms, launches) of the forward kernel since the last reset (option time_forward=1)."""
+        ms, n = C.c_double(), C.c_int64()
+        L.check(self.lib.bnn_forward_time(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
+    def measure_fp64_peak(self) -> float:
+        tf = C.c_double()
+        L.check(self.lib.bnn_measure_fp64_peak(self._h, C.byref(tf)))
+        return tf.value
+
     def synchronize(self):
         torch.cuda.current_stream(self.device).synchronize()
 
