@@ -92,40 +92,44 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
   return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
 
-// exp with results below 2^-1022 flushed to 0 and overflow to +inf (NaN propagates).
-__device__ __forceinline__ double bnn_exp(double x, const double* __restrict__ tab) {
-  int hx = __double2hiint(x);
-  int ax = hx & 0x7fffffff;
-  double res = bnn_exp_core(x, tab);
-  if (ax >= 0x40862278) {                   // |x| >= ~708.27: slow path
-    if (ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0)) return x + x;   // NaN
-    if (hx < 0) return (x < -708.3964185322641) ? 0.0 : res;
-    return (x > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000LL) : res;
-  }
-  return res;
+// Branch-free range handling (selects on the integer view of x; no BSSY/BSYNC, so ptxas can interleave the
+// FP64 chains of several independent evaluations with the surrounding DMMAs).
+//
+// exp for arguments <= 0 (softmax): results below 2^-1022 flush to 0, NaN propagates.
+__device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict__ tab) {
+  const int hx = __double2hiint(x);
+  const int ax = hx & 0x7fffffff;
+  const bool big = ax >= 0x4086232c;                  // |x| >= 708.3965 (also inf / NaN): exp(x) < 2^-1022
+  double res = bnn_exp_core(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
+  res = big ? 0.0 : res;
+  const bool is_nan = ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0);
+  return is_nan ? x : res;
 }
 
-// exp for activations: saturates at 2^1023 instead of +inf so that 1/(1+e) stays NaN-free.
-__device__ __forceinline__ double bnn_exp_sat(double x, const double* __restrict__ tab) {
-  int hx = __double2hiint(x);
-  int ax = hx & 0x7fffffff;
-  double res = bnn_exp_core(x, tab);
-  if (ax >= 0x40862278) {
-    if (ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0)) return x + x;
-    if (hx < 0) return (x < -708.3964185322641) ? 0.0 : res;
-    return (x > 709.08) ? 8.98846567431158e307 : res;
-  }
-  return res;
+// exp for activations: argument clamped to [-708, 708] (1/(1+e) is then NaN-free and the clamped tails
+// differ from the exact value by < 1e-300 in the activation); NaN handling is done by the caller.
+__device__ __forceinline__ double bnn_exp_clamped(double x, const double* __restrict__ tab) {
+  const int hx = __double2hiint(x);
+  const bool big = (hx & 0x7fffffff) >= 0x40862000;           // |x| >= 708 (also inf / NaN)
+  const double xc = big ? __hiloint2double((hx & 0x80000000) | 0x40862000, 0) : x;
+  return bnn_exp_core(xc, tab);
 }
 
-// 1/d for d >= 1 (finite).  rcp.approx.ftz.f64 = MUFU.RCP64H (about 20 good bits).
+// 1/d for finite d >= 1: MUFU.RCP64H seed (rcp.approx.ftz.f64) + one third-order step
+//   e = 1 - d*y0 ; y = y0 + y0*(e + e*e)      (error e^3)
+// followed by one Newton step when BNN_RCP_EXTRA_STEP is defined (set after measuring the seed accuracy).
 __device__ __forceinline__ double bnn_rcp(double d) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   double e = fma(-d, y, 1.0);
+#ifdef BNN_RCP_HALLEY
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+#else
   y = fma(y, e, y);
   e = fma(-d, y, 1.0);
   y = fma(y, e, y);
+#endif
   return y;
 }
 
@@ -136,11 +140,16 @@ __device__ __forceinline__ double bnn_act(double z, double alpha, const double* 
   if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
   if (ACT == BNN_ACT_SWISH) {
-    double e = bnn_exp_sat(-z, tab);
+    // NaN: z * finite = NaN.  +-inf: inf * 1 = inf, -inf * ~0 -> the reference gives NaN (-inf * 0); here
+    // -inf * 3e-308 = -inf.  Both poison the likelihood (NaN or -inf log-posterior => proposal rejected).
+    double e = bnn_exp_clamped(-z, tab);
     return z * bnn_rcp(1.0 + e);
   }
-  double e = bnn_exp_sat(2.0 * z, tab);
-  return fma(-2.0, bnn_rcp(e + 1.0), 1.0);
+  double e = bnn_exp_clamped(2.0 * z, tab);
+  double r = fma(-2.0, bnn_rcp(e + 1.0), 1.0);
+  const int hz = __double2hiint(z);
+  const bool is_nan = (hz & 0x7fffffff) > 0x7ff00000 || ((hz & 0x7fffffff) == 0x7ff00000 && __double2loint(z) != 0);
+  return is_nan ? z : r;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
         if (v > m) { m = v; arg = k; }   // first maximum wins, as np.argmax
       }
       if (!PREDICT && is_train) {
-        for (int k = 0; k < K; ++k) S += bnn_exp(z[k] - m, tab);
+        for (int k = 0; k < K; ++k) S += bnn_exp_neg(z[k] - m, tab);
       }
     }
     if (!PREDICT) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
     } else {
       if (active) {
         double* zw = const_cast<double*>(z);     // the staged row is private to this lane: reuse as scratch
-        for (int k = 0; k < K; ++k) { double e = bnn_exp(z[k] - m, tab); zw[k] = e; S += e; }
+        for (int k = 0; k < K; ++k) { double e = bnn_exp_neg(z[k] - m, tab); zw[k] = e; S += e; }
         double inv = 1.0 / S;
         double* pa = pacc + (lane & 15) * K;
         for (int k = 0; k < K; ++k) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
 }
 
 // =============================================================================================
-// specialised 3-layer kernel (compile-time padded widths KP0 -> N1 -> N2 -> N3)
+// specialised 3-layer kernel (compile-time padded widths KP0 -> N1 -> N2 -> N3), categorical likelihood
 // =============================================================================================
 template <int KP0, int N1, int N2, int N3>
 struct Fwd3Geom {
@@ -286,8 +286,108 @@ struct Fwd3Geom {
   static constexpr int W2_OFF = B1_OFF + N1, B2_OFF = W2_OFF + N2 * N1;
   static constexpr int W3_OFF = B2_OFF + N2, B3_OFF = W3_OFF + N3 * N2;
   static constexpr int PB = B3_OFF + N3;
-  static constexpr int ZS = N3 + 1;
 };
+
+#ifndef FWD3_WARPS
+#define FWD3_WARPS 12
+#endif
+
+template <int ACT>
+__device__ __forceinline__ void act_tile(double (&a)[4], double alpha, const double* tab) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) a[e] = bnn_act<ACT>(a[e], alpha, tab);
+}
+
+// Softmax / log-likelihood / counters (or posterior summaries) on the accumulator fragments of the last
+// layer: the 4 lanes of a quad hold one row pair (rows g and g+8), columns 8j+2t+{0,1}.  All exps of a
+// thread are independent (ILP), row statistics are combined with two xor-shuffles.
+template <int N3, bool PREDICT>
+__device__ __forceinline__ void quad_epilogue_cat(const FwdParams& p, int c, long long wt, int lane,
+                                                  const double (&acc)[N3 / 8][4], const double* tab, int* cnt,
+                                                  const int (&y)[2], const double (&wgt)[2],
+                                                  double (&pacc)[2][N3 / 4], int (&pvote)[2][N3 / 4]) {
+  const int K = p.g.K;
+  const int gq = lane >> 2, t = lane & 3;
+  double ll_sum = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long row = wt * 16 + gq + 8 * h;
+    const bool active = row < p.n_total;
+    const bool is_train = row < p.n_train;
+    double m = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * j + 2 * t + e;
+        const double v = acc[j][2 * h + e];
+        if (col < K && v > m) { m = v; arg = col; }      // columns ascend within a thread: first maximum wins
+      }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const double om = __shfl_xor_sync(FULL_MASK, m, o);
+      const int oa = __shfl_xor_sync(FULL_MASK, arg, o);
+      if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+    }
+    if (arg == 0x7fffffff) arg = 0;
+    double ev[N3 / 4];
+    double S = 0.0, zy = 0.0;
+#pragma unroll
+    for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * j + 2 * t + e;
+        const double v = acc[j][2 * h + e];
+        double ex = 0.0;
+        if (col < K) ex = bnn_exp_neg(v - m, tab);
+        ev[2 * j + e] = ex;
+        S += ex;
+        if (col == y[h]) zy = v;
+      }
+    S += __shfl_xor_sync(FULL_MASK, S, 1);
+    S += __shfl_xor_sync(FULL_MASK, S, 2);
+    if (!PREDICT) {
+      zy += __shfl_xor_sync(FULL_MASK, zy, 1);
+      zy += __shfl_xor_sync(FULL_MASK, zy, 2);
+      if (t == 0 && active) {
+        const bool ok = (arg == y[h]);
+        int* cc = cnt + c * (2 + 2 * K);
+        if (is_train) {
+          const double d = zy - m;
+          // log(softmax) of the reference is -inf once exp(d) underflows to 0 (BNN_lib.py:121,168)
+          double ll = (d < -745.1332191019412) ? -INFINITY : d - log(S);
+          ll_sum += ll * wgt[h];
+          if (ok) { atomicAdd(&cc[2 + y[h]], 1); atomicAdd(&cc[0], 1); }
+          atomicAdd(&cc[2 + K + arg], 1);
+        } else if (ok) {
+          atomicAdd(&cc[1], 1);
+        }
+      }
+    } else if (active) {
+      const double inv = 1.0 / S;
+#pragma unroll
+      for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * j + 2 * t + e;
+          if (col < K) {
+            const double pk = ev[2 * j + e] * inv;
+            pacc[h][2 * j + e] += pk;
+            if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + col] = pk;
+            if (col == arg) pvote[h][2 * j + e] += 1;
+          }
+        }
+    }
+  }
+  if (!PREDICT) {
+    // fixed xor tree over the 8 row pairs of the warp tile (lanes with t != 0 hold 0)
+    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 4);
+    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 8);
+    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 16);
+    if (lane == 0) p.part[((long long)c * p.NF) * p.n_tiles16 + wt] = ll_sum;
+  }
+}
 
 template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__ FwdParams p) {
@@ -296,23 +396,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
-  const int PW = bnn_pred_width(g);
 
   // ---- shared memory carve-up
-  double* wbuf = reinterpret_cast<double*>(smem_raw);                  // [2][PB]
-  double* xs = wbuf + 2 * G3::PB + warp * 16 * KP0;                     // [NWARPS][16*KP0]
-  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // [256]
-  double* zs = tab + BNN_EXP_TAB_SIZE + warp * 16 * G3::ZS;             // [NWARPS][16*ZS]
-  double* pacc_base = tab + BNN_EXP_TAB_SIZE + NWARPS * 16 * G3::ZS;
-  double* pacc = pacc_base + warp * (PREDICT ? 16 * PW : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pacc_base + NWARPS * (PREDICT ? 16 * PW : 0));
+  double* wbuf = reinterpret_cast<double*>(smem_raw);                  // [2][PB]   weight-set ring
+  double* xs = wbuf + 2 * G3::PB + warp * 16 * KP0;                     // [NWARPS][16*KP0] X warp tiles
+  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // [256] exp table
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + BNN_EXP_TAB_SIZE);
   uint64_t* full = bars;            // [2]
   uint64_t* empty = bars + 2;       // [2]
   uint64_t* xbar = bars + 4 + warp; // [NWARPS]
-  int* ibase = reinterpret_cast<int*>(bars + 4 + NWARPS);
-  int* pvote = ibase + warp * (PREDICT ? 16 * PW : 0);
-  int* cnt = ibase;
-  const int n_cnt = (!PREDICT && g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+  int* cnt = reinterpret_cast<int*>(bars + 4 + NWARPS);
+  const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
 
   for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
@@ -342,6 +436,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   for (long long it = 0; it < n_iter; ++it) {
     const long long wt = it * total_warps + (long long)blockIdx.x * NWARPS + warp;
     const bool have_tile = wt < p.n_tiles16;
+    int y[2] = {0, 0};
+    double wgt[2] = {1.0, 1.0};
+    double pacc[2][N3 / 4];
+    int pvote[2][N3 / 4];
     if (have_tile) {
       if (lane == 0) {
         // order this warp's earlier generic-proxy reads of xs before the async-proxy overwrite
@@ -349,8 +447,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         mbar_arrive_expect_tx(xbar, X_BYTES);
         bulk_g2s(xs, p.x + wt * 16 * KP0, X_BYTES, xbar);
       }
-      if (PREDICT) {
-        for (int i = lane; i < 16 * PW; i += 32) { pacc[i] = 0.0; pvote[i] = 0; }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long row = wt * 16 + gq + 8 * h;
+        if (!PREDICT && row < p.n_total) {
+          y[h] = p.labels[row];
+          if (p.class_w) wgt[h] *= p.class_w[y[h]];
+          if (p.inst_w && row < p.n_train) wgt[h] *= p.inst_w[row];
+        }
+#pragma unroll
+        for (int i = 0; i < N3 / 4; ++i) { pacc[h][i] = 0.0; pvote[h][i] = 0; }
       }
       mbar_wait(xbar, (uint32_t)(it & 1));
     }
@@ -393,11 +499,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < N1 / 8; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc1[j][e] = bnn_act<ACT>(acc1[j][e], a1, tab);
-        // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = acc1, no data movement)
+        // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = activated acc1, no data movement).
+        // The activation of k-group kg+1 is independent of the MMAs of k-group kg, so its FP64 chains fill
+        // the issue slots between the DMMAs instead of running as a separate latency-bound phase.
         double acc2[N2 / 8][4];
 #pragma unroll
         for (int j = 0; j < N2 / 8; ++j) {
@@ -407,8 +511,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         {
           const double* wr = W + G3::W2_OFF + gq * N1;
           const int sw = (gq & 1) * G3::SW1;
+          act_tile<ACT>(acc1[0], a1, tab);
 #pragma unroll
           for (int kg = 0; kg < N1 / 8; ++kg) {
+            if (kg + 1 < N1 / 8) act_tile<ACT>(acc1[kg + 1], a1, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
@@ -417,10 +523,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < N2 / 8; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc2[j][e] = bnn_act<ACT>(acc2[j][e], a2, tab);
         // ---------------- layer 3: [16 x N2] x [N2 x N3]
         double acc3[N3 / 8][4];
 #pragma unroll
@@ -431,8 +533,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         {
           const double* wr = W + G3::W3_OFF + gq * N2;
           const int sw = (gq & 1) * G3::SW2;
+          act_tile<ACT>(acc2[0], a2, tab);
 #pragma unroll
           for (int kg = 0; kg < N2 / 8; ++kg) {
+            if (kg + 1 < N2 / 8) act_tile<ACT>(acc2[kg + 1], a2, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N3 / 8; ++j) {
@@ -444,20 +548,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[b]);
-#pragma unroll
-        for (int j = 0; j < N3 / 8; ++j) {
-          const int cn = 8 * j + 2 * t;
-          zs[gq * G3::ZS + cn] = acc3[j][0]; zs[gq * G3::ZS + cn + 1] = acc3[j][1];
-          zs[(gq + 8) * G3::ZS + cn] = acc3[j][2]; zs[(gq + 8) * G3::ZS + cn + 1] = acc3[j][3];
-        }
-        __syncwarp();
-        bnn_epilogue<PREDICT>(p, c, wt, lane, zs, G3::ZS, tab, cnt, pacc, pvote);
-        __syncwarp();
+        quad_epilogue_cat<N3, PREDICT>(p, c, wt, lane, acc3, tab, cnt, y, wgt, pacc, pvote);
       } else {
         if (lane == 0) mbar_arrive(&empty[b]);
       }
     }
-    if (have_tile) bnn_pred_flush<PREDICT>(p, wt, lane, pacc, pvote);
+    if (PREDICT && have_tile) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long row = wt * 16 + gq + 8 * h;
+#pragma unroll
+        for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 8 * j + 2 * t + e;
+            if (row < p.n_total && col < g.K) {
+              if (p.mean_out) p.mean_out[row * g.K + col] = pacc[h][2 * j + e] / p.inv_sets;
+              if (p.votes_out) p.votes_out[row * g.K + col] = (double)pvote[h][2 * j + e] / p.inv_sets;
+            }
+          }
+      }
+    }
   }
   if (n_cnt) {
     __syncthreads();
@@ -472,12 +583,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 template <int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
 static size_t fwd3_smem_bytes(const FwdParams& p) {
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
-  const int PW = (p.g.lik == BNN_LIK_CATEGORICAL) ? p.g.K : p.g.O;
-  size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE + (size_t)NWARPS * 16 * G3::ZS +
-             (PREDICT ? (size_t)NWARPS * 16 * PW : 0);
+  size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE;
   size_t bytes = d * sizeof(double) + (4 + NWARPS) * sizeof(uint64_t);
-  size_t ints = PREDICT ? (size_t)NWARPS * 16 * PW
-                        : (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) : 0);
+  size_t ints = PREDICT ? 0 : (size_t)p.C * (2 + 2 * p.g.K);
   return bytes + ints * sizeof(int);
 }
 
@@ -541,10 +649,10 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
   if (!force_generic && g.L == 3) {
     const int k0 = g.F_pad, n1 = g.l[0].out_pad, n2 = g.l[1].out_pad, n3 = g.l[2].out_pad;
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
-    if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH) {
+    if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {
       if (which) *which = "k_fwd3<swish,64,64,32,16>";
       return predict ? launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, true>(p, n_sms, st)
-                     : launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, false>(p, n_sms, st);
+                     : launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, false>(p, n_sms, st);
     }
   }
   if (which) *which = "k_fwd_generic";
