@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnpbnn_b200.so")
+LIB_PATH = os.environ.get("NPBNN_B200_LIB") or os.path.join(HERE, "libnpbnn_b200.so")   # override: tuning variants
 
 MAX_LAYERS = 8
 MAX_OUT = 32

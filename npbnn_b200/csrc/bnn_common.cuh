@@ -13,7 +13,9 @@
 #include <stdint.h>
 #include "../../include/npbnn_b200.h"
 
-#define BNN_EXP_TAB_BITS 8
+#ifndef BNN_EXP_TAB_BITS
+#define BNN_EXP_TAB_BITS 11      // 2048-entry table of 2^(j/2048) (16 KB of shared memory) + degree-3 polynomial
+#endif
 #define BNN_EXP_TAB_SIZE (1 << BNN_EXP_TAB_BITS)
 
 struct LayerGeom {
@@ -69,21 +71,34 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1,
 // ---------------------------------------------------------------------------------------------
 // FP64 transcendentals tuned for the shared FP64 pipe (DMMA and DFMA issue to the same pipe on B200,
 // profiles/r01_fp64_peaks.log), i.e. as few FP64 instructions as possible:
-//   exp : 256-entry table of 2^(j/256) + degree-4 polynomial, 9 FP64 instructions, |rel err| < 3e-16
-//   rcp : MUFU.RCP64H seed + 2 Newton steps, 4 FP64 instructions
+//   exp : 2048-entry table of 2^(j/2048) + degree-3 polynomial, 8 FP64 instructions, |rel err| < 3e-16
+//         (BNN_EXP_TAB_BITS=8: 256 entries + degree 4, 9 instructions)
+//   rcp : MUFU.RCP64H seed + one third-order step, 3 FP64 instructions
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bnn_exp_core(double x, const double* __restrict__ tab) {
-  const double INV = 369.3299304675746271;           // 256 / ln 2
   const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest-integer trick
+#if BNN_EXP_TAB_BITS == 11
+  const double INV = 2954.639443740597;              // 2048 / ln 2
+  const double C_HI = 0.0003384507708688034;         // ln2/2048, low 24 mantissa bits zero (0x1.62e42fe000000p-12)
+  const double C_LO = 8.889824211446026e-13;         // ln2/2048 - C_HI
+#elif BNN_EXP_TAB_BITS == 8
+  const double INV = 369.3299304675746271;           // 256 / ln 2
   const double C_HI = 0.00270760617331689;           // ln2/256, low 21 mantissa bits zero (0x1.62e42fee00000p-9)
   const double C_LO = 7.453964567463233e-13;         // ln2/256 - C_HI
+#else
+#error "BNN_EXP_TAB_BITS must be 8 or 11"
+#endif
   double t = fma(x, INV, MAGIC);
   int k = __double2loint(t);
   double kd = t - MAGIC;
   double r = fma(kd, -C_HI, x);
   r = fma(kd, -C_LO, r);
+#if BNN_EXP_TAB_BITS == 11
+  double q = fma(r, 1.66666666666666657e-01, 0.5);   // |r| <= ln2/4096: r^4/24 < 4e-17
+#else
   double q = fma(r, 4.16666666666666644e-02, 1.66666666666666657e-01);
   q = fma(r, q, 0.5);
+#endif
   double r2 = r * r;
   double p = fma(r2, q, r);
   double T = tab[k & (BNN_EXP_TAB_SIZE - 1)];
@@ -116,13 +131,13 @@ __device__ __forceinline__ double bnn_exp_clamped(double x, const double* __rest
 }
 
 // 1/d for finite d >= 1: MUFU.RCP64H seed (rcp.approx.ftz.f64) + one third-order step
-//   e = 1 - d*y0 ; y = y0 + y0*(e + e*e)      (error e^3)
-// followed by one Newton step when BNN_RCP_EXTRA_STEP is defined (set after measuring the seed accuracy).
+//   e = 1 - d*y0 ; y = y0 + y0*(e + e*e)      (error e^3; parity tests pass at 1e-9 with margin ~1e-13)
+// BNN_RCP_NEWTON2 selects two Newton steps (4 instructions) instead.
 __device__ __forceinline__ double bnn_rcp(double d) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   double e = fma(-d, y, 1.0);
-#ifdef BNN_RCP_HALLEY
+#ifndef BNN_RCP_NEWTON2
   e = fma(e, e, e);
   y = fma(y, e, y);
 #else

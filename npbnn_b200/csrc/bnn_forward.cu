@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           const double* wr = W + G3::W1_OFF + gq * KP0;
           const int sw = (gq & 1) * G3::SW0;
 #pragma unroll 2
-          for (int kg = 0; kg < KP0 / 8; ++kg) {
+          for (int kg = 0; kg < KP0 / 8 - 2; ++kg) {
             const int col = (8 * kg + 2 * t) ^ sw;
             const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
@@ -496,6 +496,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             for (int j = 0; j < N1 / 8; ++j) {
               const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
               dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+            }
+          }
+          // last two k-groups tile by tile: acc1[0] is complete first, so its activation (below, same basic
+          // block) overlaps with the MMAs that finish the other tiles
+          {
+            const int c0 = (8 * (KP0 / 8 - 2) + 2 * t) ^ sw, c1 = (8 * (KP0 / 8 - 1) + 2 * t) ^ sw;
+            const double2 alo0 = *reinterpret_cast<const double2*>(xr0 + c0), ahi0 = *reinterpret_cast<const double2*>(xr1 + c0);
+            const double2 alo1 = *reinterpret_cast<const double2*>(xr0 + c1), ahi1 = *reinterpret_cast<const double2*>(xr1 + c1);
+#pragma unroll
+            for (int j = 0; j < N1 / 8; ++j) {
+              const double2 b0 = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + c0);
+              const double2 b1 = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + c1);
+              dmma16x8x8(acc1[j], alo0.x, ahi0.x, alo0.y, ahi0.y, b0.x, b0.y);
+              dmma16x8x8(acc1[j], alo1.x, ahi1.x, alo1.y, ahi1.y, b1.x, b1.y);
             }
           }
         }
@@ -513,13 +527,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           const int sw = (gq & 1) * G3::SW1;
           act_tile<ACT>(acc1[0], a1, tab);
 #pragma unroll
-          for (int kg = 0; kg < N1 / 8; ++kg) {
-            if (kg + 1 < N1 / 8) act_tile<ACT>(acc1[kg + 1], a1, tab);
+          for (int kg = 0; kg < N1 / 8 - 2; ++kg) {
+            act_tile<ACT>(acc1[kg + 1], a1, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
               const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + col);
               dmma16x8x8(acc2[j], acc1[kg][0], acc1[kg][2], acc1[kg][1], acc1[kg][3], bb.x, bb.y);
+            }
+          }
+          {
+            constexpr int k0 = N1 / 8 - 2, k1 = N1 / 8 - 1;
+            act_tile<ACT>(acc1[k1], a1, tab);
+            const int c0 = (8 * k0 + 2 * t) ^ sw, c1 = (8 * k1 + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N2 / 8; ++j) {
+              const double2 b0 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c0);
+              const double2 b1 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c1);
+              dmma16x8x8(acc2[j], acc1[k0][0], acc1[k0][2], acc1[k0][1], acc1[k0][3], b0.x, b0.y);
+              dmma16x8x8(acc2[j], acc1[k1][0], acc1[k1][2], acc1[k1][1], acc1[k1][3], b1.x, b1.y);
             }
           }
         }
