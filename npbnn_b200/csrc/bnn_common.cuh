@@ -117,8 +117,10 @@ __device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict
   const bool big = ax >= 0x4086232c;                  // |x| >= 708.3965 (also inf / NaN): exp(x) < 2^-1022
   double res = bnn_exp_core(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
   res = big ? 0.0 : res;
-  const bool is_nan = ax > 0x7ff00000 || (ax == 0x7ff00000 && __double2loint(x) != 0);
-  return is_nan ? x : res;
+  // NaN in => NaN out, by OR-ing quiet-NaN bits into the result (an integer op: a select here makes ptxas
+  // branch around the whole evaluation, which breaks the interleaving with the surrounding MMAs)
+  const bool is_nan = ((unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL;
+  return __hiloint2double(__double2hiint(res) | (is_nan ? 0x7ff80000 : 0), __double2loint(res));
 }
 
 // exp for activations: argument clamped to [-708, 708] (1/(1+e) is then NaN-free and the clamped tails
@@ -148,6 +150,32 @@ __device__ __forceinline__ double bnn_rcp(double d) {
   return y;
 }
 
+// log(x) for finite x >= 1 (sum of softmax terms, or a product of up to 16 of them), branch-free, ~22 FP64
+// instructions: x = 2^e m, m in [0.71, 1.42); log m = 2 atanh(f), f = (m-1)/(m+1), series to f^21; |err| < 3e-16.
+__device__ __forceinline__ double bnn_log_ge1(double x) {
+  int hi = __double2hiint(x);
+  int e = (hi >> 20) - 1023;
+  const int up = ((hi & 0xfffff) > 0x6a09e) ? 1 : 0;           // mantissa above sqrt(2): halve it
+  e += up;
+  const double m = __hiloint2double((hi & 0xfffff) | ((0x3ff - up) << 20), __double2loint(x));
+  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;   // (double)e
+  const double f = (m - 1.0) * bnn_rcp(m + 1.0);
+  const double f2 = f * f;
+  double p = 4.76190476190476164e-02;                           // 1/21
+  p = fma(p, f2, 5.26315789473684181e-02);                      // 1/19
+  p = fma(p, f2, 5.88235294117647051e-02);                      // 1/17
+  p = fma(p, f2, 6.66666666666666657e-02);                      // 1/15
+  p = fma(p, f2, 7.69230769230769273e-02);                      // 1/13
+  p = fma(p, f2, 9.09090909090909116e-02);                      // 1/11
+  p = fma(p, f2, 1.11111111111111105e-01);                      // 1/9
+  p = fma(p, f2, 1.42857142857142849e-01);                      // 1/7
+  p = fma(p, f2, 2.00000000000000011e-01);                      // 1/5
+  p = fma(p, f2, 3.33333333333333315e-01);                      // 1/3
+  const double f2x = f + f;
+  const double lm = fma(f2x * f2, p, f2x);
+  return fma(ed, 0.6931471675634384, fma(ed, 1.2996506893889889e-08, lm));   // ln2 split hi (26 bits) + lo
+}
+
 // Hidden-layer activation, matching the reference formulas (BNN_lib.py:50-66):
 //   swish z*(1+exp(-z))^-1 ; tanh 1 - 2/(exp(2z)+1) ; ReLU ; leaky (alpha*z for z<0)
 template <int ACT>
@@ -162,9 +190,8 @@ __device__ __forceinline__ double bnn_act(double z, double alpha, const double* 
   }
   double e = bnn_exp_clamped(2.0 * z, tab);
   double r = fma(-2.0, bnn_rcp(e + 1.0), 1.0);
-  const int hz = __double2hiint(z);
-  const bool is_nan = (hz & 0x7fffffff) > 0x7ff00000 || ((hz & 0x7fffffff) == 0x7ff00000 && __double2loint(z) != 0);
-  return is_nan ? z : r;
+  const bool is_nan = ((unsigned long long)__double_as_longlong(z) & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL;
+  return __hiloint2double(__double2hiint(r) | (is_nan ? 0x7ff80000 : 0), __double2loint(r));
 }
 
 // ---------------------------------------------------------------------------------------------

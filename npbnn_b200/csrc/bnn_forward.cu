@@ -294,26 +294,30 @@ struct Fwd3Geom {
 
 template <int ACT>
 __device__ __forceinline__ void act_tile(double (&a)[4], double alpha, const double* tab) {
+#ifdef BNN_DBG_NOACT      // tuning experiment only: how fast is the kernel without activations?
+  return;
+#endif
 #pragma unroll
   for (int e = 0; e < 4; ++e) a[e] = bnn_act<ACT>(a[e], alpha, tab);
 }
 
-// Softmax / log-likelihood / counters (or posterior summaries) on the accumulator fragments of the last
-// layer: the 4 lanes of a quad hold one row pair (rows g and g+8), columns 8j+2t+{0,1}.  All exps of a
-// thread are independent (ILP), row statistics are combined with two xor-shuffles.
-template <int N3, bool PREDICT>
-__device__ __forceinline__ void quad_epilogue_cat(const FwdParams& p, int c, long long wt, int lane,
-                                                  const double (&acc)[N3 / 8][4], const double* tab, int* cnt,
-                                                  const int (&y)[2], const double (&wgt)[2],
-                                                  double (&pacc)[2][N3 / 4], int (&pvote)[2][N3 / 4]) {
-  const int K = p.g.K;
-  const int gq = lane >> 2, t = lane & 3;
-  double ll_sum = 0.0;
+// ---------------------------------------------------------------------------------------------
+// Epilogues on the accumulator fragments of the last layer.  The 4 lanes of a quad hold one row pair
+// (rows g and g+8), columns 8j+2t+{0,1}; row statistics are combined with two xor-shuffles and all exps
+// of a thread are independent (ILP).
+// ---------------------------------------------------------------------------------------------
+template <int N3>
+struct RowStats {
+  double m[2], S[2], zy[2];
+  int arg[2];
+  double ev[2][N3 / 4];
+};
+
+// stage 1: row maximum and arg-max (first maximum wins, as np.argmax)
+template <int N3>
+__device__ __forceinline__ void qs_max(const double (&acc)[N3 / 8][4], int K, int t, RowStats<N3>& r) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const long long row = wt * 16 + gq + 8 * h;
-    const bool active = row < p.n_total;
-    const bool is_train = row < p.n_train;
     double m = -INFINITY;
     int arg = 0x7fffffff;
 #pragma unroll
@@ -322,76 +326,173 @@ __device__ __forceinline__ void quad_epilogue_cat(const FwdParams& p, int c, lon
       for (int e = 0; e < 2; ++e) {
         const int col = 8 * j + 2 * t + e;
         const double v = acc[j][2 * h + e];
-        if (col < K && v > m) { m = v; arg = col; }      // columns ascend within a thread: first maximum wins
+        const bool take = col < K && v > m;      // columns ascend within a thread
+        m = take ? v : m;
+        arg = take ? col : arg;
       }
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
       const double om = __shfl_xor_sync(FULL_MASK, m, o);
       const int oa = __shfl_xor_sync(FULL_MASK, arg, o);
-      if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+      const bool take = om > m || (om == m && oa < arg);
+      m = take ? om : m;
+      arg = take ? oa : arg;
     }
-    if (arg == 0x7fffffff) arg = 0;
-    double ev[N3 / 4];
-    double S = 0.0, zy = 0.0;
+    r.m[h] = m;
+    r.arg[h] = (arg == 0x7fffffff) ? 0 : arg;
+  }
+}
+
+// stage 2: exp(z - max) of this thread's columns of row h, local sums
+template <int N3, int H, bool NEED_ZY>
+__device__ __forceinline__ void qs_exp(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
+                                       const double* tab, RowStats<N3>& r) {
+  double S = 0.0, zy = 0.0;
 #pragma unroll
-    for (int j = 0; j < N3 / 8; ++j)
+  for (int j = 0; j < N3 / 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = 8 * j + 2 * t + e;
-        const double v = acc[j][2 * h + e];
-        double ex = 0.0;
-        if (col < K) ex = bnn_exp_neg(v - m, tab);
-        ev[2 * j + e] = ex;
-        S += ex;
-        if (col == y[h]) zy = v;
-      }
-    S += __shfl_xor_sync(FULL_MASK, S, 1);
-    S += __shfl_xor_sync(FULL_MASK, S, 2);
-    if (!PREDICT) {
-      zy += __shfl_xor_sync(FULL_MASK, zy, 1);
-      zy += __shfl_xor_sync(FULL_MASK, zy, 2);
-      if (t == 0 && active) {
-        const bool ok = (arg == y[h]);
-        int* cc = cnt + c * (2 + 2 * K);
-        if (is_train) {
-          const double d = zy - m;
-          // log(softmax) of the reference is -inf once exp(d) underflows to 0 (BNN_lib.py:121,168)
-          double ll = (d < -745.1332191019412) ? -INFINITY : d - log(S);
-          ll_sum += ll * wgt[h];
-          if (ok) { atomicAdd(&cc[2 + y[h]], 1); atomicAdd(&cc[0], 1); }
-          atomicAdd(&cc[2 + K + arg], 1);
-        } else if (ok) {
-          atomicAdd(&cc[1], 1);
-        }
-      }
-    } else if (active) {
-      const double inv = 1.0 / S;
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * j + 2 * t + e;
+      const double v = acc[j][2 * H + e];
+      // padded columns: argument -1000 => exp flushes to exactly 0 (no branch around the evaluation)
+      const double ex = bnn_exp_neg((col < K) ? v - r.m[H] : -1000.0, tab);
+      r.ev[H][2 * j + e] = ex;
+      S += ex;
+      if (NEED_ZY) zy = (col == y[H]) ? v : zy;
+    }
+  r.S[H] = S;
+  r.zy[H] = zy;
+}
+
+// stage 3: quad reductions of the sums
+template <int N3, bool NEED_ZY>
+__device__ __forceinline__ void qs_reduce(RowStats<N3>& r) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    r.S[h] += __shfl_xor_sync(FULL_MASK, r.S[h], 1);
+    r.S[h] += __shfl_xor_sync(FULL_MASK, r.S[h], 2);
+    if (NEED_ZY) {
+      r.zy[h] += __shfl_xor_sync(FULL_MASK, r.zy[h], 1);
+      r.zy[h] += __shfl_xor_sync(FULL_MASK, r.zy[h], 2);
+    }
+  }
+}
+
+template <int N3, bool NEED_ZY>
+__device__ __forceinline__ void quad_softmax_stats(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
+                                                   const double* tab, RowStats<N3>& r) {
+  qs_max<N3>(acc, K, t, r);
+  qs_exp<N3, 0, NEED_ZY>(acc, K, t, y, tab, r);
+  qs_exp<N3, 1, NEED_ZY>(acc, K, t, y, tab, r);
+  qs_reduce<N3, NEED_ZY>(r);
+}
+
+// Likelihood + accuracy counters of one (warp tile, weight set), in two parts so that the kernel can place
+// the arithmetic (part 1: softmax statistics and log-likelihood, branch-free, latency-bound FP64 chains and
+// shuffles) in the same basic block as the first MMAs of the NEXT weight set -- ptxas then interleaves the
+// two -- and the side effects (part 2: counters and the partial-sum store) at the end of that block.
+//   * without class / instance weights  sum_r log softmax = sum_r (z_y - max) - log(prod_r S_r): ONE log per
+//     warp tile (the product of 16 sums of at most 32 terms each stays below 2^80)
+//   * counters: ballots for n_correct, full-mask match.any groups for the per-class counters: at most one
+//     shared-memory atomic per distinct class and warp tile instead of three per row
+struct LikRow {
+  double ll;          // warp-tile log-likelihood (all lanes)
+  int my_y, my_arg;   // lane t == 0 speaks for row g, lane t == 1 for row g + 8
+  bool ok, train, role;
+};
+
+// stage 4: per-row roles, warp-tile reduction and the logarithm
+template <int N3, bool WEIGHTED>
+__device__ __forceinline__ LikRow quad_lik_finish(const FwdParams& p, long long wt, int lane, const RowStats<N3>& r,
+                                                  const int (&y)[2], const double (&wgt)[2], bool valid) {
+  const int gq = lane >> 2, t = lane & 3;
+  LikRow o;
+  const int h = t & 1;
+  const long long row = wt * 16 + gq + 8 * h;
+  o.role = valid && t < 2 && row < p.n_total;
+  o.train = o.role && row < p.n_train;
+  o.my_y = h ? y[1] : y[0];
+  o.my_arg = h ? r.arg[1] : r.arg[0];
+  const double my_S = h ? r.S[1] : r.S[0];
+  const double d = (h ? r.zy[1] : r.zy[0]) - (h ? r.m[1] : r.m[0]);
+  o.ok = o.role && o.my_arg == o.my_y;
+  // log(softmax) of the reference is -inf once exp(d) underflows to 0 (BNN_lib.py:121,168)
+  const bool neg_inf = o.train && d < -745.1332191019412;
+  double ll;
+  if (!WEIGHTED) {
+    double sd = o.train ? d : 0.0, ps = o.train ? my_S : 1.0;
+#pragma unroll
+    for (int s = 1; s <= 16; s <<= 1) {        // fixed xor tree => deterministic
+      sd += __shfl_xor_sync(FULL_MASK, sd, s);
+      ps *= __shfl_xor_sync(FULL_MASK, ps, s);
+    }
+    ll = sd - bnn_log_ge1(ps);
+  } else {
+    ll = o.train ? (d - bnn_log_ge1(my_S)) * (h ? wgt[1] : wgt[0]) : 0.0;
+#pragma unroll
+    for (int s = 1; s <= 16; s <<= 1) ll += __shfl_xor_sync(FULL_MASK, ll, s);
+  }
+  o.ll = __any_sync(FULL_MASK, neg_inf) ? -INFINITY : ll;
+  return o;
+}
+
+__device__ __forceinline__ void quad_lik_commit(const FwdParams& p, int c, long long wt, int lane, int* cnt,
+                                                const LikRow& o, bool valid) {
+  const int K = p.g.K;
+  int* cc = cnt + c * (2 + 2 * K);
+  const unsigned ok_train = __ballot_sync(FULL_MASK, o.ok && o.train);
+  const unsigned ok_test = __ballot_sync(FULL_MASK, o.ok && !o.train);
+  if (lane == 0 && ok_train) atomicAdd(&cc[0], __popc(ok_train));
+  if (lane == 0 && ok_test) atomicAdd(&cc[1], __popc(ok_test));
+  {
+    const unsigned grp = __match_any_sync(FULL_MASK, (o.ok && o.train) ? o.my_y : 64 + lane);
+    if (o.ok && o.train && lane == __ffs(grp) - 1) atomicAdd(&cc[2 + o.my_y], __popc(grp));
+  }
+  {
+    const unsigned grp = __match_any_sync(FULL_MASK, o.train ? o.my_arg : 64 + lane);
+    if (o.train && lane == __ffs(grp) - 1) atomicAdd(&cc[2 + K + o.my_arg], __popc(grp));
+  }
+  if (valid && lane == 0) p.part[((long long)c * p.NF) * p.n_tiles16 + wt] = o.ll;
+}
+
+// Posterior summaries: softmax probabilities accumulated per (row, class) in registers over the weight sets.
+template <int N3>
+__device__ __forceinline__ void quad_epilogue_pred(const FwdParams& p, int c, long long wt, int lane,
+                                                   const double (&acc)[N3 / 8][4], const double* tab,
+                                                   double (&pacc)[2][N3 / 4], int (&pvote)[2][N3 / 4]) {
+  const int K = p.g.K;
+  const int gq = lane >> 2, t = lane & 3;
+  const int y[2] = {-1, -1};
+  RowStats<N3> r;
+  quad_softmax_stats<N3, false>(acc, K, t, y, tab, r);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long row = wt * 16 + gq + 8 * h;
+    if (row < p.n_total) {
+      const double inv = 1.0 / r.S[h];
 #pragma unroll
       for (int j = 0; j < N3 / 8; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = 8 * j + 2 * t + e;
           if (col < K) {
-            const double pk = ev[2 * j + e] * inv;
+            const double pk = r.ev[h][2 * j + e] * inv;
             pacc[h][2 * j + e] += pk;
             if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + col] = pk;
-            if (col == arg) pvote[h][2 * j + e] += 1;
+            if (col == r.arg[h]) pvote[h][2 * j + e] += 1;
           }
         }
     }
   }
-  if (!PREDICT) {
-    // fixed xor tree over the 8 row pairs of the warp tile (lanes with t != 0 hold 0)
-    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 4);
-    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 8);
-    ll_sum += __shfl_xor_sync(FULL_MASK, ll_sum, 16);
-    if (lane == 0) p.part[((long long)c * p.NF) * p.n_tiles16 + wt] = ll_sum;
-  }
 }
 
-template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+// MODE: 0 likelihood, 1 likelihood with class / instance weights, 2 posterior prediction
+enum { FWD3_LIK = 0, FWD3_LIK_W = 1, FWD3_PRED = 2 };
+
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__ FwdParams p) {
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
+  constexpr bool PREDICT = (MODE == FWD3_PRED);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -400,7 +501,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   // ---- shared memory carve-up
   double* wbuf = reinterpret_cast<double*>(smem_raw);                  // [2][PB]   weight-set ring
   double* xs = wbuf + 2 * G3::PB + warp * 16 * KP0;                     // [NWARPS][16*KP0] X warp tiles
-  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // [256] exp table
+  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // exp table
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab + BNN_EXP_TAB_SIZE);
   uint64_t* full = bars;            // [2]
   uint64_t* empty = bars + 2;       // [2]
@@ -440,6 +541,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
     double wgt[2] = {1.0, 1.0};
     double pacc[2][N3 / 4];
     int pvote[2][N3 / 4];
+    double acc3[N3 / 8][4];          // last-layer accumulators of the previous weight set (likelihood modes)
+    bool prev_valid = false;
+#pragma unroll
+    for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
     if (have_tile) {
       if (lane == 0) {
         // order this warp's earlier generic-proxy reads of xs before the async-proxy overwrite
@@ -452,8 +557,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         const long long row = wt * 16 + gq + 8 * h;
         if (!PREDICT && row < p.n_total) {
           y[h] = p.labels[row];
-          if (p.class_w) wgt[h] *= p.class_w[y[h]];
-          if (p.inst_w && row < p.n_train) wgt[h] *= p.inst_w[row];
+          if (MODE == FWD3_LIK_W) {
+            if (p.class_w) wgt[h] *= p.class_w[y[h]];
+            if (p.inst_w && row < p.n_train) wgt[h] *= p.inst_w[row];
+          }
         }
 #pragma unroll
         for (int i = 0; i < N3 / 4; ++i) { pacc[h][i] = 0.0; pvote[h][i] = 0; }
@@ -487,8 +594,46 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           const double* xr1 = xs + (gq + 8) * KP0;
           const double* wr = W + G3::W1_OFF + gq * KP0;
           const int sw = (gq & 1) * G3::SW0;
+          // Software pipeline over weight sets: the epilogue of the PREVIOUS set (softmax, log-likelihood,
+          // counters -- latency-bound FP64 chains and shuffles) sits in the same basic block as the first two
+          // k-groups of this set's layer 1, whose 64 DMMAs need no FP64 issue slots of their own.
+          // Software pipeline over weight sets: the epilogue of the PREVIOUS set (softmax statistics, log-
+          // likelihood: latency-bound FP64 chains and shuffles) is cut into four stages that are placed
+          // between the MMA groups of the first two k-groups of this set's layer 1, whose DMMAs leave the
+          // FP64 issue slots free.
+          RowStats<N3> rs;
+          LikRow lr;
+          const int K = g.K;
+#pragma unroll
+          for (int kg = 0; kg < 2; ++kg) {
+            const int col = (8 * kg + 2 * t) ^ sw;
+            const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
+            const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
+            if (!PREDICT) {
+              if (kg == 0) qs_max<N3>(acc3, K, t, rs);
+              else qs_exp<N3, 1, true>(acc3, K, t, y, tab, rs);
+            }
+#pragma unroll
+            for (int j = 0; j < N1 / 16; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
+              dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+            }
+            if (!PREDICT) {
+              if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, y, tab, rs);
+              else {
+                qs_reduce<N3, true>(rs);
+                lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, prev_valid);
+              }
+            }
+#pragma unroll
+            for (int j = N1 / 16; j < N1 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
+              dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+            }
+          }
+          if (!PREDICT) quad_lik_commit(p, c - 1, wt, lane, cnt, lr, prev_valid);
 #pragma unroll 2
-          for (int kg = 0; kg < KP0 / 8 - 2; ++kg) {
+          for (int kg = 2; kg < KP0 / 8 - 2; ++kg) {
             const int col = (8 * kg + 2 * t) ^ sw;
             const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
@@ -550,7 +695,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           }
         }
         // ---------------- layer 3: [16 x N2] x [N2 x N3]
-        double acc3[N3 / 8][4];
 #pragma unroll
         for (int j = 0; j < N3 / 8; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
@@ -574,25 +718,35 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[b]);
-        quad_epilogue_cat<N3, PREDICT>(p, c, wt, lane, acc3, tab, cnt, y, wgt, pacc, pvote);
+        prev_valid = true;
+        if (PREDICT) quad_epilogue_pred<N3>(p, c, wt, lane, acc3, tab, pacc, pvote);
       } else {
         if (lane == 0) mbar_arrive(&empty[b]);
       }
     }
-    if (PREDICT && have_tile) {
+    if (have_tile) {
+      // drain the software pipeline: epilogue of the last weight set of this tile
+      if (!PREDICT) {
+        RowStats<N3> rs;
+        quad_softmax_stats<N3, true>(acc3, g.K, t, y, tab, rs);
+        const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, true);
+        quad_lik_commit(p, p.C - 1, wt, lane, cnt, lr, true);
+      }
+      if (PREDICT) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const long long row = wt * 16 + gq + 8 * h;
+        for (int h = 0; h < 2; ++h) {
+          const long long row = wt * 16 + gq + 8 * h;
 #pragma unroll
-        for (int j = 0; j < N3 / 8; ++j)
+          for (int j = 0; j < N3 / 8; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = 8 * j + 2 * t + e;
-            if (row < p.n_total && col < g.K) {
-              if (p.mean_out) p.mean_out[row * g.K + col] = pacc[h][2 * j + e] / p.inv_sets;
-              if (p.votes_out) p.votes_out[row * g.K + col] = (double)pvote[h][2 * j + e] / p.inv_sets;
+            for (int e = 0; e < 2; ++e) {
+              const int col = 8 * j + 2 * t + e;
+              if (row < p.n_total && col < g.K) {
+                if (p.mean_out) p.mean_out[row * g.K + col] = pacc[h][2 * j + e] / p.inv_sets;
+                if (p.votes_out) p.votes_out[row * g.K + col] = (double)pvote[h][2 * j + e] / p.inv_sets;
+              }
             }
-          }
+        }
       }
     }
   }
@@ -606,8 +760,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 // =============================================================================================
 // host-side launchers
 // =============================================================================================
-template <int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+template <int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
 static size_t fwd3_smem_bytes(const FwdParams& p) {
+  constexpr bool PREDICT = (MODE == FWD3_PRED);
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE;
   size_t bytes = d * sizeof(double) + (4 + NWARPS) * sizeof(uint64_t);
@@ -615,10 +770,10 @@ static size_t fwd3_smem_bytes(const FwdParams& p) {
   return bytes + ints * sizeof(int);
 }
 
-template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, bool PREDICT>
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
 static cudaError_t launch_fwd3(const FwdParams& p, int n_sms, cudaStream_t st) {
-  auto kern = k_fwd3<ACT, KP0, N1, N2, N3, NWARPS, PREDICT>;
-  size_t smem = fwd3_smem_bytes<KP0, N1, N2, N3, NWARPS, PREDICT>(p);
+  auto kern = k_fwd3<ACT, KP0, N1, N2, N3, NWARPS, MODE>;
+  size_t smem = fwd3_smem_bytes<KP0, N1, N2, N3, NWARPS, MODE>(p);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -677,8 +832,9 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
     if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {
       if (which) *which = "k_fwd3<swish,64,64,32,16>";
-      return predict ? launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, true>(p, n_sms, st)
-                     : launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, false>(p, n_sms, st);
+      if (predict) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, FWD3_PRED>(p, n_sms, st);
+      if (p.class_w || p.inst_w) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK_W>(p, n_sms, st);
+      return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK>(p, n_sms, st);
     }
   }
   if (which) *which = "k_fwd_generic";
