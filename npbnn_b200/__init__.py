@@ -1,0 +1,12 @@
+"""npbnn_b200 -- B200-native (sm_100a CUDA behind a C ABI) implementation of the npBNN MCMC hot path.
+
+The names below mirror the reference package (np_bnn/__init__.py:6-25) for the path that is rebuilt here:
+model / sampler state, the MH drivers, MC3, block masks and the posterior-prediction callers.
+"""
+__version__ = "0.1.0"
+
+from .api import (ActFun, MC3, MCMC, RegressTransform, RegressTransformError, RunPredict, RunPredictInd, SaveObject,  # noqa: F401
+                  SoftMax, UpdateNormal, calc_likelihood, calc_likelihood_regression, calc_likelihood_regression_error,
+                  create_mask, get_pdp, get_posterior_cat_prob, get_posterior_est, init_weight_prm, load_obj,
+                  make_pdp_features, npBNN, pdp, postLogger, predict, run_mcmc)
+from .engine import Engine, NetShape  # noqa: F401

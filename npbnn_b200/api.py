@@ -1,0 +1,867 @@
+"""Host-side mirror of the reference's Python interface for the MCMC hot path.
+
+Same names, argument meaning and attribute surface as `np_bnn` (reference np_bnn/__init__.py:6-25), so
+the reference's scripts and the parity tests read the same; the arithmetic of every call runs in the
+CUDA library behind the C ABI (include/npbnn_b200.h).  There is no CPU fallback.
+
+What is on the device path            reference
+  npBNN.calc_prior                    BNN_env.py:180-194
+  MCMC.__init__ / MCMC.mh_step        BNN_env.py:274-532   (update_function = UpdateNormal)
+  run_mcmc                            BNN_mcmc.py:153-170
+  MC3.run_mcmc                        BNN_mc3.py:87-126
+  RunPredict / RunPredictInd / predict  BNN_lib.py:245-272, BNN_env.py:662-670
+  get_posterior_cat_prob (modes 0, 1) BNN_lib.py:352-397
+  get_posterior_est                   BNN_lib.py:715-748
+  get_pdp / pdp                       BNN_pdp.py:48-108
+
+Random numbers.  `rng="host"` (default of MCMC) draws every proposal from `self._rs`
+(np.random.default_rng(1234), BNN_env.py:362) with exactly the reference's call sequence and replays
+the draws on the device: the chain is then the reference's chain (same accept/reject decisions; the
+log-likelihood differs in the last bits because of the summation order).  `rng="philox"` generates the
+proposals on the device and never leaves it between logging points.
+
+Options of the reference that are not on the device path raise NotImplementedError at construction:
+trainable activation parameters, feature / weight indicators, hyper-priors, user-supplied likelihood /
+proposal / output functions, the regression error-parameter proposal (estimate_error with
+empirical_error=False once the iteration passes `_estimate_error`).
+"""
+import csv
+import os
+import pickle
+from copy import deepcopy
+
+import numpy as np
+
+from . import _lib as L
+from . import mc3 as _mc3
+from .engine import Engine, NetShape, flatten_weights, unflatten_weights
+
+small_number = 1e-10
+
+
+# ------------------------------------------------------------------------------------------------------
+# names the reference exports and user code passes around (identity tokens: they select device code)
+# ------------------------------------------------------------------------------------------------------
+def _device_only(name):
+    raise NotImplementedError("%s is evaluated inside the CUDA kernels of npbnn_b200; call RunPredict / MCMC instead" % name)
+
+
+# module-level functions (not closures) so that objects holding them pickle by reference
+def SoftMax(z):                                           # BNN_lib.py:166-168
+    _device_only("SoftMax")
+
+
+def RegressTransform(z):                                  # BNN_lib.py:174-175
+    _device_only("RegressTransform")
+
+
+def RegressTransformError(z, ind=None):                   # BNN_lib.py:177-182
+    _device_only("RegressTransformError")
+
+
+def calc_likelihood(*a, **k):                             # BNN_lib.py:100-121
+    _device_only("calc_likelihood")
+
+
+def calc_likelihood_regression(*a, **k):                  # BNN_lib.py:123-131
+    _device_only("calc_likelihood_regression")
+
+
+def calc_likelihood_regression_error(*a, **k):            # BNN_lib.py:134-143
+    _device_only("calc_likelihood_regression_error")
+
+
+def UpdateNormal(*a, **k):                                # BNN_mcmc.py:57-69
+    _device_only("UpdateNormal")
+
+
+class ActFun:
+    """Activation selector (BNN_lib.py:68-94).  Later `if`s override earlier ones exactly as in the reference:
+    fun="ReLU" with trainable=True still evaluates as plain ReLU (eval passes prm 0 unless fun=="genReLU")."""
+
+    def __init__(self, fun="ReLU", prm=np.zeros(1), trainable=False):
+        if trainable:
+            raise NotImplementedError("trainable activation parameters are not on the device path")
+        if fun not in ("ReLU", "genReLU", "swish", "tanh"):
+            raise ValueError("unknown activation %r" % (fun,))
+        self._prm = prm
+        self._acc_prm = prm
+        self._trainable = trainable
+        self._function = fun
+
+    def reset_prm(self, prm):
+        self._prm = prm
+
+    def reset_accepted_prm(self):
+        self._acc_prm = self._prm + 0
+
+    def alphas(self, n_layers):
+        if self._function != "genReLU":
+            return None
+        a = np.zeros(n_layers)
+        p = np.atleast_1d(np.asarray(self._prm, dtype=np.float64))
+        a[:min(len(p), n_layers)] = p[:n_layers]
+        return a
+
+
+def init_weight_prm(n_nodes, n_features, size_output, init_std=0.1, bias_node=0):
+    """N(0, init_std) weights from the global numpy state; bias columns per `bias_node`
+    (>=1 first layer, >=2 hidden layers, 3 or -1 last layer), as BNN_mcmc.py:9-25."""
+    b_first = 1 if bias_node >= 1 else 0
+    b_hidden = 1 if bias_node >= 2 else 0
+    b_last = 1 if bias_node in (3, -1) else 0
+    widths = [n_features] + list(n_nodes)
+    layers = []
+    for i, out in enumerate(n_nodes):
+        layers.append(np.random.normal(0, init_std, (out, widths[i] + (b_first if i == 0 else b_hidden))))
+    layers.append(np.random.normal(0, init_std, (size_output, n_nodes[-1] + b_last)))
+    return layers
+
+
+def create_mask(w_layers, indx_input_list, nodes_per_feature_list):
+    """Block masks (BNN_lib.py:16-47): in layer l, input column i belongs to group indx_input_list[l][i];
+    consecutive columns of one group share a block of nodes_per_feature_list[l][group] rows; blocks stack
+    downwards; an empty list means fully connected."""
+    masks = []
+    for l, w in enumerate(w_layers):
+        groups, rows = indx_input_list[l], nodes_per_feature_list[l]
+        if len(groups) == 0:
+            masks.append(np.ones(w.shape))
+            continue
+        m = np.zeros(w.shape)
+        g, row0 = 0, 0
+        for col in range(len(groups)):
+            if col > 0 and groups[col] != groups[col - 1]:
+                row0 += rows[g]
+                g += 1
+            m[row0:row0 + rows[g], col] = 1
+        masks.append(m)
+    return masks
+
+
+_LIK = {"classification": L.LIK_CATEGORICAL, "regression": L.LIK_GAUSSIAN, "regression-error": L.LIK_GAUSSIAN_HEAD}
+
+
+def _net_of(weights, n_features, act_fun, estimation_mode):
+    return NetShape.from_weights(weights, n_features, act=act_fun._function, lik=_LIK[estimation_mode])
+
+
+class npBNN:
+    """Model state (BNN_env.py:19-270).  Same constructor signature and attributes as the reference."""
+
+    def __init__(self, dat, n_nodes=[50, 5], use_bias_node=1, init_std=0.1, p_scale=1, prior_ind1=0.5, prior_f=1,
+                 hyper_p=0, freq_indicator=0, w_bound=np.inf, pickle_file="", seed=1234, use_class_weights=0,
+                 actFun=None, init_weights=None, estimation_mode="classification", instance_weights=None,
+                 empirical_error=False, size_output=None, output_act_fun=None, feature_indicators=None):
+        if actFun is None:
+            actFun = ActFun()
+        if hyper_p or freq_indicator or feature_indicators:
+            raise NotImplementedError("hyper-priors / weight indicators / feature indicators are not on the device path")
+        if estimation_mode not in _LIK:
+            raise NotImplementedError("estimation_mode=%r (custom likelihoods) is not on the device path" % (estimation_mode,))
+        if output_act_fun is not None and not (estimation_mode == "regression-error" and output_act_fun is RegressTransformError) \
+                and not (estimation_mode == "regression" and output_act_fun is RegressTransform):
+            raise NotImplementedError("user-supplied output_act_fun is not on the device path")
+        data, labels = dat["data"], dat["labels"]
+        self._seed = seed
+        self._data = np.ascontiguousarray(data, dtype=np.float64)
+        self._labels = labels.astype(int) if estimation_mode == "classification" else np.asarray(labels, dtype=np.float64)
+        self._test_data = dat["test_data"]
+        tl = dat["test_labels"]
+        if len(tl) > 0:
+            self._test_labels = tl.astype(int) if estimation_mode == "classification" else np.asarray(tl, dtype=np.float64)
+        else:
+            self._test_labels = []
+        self._error_prm = []
+        if estimation_mode == "classification":
+            self._size_output = len(np.unique(self._labels))
+            self._n_output_prm = self._size_output
+            self._output_act_fun = SoftMax
+        elif estimation_mode == "regression":
+            self._output_act_fun = RegressTransform
+            self._size_output = self._labels.shape[1]
+            self._n_output_prm = self._labels.shape[1]
+            self._error_prm = np.ones(self._size_output)
+        else:
+            self._output_act_fun = RegressTransformError
+            self._size_output = self._labels.shape[1] * 2
+            self._n_output_prm = self._labels.shape[1]
+        self._empirical_error = empirical_error
+        self._init_std = init_std
+        try:
+            n_nodes = list(n_nodes)
+        except TypeError:
+            n_nodes = [n_nodes]
+        self._n_layers = len(n_nodes) + 1
+        self._n_nodes = n_nodes
+        self._use_bias_node = use_bias_node
+        self._n_samples, self._n_features = self._data.shape
+        self._w_bound = w_bound
+        self._freq_indicator = freq_indicator
+        self._hyper_p = hyper_p
+        self._sample_id = np.arange(self._n_samples)
+        self._prior = prior_f
+        self._p_scale = p_scale
+        self._prior_ind1 = prior_ind1
+        self._estimation_mode = estimation_mode
+        self._mask = None
+        self._feature_indicators = None
+        self._feature_means = None
+        if use_class_weights:
+            counts = np.unique(self._labels, return_counts=True)[1]
+            cw = 1 / (counts / np.max(counts))
+            self._class_w = cw / np.mean(cw)
+        else:
+            self._class_w = []
+        self._instance_weights = instance_weights
+        if init_weights is None:
+            if pickle_file == "":
+                # the reference passes the literal 0.1 here, ignoring its init_std argument (BNN_env.py:111-115)
+                w_layers = init_weight_prm(self._n_nodes, self._n_features, self._size_output, init_std=0.1,
+                                           bias_node=use_bias_node)
+            else:
+                _, _, logger_obj = load_obj(pickle_file)
+                w_layers = logger_obj._post_weight_samples[-1]["weights"]
+        else:
+            w_layers = init_weights
+        self._w_layers = w_layers
+        self._indicators = np.ones(self._w_layers[0].shape)
+        self._act_fun = actFun
+        if self._prior == 0:
+            self._w_bound = self._p_scale            # uniform prior: bounds = p_scale (BNN_env.py:135-137)
+        self._prior_scale = np.ones(self._n_layers) * self._p_scale
+        self._n_params = int(np.sum([np.size(w) for w in self._w_layers]))
+        self._eng = None
+
+    # prior_f: 0 uniform, 2 Cauchy, 3 Laplace, anything else Normal (selection quirk of BNN_env.py:139-150)
+    def _prior_kind(self):
+        return self._prior if self._prior in (0, 2, 3) else 1
+
+    def _net(self):
+        return _net_of(self._w_layers, self._n_features, self._act_fun, self._estimation_mode)
+
+    def _engine(self):
+        if self._eng is None:
+            self._eng = Engine(self._net())
+        return self._eng
+
+    def calc_prior(self, w=0, ind=[]):
+        if isinstance(w, int) and w == 0:
+            w = self._w_layers
+        if self._prior == 0:
+            return 0
+        return float(self._engine().log_prior([w], self._prior_kind(), self._prior_scale)[0])
+
+    def reset_weights(self, w):
+        self._w_layers = w
+
+    def reset_indicators(self, ind):
+        self._indicators = ind
+
+    def reset_error_prm(self, p):
+        self._error_prm = p
+
+    def update_data(self, data_dict):
+        self._data = np.ascontiguousarray(data_dict["data"], dtype=np.float64)
+        self._labels = data_dict["labels"]
+        self._test_data = data_dict["test_data"]
+        self._test_labels = data_dict["test_labels"]
+
+    def apply_mask(self, m=None):
+        if m is not None:
+            self._mask = m
+        self._w_layers = [self._w_layers[i] * self._mask[i] for i in range(self._n_layers)]
+
+    def reset_seed(self, seed):
+        self._seed = seed
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_eng"] = None          # device handles never enter a pickle (postLogger pickles the live objects)
+        return d
+
+
+def _has_test(bnn):
+    return len(bnn._test_data) > 0
+
+
+class _ChainGroup:
+    """C chains of one model on one GPU: engine + the host bookkeeping that turns numpy draws into the
+    injection arrays of bnn_mh_steps."""
+
+    def __init__(self, bnn, weights_per_chain, temperatures, update_f, update_ws, lik_temp, adapt_f, adapt_fM,
+                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0):
+        self.bnn = bnn
+        net = _net_of(weights_per_chain[0], bnn._n_features, bnn._act_fun, bnn._estimation_mode)
+        self.net = net
+        self.eng = Engine(net, device=device)
+        cw = bnn._class_w if len(bnn._class_w) else None
+        self.eng.set_data(bnn._data, bnn._labels, bnn._test_data if _has_test(bnn) else None,
+                          bnn._test_labels if _has_test(bnn) else None, inst_w=bnn._instance_weights, class_w=cw)
+        self.n = len(weights_per_chain)
+        sigma0 = None
+        if bnn._estimation_mode == "regression":
+            sigma0 = np.ones(bnn._size_output) * np.asarray(bnn._error_prm, dtype=np.float64)
+        self.eng.chains_init(weights_per_chain, temperature=temperatures, update_f=update_f, update_ws=update_ws,
+                             prior=bnn._prior_kind(), prior_scale=bnn._prior_scale, w_bound=bnn._w_bound,
+                             mask=bnn._mask, alphas=bnn._act_fun.alphas(net.n_layers), sigma0=sigma0,
+                             sigma_mode=L.SIGMA_EMPIRICAL if (bnn._estimation_mode == "regression" and bnn._empirical_error)
+                             else L.SIGMA_FIXED,
+                             lik_temp=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq,
+                             adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed)
+        self.labels_count = None
+        if bnn._estimation_mode == "classification":
+            self.labels_count = np.bincount(bnn._labels, minlength=bnn._size_output)
+
+    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None):
+        """Consume each chain's generator exactly as mh_step + UpdateNormal do (BNN_env.py:446-453,493;
+        BNN_mcmc.py:62-65) for n_steps iterations during which no adaptation fires.
+        reseed(chain, iteration) -> Generator implements randomize_seed (BNN_env.py:383-384)."""
+        nl = self.net.n_layers
+        shapes = self.net.shapes
+        cap = max(1, int(np.max(np.sum(state.update_n, axis=1))))
+        inj = {"proposed": np.zeros((n_steps, self.n, nl), np.int32), "count": np.zeros((n_steps, self.n, nl), np.int32),
+               "ix": np.zeros((n_steps, self.n, cap), np.int32), "iy": np.zeros((n_steps, self.n, cap), np.int32),
+               "dz": np.zeros((n_steps, self.n, cap)), "log_u": np.zeros((n_steps, self.n))}
+        for c in range(self.n):
+            flu, un, uws = state.freq_layer_update[c], state.update_n[c], state.update_ws[c]
+            for s in range(n_steps):
+                rs = rngs[c] if reseed is None else reseed(chain_ids[c], int(state.iteration[c]) + s)
+                rr = rs.random(nl)
+                rr[np.argmin(rr)] = 0
+                o = 0
+                for l in range(nl):
+                    if rr[l] < flu[l]:
+                        n = int(un[l])
+                        ix = rs.integers(0, shapes[l][0], n)
+                        iy = rs.integers(0, shapes[l][1], n)
+                        dz = rs.normal(0, np.full(n, uws[l]), n)
+                        inj["proposed"][s, c, l] = 1
+                        inj["count"][s, c, l] = n
+                        inj["ix"][s, c, o:o + n], inj["iy"][s, c, o:o + n], inj["dz"][s, c, o:o + n] = ix, iy, dz
+                        o += n
+                with np.errstate(divide="ignore"):
+                    inj["log_u"][s, c] = np.log(rs.random())
+        return inj
+
+
+def _steps_to_adaptation(it, adapt_freq, adapt_stop):
+    """How many iterations can run from `it` (inclusive) before the adaptation block (BNN_env.py:392) can
+    fire again.  The iteration `it` itself may adapt (the device does it); the host only needs the state
+    AFTER that adaptation to draw, so a batch never crosses a firing iteration except at its start."""
+    if it >= adapt_stop:
+        return 1 << 30
+    nxt = (it // adapt_freq + 1) * adapt_freq
+    return max(1, nxt - it) if nxt < adapt_stop else 1 << 30
+
+
+class MCMC:
+    """Sampler state + step (BNN_env.py:273-550) for one chain, resident on the GPU."""
+
+    def __init__(self, bnn_obj, update_f=None, update_ws=None, temperature=1, n_iteration=100000, sampling_f=100,
+                 print_f=1000, n_post_samples=1000, update_function=UpdateNormal, sample_from_prior=0, run_ID="",
+                 init_additional_prob=0, likelihood_tempering=1, mcmc_id=0, randomize_seed=False, adapt_f=0,
+                 estimate_error=True, adapt_fM=1, adapt_freq=1000, adapt_stop=None, likelihood_f=None,
+                 adapt_verbose=False, accuracy_f=None, accuracy_lab_f=None, rng="host", device=0, _group=None, _slot=0):
+        if update_function is not UpdateNormal:
+            raise NotImplementedError("only update_function=UpdateNormal runs on the device")
+        if likelihood_f is not None or accuracy_f is not None or accuracy_lab_f is not None:
+            raise NotImplementedError("user-supplied likelihood / accuracy functions are not on the device path")
+        if init_additional_prob:
+            raise NotImplementedError("init_additional_prob is not on the device path")
+        if rng not in ("host", "philox"):
+            raise ValueError("rng must be 'host' or 'philox'")
+        nl = bnn_obj._n_layers
+        if update_ws is None:
+            update_ws = [0.075] * nl
+        if update_f is None:
+            update_f = [0.05] * nl
+        self._runID = bnn_obj._seed if run_ID == "" else run_ID
+        self._n_iterations = n_iteration
+        self._sampling_f = sampling_f
+        self._print_f = print_f
+        self._n_post_samples = n_post_samples
+        self._sample_from_prior = sample_from_prior
+        self._lik_temp = likelihood_tempering
+        self._mcmc_id = mcmc_id
+        self._randomize_seed = randomize_seed
+        self._rs = np.random.default_rng(1234)        # BNN_env.py:362
+        self._adapt_f, self._adapt_fM, self._adapt_freq = adapt_f, adapt_fM, adapt_freq
+        self._adapt_stop = int(n_iteration * 0.05) if adapt_stop is None else adapt_stop
+        self._adapt_verbose = adapt_verbose
+        self._max_n = np.array([w.size for w in bnn_obj._w_layers]).astype(int)
+        self._estimate_error = np.min([20000, 0.1 * n_iteration]) if estimate_error else n_iteration
+        self._rng_mode = rng
+        self._regression_error_proposal = (bnn_obj._estimation_mode == "regression" and not bnn_obj._empirical_error)
+        self.update_function = update_function
+        self._own_group = _group is None
+        if _group is None:
+            _group = _ChainGroup(bnn_obj, [bnn_obj._w_layers], [temperature], list(update_f)[:nl], list(update_ws)[:nl],
+                                 likelihood_tempering, adapt_f, adapt_fM, adapt_freq, self._adapt_stop, sample_from_prior,
+                                 seed=int(bnn_obj._seed) + 7919 * int(mcmc_id), device=device)
+        self._group, self._slot = _group, _slot
+        self._bnn_shapes = [w.shape for w in bnn_obj._w_layers]
+        self._sync(bnn_obj, self._group.eng.read_state())
+
+    # ---------------------------------------------------------------- state export
+    def _sync(self, bnn_obj, st):
+        c = self._slot
+        g = self._group
+        self._logLik = float(st.logLik[c])
+        self._logPrior = float(st.logPrior[c])
+        self._logPost = float(st.logPost[c])
+        self._temperature = float(st.temperature[c])
+        self._acceptance_rate = float(st.acceptance_rate[c])
+        self._last_accepted = int(st.last_accepted[c])
+        self._current_iteration = int(st.iteration[c])
+        self._update_f = np.array(st.update_f[c])
+        self._update_n = np.array(st.update_n[c])
+        self._update_ws = [np.ones(s) * st.update_ws[c][i] for i, s in enumerate(self._bnn_shapes)]
+        self._freq_layer_update = np.array(st.freq_layer_update[c])
+        n = bnn_obj._n_samples
+        nt = len(bnn_obj._test_data) if _has_test(bnn_obj) else 0
+        if bnn_obj._estimation_mode == "classification":
+            self._accuracy = st.n_correct[c] / n
+            present = g.labels_count > 0
+            self._label_acc = st.class_correct[c][present] / g.labels_count[present]
+            self._label_freq = st.pred_hist[c] / n
+            self._test_accuracy = st.n_correct_test[c] / nt if nt else 0
+        else:
+            o = bnn_obj._n_output_prm
+            self._accuracy = float(np.sum(st.sum_r2[c]) / (n * o))
+            self._label_acc = np.array(st.sum_r2[c]) / n
+            self._label_freq = None
+            self._test_accuracy = float(np.sum(st.sum_r2_test[c]) / (nt * o)) if nt else 0
+            if bnn_obj._estimation_mode == "regression":
+                bnn_obj._error_prm = np.array(st.sigma[c])
+        if st.w is not None:
+            bnn_obj._w_layers = st.weights(c)        # fresh arrays: logged samples keep their own copies
+        self._y_cache = None
+
+    def _materialise_y(self, bnn_obj, test=False):
+        x = bnn_obj._test_data if test else bnn_obj._data
+        al = bnn_obj._act_fun.alphas(bnn_obj._n_layers)
+        out = self._group.eng.predict(x, [bnn_obj._w_layers], alphas=None if al is None else al[None, :], mean=False, dense=True)
+        return out["dense"][0]
+
+    # `_y` / `_y_test` (N x K predictions of the current state, BNN_env.py:299,507) are materialised on demand
+    def y(self, bnn_obj):
+        return self._materialise_y(bnn_obj, False)
+
+    def y_test(self, bnn_obj):
+        return self._materialise_y(bnn_obj, True) if _has_test(bnn_obj) else []
+
+    def _check_supported(self, n_steps):
+        if self._regression_error_proposal and self._current_iteration + n_steps - 1 > self._estimate_error:
+            raise NotImplementedError("the regression error-parameter proposal (BNN_env.py:435-442) is not on the device path; "
+                                      "use empirical_error=True or estimate_error=False")
+
+    # ---------------------------------------------------------------- stepping
+    def run(self, bnn_obj, n_steps):
+        """n_steps MH iterations (BNN_env.py:381-532 each) with as few host round trips as the rng mode allows."""
+        self._check_supported(n_steps)
+        g = self._group
+        if not self._own_group:
+            raise RuntimeError("this MCMC belongs to an MC3 group; step the group instead")
+        done = 0
+        while done < n_steps:
+            if self._rng_mode == "philox":
+                g.eng.mh_steps(n_steps - done)
+                done = n_steps
+            else:
+                st = g.eng.read_state(weights=False)
+                it = int(st.iteration[0])
+                # the adaptation of iteration `it` happens on the device before the draw is used; mirror it on
+                # the host copy of the state so that the draw uses the post-adaptation sizes
+                _mirror_adaptation(st, 0, it, self._adapt_freq, self._adapt_stop, self._adapt_f, self._adapt_fM,
+                                   self._max_n, int(np.sum(self._max_n)))
+                k = min(n_steps - done, _steps_to_adaptation(it, self._adapt_freq, self._adapt_stop))
+                reseed = (lambda cid, i: np.random.default_rng(i + self._mcmc_id)) if self._randomize_seed else None
+                inj = g.draw_steps([self._rs], st, [self._mcmc_id], k, reseed)
+                g.eng.mh_steps(k, inj)
+                done += k
+        self._sync(bnn_obj, g.eng.read_state())
+
+    def mh_step(self, bnn_obj, additional_prob=0, return_bnn=False):
+        if additional_prob:
+            raise NotImplementedError("additional_prob is not on the device path")
+        self.run(bnn_obj, 1)
+        if return_bnn:
+            return bnn_obj, self
+
+    def reset_temperature(self, temp):
+        self._temperature = temp
+        if self._own_group:
+            self._group.eng.set_temperature([temp])
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_group"] = None
+        d["_rs"] = None
+        d["update_function"] = None
+        return d
+
+
+def _mirror_adaptation(st, c, it, adapt_freq, adapt_stop, adapt_f, adapt_fM, max_n, n_params):
+    """Host copy of the adaptation block (BNN_env.py:392-413) applied to the exported state of chain c, so that
+    host-drawn proposals use the sizes the device will use in iteration `it`."""
+    if it % adapt_freq == 0 and it < adapt_stop:
+        ar = st.acceptance_rate[c]
+        if ar < adapt_f:
+            st.freq_layer_update[c] *= 0.8
+            st.update_f[c] *= 0.85
+            n = (max_n * st.update_f[c]).astype(int)
+            n[n < 1] = 1
+            st.update_n[c] = n
+            st.update_ws[c] *= 0.9
+        if ar > adapt_fM and np.sum(st.update_n[c]) < n_params:
+            st.update_f[c] = np.exp(np.log(st.update_f[c]) * 0.85)
+            n = (max_n * st.update_f[c]).astype(int)
+            n[n < 1] = 1
+            st.update_n[c] = n
+            st.update_ws[c] *= 1.2
+
+
+def run_mcmc(bnn, mcmc, logger):
+    """The driver loop of BNN_mcmc.py:153-170, batched: the device runs up to the next print / sampling /
+    final iteration without returning to the host."""
+    while True:
+        it = mcmc._current_iteration
+        nxt = [mcmc._n_iterations]
+        if it == 0:
+            nxt.append(1)                                  # the reference prints at iteration 1
+        nxt.append((it // mcmc._print_f + 1) * mcmc._print_f)
+        nxt.append((it // mcmc._sampling_f + 1) * mcmc._sampling_f)
+        mcmc.run(bnn, max(1, min(nxt) - it))
+        if mcmc._current_iteration % mcmc._print_f == 0 or mcmc._current_iteration == 1:
+            print(mcmc._current_iteration, np.round([mcmc._logLik, mcmc._accuracy, mcmc._test_accuracy,
+                                                      mcmc._acceptance_rate], 3), flush=True)
+            if bnn._estimation_mode == "regression":
+                print(bnn._error_prm)
+        if mcmc._current_iteration % mcmc._sampling_f == 0:
+            logger.log_sample(bnn, mcmc)
+            logger.log_weights(bnn, mcmc)
+        if mcmc._current_iteration >= mcmc._n_iterations:
+            break
+
+
+class MC3:
+    """Metropolis-coupled chains (BNN_mc3.py:8-126).  All chains live on the GPU(s); there is no fork pool
+    and nothing is pickled between swap periods.  With torch.distributed initialised the chains are
+    sharded over the ranks and the swap step all-gathers the log-posteriors (npbnn_b200/mc3.py)."""
+
+    def __init__(self, data, logger, n_post_samples=100, sampling_f=100, n_chains=4, swap_frequency=100, verbose=1,
+                 print_f=100, temperatures=None, min_temperature=0.8, likelihood_f=None, accuracy_f=None, adapt_freq=50,
+                 adapt_f=0.1, adapt_fM=0.6, adapt_stop=1000, n_iteration=100000, rng="host", device=0, swap_seed=None):
+        if likelihood_f is not None or accuracy_f is not None:
+            raise NotImplementedError("user-supplied likelihood / accuracy functions are not on the device path")
+        import torch.distributed as dist
+        self.n_chains = n_chains
+        self.swap_frequency = swap_frequency
+        self.verbose = verbose
+        self.print_f = print_f / swap_frequency
+        self.n_post_samples = n_post_samples
+        self.sampling_f = sampling_f
+        self.adapt_freq, self.adapt_f, self.adapt_fM, self.adapt_stop = adapt_freq, adapt_f, adapt_fM, adapt_stop
+        self.n_mc3_iteration = np.round(n_iteration / swap_frequency).astype(int)
+        self.rseeds = np.random.choice(range(1000, 9999), n_chains, replace=False)     # BNN_mc3.py:44
+        if temperatures is None:
+            temperatures = _mc3.default_temperatures(n_chains, min_temperature)
+        self.temperatures = np.array(temperatures, dtype=np.float64)
+        self.logger = logger
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.start, self.n_local = _mc3.chain_partition(n_chains, self.world, self.rank)
+        self._rng_mode = rng
+        self._swap_rng = _mc3.SwapRNG(int(self.rseeds[0]) if swap_seed is None else swap_seed)
+        nl = data._n_layers
+        self._bnn = data
+        self._group = _ChainGroup(data, [data._w_layers] * self.n_local,
+                                  self.temperatures[self.start:self.start + self.n_local], [0.05] * nl, [0.075] * nl,
+                                  1, adapt_f, adapt_fM, adapt_freq, adapt_stop, 0, seed=int(self.rseeds[0]), device=device)
+        # per-chain views with the reference's attribute surface (singleChainArgs[i] = [bnn, mcmc])
+        self.singleChainArgs = []
+        for i in range(self.n_local):
+            b = deepcopy(data)
+            b.reset_seed(self.rseeds[self.start + i])
+            m = MCMC(b, temperature=self.temperatures[self.start + i], n_iteration=swap_frequency, sampling_f=sampling_f,
+                     print_f=swap_frequency * 10, n_post_samples=n_post_samples, mcmc_id=self.start + i, randomize_seed=True,
+                     adapt_freq=adapt_freq, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_stop=adapt_stop, rng=rng,
+                     _group=self._group, _slot=i)
+            self.singleChainArgs.append([b, m])
+        self.current_temperatures = self.temperatures.copy()
+
+    def _run_period(self):
+        g = self._group
+        n = self.swap_frequency
+        if self._rng_mode == "philox":
+            g.eng.mh_steps(n)
+            return
+        mc0 = self.singleChainArgs[0][1]
+        max_n = mc0._max_n
+        done = 0
+        while done < n:
+            st = g.eng.read_state(weights=False)
+            it = int(st.iteration[0])
+            for c in range(self.n_local):
+                _mirror_adaptation(st, c, it, self.adapt_freq, self.adapt_stop, self.adapt_f, self.adapt_fM, max_n,
+                                   int(np.sum(max_n)))
+            k = min(n - done, _steps_to_adaptation(it, self.adapt_freq, self.adapt_stop))
+            # randomize_seed=True: every step reseeds default_rng(iteration + mcmc_id) (BNN_env.py:383-384)
+            inj = g.draw_steps([None] * self.n_local, st, [self.start + c for c in range(self.n_local)], k,
+                               reseed=lambda cid, i: np.random.default_rng(i + cid))
+            g.eng.mh_steps(k, inj)
+            done += k
+
+    def run_mcmc(self):
+        g = self._group
+        for mc3_it in range(self.n_mc3_iteration):
+            self._run_period()
+            if self.n_chains > 1:
+                temps, swapped, (j, k), lp = _mc3.exchange(g.eng.gather(L.F_LOGPOST), self.current_temperatures,
+                                                           self._swap_rng, None, self.world)
+                if swapped:
+                    if self.verbose > 0 and self.rank == 0:
+                        print(mc3_it, "SWAPPED", lp[j], lp[k], self.current_temperatures[j], self.current_temperatures[k])
+                    self.current_temperatures = temps
+                    g.eng.set_temperature(temps[self.start:self.start + self.n_local])
+            st = g.eng.read_state()
+            for i, (b, m) in enumerate(self.singleChainArgs):
+                m._sync(b, st)
+                if m._temperature == 1:                     # the logger follows the cold chain (BNN_mc3.py:118-122)
+                    self.logger.log_sample(b, m)
+                    self.logger.log_weights(b, m)
+            if mc3_it % self.print_f == 0 and self.rank == 0 and self.n_local:
+                b0, m0 = self.singleChainArgs[0]
+                print(mc3_it, m0._logPost, b0._w_layers[0][0][0:5])
+
+
+# ------------------------------------------------------------------------------------------------------
+# prediction callers
+# ------------------------------------------------------------------------------------------------------
+def _lik_of_output(output_act_fun):
+    if output_act_fun is RegressTransformError:
+        return L.LIK_GAUSSIAN_HEAD
+    if output_act_fun is RegressTransform:
+        return L.LIK_GAUSSIAN
+    if output_act_fun is SoftMax or output_act_fun is None:
+        return L.LIK_CATEGORICAL
+    raise NotImplementedError("user-supplied output_act_fun is not on the device path")
+
+
+_ENGINE_CACHE = {}
+
+
+def _predict_engine(weights, n_features, actFun, output_act_fun):
+    key = (tuple(tuple(w.shape) for w in weights), n_features, actFun._function, _lik_of_output(output_act_fun))
+    if key not in _ENGINE_CACHE:
+        _ENGINE_CACHE[key] = Engine(NetShape.from_weights(weights, n_features, act=actFun._function,
+                                                          lik=_lik_of_output(output_act_fun)))
+    return _ENGINE_CACHE[key]
+
+
+def _alpha_rows(post_alphas, actFun, n_layers):
+    if actFun._function != "genReLU":
+        return None
+    rows = []
+    for a in post_alphas:
+        r = np.zeros(n_layers)
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        r[:min(len(a), n_layers)] = a[:n_layers]
+        rows.append(r)
+    return np.stack(rows)
+
+
+def RunPredict(data, weights, actFun, output_act_fun, data_transform=None):
+    """Forward pass of one weight set (BNN_lib.py:245-256) -> [N, O]."""
+    if data_transform is not None:
+        raise NotImplementedError("data_transform (feature indicators) is not on the device path")
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    eng = _predict_engine(weights, data.shape[1], actFun, output_act_fun)
+    al = _alpha_rows([actFun._prm], actFun, len(weights))
+    return eng.predict(data, [weights], alphas=al, mean=False, dense=True)["dense"][0]
+
+
+def RunPredictInd(data, weights, ind, actFun, output_act_fun, data_transform=None):
+    """BNN_lib.py:258-272: layer-0 weights multiplied by the indicator matrix."""
+    w = [weights[0] * ind] + list(weights[1:])
+    return RunPredict(data, w, actFun, output_act_fun, data_transform)
+
+
+def predict(bnn_obj, data):
+    """BNN_env.py:662-670."""
+    return RunPredict(data, bnn_obj._w_layers, actFun=bnn_obj._act_fun, output_act_fun=bnn_obj._output_act_fun)
+
+
+def get_posterior_cat_prob(pred_features, post_samples=None, feature_index_to_shuffle=None, post_summary_mode=0,
+                           unlink_features_within_block=False, actFun=None, output_act_fun=None, return_dense=True):
+    """BNN_lib.py:352-397 with all posterior samples scored in ONE pass over the features.
+    return_dense=False skips the [S, N, K] tensor (it is 800 GB at BASELINE config 5) and returns None for it."""
+    if len(pred_features) == 0:
+        print("Data not found.")
+        return 0
+    x = np.array(pred_features, dtype=np.float64, copy=True)
+    if feature_index_to_shuffle:
+        if unlink_features_within_block and type(feature_index_to_shuffle) == list:
+            for fi in feature_index_to_shuffle:
+                x[:, fi] = np.random.permutation(x[:, fi])
+        else:
+            x[:, feature_index_to_shuffle] = np.random.permutation(x[:, feature_index_to_shuffle])
+    weights = [s["weights"] for s in post_samples]
+    if post_summary_mode not in (0, 1):
+        raise NotImplementedError("post_summary_mode 2 (categorical resampling) is not on the device path")
+    eng = _predict_engine(weights[0], x.shape[1], actFun, output_act_fun)
+    al = _alpha_rows([s["alphas"] for s in post_samples], actFun, len(weights[0]))
+    out = eng.predict(x, weights, alphas=al, mean=(post_summary_mode == 1), votes=(post_summary_mode == 0), dense=return_dense)
+    return out.get("dense"), out["votes" if post_summary_mode == 0 else "mean"]
+
+
+def get_posterior_est(pkl_file):
+    """BNN_lib.py:715-748."""
+    bnn_obj, mcmc_obj, logger_obj = load_obj(pkl_file)
+    ps = logger_obj._post_weight_samples
+    weights = [s["weights"] for s in ps]
+    res = {"error_prm": [s["error_prm"] for s in ps] if "error_prm" in ps[0] else []}
+    for key, x in (("", bnn_obj._data), ("_test", bnn_obj._test_data)):
+        if len(x) == 0:
+            res["post_est" + key], res["prm_mean" + key] = np.array([]), np.nan
+            continue
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        eng = _predict_engine(weights[0], x.shape[1], bnn_obj._act_fun, bnn_obj._output_act_fun)
+        al = _alpha_rows([s["alphas"] for s in ps], bnn_obj._act_fun, len(weights[0]))
+        out = eng.predict(x, weights, alphas=al, mean=True, dense=True)
+        res["post_est" + key], res["prm_mean" + key] = out["dense"], out["mean"]
+    return res
+
+
+def make_pdp_features(data, focal_features, steps_continuous=100):
+    """The feature grid of a partial-dependence curve (BNN_pdp.py:14-45): ordinal / binary features step
+    through their integer range, a single continuous feature through 100 equally spaced values, several
+    focal features are treated as one-hot."""
+    lo = np.array([np.nanmin(data[:, f]) for f in focal_features])
+    hi = np.array([np.nanmax(data[:, f]) for f in focal_features])
+    integer_like = [bool(np.all(np.isin(np.unique(data[:, f]), np.arange(l, h + 1)))) for f, l, h in zip(focal_features, lo, hi)]
+    if len(focal_features) == 1 and not integer_like[0]:
+        return np.linspace(lo[0], hi[0], num=steps_continuous).reshape(steps_continuous, 1)
+    if len(focal_features) == 1:
+        m = int(hi[0])
+        return np.linspace(lo[0], m, num=m + 1).reshape((m + 1, 1))
+    return np.eye(len(focal_features))
+
+
+def get_pdp(data, focal_features, estimation_mode, size_output, actFun, output_act_fun, weights, alphas, data_transform):
+    """Partial dependence (BNN_pdp.py:48-84).  Per grid step the focal columns are overwritten while X is
+    staged (no host copy of the data), all posterior samples run in one pass and only the per-row mean over
+    samples comes back: cumsum over classes, mean over rows and the 2.5 / 97.5 % row quantiles commute with it."""
+    if data_transform is not None:
+        raise NotImplementedError("data_transform (feature indicators) is not on the device path")
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    grid = make_pdp_features(data, focal_features)
+    out = np.zeros((grid.shape[0], size_output, 3))
+    eng = _predict_engine(weights[0], data.shape[1], actFun, output_act_fun)
+    al = _alpha_rows(alphas, actFun, len(weights[0]))
+    for n in range(grid.shape[0]):
+        smean = eng.predict(data, weights, alphas=al, override=(list(focal_features), grid[n, :]), mean=True)["mean"]
+        if estimation_mode == "classification":
+            smean = np.cumsum(smean, axis=1)
+        out[n, :, 0] = np.mean(smean, axis=0)
+        q = np.quantile(smean, q=(0.025, 0.975), axis=0)
+        out[n, :, 1], out[n, :, 2] = q[0, :], q[1, :]
+    return {"feature": grid, "pdp": out}
+
+
+def pdp(pickle_file, pdp_features):
+    """BNN_pdp.py:87-108."""
+    bnn_obj, mcmc_obj, logger_obj = load_obj(pickle_file)
+    ps = logger_obj._post_weight_samples
+    weights, alphas = [s["weights"] for s in ps], [s["alphas"] for s in ps]
+    return [get_pdp(bnn_obj._data, f, bnn_obj._estimation_mode, bnn_obj._size_output, bnn_obj._act_fun,
+                    bnn_obj._output_act_fun, weights, alphas, None) for f in pdp_features]
+
+
+# ------------------------------------------------------------------------------------------------------
+# logger / pickle helpers the drivers need (I/O, host side; same file formats as BNN_env.py:553-658)
+# ------------------------------------------------------------------------------------------------------
+def load_obj(file_name):
+    with open(file_name, "rb") as f:
+        return pickle.load(f)
+
+
+def SaveObject(obj, filename):
+    with open(filename, "wb") as output:
+        pickle.dump(obj, output, pickle.HIGHEST_PROTOCOL)
+
+
+class postLogger:
+    """Tab-separated .log of the chain statistics and a .pkl with [bnn, mcmc, logger] holding the last
+    n_post_samples weight sets -- the formats predictBNN / pdp / npBNN(pickle_file=) consume."""
+
+    def __init__(self, bnn_obj, filename="BNN", wdir="", sample_from_prior=0, add_prms=None, continue_logfile=False,
+                 log_all_weights=0):
+        outdir = os.path.dirname(filename)
+        if outdir and not os.path.exists(outdir):
+            os.makedirs(outdir)
+        stem = "%s_l%s" % (filename, "_".join(map(str, bnn_obj._n_nodes)))          # BNN_files.py:127
+        self._logfile = os.path.join(wdir, stem + ".log")
+        self._w_file = os.path.join(wdir, stem + "_W.log") if log_all_weights else None
+        self._pklfile = os.path.join(wdir, stem + ".pkl")
+        self._log_all_weights = log_all_weights
+        self._post_weight_samples = []
+        self._estimation_mode = bnn_obj._estimation_mode
+        head = ["it", "posterior", "likelihood", "prior"]
+        if self._estimation_mode == "classification":
+            head += ["accuracy", "test_accuracy"] + ["acc_C%s" % i for i in range(bnn_obj._n_output_prm)]
+        else:
+            head += ["MSE", "test_MSE"] + ["MSE_prm%s" % i for i in range(bnn_obj._n_output_prm)]
+        for i in range(bnn_obj._n_layers):
+            head += ["mean_w%s" % i, "std_w%s" % i]
+        if add_prms:
+            head += add_prms
+        head += ["sig_%s" % i for i in range(len(bnn_obj._error_prm))]
+        head += ["acc_prob", "mcmc_id"]
+        if not continue_logfile:
+            with open(self._logfile, "w", newline="") as f:
+                csv.writer(f, delimiter="\t").writerow(head)
+        if log_all_weights:
+            with open(self._w_file, "w", newline="") as f:
+                csv.writer(f, delimiter="\t").writerow(
+                    ["it"] + ["w_%s_%s" % (i, j) for i in range(bnn_obj._n_layers) for j in range(bnn_obj._w_layers[i].size)])
+
+    def update_post_weight_samples(self, row):
+        self._post_weight_samples += [row]
+
+    def replace_post_weight_samples(self, post_weight_samples):
+        self._post_weight_samples = post_weight_samples
+
+    def control_weight_sample_length(self, maxlength):
+        if len(self._post_weight_samples) > maxlength:
+            self._post_weight_samples = self._post_weight_samples[-maxlength:]
+
+    def log_sample(self, bnn_obj, mcmc_obj, add_prms=None):
+        row = [mcmc_obj._current_iteration, mcmc_obj._logPost, mcmc_obj._logLik, mcmc_obj._logPrior, mcmc_obj._accuracy,
+               mcmc_obj._test_accuracy] + list(mcmc_obj._label_acc)
+        for w in bnn_obj._w_layers:
+            row += [np.mean(w), np.std(w)]
+        if add_prms:
+            row += add_prms
+        if self._estimation_mode == "regression":
+            row += list(bnn_obj._error_prm)
+        row += [mcmc_obj._acceptance_rate, mcmc_obj._mcmc_id]
+        with open(self._logfile, "a", newline="") as f:
+            csv.writer(f, delimiter="\t").writerow(row)
+
+    def log_weights(self, bnn_obj, mcmc_obj, add_prms=None, add_obj=None):
+        if self._log_all_weights:
+            row = [mcmc_obj._current_iteration] + [v for w in bnn_obj._w_layers for v in w.flatten()]
+            with open(self._w_file, "a", newline="") as f:
+                csv.writer(f, delimiter="\t").writerow(row)
+        else:
+            post = {"weights": bnn_obj._w_layers, "alphas": list(np.atleast_1d(bnn_obj._act_fun._acc_prm)),
+                    "mcmc_it": mcmc_obj._current_iteration}
+            if len(bnn_obj._error_prm):
+                post["error_prm"] = list(bnn_obj._error_prm)
+            if add_prms:
+                post["additional_prm"] = list(add_prms)
+            self.update_post_weight_samples(post)
+            self.control_weight_sample_length(mcmc_obj._n_post_samples)
+        SaveObject([bnn_obj, mcmc_obj, self] + ([add_obj] if add_obj else []), self._pklfile)

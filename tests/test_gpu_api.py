@@ -1,0 +1,190 @@
+"""GPU: the reference-facing Python interface (npbnn_b200.api) against the reference's recorded chains."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _dat(z):
+    return {"data": np.array(z["x"]), "labels": np.array(z["labels"]), "test_data": np.array(z["x_test"]) if len(z["x_test"]) else [],
+            "test_labels": np.array(z["labels_test"]) if len(z["x_test"]) else []}
+
+
+def _close(a, b, rtol=1e-9):
+    return np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=1e-12)
+
+
+def _follow(z, meta, bnn, mcmc, n_steps, bn):
+    assert _close(mcmc._logLik, z["init_logLik"]) and _close(mcmc._logPrior, z["init_logPrior"])
+    assert _close(mcmc._accuracy, z["init_accuracy"]) and _close(mcmc._test_accuracy, z["init_test_accuracy"])
+    assert np.array_equal(mcmc._update_n, z["init_update_n"])
+    for t in range(n_steps):
+        mcmc.mh_step(bnn)
+        assert mcmc._last_accepted == int(z["steps_accepted"][t]), t
+        assert _close(mcmc._logLik, z["steps_logLik"][t]) and _close(mcmc._logPrior, z["steps_logPrior"][t]), t
+        assert _close(mcmc._logPost, z["steps_logPost"][t])
+        assert _close(mcmc._accuracy, z["steps_accuracy"][t]) and _close(mcmc._test_accuracy, z["steps_test_accuracy"][t])
+        assert _close(mcmc._label_acc, z["steps_label_acc"][t])
+        assert abs(mcmc._acceptance_rate - float(z["steps_acceptance_rate"][t])) < 1e-15
+        assert np.array_equal(mcmc._update_n, z["steps_update_n"][t]), t
+        assert mcmc._current_iteration == t + 1
+    return mcmc
+
+
+def test_classify_script_flow_reproduces_reference_chain():
+    """bnn_classify.py:45-70 through the mirrored API with the reference's own generator sequence: the chain
+    (accept decisions, log-likelihoods, accuracies, adaptation) is the reference's chain."""
+    import npbnn_b200 as bn
+    z, meta = G.load("c1_classify")
+    np.random.seed(1234)
+    bnn = bn.npBNN(_dat(z), n_nodes=[5, 5], use_class_weights=0, actFun=bn.ActFun(fun="tanh"), use_bias_node=2,
+                   prior_f=1, p_scale=1, seed=1234, init_std=0.1, instance_weights=None)
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["w0_%d" % i])        # same initial weights as the reference
+    assert _close(bnn.calc_prior(), z["init_logPrior"])
+    mcmc = bn.MCMC(bnn, update_f=[0.05, 0.05, 0.07], update_ws=[0.075, 0.075, 0.075], n_iteration=10000, sampling_f=10,
+                   print_f=1000, n_post_samples=100, sample_from_prior=0, adapt_f=0.3, adapt_fM=0.6)
+    _follow(z, meta, bnn, mcmc, 120, bn)
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])
+    y = mcmc.y(bnn)
+    assert np.allclose(y, z["yN"], rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize("emp", [1, 0])
+def test_regress_script_flow_reproduces_reference_chain(emp):
+    import npbnn_b200 as bn
+    z, meta = G.load("c2_regress_emp%d" % emp)
+    np.random.seed(1234)
+    bnn = bn.npBNN(_dat(z), n_nodes=[10, 5], estimation_mode="regression", actFun=bn.ActFun(fun="ReLU"), p_scale=1,
+                   use_bias_node=2, empirical_error=bool(emp))
+    mcmc = bn.MCMC(bnn, update_ws=[0.025, 0.025, 0.05], update_f=[0.005, 0.005, 0.05], n_iteration=20000, sampling_f=100,
+                   print_f=1000, n_post_samples=100, likelihood_tempering=1, adapt_f=0.3, estimate_error=False)
+    _follow(z, meta, bnn, mcmc, 100, bn)
+    assert _close(bnn._error_prm, z["steps_error_prm"][99])
+
+
+def test_batched_run_with_adaptation_matches_single_steps():
+    """MCMC.run(n) batches host-drawn proposals between adaptation points; the chain must not change."""
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_adapt")
+    np.random.seed(7)
+    dat = _dat(z)
+    bnn = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, seed=7)
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["w0_%d" % i])
+    mcmc = bn.MCMC(bnn, update_f=[0.3, 0.3, 0.3], adapt_f=0.3, adapt_fM=0.6, adapt_freq=10, n_iteration=1000)
+    mcmc.run(bnn, 80)
+    assert mcmc._current_iteration == 80
+    assert _close(mcmc._logLik, z["steps_logLik"][79]) and _close(mcmc._logPrior, z["steps_logPrior"][79])
+    assert np.array_equal(mcmc._update_n, z["steps_update_n"][79])
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])
+
+
+def test_block_mask_network_flow():
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_block_mask")
+    np.random.seed(7)
+    bnn = bn.npBNN(_dat(z), n_nodes=[24, 16], actFun=bn.ActFun(fun="tanh"), use_bias_node=-1, seed=7)
+    m = bn.create_mask(bnn._w_layers, indx_input_list=[list(range(8)), sum(([g] * 3 for g in range(8)), []), []],
+                       nodes_per_feature_list=[[3] * 8, [2] * 8, []])
+    for i in range(3):
+        assert np.array_equal(m[i], z["mask_%d" % i])
+    bnn.apply_mask(m)
+    mcmc = bn.MCMC(bnn, n_iteration=1000)
+    _follow(z, meta, bnn, mcmc, 60, bn)
+
+
+def test_run_mcmc_logger_pickle_and_prediction(tmp_path):
+    """run_mcmc (BNN_mcmc.py:153-170) + postLogger files + the prediction callers on the pickled samples."""
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_swish_cauchy")
+    np.random.seed(7)
+    dat = _dat(z)
+    bnn = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="swish"), use_bias_node=2, prior_f=2, p_scale=0.7, seed=7)
+    mcmc = bn.MCMC(bnn, n_iteration=200, sampling_f=20, print_f=100, n_post_samples=5, rng="philox")
+    logger = bn.postLogger(bnn, filename="t", wdir=str(tmp_path))
+    bn.run_mcmc(bnn, mcmc, logger)
+    assert mcmc._current_iteration == 200
+    rows = open(logger._logfile).read().strip().split("\n")
+    assert rows[0].split("\t")[:4] == ["it", "posterior", "likelihood", "prior"] and len(rows) == 1 + 10
+    b2, m2, l2 = bn.load_obj(logger._pklfile)
+    assert len(l2._post_weight_samples) == 5 and m2._current_iteration == 200
+    dense, votes = bn.get_posterior_cat_prob(dat["test_data"], l2._post_weight_samples, post_summary_mode=0,
+                                             actFun=b2._act_fun, output_act_fun=b2._output_act_fun)
+    _, mean = bn.get_posterior_cat_prob(dat["test_data"], l2._post_weight_samples, post_summary_mode=1,
+                                        actFun=b2._act_fun, output_act_fun=b2._output_act_fun)
+    assert dense.shape == (5, len(dat["test_data"]), 3)
+    assert np.allclose(mean, dense.mean(0), rtol=1e-12) and np.allclose(votes.sum(1), 1.0)
+    # single-set forward agrees with the dense tensor; restart from the pickle takes the last sample
+    y = bn.RunPredict(dat["test_data"], l2._post_weight_samples[-1]["weights"], b2._act_fun, b2._output_act_fun)
+    assert np.allclose(y, dense[-1], rtol=1e-12)
+    b3 = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="swish"), use_bias_node=2, pickle_file=logger._pklfile)
+    assert all(np.array_equal(a, b) for a, b in zip(b3._w_layers, l2._post_weight_samples[-1]["weights"]))
+    res = bn.pdp(logger._pklfile, [[1], [0, 2]])
+    assert res[0]["pdp"].shape == (100, 3, 3) and res[1]["pdp"].shape == (2, 3, 3)
+    assert np.allclose(res[0]["pdp"][:, -1, 0], 1.0)     # cumulative class probability ends at 1
+
+
+class _ReplaySwap:
+    def __init__(self, z, n):
+        self.z, self.i, self.n = z, 0, n
+
+    def pair(self, n):
+        j, k = [int(v) for v in self.z["it%d_pair" % self.i]]
+        return j, k
+
+    def log_uniform(self):
+        v = float(self.z["it%d_log_u" % self.i])
+        self.i += 1
+        return v
+
+
+def test_mc3_reproduces_reference_run(tmp_path):
+    """BNN_mc3.py:87-126 with the reference's per-step reseeding (default_rng(it + id)) and its recorded swap
+    draws: log-posteriors, temperatures and weights of every chain after every swap period are the reference's."""
+    import npbnn_b200 as bn
+    z, meta = G.load("mc3")
+    dat = {"data": np.array(z["x"]), "labels": np.array(z["labels"]), "test_data": [], "test_labels": []}
+    bnn = bn.npBNN(dat, n_nodes=[4, 3], use_bias_node=-1, seed=1, actFun=bn.ActFun(fun="swish"),
+                   init_weights=[np.array(z["w0_%d" % i]) for i in range(3)])
+    logger = bn.postLogger(bnn, filename="mc3", wdir=str(tmp_path))
+    mc3 = bn.MC3(bnn, logger=logger, n_post_samples=10, sampling_f=5, n_iteration=40, n_chains=3, swap_frequency=5,
+                 verbose=0, adapt_freq=50, adapt_f=0.1, adapt_fM=0.6, adapt_stop=1000)
+    mc3._swap_rng = _ReplaySwap(z, 3)
+    n_it = int(mc3.n_mc3_iteration)
+    mc3.n_mc3_iteration = 1
+    for it in range(n_it):
+        assert np.array_equal(mc3.current_temperatures, z["it%d_temps_before" % it])
+        mc3.run_mcmc()
+        lp = np.array([a[1]._logPost for a in mc3.singleChainArgs])
+        assert _close(lp, z["it%d_logPost" % it]), it
+        assert np.array_equal(mc3.current_temperatures, z["it%d_temps_after" % it]), it
+        for c in range(3):
+            for li in range(3):
+                assert np.array_equal(mc3.singleChainArgs[c][0]._w_layers[li], z["it%d_c%d_w%d" % (it, c, li)]), (it, c, li)
+    assert os.path.exists(logger._pklfile)
+    assert pickle.load(open(logger._pklfile, "rb"))[2]._post_weight_samples
+
+
+def test_unsupported_options_raise():
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_swish_cauchy")
+    dat = _dat(z)
+    with pytest.raises(NotImplementedError):
+        bn.ActFun(fun="genReLU", trainable=True)
+    with pytest.raises(NotImplementedError):
+        bn.npBNN(dat, n_nodes=[4, 3], freq_indicator=0.1)
+    with pytest.raises(NotImplementedError):
+        bn.npBNN(dat, n_nodes=[4, 3], estimation_mode="custom", size_output=3)
+    bnn = bn.npBNN(dat, n_nodes=[4, 3])
+    with pytest.raises(NotImplementedError):
+        bn.MCMC(bnn, likelihood_f=lambda *a, **k: 0.0)
+    with pytest.raises(NotImplementedError):
+        bn.MCMC(bnn, update_function=lambda *a, **k: None)
