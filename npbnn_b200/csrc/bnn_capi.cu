@@ -72,6 +72,13 @@ struct bnn_ctx {
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
   const char* last_kernel = "";
+  // block-masked networks: dense-block item lists of the chains' mask (k_fwd_sparse)
+  DevBuf sp_items;
+  int sp_off[BNN_MAX_LAYERS + 1] = {0};
+  int sp_wA = 0, sp_wB = 0;
+  bool use_sparse = false;
+  int opt_sparse = 1;               // option "sparse": 0 forces the dense kernels for masked chains
+  long long sp_fma = 0, dense_fma = 0;
   // optional per-launch timing of the forward kernel (bench.py roofline): event pairs on the launch stream
   int time_forward = 0;
   std::vector<cudaEvent_t> ev;      // start/stop pairs, recorded but not yet read
@@ -171,7 +178,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu};
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -182,6 +189,7 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   REQUIRE(c && name, "bnn_set_option: null argument");
   if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
   if (strcmp(name, "time_forward") == 0) { c->time_forward = value; return 0; }
+  if (strcmp(name, "sparse") == 0) { c->opt_sparse = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
 
@@ -373,6 +381,57 @@ int bnn_log_prior(bnn_ctx* c, const double* w_dev, int32_t n_sets, int32_t prior
   return 0;
 }
 
+// Dense-block cover of a mask (create_mask, BNN_lib.py:16-47): per layer, consecutive rows whose kept
+// columns span the same range [c0, c0+nc) form a block; blocks are cut into items of at most 4 rows.
+// Columns inside the range that the mask drops are harmless (their weights are exactly zero).
+// Returns false when the cover is not worth it (more than a quarter of the dense work) or does not fit.
+static bool build_sparse_items(bnn_ctx* c, const double* mask_host, std::vector<int4>& items) {
+  const NetGeom& g = c->g;
+  items.clear();
+  long long sp = 0, dense = 0;
+  c->sp_wA = c->sp_wB = 1;
+  for (int l = 0; l < g.L; ++l) {
+    const LayerGeom& lg = g.l[l];
+    const int cols = lg.in + lg.bias;
+    c->sp_off[l] = (int)items.size();
+    if (l < g.L - 1) {
+      int& w = (l % 2 == 0) ? c->sp_wA : c->sp_wB;
+      if (lg.out > w) w = lg.out;
+    }
+    int r = 0;
+    auto range_of = [&](int row, int& c0, int& nc) {
+      int lo = -1, hi = -1;
+      for (int k = 0; k < lg.in; ++k)
+        if (mask_host[lg.c_off + row * cols + lg.bias + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+      c0 = lo < 0 ? 0 : lo;
+      nc = lo < 0 ? 0 : hi - lo + 1;
+    };
+    while (r < lg.out) {
+      int c0, nc;
+      range_of(r, c0, nc);
+      int r1 = r + 1;
+      while (r1 < lg.out) {
+        int d0, dn;
+        range_of(r1, d0, dn);
+        if (d0 != c0 || dn != nc) break;
+        ++r1;
+      }
+      for (int q = r; q < r1; q += 4) {
+        const int nr = (r1 - q < 4) ? r1 - q : 4;
+        items.push_back(make_int4(q, nr, c0, nc));
+        sp += (long long)nr * nc;
+      }
+      r = r1;
+    }
+    dense += (long long)lg.out * lg.in;
+  }
+  c->sp_off[g.L] = (int)items.size();
+  for (int l = g.L + 1; l <= BNN_MAX_LAYERS; ++l) c->sp_off[l] = c->sp_off[g.L];
+  c->sp_fma = sp;
+  c->dense_fma = dense;
+  return sp * 4 <= dense;
+}
+
 static ChainDev chain_dev(bnn_ctx* c) {
   ChainDev d{};
   d.g = c->g;
@@ -400,6 +459,12 @@ static int chains_forward(bnn_ctx* c, cudaStream_t st) {
   const int NC = 2 + 2 * g.K;
   const int per = sets_per_pass(g);
   FwdParams p = base_params(c);
+  if (c->use_sparse && c->opt_sparse) {
+    p.sp_items = c->sp_items.as<int4>();
+    for (int l = 0; l <= BNN_MAX_LAYERS; ++l) p.sp_off[l] = c->sp_off[l];
+    p.sp_wA = c->sp_wA;
+    p.sp_wB = c->sp_wB;
+  }
   for (int s0 = 0; s0 < c->C; s0 += per) {
     const int n = (c->C - s0 < per) ? c->C - s0 : per;
     p.wp = c->wp_prop.as<double>() + (size_t)s0 * g.PB;
@@ -438,9 +503,25 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   CUDA_TRY(c->counts_prop.ensure(sizeof(int) * (size_t)C * NC, false, st));
   CUDA_TRY(c->alpha_chain.ensure(sizeof(double) * (size_t)C * g.L, false, st));
   CUDA_TRY(c->part.ensure(sizeof(double) * (size_t)n_slots(g) * C * c->n_tiles16, false, st));
+  c->use_sparse = false;
   if (cfg->use_mask) {
     CUDA_TRY(c->mask.ensure(sizeof(double) * g.P, false, st));
     CUDA_TRY(cudaMemcpyAsync(c->mask.p, mask_host, sizeof(double) * g.P, cudaMemcpyHostToDevice, st));
+    // block-sparse forward: only when the cover is thin and the initial weights respect the mask (the
+    // reference applies the mask at construction, BNN_env.py:259-267; proposals are masked in k_mh_update)
+    std::vector<int4> items;
+    bool ok = build_sparse_items(c, mask_host, items);
+    for (size_t i = 0; ok && i < (size_t)C * g.P; ++i)
+      if (mask_host[i % g.P] == 0.0 && w0_host[i] != 0.0) ok = false;
+    if (ok) {
+      FwdParams probe{};
+      probe.g = g; probe.sp_wA = c->sp_wA; probe.sp_wB = c->sp_wB;
+      ok = bnn_sparse_fits(probe);
+    }
+    if (ok) {
+      if (upload(c->sp_items, items.data(), items.size(), st)) return 1;
+      c->use_sparse = true;
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(c->w_cur.p, w0_host, sizeof(double) * (size_t)C * g.P, cudaMemcpyHostToDevice, st));
 

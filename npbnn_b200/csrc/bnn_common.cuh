@@ -256,4 +256,9 @@ struct FwdParams {
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
   const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j/256)
+  // block-masked networks (create_mask, BNN_lib.py:16-47): per layer a list of dense blocks
+  // {r0, nr <= 4, c0, nc} covering every non-zero of the mask; null = dense evaluation
+  const int4* sp_items;
+  int sp_off[BNN_MAX_LAYERS + 1];
+  int sp_wA, sp_wB;         // widths of the two hidden-activation staging buffers (units)
 };

@@ -275,6 +275,98 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
 }
 
 // =============================================================================================
+// block-masked networks (create_mask, BNN_lib.py:16-47; apply_mask, BNN_env.py:259-267)
+// =============================================================================================
+// A masked layer is a list of small dense blocks {r0, nr <= 4, c0, nc} (built on the host from the mask,
+// bnn_capi.cu) that cover every entry the mask keeps; entries outside the blocks are exactly zero in every
+// proposal (w' *= mask, BNN_env.py:461-462), so skipping them changes nothing but the order of the sum.
+// At the block sizes create_mask produces (a feature feeds a handful of nodes) the contraction is far too
+// thin for tensor-core tiles, and the FP64 work is dominated by the activations, so this kernel is plain
+// DFMA: a warp owns 16 rows of X; lane & 15 = row, the two half-warps take alternate blocks.  Activations
+// are staged per warp in shared memory as [unit][16 rows] (stride 17: conflict-free column reads).
+constexpr int SP_US = 17;
+
+template <int ACT>
+__global__ void __launch_bounds__(256) k_fwd_sparse(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const NetGeom& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lr = lane & 15, half = lane >> 4;
+  const int ZS = bnn_round_up(g.O, 8) + 1;
+
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  const int per_warp = (g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS;
+  double* bx = tab + BNN_EXP_TAB_SIZE + warp * per_warp;
+  double* bA = bx + g.F * SP_US;
+  double* bB = bA + p.sp_wA * SP_US;
+  double* zs = bB + p.sp_wB * SP_US;
+  int* cnt = reinterpret_cast<int*>(tab + BNN_EXP_TAB_SIZE + nwarps * per_warp);
+  const int n_cnt = (g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+
+  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+
+  const long long total_warps = (long long)gridDim.x * nwarps;
+  for (long long wt = (long long)blockIdx.x * nwarps + warp; wt < p.n_tiles16; wt += total_warps) {
+    // X warp tile -> [feature][row]; global reads are contiguous (the tile is 16 * F_pad consecutive doubles)
+    const double* xt = p.x + wt * 16 * (long long)g.F_pad;
+    for (int idx = lane; idx < 16 * g.F_pad; idx += 32) {
+      const int r = idx / g.F_pad, cp = idx - r * g.F_pad;
+      const int c = cp ^ ((r & 1) * g.x_swz);
+      if (c < g.F) bx[c * SP_US + r] = __ldg(xt + idx);
+    }
+    __syncwarp();
+    for (int c = 0; c < p.C; ++c) {
+      const double* W = p.wp + (long long)c * g.PB;
+      const double* in = bx;
+      double* out = bA;
+      for (int l = 0; l < g.L; ++l) {
+        const LayerGeom& lg = g.l[l];
+        const bool last = (l == g.L - 1);
+        const double alpha = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * g.L + l] : 0.0;
+        for (int it = p.sp_off[l] + half; it < p.sp_off[l + 1]; it += 2) {
+          const int4 I = __ldg(p.sp_items + it);
+          const int r0 = I.x, nr = I.y, c0 = I.z, c1 = I.z + I.w;
+          double acc[4];
+          const double* wr[4];
+          int sw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + (i < nr ? i : nr - 1);
+            acc[i] = __ldg(W + lg.b_off + r);
+            wr[i] = W + lg.w_off + r * lg.stride;
+            sw[i] = (r & 1) * lg.swz;
+          }
+          for (int cc = c0; cc < c1; ++cc) {
+            const double a = in[cc * SP_US + lr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fma(__ldg(wr[i] + (cc ^ sw[i])), a, acc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nr) {
+              if (!last) out[(r0 + i) * SP_US + lr] = bnn_act<ACT>(acc[i], alpha, tab);
+              else zs[lr * ZS + r0 + i] = acc[i];
+            }
+          }
+        }
+        __syncwarp();
+        in = out;
+        out = (out == bA) ? bB : bA;
+      }
+      bnn_epilogue<false>(p, c, wt, lane, zs, ZS, tab, cnt, nullptr, nullptr);
+      __syncwarp();
+    }
+  }
+  if (n_cnt) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
+      if (cnt[i]) atomicAdd(&p.counts[i], cnt[i]);
+  }
+}
+
+// =============================================================================================
 // specialised 3-layer kernel (compile-time padded widths KP0 -> N1 -> N2 -> N3), categorical likelihood
 // =============================================================================================
 template <int KP0, int N1, int N2, int N3>
@@ -822,11 +914,55 @@ static cudaError_t launch_generic(const FwdParams& p, int n_sms, cudaStream_t st
   }
 }
 
+template <int ACT>
+static cudaError_t launch_sparse_t(const FwdParams& p, int n_sms, cudaStream_t st) {
+  auto kern = k_fwd_sparse<ACT>;
+  const int ZS = bnn_round_up(p.g.O, 8) + 1;
+  const size_t per_warp = ((size_t)(p.g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS) * sizeof(double);
+  const size_t fixed = BNN_EXP_TAB_SIZE * sizeof(double) +
+                       (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) * sizeof(int) : 0);
+  if (fixed + per_warp > 232448) return cudaErrorInvalidConfiguration;
+  int nwarps = (int)((232448 - fixed) / per_warp);
+  if (nwarps > 8) nwarps = 8;
+  const size_t bytes = fixed + nwarps * per_warp;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  long long ctas = (p.n_tiles16 + nwarps - 1) / nwarps;
+  int grid = (int)(ctas < n_sms ? ctas : n_sms);
+  kern<<<grid, nwarps * 32, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+// true when the block-sparse kernel can run this problem (shared-memory footprint of one warp)
+bool bnn_sparse_fits(const FwdParams& p) {
+  const int ZS = bnn_round_up(p.g.O, 8) + 1;
+  const size_t per_warp = ((size_t)(p.g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS) * sizeof(double);
+  const size_t fixed = BNN_EXP_TAB_SIZE * sizeof(double) + (size_t)BNN_MAX_SETS_PER_PASS * (2 + 2 * BNN_MAX_OUT) * sizeof(int);
+  return fixed + per_warp <= 232448;
+}
+
+static cudaError_t launch_sparse(const FwdParams& p, int n_sms, cudaStream_t st) {
+  switch (p.g.act) {
+    case BNN_ACT_RELU: return launch_sparse_t<BNN_ACT_RELU>(p, n_sms, st);
+    case BNN_ACT_LEAKY: return launch_sparse_t<BNN_ACT_LEAKY>(p, n_sms, st);
+    case BNN_ACT_SWISH: return launch_sparse_t<BNN_ACT_SWISH>(p, n_sms, st);
+    default: return launch_sparse_t<BNN_ACT_TANH>(p, n_sms, st);
+  }
+}
+
 // Dispatch: specialised kernel when the padded shape is one of the compiled instantiations.
 // force_generic != 0 disables the specialised path (used by the tests to cross-check both kernels).
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
                                const char** which) {
   const NetGeom& g = p.g;
+  if (p.sp_items && !predict) {
+    if (which) *which = "k_fwd_sparse";
+    return launch_sparse(p, n_sms, st);
+  }
   if (!force_generic && g.L == 3) {
     const int k0 = g.F_pad, n1 = g.l[0].out_pad, n2 = g.l[1].out_pad, n3 = g.l[2].out_pad;
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish

@@ -36,6 +36,7 @@ struct ChainDev {
 
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
                                const char** which);
+bool bnn_sparse_fits(const FwdParams& p);
 cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
                               const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st);
 cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st);

@@ -285,3 +285,70 @@ def test_philox_chains_run_and_agree_with_oracle_state():
         assert rel_close(st.logPrior[c], orc.log_prior(w, 1, np.ones(3)))
         assert st.n_correct[c] == ref["n_correct"]
     eng.close()
+
+
+def _random_block_net(rng, f, groups_nodes1, groups_nodes2, k):
+    """A create_mask-style block network: feature g -> n1 nodes -> n2 nodes -> dense K outputs (bias on the last layer)."""
+    h1, h2 = f * groups_nodes1, f * groups_nodes2
+    shapes = [(h1, f), (h2, h1), (k, h2 + 1)]
+    mask = [np.zeros(s) for s in shapes]
+    for g in range(f):
+        mask[0][g * groups_nodes1:(g + 1) * groups_nodes1, g] = 1
+        mask[1][g * groups_nodes2:(g + 1) * groups_nodes2, g * groups_nodes1:(g + 1) * groups_nodes1] = 1
+    mask[2][:] = 1
+    w = [rng.normal(0, 0.4, s) * m for s, m in zip(shapes, mask)]
+    return shapes, mask, w
+
+
+@pytest.mark.parametrize("act", ["tanh", "swish", "ReLU"])
+@pytest.mark.parametrize("n", [37, 3000])
+def test_block_sparse_kernel_matches_dense_and_oracle(act, n):
+    """Masked chains run k_fwd_sparse (dense-block cover of the mask); the same chains with option sparse=0
+    run the dense DMMA kernels; both must agree with the oracle at 1e-9 and with each other on every decision."""
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(11)
+    f, k = 12, 4
+    shapes, mask, w = _random_block_net(rng, f, 3, 2, k)
+    x = rng.standard_normal((n, f))
+    labels = rng.integers(0, k, n)
+    states = []
+    for sparse in (1, 0):
+        eng = Engine(NetShape(f, shapes, act=act, lik=0))
+        eng.set_option("sparse", sparse)
+        eng.set_data(x, labels)
+        sets = [w, [a + rng.normal(0, 0.2, a.shape) * m for a, m in zip(w, mask)]] if sparse else sets
+        eng.chains_init(sets, mask=mask, seed=5)
+        assert eng.last_kernel == ("k_fwd_sparse" if sparse else "k_fwd_generic")
+        st = eng.read_state()
+        for c, ws in enumerate(sets):
+            y = orc.forward(x, ws, act, None, "softmax")
+            assert rel_close(st.logLik[c], orc.loglik_categorical(y, labels)), (act, n, sparse, c)
+            nc, ck, _, hist = orc.class_counters(y, labels)
+            assert st.n_correct[c] == nc and np.array_equal(st.class_correct[c], ck) and np.array_equal(st.pred_hist[c], hist)
+        eng.mh_steps(25)
+        states.append(eng.read_state())
+        eng.close()
+    a, b = states
+    assert np.array_equal(a.n_accepted, b.n_accepted)
+    assert np.array_equal(a.w, b.w)                         # identical decisions => bit-identical weights
+    assert rel_close(a.logLik, b.logLik)
+    for c in range(2):                                      # masked entries stay exactly zero
+        for wl_, m in zip(a.weights(c), mask):
+            assert np.all(wl_[m == 0] == 0)
+
+
+def test_block_sparse_falls_back_when_weights_violate_mask():
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(2)
+    shapes, mask, w = _random_block_net(rng, 6, 2, 2, 3)
+    w[0][0, 5] = 0.3                                        # outside the mask
+    x = rng.standard_normal((100, 6))
+    labels = rng.integers(0, 3, 100)
+    eng = Engine(NetShape(6, shapes, act="tanh", lik=0))
+    eng.set_data(x, labels)
+    eng.chains_init([w], mask=mask)
+    assert eng.last_kernel == "k_fwd_generic"
+    st = eng.read_state()
+    y = orc.forward(x, w, "tanh", None, "softmax")
+    assert rel_close(st.logLik[0], orc.loglik_categorical(y, labels))
+    eng.close()
