@@ -72,10 +72,9 @@ struct bnn_ctx {
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
   const char* last_kernel = "";
-  // block-masked networks: dense-block item lists of the chains' mask (k_fwd_sparse)
-  DevBuf sp_items;
-  int sp_off[BNN_MAX_LAYERS + 1] = {0};
-  int sp_wA = 0, sp_wB = 0;
+  // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
+  DevBuf sp_items, sp_widx;
+  int sp_prog_len = 0, sp_n_items = 0, sp_slots = 1, sp_wlen = 0;
   bool use_sparse = false;
   int opt_sparse = 1;               // option "sparse": 0 forces the dense kernels for masked chains
   long long sp_fma = 0, dense_fma = 0;
@@ -178,7 +177,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items};
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items, &c->sp_widx};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -381,31 +380,45 @@ int bnn_log_prior(bnn_ctx* c, const double* w_dev, int32_t n_sets, int32_t prior
   return 0;
 }
 
-// Dense-block cover of a mask (create_mask, BNN_lib.py:16-47): per layer, consecutive rows whose kept
-// columns span the same range [c0, c0+nc) form a block; blocks are cut into items of at most 4 rows.
-// Columns inside the range that the mask drops are harmless (their weights are exactly zero).
-// Returns false when the cover is not worth it (more than a quarter of the dense work) or does not fit.
-static bool build_sparse_items(bnn_ctx* c, const double* mask_host, std::vector<int4>& items) {
+// Dataflow program of a block-masked network for k_fwd_sparse (format: bnn_forward.cu).
+// Per hidden layer, consecutive rows whose kept columns span the same range [c0, c0+nc) form a block
+// (create_mask, BNN_lib.py:16-47 produces exactly such blocks); blocks are cut into items of at most 4 rows.
+// Columns inside the range that the mask drops are harmless (their weights are exactly zero).  Items are
+// emitted in dependency order starting from the last hidden layer, each unit of an earlier layer gets a
+// scratch slot that is released after its last reader.  The output layer is evaluated densely.
+// Returns false when the cover is not worth it (more than a quarter of the dense work).
+namespace {
+struct SpItem { int r0, nr, c0, nc; };
+}
+static bool build_sparse_program(bnn_ctx* c, const double* mask_host, std::vector<int>& prog, std::vector<int>& widx) {
   const NetGeom& g = c->g;
-  items.clear();
+  const int US = 33;                            // SP_US of bnn_forward.cu
+  prog.clear();
+  widx.clear();
+  c->sp_n_items = 0;
+  c->sp_slots = 1;
+  if (g.L < 2 || g.O > 8) return false;
+  const int H = g.L - 1;                        // hidden layers
+  const LayerGeom& lo = g.l[H];
+  const int op = (lo.out + 1) & ~1;
+  std::vector<std::vector<SpItem>> items(H);
+  std::vector<std::vector<int>> unit_item(H), readers(H), slot(H);
   long long sp = 0, dense = 0;
-  c->sp_wA = c->sp_wB = 1;
-  for (int l = 0; l < g.L; ++l) {
+  for (int l = 0; l < g.L; ++l) dense += (long long)g.l[l].out * g.l[l].in;
+  for (int l = 0; l < H; ++l) {
     const LayerGeom& lg = g.l[l];
     const int cols = lg.in + lg.bias;
-    c->sp_off[l] = (int)items.size();
-    if (l < g.L - 1) {
-      int& w = (l % 2 == 0) ? c->sp_wA : c->sp_wB;
-      if (lg.out > w) w = lg.out;
-    }
-    int r = 0;
     auto range_of = [&](int row, int& c0, int& nc) {
-      int lo = -1, hi = -1;
+      int lo_ = -1, hi = -1;
       for (int k = 0; k < lg.in; ++k)
-        if (mask_host[lg.c_off + row * cols + lg.bias + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
-      c0 = lo < 0 ? 0 : lo;
-      nc = lo < 0 ? 0 : hi - lo + 1;
+        if (mask_host[lg.c_off + row * cols + lg.bias + k] != 0.0) { if (lo_ < 0) lo_ = k; hi = k; }
+      c0 = lo_ < 0 ? 0 : lo_;
+      nc = lo_ < 0 ? 0 : hi - lo_ + 1;
     };
+    unit_item[l].assign(lg.out, -1);
+    readers[l].assign(lg.out, 0);
+    slot[l].assign(lg.out, -1);
+    int r = 0;
     while (r < lg.out) {
       int c0, nc;
       range_of(r, c0, nc);
@@ -418,18 +431,96 @@ static bool build_sparse_items(bnn_ctx* c, const double* mask_host, std::vector<
       }
       for (int q = r; q < r1; q += 4) {
         const int nr = (r1 - q < 4) ? r1 - q : 4;
-        items.push_back(make_int4(q, nr, c0, nc));
+        for (int i = 0; i < nr; ++i) unit_item[l][q + i] = (int)items[l].size();
+        items[l].push_back({q, nr, c0, nc});
         sp += (long long)nr * nc;
       }
       r = r1;
     }
-    dense += (long long)lg.out * lg.in;
+    if (l > 0)
+      for (const SpItem& it : items[l])
+        for (int k = 0; k < it.nc; ++k) readers[l - 1][it.c0 + k]++;
   }
-  c->sp_off[g.L] = (int)items.size();
-  for (int l = g.L + 1; l <= BNN_MAX_LAYERS; ++l) c->sp_off[l] = c->sp_off[g.L];
+  sp += (long long)lo.out * lo.in;
   c->sp_fma = sp;
   c->dense_fma = dense;
-  return sp * 4 <= dense;
+  if (sp * 4 > dense) return false;
+
+  // weight stream starts with the output-layer bias (8 entries)
+  for (int o = 0; o < 8; ++o) widx.push_back(o < lo.out ? lo.b_off + o : -1);
+
+  std::vector<std::vector<char>> done(H);
+  for (int l = 0; l < H; ++l) done[l].assign(items[l].size(), 0);
+  std::vector<int> free_slots;                  // released slots, reused lowest first
+  int n_slots = 0;
+  auto take_slot = [&]() {
+    if (free_slots.empty()) return n_slots++;
+    size_t best = 0;
+    for (size_t i = 1; i < free_slots.size(); ++i) if (free_slots[i] < free_slots[best]) best = i;
+    int v = free_slots[best];
+    free_slots.erase(free_slots.begin() + best);
+    return v;
+  };
+  // explicit stack instead of recursion: (layer, item, next column to check)
+  struct Frame { int l, idx, k; };
+  for (size_t top = 0; top < items[H - 1].size(); ++top) {
+    std::vector<Frame> st{{H - 1, (int)top, 0}};
+    while (!st.empty()) {
+      Frame& f = st.back();
+      const SpItem it = items[f.l][f.idx];
+      if (done[f.l][f.idx]) { st.pop_back(); continue; }
+      bool pushed = false;
+      if (f.l > 0) {
+        for (; f.k < it.nc; ++f.k) {
+          const int prod = unit_item[f.l - 1][it.c0 + f.k];
+          if (!done[f.l - 1][prod]) { st.push_back({f.l - 1, prod, 0}); pushed = true; break; }
+        }
+      }
+      if (pushed) continue;
+      // emit the item: program entry ...
+      const int l = f.l, idx = f.idx;
+      const LayerGeom& lg = g.l[l];
+      const bool to_out = (l == H - 1);
+      prog.push_back(l | (it.nr << 8) | (to_out ? (1 << 16) : 0));
+      prog.push_back(it.nc);
+      prog.push_back(l > 0 ? 1 : 0);
+      prog.push_back(0);
+      for (int i = 0; i < 4; ++i) {
+        int off = 0;
+        if (!to_out && i < it.nr) {
+          const int s = take_slot();
+          slot[l][it.r0 + i] = s;
+          off = (g.F + s) * US;
+        }
+        prog.push_back(off);
+      }
+      for (int k = 0; k < it.nc; ++k)
+        prog.push_back(l == 0 ? (it.c0 + k) * US : (g.F + slot[l - 1][it.c0 + k]) * US);
+      while (prog.size() % 4) prog.push_back(0);
+      // ... and its weights in consumption order
+      const int nrp = (it.nr + 1) & ~1;
+      for (int i = 0; i < nrp; ++i) widx.push_back(i < it.nr ? lg.b_off + it.r0 + i : -1);
+      for (int k = 0; k < it.nc; ++k)
+        for (int i = 0; i < nrp; ++i) {
+          const int r = it.r0 + i, cc = it.c0 + k;
+          widx.push_back(i < it.nr ? lg.w_off + r * lg.stride + (cc ^ ((r & 1) * lg.swz)) : -1);
+        }
+      if (to_out)
+        for (int i = 0; i < it.nr; ++i)
+          for (int o = 0; o < op; ++o) {
+            const int u = it.r0 + i;
+            widx.push_back(o < lo.out ? lo.w_off + o * lo.stride + (u ^ ((o & 1) * lo.swz)) : -1);
+          }
+      if (l > 0)
+        for (int k = 0; k < it.nc; ++k)
+          if (--readers[l - 1][it.c0 + k] == 0) free_slots.push_back(slot[l - 1][it.c0 + k]);
+      done[l][idx] = 1;
+      c->sp_n_items++;
+      st.pop_back();
+    }
+  }
+  c->sp_slots = n_slots < 1 ? 1 : n_slots;
+  return true;
 }
 
 static ChainDev chain_dev(bnn_ctx* c) {
@@ -460,10 +551,12 @@ static int chains_forward(bnn_ctx* c, cudaStream_t st) {
   const int per = sets_per_pass(g);
   FwdParams p = base_params(c);
   if (c->use_sparse && c->opt_sparse) {
-    p.sp_items = c->sp_items.as<int4>();
-    for (int l = 0; l <= BNN_MAX_LAYERS; ++l) p.sp_off[l] = c->sp_off[l];
-    p.sp_wA = c->sp_wA;
-    p.sp_wB = c->sp_wB;
+    p.sp_prog = c->sp_items.as<int>();
+    p.sp_widx = c->sp_widx.as<int>();
+    p.sp_wlen = c->sp_wlen;
+    p.sp_prog_len = c->sp_prog_len;
+    p.sp_n_items = c->sp_n_items;
+    p.sp_slots = c->sp_slots;
   }
   for (int s0 = 0; s0 < c->C; s0 += per) {
     const int n = (c->C - s0 < per) ? c->C - s0 : per;
@@ -509,17 +602,20 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
     CUDA_TRY(cudaMemcpyAsync(c->mask.p, mask_host, sizeof(double) * g.P, cudaMemcpyHostToDevice, st));
     // block-sparse forward: only when the cover is thin and the initial weights respect the mask (the
     // reference applies the mask at construction, BNN_env.py:259-267; proposals are masked in k_mh_update)
-    std::vector<int4> items;
-    bool ok = build_sparse_items(c, mask_host, items);
+    std::vector<int> items, widx;
+    bool ok = build_sparse_program(c, mask_host, items, widx);
     for (size_t i = 0; ok && i < (size_t)C * g.P; ++i)
       if (mask_host[i % g.P] == 0.0 && w0_host[i] != 0.0) ok = false;
     if (ok) {
       FwdParams probe{};
-      probe.g = g; probe.sp_wA = c->sp_wA; probe.sp_wB = c->sp_wB;
+      probe.g = g; probe.sp_slots = c->sp_slots; probe.sp_prog_len = (int)items.size(); probe.sp_wlen = (int)widx.size();
       ok = bnn_sparse_fits(probe);
     }
     if (ok) {
       if (upload(c->sp_items, items.data(), items.size(), st)) return 1;
+      if (upload(c->sp_widx, widx.data(), widx.size(), st)) return 1;
+      c->sp_prog_len = (int)items.size();
+      c->sp_wlen = (int)widx.size();
       c->use_sparse = true;
     }
   }

@@ -194,6 +194,23 @@ __device__ __forceinline__ double bnn_act(double z, double alpha, const double* 
   return __hiloint2double(__double2hiint(r) | (is_nan ? 0x7ff80000 : 0), __double2loint(r));
 }
 
+// Fast-path activation for callers that have established (e.g. by a warp vote on bnn_act_needs_care) that the
+// argument of the exponential is finite and below 708 in magnitude: no clamp, no NaN fix-up -- the integer
+// instructions of those two are a third of the slow path's issue slots.
+template <int ACT>
+__device__ __forceinline__ bool bnn_act_needs_care(double z) {
+  if (ACT == BNN_ACT_RELU || ACT == BNN_ACT_LEAKY) return false;
+  // swish: exp(-z), |z| < 708 ; tanh: exp(2z), |z| < 354 (inf / NaN compare as large)
+  return (__double2hiint(z) & 0x7fffffff) >= (ACT == BNN_ACT_SWISH ? 0x40862000 : 0x40762000);
+}
+template <int ACT>
+__device__ __forceinline__ double bnn_act_fast(double z, double alpha, const double* __restrict__ tab) {
+  if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
+  if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
+  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_core(-z, tab));
+  return fma(-2.0, bnn_rcp(bnn_exp_core(z + z, tab) + 1.0), 1.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA 1-D) helpers
 // ---------------------------------------------------------------------------------------------
@@ -256,9 +273,11 @@ struct FwdParams {
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
   const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j/256)
-  // block-masked networks (create_mask, BNN_lib.py:16-47): per layer a list of dense blocks
-  // {r0, nr <= 4, c0, nc} covering every non-zero of the mask; null = dense evaluation
-  const int4* sp_items;
-  int sp_off[BNN_MAX_LAYERS + 1];
-  int sp_wA, sp_wB;         // widths of the two hidden-activation staging buffers (units)
+  // block-masked networks (create_mask, BNN_lib.py:16-47): dataflow program over the dense blocks that cover
+  // the mask of the hidden layers (format: bnn_forward.cu, k_fwd_sparse); null = dense evaluation
+  const int* sp_prog;
+  const int* sp_widx;       // [sp_wlen] offset inside a packed weight set of each weight-stream entry (-1: 0.0)
+  int sp_prog_len, sp_n_items, sp_wlen;
+  int sp_slots;             // scratch slots (hidden units alive at the same time) per row and chain
+  int sp_group;             // chains whose weight streams are resident in shared memory (set by the launcher)
 };

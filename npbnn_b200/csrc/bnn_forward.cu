@@ -39,16 +39,22 @@ __device__ __forceinline__ double softplus_ref(double z) {
 // Likelihood mode (PREDICT=false): writes part[(c*NF+slot)*n_tiles16 + wt] and bumps the CTA counters.
 // Prediction mode: accumulates transformed outputs into pacc/pvote (per warp, [16][K_out]) and
 // optionally writes the dense tensor.
-template <bool PREDICT>
+// R32 (likelihood mode only): the warp owns 32 rows = warp tiles wt and wt + 1, lane r owns row r; the xor
+// trees of warp16_sum stay inside each half-warp, so lanes 0 and 16 hold the two warp-tile sums.
+template <bool PREDICT, bool R32 = false>
 __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long long wt, int lane, const double* zs,
                                              int ZS, const double* tab, int* cnt_smem, double* pacc, int* pvote) {
   const NetGeom& g = p.g;
-  const long long row = wt * 16 + (lane & 15);
-  const bool active = lane < 16 && row < p.n_total;
+  const int rl = R32 ? lane : (lane & 15);
+  const long long row = wt * 16 + rl;
+  const bool active = (R32 || lane < 16) && row < p.n_total;
   const bool is_train = active && row < p.n_train;
   const bool is_test = active && !is_train;
-  const double* z = zs + (lane & 15) * ZS;
+  const double* z = zs + rl * ZS;
   const long long nt = p.n_tiles16;
+  // lane that stores the warp-tile partial sums, and the tile it stores them for
+  const bool writer = (lane == 0) || (R32 && lane == 16 && wt + 1 < nt);
+  const long long wts = wt + (R32 ? (lane >> 4) : 0);
 
   if (g.lik == BNN_LIK_CATEGORICAL) {
     const int K = g.K;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
         }
       }
       double s = warp16_sum(is_train ? ll : 0.0);
-      if (lane == 0) p.part[((long long)c * p.NF) * nt + wt] = s;
+      if (writer) p.part[((long long)c * p.NF) * nt + wts] = s;
     } else {
       if (active) {
         double* zw = const_cast<double*>(z);     // the staged row is private to this lane: reuse as scratch
@@ -122,14 +128,14 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
       double sr = warp16_sum(is_train ? r : 0.0);
       double sr2 = warp16_sum(is_train ? r * r : 0.0);
       double st2 = warp16_sum(is_test ? r * r : 0.0);
-      if (lane == 0) {
-        p.part[((long long)c * p.NF + 1 + j) * nt + wt] = sr;
-        p.part[((long long)c * p.NF + 1 + K + j) * nt + wt] = sr2;
-        p.part[((long long)c * p.NF + 1 + 2 * K + j) * nt + wt] = st2;
+      if (writer) {
+        p.part[((long long)c * p.NF + 1 + j) * nt + wts] = sr;
+        p.part[((long long)c * p.NF + 1 + K + j) * nt + wts] = sr2;
+        p.part[((long long)c * p.NF + 1 + 2 * K + j) * nt + wts] = st2;
       }
     }
     double s = warp16_sum(ll);
-    if (lane == 0) p.part[((long long)c * p.NF) * nt + wt] = s;
+    if (writer) p.part[((long long)c * p.NF) * nt + wts] = s;
   } else {
     if (active) {
       const int O = g.O;
@@ -277,86 +283,223 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
 // =============================================================================================
 // block-masked networks (create_mask, BNN_lib.py:16-47; apply_mask, BNN_env.py:259-267)
 // =============================================================================================
-// A masked layer is a list of small dense blocks {r0, nr <= 4, c0, nc} (built on the host from the mask,
-// bnn_capi.cu) that cover every entry the mask keeps; entries outside the blocks are exactly zero in every
+// A masked hidden layer is a list of small dense blocks ("items": rows r0..r0+nr-1, nr <= 4, columns
+// c0..c0+nc-1) that cover every entry the mask keeps; entries outside the blocks are exactly zero in every
 // proposal (w' *= mask, BNN_env.py:461-462), so skipping them changes nothing but the order of the sum.
 // At the block sizes create_mask produces (a feature feeds a handful of nodes) the contraction is far too
-// thin for tensor-core tiles, and the FP64 work is dominated by the activations, so this kernel is plain
-// DFMA: a warp owns 16 rows of X; lane & 15 = row, the two half-warps take alternate blocks.  Activations
-// are staged per warp in shared memory as [unit][16 rows] (stride 17: conflict-free column reads).
-constexpr int SP_US = 17;
+// thin for tensor-core tiles and the FP64 work is dominated by the activations, so this kernel is plain DFMA
+// with one THREAD per row: lane = row of a 32-row tile, every lane runs the same item, weights are warp-
+// uniform shared-memory loads.  The host (build_sparse_program, bnn_capi.cu) orders the items of all hidden
+// layers as a dataflow program -- an item runs as soon as the units it reads exist -- and assigns each hidden
+// unit a scratch slot that is recycled after its last reader, so a thread needs F + (live units) doubles of
+// shared memory instead of every layer's width; the units of the LAST hidden layer are never stored: they are
+// multiplied into the (dense, O <= 8) output layer's accumulators, which stay in registers.
+//   * the weights the program touches are gathered once per CTA from the packed weight sets into shared
+//     memory IN PROGRAM ORDER (sp_widx), so the item loop reads them with a running pointer and 16-byte
+//     loads -- no address arithmetic per multiply-add;
+//   * four (or two) chains are evaluated together (same program, different weights) for instruction-level
+//     parallelism;
+//   * a work unit is (32-row tile, chain subset); a CTA owns a contiguous range of tiles and its warps draw
+//     units from a shared counter, so the load is balanced to one unit.
+//
+// program (ints), per item: [0] layer | nr << 8 | to_out << 16  [1] nc  [2] 1 if the inputs are scratch slots
+//     (0: X columns, shared by both chains)  [3] 0  [4..7] element offset of each produced unit's slot
+//     [8..8+nc) element offset of each input, padded to a multiple of 4 ints (offsets are for the first chain of the unit; chain q's
+//     scratch slots follow q * sp_slots * SP_US elements later)
+// weight stream (doubles), per chain: [0..8) output-layer bias; then per item: bias[nrp], nc x w[nrp] (column
+//     c0+k, rows r0..r0+nr-1) and, for to_out items, nr x w_out[op] (the output-layer column of each produced
+//     unit); nrp / op = nr / O rounded up to even, padding is 0.
+constexpr int SP_US = 33;        // per-unit stride in doubles (32 rows + 1: conflict-free transposed stores)
+constexpr int SP_MAX_O = 8;
+constexpr int SP_HDR = 8;
 
-template <int ACT>
-__global__ void __launch_bounds__(256) k_fwd_sparse(const __grid_constant__ FwdParams p) {
+template <int ACT, int NCH, int NR>
+__device__ __forceinline__ void sparse_item(const int* it, int nc, int qs, int sq, bool to_out, int O,
+                                            const double* (&w)[NCH], double* bufl, const double (&alpha)[NCH],
+                                            const double* tab, double (&out)[NCH][SP_MAX_O]) {
+  constexpr int NRP = (NR + 1) & ~1;
+  double acc[NCH][NRP];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int i = 0; i < NRP; i += 2) {
+      const double2 b = *reinterpret_cast<const double2*>(w[q] + i);
+      acc[q][i] = b.x; acc[q][i + 1] = b.y;
+    }
+#pragma unroll 2
+  for (int k = 0; k < nc; ++k) {
+    const int src = it[SP_HDR + k];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+      const double a = bufl[src + q * qs];
+#pragma unroll
+      for (int i = 0; i < NRP; i += 2) {
+        const double2 ww = *reinterpret_cast<const double2*>(w[q] + (k + 1) * NRP + i);
+        acc[q][i] = fma(ww.x, a, acc[q][i]);
+        if (i + 1 < NR) acc[q][i + 1] = fma(ww.y, a, acc[q][i + 1]);
+      }
+    }
+  }
+  bool care = false;
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int i = 0; i < NR; ++i) care |= bnn_act_needs_care<ACT>(acc[q][i]);
+  if (!__any_sync(FULL_MASK, care)) {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR; ++i) acc[q][i] = bnn_act_fast<ACT>(acc[q][i], alpha[q], tab);
+  } else {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR; ++i) acc[q][i] = bnn_act<ACT>(acc[q][i], alpha[q], tab);
+  }
+  int adv = (nc + 1) * NRP;
+  if (to_out) {
+    const int op = (O + 1) & ~1;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+#pragma unroll
+      for (int j = 0; j < SP_MAX_O / 2; ++j) {
+        if (2 * j < O) {
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+            const double2 ww = *reinterpret_cast<const double2*>(w[q] + adv + i * op + 2 * j);
+            out[q][2 * j] = fma(ww.x, acc[q][i], out[q][2 * j]);
+            out[q][2 * j + 1] = fma(ww.y, acc[q][i], out[q][2 * j + 1]);
+          }
+        }
+      }
+    }
+    adv += NR * op;
+  } else {
+    const int4 sl = *reinterpret_cast<const int4*>(it + 4);
+    const int slot[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR; ++i) bufl[slot[i] + q * sq] = acc[q][i];
+  }
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) w[q] += adv;
+}
+
+// NCH chains per work unit: 4 (at most 10 warps, <= 204 registers) or 2 (at most 16 warps, <= 128 registers)
+template <int ACT, int NCH>
+__global__ void __launch_bounds__(NCH == 4 ? 320 : 512, 1) k_fwd_sparse(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int lr = lane & 15, half = lane >> 4;
-  const int ZS = bnn_round_up(g.O, 8) + 1;
+  constexpr int ZS = SP_MAX_O + 1;
+  const int O = g.O;
+  const int G = p.sp_group;                                   // chains whose weight streams are resident
+  const int sq = p.sp_slots * SP_US;
 
   double* tab = reinterpret_cast<double*>(smem_raw);
-  const int per_warp = (g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS;
-  double* bx = tab + BNN_EXP_TAB_SIZE + warp * per_warp;
-  double* bA = bx + g.F * SP_US;
-  double* bB = bA + p.sp_wA * SP_US;
-  double* zs = bB + p.sp_wB * SP_US;
-  int* cnt = reinterpret_cast<int*>(tab + BNN_EXP_TAB_SIZE + nwarps * per_warp);
+  double* wsm = tab + BNN_EXP_TAB_SIZE;                       // [G][sp_wlen]
+  const int per_warp = (g.F + NCH * p.sp_slots) * SP_US + 32 * ZS;
+  double* buf = wsm + (size_t)G * p.sp_wlen + warp * per_warp;
+  double* zs = buf + (g.F + NCH * p.sp_slots) * SP_US;
+  int* cnt = reinterpret_cast<int*>(wsm + (size_t)G * p.sp_wlen + nwarps * per_warp);
   const int n_cnt = (g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+  int* next_unit = cnt + n_cnt;
+  int* prog = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(next_unit + 1) + 15) & ~(uintptr_t)15);
 
   for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
-  __syncthreads();
+  for (int i = threadIdx.x; i < p.sp_prog_len; i += blockDim.x) prog[i] = p.sp_prog[i];
 
-  const long long total_warps = (long long)gridDim.x * nwarps;
-  for (long long wt = (long long)blockIdx.x * nwarps + warp; wt < p.n_tiles16; wt += total_warps) {
-    // X warp tile -> [feature][row]; global reads are contiguous (the tile is 16 * F_pad consecutive doubles)
-    const double* xt = p.x + wt * 16 * (long long)g.F_pad;
-    for (int idx = lane; idx < 16 * g.F_pad; idx += 32) {
-      const int r = idx / g.F_pad, cp = idx - r * g.F_pad;
-      const int c = cp ^ ((r & 1) * g.x_swz);
-      if (c < g.F) bx[c * SP_US + r] = __ldg(xt + idx);
+  // this CTA's contiguous range of 32-row tiles
+  const long long n_tiles32 = (p.n_tiles16 + 1) >> 1;
+  const long long n_pad = p.n_tiles16 * 16;
+  const long long t0 = n_tiles32 * blockIdx.x / gridDim.x, t1 = n_tiles32 * (blockIdx.x + 1) / gridDim.x;
+  double* bufl = buf + lane;
+
+  for (int c0 = 0; c0 < p.C; c0 += G) {
+    const int gc = min(G, p.C - c0);                          // chains of this group
+    const int n_sub = (gc + NCH - 1) / NCH;                   // chain subsets of NCH
+    __syncthreads();                                           // previous group's readers are done
+    for (int i = threadIdx.x; i < gc * p.sp_wlen; i += blockDim.x) {
+      const int c = i / p.sp_wlen, j = i - c * p.sp_wlen;
+      const int idx = __ldg(p.sp_widx + j);
+      wsm[i] = idx < 0 ? 0.0 : __ldg(p.wp + (long long)(c0 + c) * g.PB + idx);
     }
-    __syncwarp();
-    for (int c = 0; c < p.C; ++c) {
-      const double* W = p.wp + (long long)c * g.PB;
-      const double* in = bx;
-      double* out = bA;
-      for (int l = 0; l < g.L; ++l) {
-        const LayerGeom& lg = g.l[l];
-        const bool last = (l == g.L - 1);
-        const double alpha = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * g.L + l] : 0.0;
-        for (int it = p.sp_off[l] + half; it < p.sp_off[l + 1]; it += 2) {
-          const int4 I = __ldg(p.sp_items + it);
-          const int r0 = I.x, nr = I.y, c0 = I.z, c1 = I.z + I.w;
-          double acc[4];
-          const double* wr[4];
-          int sw[4];
+    if (threadIdx.x == 0) *next_unit = 0;
+    __syncthreads();
+    const int n_units = (int)(t1 - t0) * n_sub;
+    long long cur_tile = -1;
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(next_unit, 1);
+      u = __shfl_sync(FULL_MASK, u, 0);
+      if (u >= n_units) break;
+      const long long w32 = t0 + u / n_sub;
+      const int sub = u - (int)(w32 - t0) * n_sub;
+      if (w32 != cur_tile) {
+        // X tile -> [feature][row]; global reads are contiguous (32 * F_pad consecutive doubles)
+        const double* xt = p.x + w32 * 32 * (long long)g.F_pad;
+        __syncwarp();
+        // 8 independent loads in flight per lane (F_pad is a multiple of 8)
+        for (int j0 = 0; j0 < g.F_pad; j0 += 8) {
+          double v[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r0 + (i < nr ? i : nr - 1);
-            acc[i] = __ldg(W + lg.b_off + r);
-            wr[i] = W + lg.w_off + r * lg.stride;
-            sw[i] = (r & 1) * lg.swz;
-          }
-          for (int cc = c0; cc < c1; ++cc) {
-            const double a = in[cc * SP_US + lr];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fma(__ldg(wr[i] + (cc ^ sw[i])), a, acc[i]);
+          for (int uu = 0; uu < 8; ++uu) {
+            const int idx = (j0 + uu) * 32 + lane;
+            v[uu] = (w32 * 32 + idx / g.F_pad < n_pad) ? __ldg(xt + idx) : 0.0;
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nr) {
-              if (!last) out[(r0 + i) * SP_US + lr] = bnn_act<ACT>(acc[i], alpha, tab);
-              else zs[lr * ZS + r0 + i] = acc[i];
-            }
+          for (int uu = 0; uu < 8; ++uu) {
+            const int idx = (j0 + uu) * 32 + lane;
+            const int r = idx / g.F_pad, cp = idx - r * g.F_pad;
+            const int cidx = cp ^ ((r & 1) * g.x_swz);
+            if (cidx < g.F) buf[cidx * SP_US + r] = v[uu];
           }
         }
         __syncwarp();
-        in = out;
-        out = (out == bA) ? bB : bA;
+        cur_tile = w32;
       }
-      bnn_epilogue<false>(p, c, wt, lane, zs, ZS, tab, cnt, nullptr, nullptr);
-      __syncwarp();
+      // chains of this unit (a short last subset repeats its last chain; the copies are not scored)
+      int ch[NCH];
+      const double* w[NCH];
+      double out[NCH][SP_MAX_O];
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        ch[q] = min(NCH * sub + q, gc - 1);
+        w[q] = wsm + (size_t)ch[q] * p.sp_wlen;
+#pragma unroll
+        for (int o = 0; o < SP_MAX_O; ++o) out[q][o] = w[q][o];
+        w[q] += SP_MAX_O;
+      }
+      const int* it = prog;
+      for (int n = 0; n < p.sp_n_items; ++n) {
+        const int4 h = *reinterpret_cast<const int4*>(it);
+        const int layer = h.x & 0xff, nr = (h.x >> 8) & 0xff, nc = h.y;
+        const bool to_out = (h.x >> 16) & 1;
+        const int qs = h.z ? sq : 0;
+        double alpha[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q)
+          alpha[q] = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[(c0 + ch[q]) * g.L + layer] : 0.0;
+        switch (nr) {
+          case 1: sparse_item<ACT, NCH, 1>(it, nc, qs, sq, to_out, O, w, bufl, alpha, tab, out); break;
+          case 2: sparse_item<ACT, NCH, 2>(it, nc, qs, sq, to_out, O, w, bufl, alpha, tab, out); break;
+          case 3: sparse_item<ACT, NCH, 3>(it, nc, qs, sq, to_out, O, w, bufl, alpha, tab, out); break;
+          default: sparse_item<ACT, NCH, 4>(it, nc, qs, sq, to_out, O, w, bufl, alpha, tab, out); break;
+        }
+        it += SP_HDR + ((nc + 3) & ~3);         // items are padded to 16 bytes
+      }
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        if (NCH * sub + q < gc) {
+          __syncwarp();
+#pragma unroll
+          for (int o = 0; o < SP_MAX_O; ++o) zs[lane * ZS + o] = out[q][o];
+          __syncwarp();
+          bnn_epilogue<false, true>(p, c0 + ch[q], w32 * 2, lane, zs, ZS, tab, cnt, nullptr, nullptr);
+        }
+      }
     }
   }
   if (n_cnt) {
@@ -914,35 +1057,71 @@ static cudaError_t launch_generic(const FwdParams& p, int n_sms, cudaStream_t st
   }
 }
 
-template <int ACT>
-static cudaError_t launch_sparse_t(const FwdParams& p, int n_sms, cudaStream_t st) {
-  auto kern = k_fwd_sparse<ACT>;
-  const int ZS = bnn_round_up(p.g.O, 8) + 1;
-  const size_t per_warp = ((size_t)(p.g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS) * sizeof(double);
-  const size_t fixed = BNN_EXP_TAB_SIZE * sizeof(double) +
-                       (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) * sizeof(int) : 0);
-  if (fixed + per_warp > 232448) return cudaErrorInvalidConfiguration;
-  int nwarps = (int)((232448 - fixed) / per_warp);
-  if (nwarps > 8) nwarps = 8;
-  const size_t bytes = fixed + nwarps * per_warp;
+// shared-memory plan of k_fwd_sparse: chains per unit, chains per resident weight group and warps per CTA
+static size_t sparse_fixed_bytes(const FwdParams& p, int C) {
+  return BNN_EXP_TAB_SIZE * sizeof(double) +
+         (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)C * (2 + 2 * p.g.K) * sizeof(int) : 0) +
+         (size_t)(p.sp_prog_len + 8) * sizeof(int) + 16;
+}
+static size_t sparse_warp_bytes(const FwdParams& p, int nch) {
+  return ((size_t)(p.g.F + nch * p.sp_slots) * SP_US + 32 * (SP_MAX_O + 1)) * sizeof(double);
+}
+static bool sparse_plan(const FwdParams& p, int C, int nch, int* group, int* nwarps) {
+  const size_t cap = 232448;
+  const size_t fixed = sparse_fixed_bytes(p, C), per_warp = sparse_warp_bytes(p, nch);
+  const size_t per_chain = (size_t)p.sp_wlen * sizeof(double);
+  const int c_up = (C + nch - 1) / nch * nch;
+  const int max_warps = (nch == 4) ? 10 : 16;
+  for (int min_warps : {8, 4, 2, 1}) {
+    if (fixed + min_warps * per_warp + nch * per_chain > cap) continue;
+    size_t g = (cap - fixed - min_warps * per_warp) / per_chain;
+    g = g / nch * nch;
+    if (g > (size_t)c_up) g = c_up;
+    size_t w = (cap - fixed - g * per_chain) / per_warp;
+    if (w > (size_t)max_warps) w = max_warps;
+    *group = (int)g;
+    *nwarps = (int)w;
+    return true;
+  }
+  return false;
+}
+
+template <int ACT, int NCH>
+static cudaError_t launch_sparse_n(const FwdParams& p0, int n_sms, cudaStream_t st) {
+  auto kern = k_fwd_sparse<ACT, NCH>;
+  FwdParams p = p0;
+  int group = 0, nwarps = 0;
+  if (!sparse_plan(p, p.C, NCH, &group, &nwarps)) return cudaErrorInvalidConfiguration;
+  p.sp_group = group;
+  const long long n_tiles32 = (p.n_tiles16 + 1) >> 1;
+  int grid = (int)(n_tiles32 < n_sms ? n_tiles32 : n_sms);
+  // small problems: no more warps than units per CTA
+  const long long units = ((n_tiles32 + grid - 1) / grid) * ((group + NCH - 1) / NCH);
+  if (units < nwarps) nwarps = (int)units;
+  const size_t bytes = sparse_fixed_bytes(p, p.C) + (size_t)group * p.sp_wlen * sizeof(double) +
+                       (size_t)nwarps * sparse_warp_bytes(p, NCH);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  long long ctas = (p.n_tiles16 + nwarps - 1) / nwarps;
-  int grid = (int)(ctas < n_sms ? ctas : n_sms);
   kern<<<grid, nwarps * 32, bytes, st>>>(p);
   return cudaGetLastError();
 }
 
-// true when the block-sparse kernel can run this problem (shared-memory footprint of one warp)
+template <int ACT>
+static cudaError_t launch_sparse_t(const FwdParams& p, int n_sms, cudaStream_t st) {
+  int group, nwarps;
+  if (p.C >= 3 && sparse_plan(p, p.C, 4, &group, &nwarps)) return launch_sparse_n<ACT, 4>(p, n_sms, st);
+  return launch_sparse_n<ACT, 2>(p, n_sms, st);
+}
+
+// true when the block-sparse kernel can run this problem (output width, shared-memory footprint)
 bool bnn_sparse_fits(const FwdParams& p) {
-  const int ZS = bnn_round_up(p.g.O, 8) + 1;
-  const size_t per_warp = ((size_t)(p.g.F + p.sp_wA + p.sp_wB) * SP_US + 16 * ZS) * sizeof(double);
-  const size_t fixed = BNN_EXP_TAB_SIZE * sizeof(double) + (size_t)BNN_MAX_SETS_PER_PASS * (2 + 2 * BNN_MAX_OUT) * sizeof(int);
-  return fixed + per_warp <= 232448;
+  if (p.g.L < 2 || p.g.O > SP_MAX_O) return false;
+  int group, nwarps;
+  return sparse_plan(p, BNN_MAX_SETS_PER_PASS, 2, &group, &nwarps);
 }
 
 static cudaError_t launch_sparse(const FwdParams& p, int n_sms, cudaStream_t st) {
@@ -959,7 +1138,7 @@ static cudaError_t launch_sparse(const FwdParams& p, int n_sms, cudaStream_t st)
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
                                const char** which) {
   const NetGeom& g = p.g;
-  if (p.sp_items && !predict) {
+  if (p.sp_prog && !predict) {
     if (which) *which = "k_fwd_sparse";
     return launch_sparse(p, n_sms, st);
   }

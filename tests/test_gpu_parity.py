@@ -352,3 +352,69 @@ def test_block_sparse_falls_back_when_weights_violate_mask():
     y = orc.forward(x, w, "tanh", None, "softmax")
     assert rel_close(st.logLik[0], orc.loglik_categorical(y, labels))
     eng.close()
+
+
+def _mask_net(rng, f, groups1, nodes1, groups2, nodes2, out, out_bias=1):
+    """create_mask-style network (oracle block_mask = BNN_lib.py:16-47), weights already masked."""
+    h1, h2 = sum(nodes1), (sum(nodes2) if len(groups2) else nodes2)
+    shapes = [(h1, f), (h2, h1), (out, h2 + out_bias)]
+    mask = [orc.block_mask(shapes[0], groups1, nodes1),
+            orc.block_mask(shapes[1], groups2, nodes2 if len(groups2) else []),
+            np.ones(shapes[2])]
+    w = [rng.normal(0, 0.4, s) * m for s, m in zip(shapes, mask)]
+    return shapes, mask, w
+
+
+@pytest.mark.parametrize("case", ["uneven_blocks", "sparse_then_dense_regression", "regression_head"])
+@pytest.mark.parametrize("n,chains", [(40, 3), (1000, 2), (517, 1)])
+def test_block_sparse_program_variants(case, n, chains):
+    """The dataflow program of k_fwd_sparse on the mask shapes of block_bnns.py:39-81: blocks of unequal size
+    (items of > 4 rows are cut), a sparse first layer followed by dense layers, Gaussian likelihoods; odd chain
+    counts (chains are evaluated in pairs) and row counts whose last 32-row tile is half empty."""
+    from npbnn_b200 import _lib as L
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(17)
+    if case == "uneven_blocks":
+        f = 28
+        groups1 = sum(([4 * r + 0, 4 * r + 1, 4 * r + 1, 4 * r + 2, 4 * r + 3, 4 * r + 3, 4 * r + 3] for r in range(4)), [])
+        nodes1 = [3, 6, 5, 2] * 4
+        groups2 = sum(([g] * k for g, k in enumerate(nodes1)), [])
+        nodes2 = [2, 3, 1, 4] * 4
+        shapes, mask, w = _mask_net(rng, f, groups1, nodes1, groups2, nodes2, 3)
+        lik, act, out_kind = L.LIK_CATEGORICAL, "tanh", "softmax"
+    else:
+        f = 30
+        head = case == "regression_head"
+        shapes, mask, w = _mask_net(rng, f, list(range(f)), [2] * f, [], 4, 4 if head else 2)
+        lik = L.LIK_GAUSSIAN_HEAD if head else L.LIK_GAUSSIAN
+        act, out_kind = "swish", ("regress-error" if head else "identity")
+    x = rng.standard_normal((n, f))
+    labels = rng.integers(0, 3, n) if lik == L.LIK_CATEGORICAL else rng.standard_normal((n, 2))
+    sets = [[a + rng.normal(0, 0.1, a.shape) * m for a, m in zip(w, mask)] for _ in range(chains)]
+    states = []
+    for sparse in (1, 0):
+        eng = Engine(NetShape(f, shapes, act=act, lik=lik))
+        eng.set_option("sparse", sparse)
+        eng.set_data(x, labels)
+        eng.chains_init(sets, mask=mask, seed=9)
+        assert eng.last_kernel == ("k_fwd_sparse" if sparse else "k_fwd_generic")
+        st = eng.read_state()
+        for c, ws in enumerate(sets):
+            y = orc.forward(x, ws, act, None, out_kind)
+            if lik == L.LIK_CATEGORICAL:
+                assert rel_close(st.logLik[c], orc.loglik_categorical(y, labels)), (case, n, sparse, c)
+                nc, ck, _, hist = orc.class_counters(y, labels)
+                assert st.n_correct[c] == nc and np.array_equal(st.class_correct[c], ck)
+                assert np.array_equal(st.pred_hist[c], hist)
+            elif lik == L.LIK_GAUSSIAN:
+                assert rel_close(st.logLik[c], orc.loglik_regression(y, labels, 1.0)), (case, n, sparse, c)
+                assert rel_close(st.sum_r2[c], orc.regression_sums(y, labels)[1])
+            else:
+                assert rel_close(st.logLik[c], orc.loglik_regression_error(y, labels)), (case, n, sparse, c)
+        eng.mh_steps(20)
+        states.append(eng.read_state())
+        eng.close()
+    a, b = states
+    assert np.array_equal(a.n_accepted, b.n_accepted)
+    assert np.array_equal(a.w, b.w)
+    assert rel_close(a.logLik, b.logLik)
