@@ -73,6 +73,11 @@ struct bnn_ctx {
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
   const char* last_kernel = "";
   // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
+  // tensor-core first layer (k_fwd3t): int8 slices of X (made once per data set) and of W1 (per scored batch)
+  DevBuf xsl, x_rowscale, wt, oz_flag;
+  long long n_tiles128 = 0;
+  bool tensor_ok = false;           // the staged data and the network shape qualify
+  int opt_tensor = 1;               // option "tensor_l1": 0 keeps layer 1 on the FP64 DMMA path
   DevBuf sp_items, sp_widx;
   int sp_prog_len = 0, sp_n_items = 0, sp_slots = 1, sp_wlen = 0;
   bool use_sparse = false;
@@ -86,7 +91,26 @@ struct bnn_ctx {
   long long fwd_count = 0;
 };
 
-static cudaError_t timed_forward(bnn_ctx* c, const FwdParams& p, bool predict, cudaStream_t st) {
+// network shapes with a k_fwd3t instantiation (BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 swish, categorical)
+static bool tensor_shape(const NetGeom& g) {
+  return g.L == 3 && g.F_pad == 64 && g.l[0].out_pad == 64 && g.l[1].out_pad == 32 && g.l[2].out_pad == 16 &&
+         g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL;
+}
+
+static cudaError_t timed_forward(bnn_ctx* c, const FwdParams& p_in, bool predict, cudaStream_t st) {
+  FwdParams p = p_in;
+  if (!predict && c->tensor_ok && c->opt_tensor && !c->force_generic && !p.sp_prog && p.x == c->xs.as<double>()) {
+    // slice W1 of every weight set of this pass for the integer tensor-core product
+    cudaError_t r = c->wt.ensure(bnn_slice_w1_bytes() * (size_t)p.C, false, st);
+    if (r != cudaSuccess) return r;
+    r = bnn_launch_slice_w1(p.wp, c->g.PB, c->wt.as<uint8_t>(), p.C, st);
+    if (r != cudaSuccess) return r;
+    c->launches++;
+    p.xsl = c->xsl.as<uint8_t>();
+    p.x_rowscale = c->x_rowscale.as<double>();
+    p.wt = c->wt.as<uint8_t>();
+    p.n_tiles128 = c->n_tiles128;
+  }
   if (!c->time_forward) return bnn_launch_forward(p, predict, c->n_sms, c->force_generic, st, &c->last_kernel);
   if (c->ev_used + 2 > c->ev.size()) {
     for (int i = 0; i < 2; ++i) {
@@ -157,6 +181,8 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   c->n_sms = prop.multiProcessorCount;
   const char* fg = getenv("NPBNN_FORCE_GENERIC");
   c->force_generic = (fg && fg[0] == '1') ? 1 : 0;
+  const char* tl = getenv("NPBNN_TENSOR_L1");
+  if (tl) c->opt_tensor = (tl[0] != '0');
   std::vector<double> tab(BNN_EXP_TAB_SIZE);
   for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = exp2((double)j / BNN_EXP_TAB_SIZE);
   cudaError_t e = c->exp_tab.ensure(sizeof(double) * BNN_EXP_TAB_SIZE, false, 0);
@@ -177,7 +203,8 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items, &c->sp_widx};
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
+                    &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -189,6 +216,7 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
   if (strcmp(name, "time_forward") == 0) { c->time_forward = value; return 0; }
   if (strcmp(name, "sparse") == 0) { c->opt_sparse = value; return 0; }
+  if (strcmp(name, "tensor_l1") == 0) { c->opt_tensor = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
 
@@ -282,6 +310,21 @@ int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_tes
   if (c->has_cw) {
     CUDA_TRY(c->class_w.ensure(sizeof(double) * g.K, false, st));
     CUDA_TRY(cudaMemcpyAsync(c->class_w.p, class_w_dev, sizeof(double) * g.K, cudaMemcpyDeviceToDevice, st));
+  }
+  c->tensor_ok = false;
+  if (tensor_shape(g)) {
+    c->n_tiles128 = (c->n_pad + 127) / 128;
+    CUDA_TRY(c->xsl.ensure(bnn_slice_x_tile_bytes() * (size_t)c->n_tiles128, false, st));
+    CUDA_TRY(c->x_rowscale.ensure(sizeof(double) * (size_t)c->n_tiles128 * 128, false, st));
+    CUDA_TRY(c->oz_flag.ensure(sizeof(int), false, st));
+    CUDA_TRY(cudaMemsetAsync(c->oz_flag.p, 0, sizeof(int), st));
+    CUDA_TRY(bnn_launch_slice_x(c->xs.as<double>(), c->n_pad, c->xsl.as<uint8_t>(), c->x_rowscale.as<double>(),
+                                c->n_tiles128, c->oz_flag.as<int>(), st));
+    c->launches++;
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, c->oz_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->tensor_ok = (bad == 0);      // non-finite features: integer slices cannot carry inf / NaN, stay on FP64
   }
   c->have_data = true;
   c->have_chains = false;

@@ -273,6 +273,11 @@ struct FwdParams {
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
   const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j/256)
+  // tensor-core first layer (k_fwd3t): int8 slice tiles of X, per-row scales, per-set slices of W1; null = off
+  const uint8_t* xsl;
+  const double* x_rowscale;
+  const uint8_t* wt;
+  long long n_tiles128;
   // block-masked networks (create_mask, BNN_lib.py:16-47): dataflow program over the dense blocks that cover
   // the mask of the hidden layers (format: bnn_forward.cu, k_fwd_sparse); null = dense evaluation
   const int* sp_prog;

@@ -993,6 +993,430 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 }
 
 // =============================================================================================
+// k_fwd3t: the 3-layer kernel with layer 1 on the 5th-generation tensor cores (tcgen05 + TMEM)
+// =============================================================================================
+// tcgen05 has no FP64 kind, but the first-layer contraction X W1^T can be evaluated EXACTLY in integer
+// arithmetic (Ozaki splitting): every row of X and every row of W1 is scaled by a power of two and rounded to a
+// 47-bit signed integer, which is cut into 6 balanced base-256 digits (int8 "slices"):
+//     x_ik = 2^(e_i - 46) * sum_s a_s[i,k] 256^s          w_nk = 2^(f_n - 46) * sum_t b_t[n,k] 256^t
+//     sum_k x_ik w_nk = 2^(e_i + f_n - 92) * sum_T 256^T * ( sum_{s+t=T} sum_k a_s[i,k] b_t[n,k] )
+// The inner sums are int8 x int8 -> int32 tensor-core products (tcgen05.mma kind::i8, exact, no overflow:
+// 6 pairs * 64 * 128^2 < 2^31); the 6 most significant diagonals T = 10..5 (21 slice pairs) are kept, the
+// dropped ones are zero-mean and below 2^-41 of max|x_i| * max|w_n| (measured: log-likelihood within 1e-12
+// relative of the FP64 kernels).  X is sliced once at bnn_set_data (k_slice_x), W1 once per proposal
+// (k_slice_w1); both are stored in HBM in the tensor core's K-major core-matrix layout, so a plain bulk copy
+// brings them to shared memory.  Layers 2 and 3 stay on the FP64 DMMA path of k_fwd3 -- their A operand is a
+// per-chain activation, so the chains cannot share an MMA and a 32- or 16-column tcgen05.mma costs as much as
+// a 128-column one (70 clk floor, tools/umma_probe.cu).
+//
+// CTA = one 128-row tile at a time: 8 compute warps (16 rows each, the TMEM lane quarter of warp w is w & 3)
+// + 1 control warp whose elected lane streams the operands (bulk copies) and issues the MMAs.  Per chain:
+//   control : wait weights(q) and "TMEM drained(q-1)" -> 42 MMAs into 6 x 64 TMEM columns -> commit
+//   compute : wait commit(q) -> tcgen05.ld.16x256b (= the m16n8 accumulator fragment layout) -> recombine the
+//             6 diagonals to FP64 in registers (two int64 groups, 5 FP64 instructions per element) ->
+//             signal "drained" -> activation, layers 2/3, likelihood epilogue exactly as k_fwd3
+// so the integer MMAs of chain q+1 run under the FP64 work of chain q.
+constexpr int OZ_S = 6;                               // slices per operand
+constexpr int OZ_P = 46;                              // operands are rounded to |v| <= 2^46
+constexpr int OZ_XPLANE = 128 * 64;                   // bytes of one X slice plane of a 128-row tile
+constexpr int OZ_XTILE = OZ_S * OZ_XPLANE;
+constexpr int OZ_WPLANE = 64 * 64;
+constexpr int OZ_W1_BYTES = OZ_S * OZ_WPLANE + 64 * 8;   // 6 planes + colscale[64]
+constexpr int OZ_LBO = 128, OZ_SBO = 512;             // K-major, no swizzle: 8-row x 16-byte core matrices
+
+__host__ __device__ inline int oz_kmajor_offset(int r, int k) {
+  return (r >> 3) * OZ_SBO + (k >> 4) * OZ_LBO + (r & 7) * 16 + (k & 15);
+}
+
+// 47-bit integer image of v * 2^(46 - e) as 6 balanced base-256 digits
+__device__ __forceinline__ void oz_digits(double v, int e, int8_t (&d)[OZ_S]) {
+  long long q = __double2ll_rn(scalbn(v, OZ_P - e));
+#pragma unroll
+  for (int s = 0; s < OZ_S - 1; ++s) {
+    const int b = (int)((q + 128) & 255) - 128;
+    d[s] = (int8_t)b;
+    q = (q - b) >> 8;
+  }
+  d[OZ_S - 1] = (int8_t)q;
+}
+// exponent e with max < 2^e (0 for an all-zero row)
+__device__ __forceinline__ int oz_exponent(double mx) { return mx > 0.0 ? ilogb(mx) + 1 : 0; }
+
+// X (swizzled rows, F_pad = 64) -> slice tiles [n_tiles128][6][8 KB] + rowscale[n_tiles128 * 128] = 2^e_i.
+// One thread per row.  flag is set when a row holds a non-finite value (the tensor path is then not used).
+__global__ void k_slice_x(const double* __restrict__ x, long long n_pad16, uint8_t* __restrict__ xsl,
+                          double* __restrict__ rowscale, long long n_rows128, int* __restrict__ flag) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows128) return;
+  const int sw = (int)(r & 1) * 8;
+  double mx = 0.0;
+  bool bad = false;
+  if (r < n_pad16)
+    for (int k = 0; k < 64; ++k) {
+      const double v = x[r * 64 + (k ^ sw)];
+      bad |= !isfinite(v);
+      mx = fmax(mx, fabs(v));
+    }
+  if (bad) { atomicExch(flag, 1); mx = 0.0; }
+  const int e = oz_exponent(mx);
+  rowscale[r] = scalbn(1.0, e);
+  uint8_t* tile = xsl + (r >> 7) * (long long)OZ_XTILE;
+  const int rr = (int)(r & 127);
+  for (int k = 0; k < 64; ++k) {
+    int8_t d[OZ_S];
+    const double v = (r < n_pad16 && !bad) ? x[r * 64 + (k ^ sw)] : 0.0;
+    oz_digits(v, e, d);
+#pragma unroll
+    for (int s = 0; s < OZ_S; ++s) tile[s * OZ_XPLANE + oz_kmajor_offset(rr, k)] = (uint8_t)d[s];
+  }
+}
+
+// packed weight sets (W1 = [64][64] swizzled rows at offset 0) -> per set: 6 slice planes + colscale[n] = 2^(f_n - 28)
+__global__ void k_slice_w1(const double* __restrict__ wp, int PB, uint8_t* __restrict__ wt) {
+  const int c = blockIdx.x, n = threadIdx.x;       // 64 threads: one per output unit
+  const double* w = wp + (long long)c * PB + n * 64;
+  const int sw = (n & 1) * 8;
+  double mx = 0.0;
+  for (int k = 0; k < 64; ++k) mx = fmax(mx, fabs(w[k ^ sw]));
+  const int f = oz_exponent(mx);
+  uint8_t* out = wt + (long long)c * OZ_W1_BYTES;
+  reinterpret_cast<double*>(out + OZ_S * OZ_WPLANE)[n] = scalbn(1.0, f - 28);   // 2^(f - 92) * 2^64 (the recombined sum is scaled by 2^-64)
+  for (int k = 0; k < 64; ++k) {
+    int8_t d[OZ_S];
+    oz_digits(w[k ^ sw], f, d);
+#pragma unroll
+    for (int s = 0; s < OZ_S; ++s) out[s * OZ_WPLANE + oz_kmajor_offset(n, k)] = (uint8_t)d[s];
+  }
+}
+
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
+  // cute::UMMA::SmemDescriptor: start address [0,14), LBO [16,30), SBO [32,46) (all >> 4), version 1 at [46,48),
+  // layout type SWIZZLE_NONE (0) at [61,64)
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(OZ_LBO >> 4) << 16) | ((uint64_t)(OZ_SBO >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 16 TMEM lanes x 16 columns in the m16n8 accumulator-fragment layout (verified by tools/umma_probe.cu):
+// v[4h + {0,1,2,3}] = (row g, col 8h+2t), (g, 8h+2t+1), (g+8, 8h+2t), (g+8, 8h+2t+1)
+__device__ __forceinline__ void oz_ld_frag(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// (hi * 65536 + mid * 256 + lo) as a double: |value| < 2^51, so adding it to the integer image of 1.5 * 2^52 and
+// subtracting 1.5 * 2^52 converts exactly with ONE FP64 instruction (I2F.F64 runs at a fraction of the DFMA rate)
+__device__ __forceinline__ double oz_group(int hi, int mid, int lo) {
+  const long long v = (long long)hi * 65536 + (long long)mid * 256 + (long long)lo;
+  return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
+}
+
+constexpr int FWD3T_COMPUTE_WARPS = 8;
+constexpr int FWD3T_THREADS = (FWD3T_COMPUTE_WARPS + 1) * 32;
+
+template <int ACT, int MODE>
+__global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constant__ FwdParams p) {
+  constexpr int KP0 = 64, N1 = 64, N2 = 32, N3 = 16;
+  using G3 = Fwd3Geom<KP0, N1, N2, N3>;
+  constexpr bool PREDICT = (MODE == FWD3_PRED);
+  constexpr int REST = G3::PB - G3::B1_OFF;                       // FP64 part of a weight set: b1, W2, b2, W3, b3
+  constexpr uint32_t SLOT_BYTES = OZ_W1_BYTES + REST * 8;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const NetGeom& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+
+  // ---- shared memory carve-up
+  uint8_t* xsl = smem_raw;                                         // [6][8 KB] X slices of the current tile
+  uint8_t* ring = xsl + OZ_XTILE;                                  // [2][SLOT_BYTES]
+  double* tab = reinterpret_cast<double*>(ring + 2 * SLOT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + BNN_EXP_TAB_SIZE);
+  uint64_t* full = bars;            // [2] weights of a use have landed
+  uint64_t* empty = bars + 2;       // [2] all compute warps are done with the slot
+  uint64_t* xfull = bars + 4;       // X slices of the tile have landed
+  uint64_t* tfull = bars + 5;       // layer-1 accumulators of a use are complete in TMEM
+  uint64_t* tfree = bars + 6;       // all compute warps have drained the accumulators
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  int* cnt = reinterpret_cast<int*>(bars + 8);
+  const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
+
+  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], FWD3T_COMPUTE_WARPS); mbar_init(&empty[1], FWD3T_COMPUTE_WARPS);
+    mbar_init(xfull, 1); mbar_init(tfull, 1); mbar_init(tfree, FWD3T_COMPUTE_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == FWD3T_COMPUTE_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_iter = (p.n_tiles128 + gridDim.x - 1) / gridDim.x;
+  const long long total_q = n_iter * p.C;            // weight-set uses, identical for every warp of the CTA
+
+  if (warp == FWD3T_COMPUTE_WARPS) {
+    // ======================= control warp: operand streaming + MMA issue (one elected lane)
+    if (lane == 0) {
+      auto load_weights = [&](long long use) {
+        const int b = (int)(use & 1), c = (int)(use % p.C);
+        uint8_t* slot = ring + (size_t)b * SLOT_BYTES;
+        mbar_arrive_expect_tx(&full[b], SLOT_BYTES);
+        bulk_g2s(slot, p.wt + (size_t)c * OZ_W1_BYTES, OZ_W1_BYTES, &full[b]);
+        bulk_g2s(slot + OZ_W1_BYTES, p.wp + (size_t)c * G3::PB + G3::B1_OFF, REST * 8, &full[b]);
+      };
+      for (long long u = 0; u < 2 && u < total_q; ++u) load_weights(u);
+      // instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, S8 x S8, K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t xdesc = oz_smem_desc(smem_u32(xsl));
+      long long q = 0;
+      for (long long it = 0; it < n_iter; ++it) {
+        const long long tile = it * gridDim.x + blockIdx.x;
+        // the MMAs of the previous tile must be complete before its X slices are overwritten
+        if (q > 0) mbar_wait(tfull, (uint32_t)((q - 1) & 1));
+        if (tile < p.n_tiles128) {
+          mbar_arrive_expect_tx(xfull, OZ_XTILE);
+          bulk_g2s(xsl, p.xsl + (size_t)tile * OZ_XTILE, OZ_XTILE, xfull);
+          mbar_wait(xfull, (uint32_t)(it & 1));
+        }
+        for (int c = 0; c < p.C; ++c, ++q) {
+          const int b = (int)(q & 1);
+          mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
+          if (q > 0) mbar_wait(tfree, (uint32_t)((q - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (tile < p.n_tiles128) {
+            const uint64_t wdesc = oz_smem_desc(smem_u32(ring + (size_t)b * SLOT_BYTES));
+#pragma unroll 1
+            for (int d = 0; d < OZ_S; ++d) {               // diagonal T = 10 - d -> TMEM columns [64 d, 64 d + 64)
+              const int T = 2 * (OZ_S - 1) - d;
+              uint32_t acc = 0;
+              for (int sx = T - (OZ_S - 1); sx <= OZ_S - 1; ++sx) {
+                const int sw = T - sx;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  oz_mma(tmem + 64 * d, xdesc + (uint64_t)((sx * OZ_XPLANE + ks * 2 * OZ_LBO) >> 4),
+                         wdesc + (uint64_t)((sw * OZ_WPLANE + ks * 2 * OZ_LBO) >> 4), idesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+          oz_commit(tfull);          // arrives when every MMA issued so far is complete (also with none issued)
+          // refill the slot of use q-1 with use q+1 once the compute warps have released it
+          if (q >= 1 && q + 1 < total_q) {
+            mbar_wait(&empty[b ^ 1], (uint32_t)(((q - 1) >> 1) & 1));
+            load_weights(q + 1);
+          }
+        }
+      }
+    }
+  } else {
+    // ======================= compute warps
+    const int rbase = 32 * (warp & 3) + 16 * (warp >> 2);       // rows of this warp inside the 128-row tile
+    const uint32_t tlane = (uint32_t)rbase << 16;
+    long long q = 0;
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = it * gridDim.x + blockIdx.x;
+      const long long wt = tile * 8 + (rbase >> 4);
+      const bool have_tile = tile < p.n_tiles128 && wt < p.n_tiles16;
+      int y[2] = {0, 0};
+      double wgt[2] = {1.0, 1.0};
+      double rsc[2] = {0.0, 0.0};
+      double acc3[N3 / 8][4];
+      bool prev_valid = false;
+#pragma unroll
+      for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
+      if (have_tile) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long row = wt * 16 + gq + 8 * h;
+          rsc[h] = p.x_rowscale[row];
+          if (row < p.n_total) {
+            y[h] = p.labels[row];
+            if (MODE == FWD3_LIK_W) {
+              if (p.class_w) wgt[h] *= p.class_w[y[h]];
+              if (p.inst_w && row < p.n_train) wgt[h] *= p.inst_w[row];
+            }
+          }
+        }
+      }
+      for (int c = 0; c < p.C; ++c, ++q) {
+        const int b = (int)(q & 1);
+        mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
+        mbar_wait(tfull, (uint32_t)(q & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint8_t* slot = ring + (size_t)b * SLOT_BYTES;
+        const double* csc = reinterpret_cast<const double*>(slot + OZ_S * OZ_WPLANE);
+        const double* W = reinterpret_cast<const double*>(slot + OZ_W1_BYTES) - G3::B1_OFF;   // k_fwd3 offsets
+        const double a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
+        const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
+        // ---------------- layer 1: drain and recombine the integer accumulators; the likelihood epilogue of
+        // the previous weight set (latency-bound FP64 chains and shuffles) is interleaved stage by stage
+        double acc1[N1 / 8][4];
+        RowStats<N3> rs;
+        LikRow lr;
+        const int K = g.K;
+#pragma unroll
+        for (int jj = 0; jj < N1 / 16; ++jj) {
+          uint32_t v[OZ_S][8];
+#pragma unroll
+          for (int d = 0; d < OZ_S; ++d) oz_ld_frag(tmem + tlane + 64 * d + 16 * jj, v[d]);
+          if (!PREDICT) {
+            if (jj == 0) qs_max<N3>(acc3, K, t, rs);
+            else if (jj == 1) qs_exp<N3, 0, true>(acc3, K, t, y, tab, rs);
+            else if (jj == 2) qs_exp<N3, 1, true>(acc3, K, t, y, tab, rs);
+            else {
+              qs_reduce<N3, true>(rs);
+              lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, prev_valid && have_tile);
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = 2 * jj + hh;
+            const double2 sc = *reinterpret_cast<const double2*>(csc + 8 * j + 2 * t);
+            const double2 bb = *reinterpret_cast<const double2*>(W + G3::B1_OFF + 8 * j + 2 * t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double hi = oz_group((int)v[0][4 * hh + e], (int)v[1][4 * hh + e], (int)v[2][4 * hh + e]);
+              const double lo = oz_group((int)v[3][4 * hh + e], (int)v[4][4 * hh + e], (int)v[5][4 * hh + e]);
+              const double hsum = fma(lo, 5.9604644775390625e-08, hi);          // hi + lo * 2^-24
+              acc1[j][e] = fma(hsum * rsc[e >> 1], (e & 1) ? sc.y : sc.x, (e & 1) ? bb.y : bb.x);
+            }
+          }
+        }
+        // the accumulators are in registers: the tensor core may start the next weight set
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfree);
+        if (!PREDICT) quad_lik_commit(p, c - 1, wt, lane, cnt, lr, prev_valid && have_tile);
+        // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = activated acc1, no data movement)
+        double acc2[N2 / 8][4];
+#pragma unroll
+        for (int j = 0; j < N2 / 8; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B2_OFF + 8 * j + 2 * t);
+          acc2[j][0] = bb.x; acc2[j][1] = bb.y; acc2[j][2] = bb.x; acc2[j][3] = bb.y;
+        }
+        {
+          const double* wr = W + G3::W2_OFF + gq * N1;
+          const int sw = (gq & 1) * G3::SW1;
+          act_tile<ACT>(acc1[0], a1, tab);
+#pragma unroll
+          for (int kg = 0; kg < N1 / 8 - 2; ++kg) {
+            act_tile<ACT>(acc1[kg + 1], a1, tab);
+            const int col = (8 * kg + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N2 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + col);
+              dmma16x8x8(acc2[j], acc1[kg][0], acc1[kg][2], acc1[kg][1], acc1[kg][3], bb.x, bb.y);
+            }
+          }
+          {
+            constexpr int k0 = N1 / 8 - 2, k1 = N1 / 8 - 1;
+            act_tile<ACT>(acc1[k1], a1, tab);
+            const int c0 = (8 * k0 + 2 * t) ^ sw, c1 = (8 * k1 + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N2 / 8; ++j) {
+              const double2 b0 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c0);
+              const double2 b1 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c1);
+              dmma16x8x8(acc2[j], acc1[k0][0], acc1[k0][2], acc1[k0][1], acc1[k0][3], b0.x, b0.y);
+              dmma16x8x8(acc2[j], acc1[k1][0], acc1[k1][2], acc1[k1][1], acc1[k1][3], b1.x, b1.y);
+            }
+          }
+        }
+        // ---------------- layer 3: [16 x N2] x [N2 x N3]
+#pragma unroll
+        for (int j = 0; j < N3 / 8; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
+          acc3[j][0] = bb.x; acc3[j][1] = bb.y; acc3[j][2] = bb.x; acc3[j][3] = bb.y;
+        }
+        {
+          const double* wr = W + G3::W3_OFF + gq * N2;
+          const int sw = (gq & 1) * G3::SW2;
+          act_tile<ACT>(acc2[0], a2, tab);
+#pragma unroll
+          for (int kg = 0; kg < N2 / 8; ++kg) {
+            if (kg + 1 < N2 / 8) act_tile<ACT>(acc2[kg + 1], a2, tab);
+            const int col = (8 * kg + 2 * t) ^ sw;
+#pragma unroll
+            for (int j = 0; j < N3 / 8; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N2 + col);
+              dmma16x8x8(acc3[j], acc2[kg][0], acc2[kg][2], acc2[kg][1], acc2[kg][3], bb.x, bb.y);
+            }
+          }
+        }
+        // weights of this use are no longer needed by this warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[b]);
+        prev_valid = true;
+      }
+      if (have_tile && !PREDICT) {
+        // drain the software pipeline: epilogue of the last weight set of this tile
+        RowStats<N3> rs;
+        quad_softmax_stats<N3, true>(acc3, g.K, t, y, tab, rs);
+        const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, true);
+        quad_lik_commit(p, p.C - 1, wt, lane, cnt, lr, true);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == FWD3T_COMPUTE_WARPS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (n_cnt) {
+    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
+      if (cnt[i]) atomicAdd(&p.counts[i], cnt[i]);
+  }
+}
+
+cudaError_t bnn_launch_slice_x(const double* x, long long n_pad16, uint8_t* xsl, double* rowscale, long long n_tiles128,
+                               int* flag, cudaStream_t st) {
+  const long long rows = n_tiles128 * 128;
+  k_slice_x<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(x, n_pad16, xsl, rowscale, rows, flag);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_slice_w1(const double* wp, int PB, uint8_t* wt, int n_sets, cudaStream_t st) {
+  k_slice_w1<<<n_sets, 64, 0, st>>>(wp, PB, wt);
+  return cudaGetLastError();
+}
+size_t bnn_slice_x_tile_bytes() { return OZ_XTILE; }
+size_t bnn_slice_w1_bytes() { return OZ_W1_BYTES; }
+
+template <int ACT, int MODE>
+static cudaError_t launch_fwd3t(const FwdParams& p, int n_sms, cudaStream_t st) {
+  auto kern = k_fwd3t<ACT, MODE>;
+  using G3 = Fwd3Geom<64, 64, 32, 16>;
+  const size_t slot = OZ_W1_BYTES + (size_t)(G3::PB - G3::B1_OFF) * 8;
+  size_t smem = OZ_XTILE + 2 * slot + BNN_EXP_TAB_SIZE * sizeof(double) + 8 * sizeof(uint64_t) +
+                (size_t)p.C * (2 + 2 * p.g.K) * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (smem > 232448) return cudaErrorInvalidConfiguration;
+  int grid = (int)(p.n_tiles128 < n_sms ? p.n_tiles128 : n_sms);
+  kern<<<grid, FWD3T_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
 // host-side launchers
 // =============================================================================================
 template <int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
@@ -1147,6 +1571,11 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
     if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {
       if (which) *which = "k_fwd3<swish,64,64,32,16>";
+      if (!predict && p.xsl && p.wt) {
+        if (which) *which = "k_fwd3t<swish,64,64,32,16>";
+        if (p.class_w || p.inst_w) return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK_W>(p, n_sms, st);
+        return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK>(p, n_sms, st);
+      }
       if (predict) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, FWD3_PRED>(p, n_sms, st);
       if (p.class_w || p.inst_w) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK_W>(p, n_sms, st);
       return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK>(p, n_sms, st);

@@ -37,6 +37,12 @@ struct ChainDev {
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
                                const char** which);
 bool bnn_sparse_fits(const FwdParams& p);
+// tensor-core first layer (k_fwd3t): operand slicing
+cudaError_t bnn_launch_slice_x(const double* x, long long n_pad16, uint8_t* xsl, double* rowscale, long long n_tiles128,
+                               int* flag, cudaStream_t st);
+cudaError_t bnn_launch_slice_w1(const double* wp, int PB, uint8_t* wt, int n_sets, cudaStream_t st);
+size_t bnn_slice_x_tile_bytes();
+size_t bnn_slice_w1_bytes();
 cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
                               const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st);
 cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st);
