@@ -203,8 +203,17 @@ int bnn_forward_time(bnn_ctx* ctx, double* total_ms, int64_t* n_launches, int32_
 int bnn_measure_fp64_peak(bnn_ctx* ctx, double* tflops);
 /* Name of the forward kernel variant used by the last call ("k_fwd3<...>" or "k_fwd_generic"). */
 const char* bnn_last_kernel(const bnn_ctx* ctx);
+
+/* Debugging / tuning aids (no reference counterpart).
+ * bnn_debug_read_part: per-warp-tile partial sums of the last forward pass, [sets in pass][slots][n_tiles16].
+ * bnn_debug_counters : 48 clock counters of k_fwd3t, all zero unless the library was built with -DBNN_DBG_WAITCLK. */
+int bnn_debug_read_part(bnn_ctx* ctx, double* out_host, int64_t n_doubles);
+int bnn_debug_counters(bnn_ctx* ctx, unsigned long long* out48_host);
 /* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests);
- * "time_forward" = 1 enables bnn_forward_time. */
+ * "time_forward" = 1 enables bnn_forward_time; "sparse" = 0 evaluates masked chains with the dense kernels;
+ * "tensor_l1" = 1 (default 0, env NPBNN_TENSOR_L1) evaluates layer 1 of the 64-64-32-10 swish network as exact
+ * int8 tensor-core products (k_fwd3t: tcgen05 + TMEM, Ozaki slicing; results agree with the FP64 kernel to
+ * 4e-16 relative; opt-in). */
 int bnn_set_option(bnn_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus

@@ -77,6 +77,8 @@ _SIGNATURES = {
     "bnn_launch_count": (C.c_int64, [C.c_void_p]),
     "bnn_last_kernel": (C.c_char_p, [C.c_void_p]),
     "bnn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bnn_debug_read_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "bnn_debug_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

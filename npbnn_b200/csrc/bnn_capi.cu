@@ -63,7 +63,7 @@ struct bnn_ctx {
   bool has_iw = false, has_cw = false;
   long long n_train = 0, n_test = 0, n_total = 0, n_pad = 0, n_tiles16 = 0;
   // workspaces
-  DevBuf exp_tab, wp_scratch, part, counts_scratch, xs_pred, ov_cols, ov_vals;
+  DevBuf exp_tab, exp_tab_small, wp_scratch, part, counts_scratch, xs_pred, ov_cols, ov_vals;
   DevBuf h_w, h_alpha, h_sigma, h_loglik, h_sums, h_counts;    // device staging of the *_host entry points
   // chains
   int C = 0;
@@ -77,7 +77,7 @@ struct bnn_ctx {
   DevBuf xsl, x_rowscale, wt, oz_flag;
   long long n_tiles128 = 0;
   bool tensor_ok = false;           // the staged data and the network shape qualify
-  int opt_tensor = 1;               // option "tensor_l1": 0 keeps layer 1 on the FP64 DMMA path
+  int opt_tensor = 0;               // option "tensor_l1" (env NPBNN_TENSOR_L1): 1 = layer 1 on the int8 tensor cores (opt-in)
   DevBuf sp_items, sp_widx;
   int sp_prog_len = 0, sp_n_items = 0, sp_slots = 1, sp_wlen = 0;
   bool use_sparse = false;
@@ -149,6 +149,7 @@ static FwdParams base_params(const bnn_ctx* c) {
   p.inst_w = c->has_iw ? c->inst_w.as<double>() : nullptr;
   p.class_w = c->has_cw ? c->class_w.as<double>() : nullptr;
   p.exp_tab = c->exp_tab.as<double>();
+  p.exp_tab_small = c->exp_tab_small.as<double>();
   p.NF = n_slots(c->g);
   p.inv_sets = 1.0;
   return p;
@@ -187,6 +188,9 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = exp2((double)j / BNN_EXP_TAB_SIZE);
   cudaError_t e = c->exp_tab.ensure(sizeof(double) * BNN_EXP_TAB_SIZE, false, 0);
   if (e == cudaSuccess) e = cudaMemcpy(c->exp_tab.p, tab.data(), sizeof(double) * BNN_EXP_TAB_SIZE, cudaMemcpyHostToDevice);
+  for (int j = 0; j < 256; ++j) tab[j] = exp2((double)j / 256.0);
+  if (e == cudaSuccess) e = c->exp_tab_small.ensure(sizeof(double) * 256, false, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(c->exp_tab_small.p, tab.data(), sizeof(double) * 256, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     delete c;
     return fail(std::string("bnn_ctx_create: ") + cudaGetErrorString(e));
@@ -199,7 +203,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->xs, &c->labels, &c->targets, &c->inst_w, &c->class_w, &c->exp_tab, &c->wp_scratch, &c->part,
+  DevBuf* bufs[] = {&c->xs, &c->labels, &c->targets, &c->inst_w, &c->class_w, &c->exp_tab, &c->exp_tab_small, &c->wp_scratch, &c->part,
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
@@ -218,6 +222,25 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   if (strcmp(name, "sparse") == 0) { c->opt_sparse = value; return 0; }
   if (strcmp(name, "tensor_l1") == 0) { c->opt_tensor = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
+}
+
+// tuning instrumentation of k_fwd3t (all zeros unless the library was built with -DBNN_DBG_WAITCLK)
+int bnn_debug_counters(bnn_ctx* c, unsigned long long* out32_host) {
+  REQUIRE(c && out32_host, "bnn_debug_counters: null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(bnn_debug_counters_read(out32_host));
+  return 0;
+}
+
+// debugging aid: per-warp-tile partial sums of the last forward pass, [n_sets_in_pass][NF][n_tiles16]
+int bnn_debug_read_part(bnn_ctx* c, double* out_host, int64_t n_doubles) {
+  REQUIRE(c && out_host, "bnn_debug_read_part: null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  REQUIRE((size_t)n_doubles * sizeof(double) <= c->part.bytes, "bnn_debug_read_part: more than the workspace holds");
+  CUDA_TRY(cudaMemcpy(out_host, c->part.p, sizeof(double) * (size_t)n_doubles, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 const char* bnn_last_kernel(const bnn_ctx* c) { return c ? c->last_kernel : ""; }
@@ -856,6 +879,7 @@ int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev,
   p.mean_out = mean_dev; p.votes_out = votes_dev; p.dense_out = dense_dev;
   p.inv_sets = (double)n_sets;   // divisor (np.mean and the vote share divide, BNN_lib.py:390-392)
   p.exp_tab = c->exp_tab.as<double>();
+  p.exp_tab_small = c->exp_tab_small.as<double>();
   CUDA_TRY(timed_forward(c, p, true, st));
   c->launches += 3;
   return 0;

@@ -62,6 +62,10 @@ __host__ __device__ inline int bnn_packed_index(const LayerGeom& g, int r, int c
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1, double a2, double a3,
                                            double b0, double b1) {
+#ifdef BNN_DBG_NODMMA         // tuning experiment only: is the FP64 MMA what something else is waiting for?
+  c[0] += a0 * b0; c[1] += a1 * b1; c[2] += a2 * b0; c[3] += a3 * b1;
+  return;
+#endif
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
@@ -75,35 +79,33 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1,
 //         (BNN_EXP_TAB_BITS=8: 256 entries + degree 4, 9 instructions)
 //   rcp : MUFU.RCP64H seed + one third-order step, 3 FP64 instructions
 // ---------------------------------------------------------------------------------------------
+// TB = log2(table entries): 11 (2048 entries + degree 3) or 8 (256 entries + degree 4, one more instruction;
+// used where shared memory is short)
+template <int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ double bnn_exp_core(double x, const double* __restrict__ tab) {
+  static_assert(TB == 8 || TB == 11, "exp table: 256 or 2048 entries");
   const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest-integer trick
-#if BNN_EXP_TAB_BITS == 11
-  const double INV = 2954.639443740597;              // 2048 / ln 2
-  const double C_HI = 0.0003384507708688034;         // ln2/2048, low 24 mantissa bits zero (0x1.62e42fe000000p-12)
-  const double C_LO = 8.889824211446026e-13;         // ln2/2048 - C_HI
-#elif BNN_EXP_TAB_BITS == 8
-  const double INV = 369.3299304675746271;           // 256 / ln 2
-  const double C_HI = 0.00270760617331689;           // ln2/256, low 21 mantissa bits zero (0x1.62e42fee00000p-9)
-  const double C_LO = 7.453964567463233e-13;         // ln2/256 - C_HI
-#else
-#error "BNN_EXP_TAB_BITS must be 8 or 11"
-#endif
+  // INV = 2^TB / ln 2 ; C_HI + C_LO = ln2 / 2^TB with the low 24 (21) mantissa bits of C_HI zero
+  const double INV = (TB == 11) ? 2954.639443740597 : 369.3299304675746271;
+  const double C_HI = (TB == 11) ? 0.0003384507708688034 : 0.00270760617331689;
+  const double C_LO = (TB == 11) ? 8.889824211446026e-13 : 7.453964567463233e-13;
   double t = fma(x, INV, MAGIC);
   int k = __double2loint(t);
   double kd = t - MAGIC;
   double r = fma(kd, -C_HI, x);
   r = fma(kd, -C_LO, r);
-#if BNN_EXP_TAB_BITS == 11
-  double q = fma(r, 1.66666666666666657e-01, 0.5);   // |r| <= ln2/4096: r^4/24 < 4e-17
-#else
-  double q = fma(r, 4.16666666666666644e-02, 1.66666666666666657e-01);
-  q = fma(r, q, 0.5);
-#endif
+  double q;
+  if (TB == 11) {
+    q = fma(r, 1.66666666666666657e-01, 0.5);        // |r| <= ln2/4096: r^4/24 < 4e-17
+  } else {
+    q = fma(r, 4.16666666666666644e-02, 1.66666666666666657e-01);
+    q = fma(r, q, 0.5);
+  }
   double r2 = r * r;
   double p = fma(r2, q, r);
-  double T = tab[k & (BNN_EXP_TAB_SIZE - 1)];
+  double T = tab[k & ((1 << TB) - 1)];
   double res = fma(T, p, T);
-  int n = k >> BNN_EXP_TAB_BITS;
+  int n = k >> TB;
   return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
 
@@ -111,11 +113,12 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
 // FP64 chains of several independent evaluations with the surrounding DMMAs).
 //
 // exp for arguments <= 0 (softmax): results below 2^-1022 flush to 0, NaN propagates.
+template <int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict__ tab) {
   const int hx = __double2hiint(x);
   const int ax = hx & 0x7fffffff;
   const bool big = ax >= 0x4086232c;                  // |x| >= 708.3965 (also inf / NaN): exp(x) < 2^-1022
-  double res = bnn_exp_core(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
+  double res = bnn_exp_core<TB>(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
   res = big ? 0.0 : res;
   // NaN in => NaN out, by OR-ing quiet-NaN bits into the result (an integer op: a select here makes ptxas
   // branch around the whole evaluation, which breaks the interleaving with the surrounding MMAs)
@@ -125,11 +128,12 @@ __device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict
 
 // exp for activations: argument clamped to [-708, 708] (1/(1+e) is then NaN-free and the clamped tails
 // differ from the exact value by < 1e-300 in the activation); NaN handling is done by the caller.
+template <int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ double bnn_exp_clamped(double x, const double* __restrict__ tab) {
   const int hx = __double2hiint(x);
   const bool big = (hx & 0x7fffffff) >= 0x40862000;           // |x| >= 708 (also inf / NaN)
   const double xc = big ? __hiloint2double((hx & 0x80000000) | 0x40862000, 0) : x;
-  return bnn_exp_core(xc, tab);
+  return bnn_exp_core<TB>(xc, tab);
 }
 
 // 1/d for finite d >= 1: MUFU.RCP64H seed (rcp.approx.ftz.f64) + one third-order step
@@ -178,17 +182,17 @@ __device__ __forceinline__ double bnn_log_ge1(double x) {
 
 // Hidden-layer activation, matching the reference formulas (BNN_lib.py:50-66):
 //   swish z*(1+exp(-z))^-1 ; tanh 1 - 2/(exp(2z)+1) ; ReLU ; leaky (alpha*z for z<0)
-template <int ACT>
+template <int ACT, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ double bnn_act(double z, double alpha, const double* __restrict__ tab) {
   if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
   if (ACT == BNN_ACT_SWISH) {
     // NaN: z * finite = NaN.  +-inf: inf * 1 = inf, -inf * ~0 -> the reference gives NaN (-inf * 0); here
     // -inf * 3e-308 = -inf.  Both poison the likelihood (NaN or -inf log-posterior => proposal rejected).
-    double e = bnn_exp_clamped(-z, tab);
+    double e = bnn_exp_clamped<TB>(-z, tab);
     return z * bnn_rcp(1.0 + e);
   }
-  double e = bnn_exp_clamped(2.0 * z, tab);
+  double e = bnn_exp_clamped<TB>(2.0 * z, tab);
   double r = fma(-2.0, bnn_rcp(e + 1.0), 1.0);
   const bool is_nan = ((unsigned long long)__double_as_longlong(z) & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL;
   return __hiloint2double(__double2hiint(r) | (is_nan ? 0x7ff80000 : 0), __double2loint(r));
@@ -239,6 +243,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// wait with back-off: for a control thread that would otherwise spin on the issue slots of the warps it feeds
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(32);
+  }
+}
 // global -> shared bulk copy, completion signalled on `bar` (bytes multiple of 16, 16-byte aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -272,7 +286,8 @@ struct FwdParams {
   double* votes_out;        // [n, K] or null
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
-  const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j/256)
+  const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j / BNN_EXP_TAB_SIZE)
+  const double* exp_tab_small;   // [256] 2^(j / 256)
   // tensor-core first layer (k_fwd3t): int8 slice tiles of X, per-row scales, per-set slices of W1; null = off
   const uint8_t* xsl;
   const double* x_rowscale;

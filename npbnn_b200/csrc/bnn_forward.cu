@@ -527,13 +527,13 @@ struct Fwd3Geom {
 #define FWD3_WARPS 12
 #endif
 
-template <int ACT>
+template <int ACT, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void act_tile(double (&a)[4], double alpha, const double* tab) {
 #ifdef BNN_DBG_NOACT      // tuning experiment only: how fast is the kernel without activations?
   return;
 #endif
 #pragma unroll
-  for (int e = 0; e < 4; ++e) a[e] = bnn_act<ACT>(a[e], alpha, tab);
+  for (int e = 0; e < 4; ++e) a[e] = bnn_act<ACT, TB>(a[e], alpha, tab);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +579,7 @@ __device__ __forceinline__ void qs_max(const double (&acc)[N3 / 8][4], int K, in
 }
 
 // stage 2: exp(z - max) of this thread's columns of row h, local sums
-template <int N3, int H, bool NEED_ZY>
+template <int N3, int H, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void qs_exp(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
                                        const double* tab, RowStats<N3>& r) {
   double S = 0.0, zy = 0.0;
@@ -590,7 +590,7 @@ __device__ __forceinline__ void qs_exp(const double (&acc)[N3 / 8][4], int K, in
       const int col = 8 * j + 2 * t + e;
       const double v = acc[j][2 * H + e];
       // padded columns: argument -1000 => exp flushes to exactly 0 (no branch around the evaluation)
-      const double ex = bnn_exp_neg((col < K) ? v - r.m[H] : -1000.0, tab);
+      const double ex = bnn_exp_neg<TB>((col < K) ? v - r.m[H] : -1000.0, tab);
       r.ev[H][2 * j + e] = ex;
       S += ex;
       if (NEED_ZY) zy = (col == y[H]) ? v : zy;
@@ -613,12 +613,12 @@ __device__ __forceinline__ void qs_reduce(RowStats<N3>& r) {
   }
 }
 
-template <int N3, bool NEED_ZY>
+template <int N3, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void quad_softmax_stats(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
                                                    const double* tab, RowStats<N3>& r) {
   qs_max<N3>(acc, K, t, r);
-  qs_exp<N3, 0, NEED_ZY>(acc, K, t, y, tab, r);
-  qs_exp<N3, 1, NEED_ZY>(acc, K, t, y, tab, r);
+  qs_exp<N3, 0, NEED_ZY, TB>(acc, K, t, y, tab, r);
+  qs_exp<N3, 1, NEED_ZY, TB>(acc, K, t, y, tab, r);
   qs_reduce<N3, NEED_ZY>(r);
 }
 
@@ -1018,8 +1018,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 // so the integer MMAs of chain q+1 run under the FP64 work of chain q.
 constexpr int OZ_S = 6;                               // slices per operand
 constexpr int OZ_P = 46;                              // operands are rounded to |v| <= 2^46
-constexpr int OZ_XPLANE = 128 * 64;                   // bytes of one X slice plane of a 128-row tile
-constexpr int OZ_XTILE = OZ_S * OZ_XPLANE;
+constexpr int OZ_XROW = OZ_S * 64;                    // bytes of one row of X slices
+constexpr int OZ_XTILE = 128 * OZ_XROW;
 constexpr int OZ_WPLANE = 64 * 64;
 constexpr int OZ_W1_BYTES = OZ_S * OZ_WPLANE + 64 * 8;   // 6 planes + colscale[64]
 constexpr int OZ_LBO = 128, OZ_SBO = 512;             // K-major, no swizzle: 8-row x 16-byte core matrices
@@ -1042,7 +1042,8 @@ __device__ __forceinline__ void oz_digits(double v, int e, int8_t (&d)[OZ_S]) {
 // exponent e with max < 2^e (0 for an all-zero row)
 __device__ __forceinline__ int oz_exponent(double mx) { return mx > 0.0 ? ilogb(mx) + 1 : 0; }
 
-// X (swizzled rows, F_pad = 64) -> slice tiles [n_tiles128][6][8 KB] + rowscale[n_tiles128 * 128] = 2^e_i.
+// X (swizzled rows, F_pad = 64) -> slices [n_rows128][6][64 B] (a row's 6 x 64 bytes are contiguous: the helper
+// thread that owns the row copies them to TMEM, where they are the A operand) + rowscale[n_rows128] = 2^e_i.
 // One thread per row.  flag is set when a row holds a non-finite value (the tensor path is then not used).
 __global__ void k_slice_x(const double* __restrict__ x, long long n_pad16, uint8_t* __restrict__ xsl,
                           double* __restrict__ rowscale, long long n_rows128, int* __restrict__ flag) {
@@ -1060,18 +1061,23 @@ __global__ void k_slice_x(const double* __restrict__ x, long long n_pad16, uint8
   if (bad) { atomicExch(flag, 1); mx = 0.0; }
   const int e = oz_exponent(mx);
   rowscale[r] = scalbn(1.0, e);
-  uint8_t* tile = xsl + (r >> 7) * (long long)OZ_XTILE;
-  const int rr = (int)(r & 127);
-  for (int k = 0; k < 64; ++k) {
-    int8_t d[OZ_S];
-    const double v = (r < n_pad16 && !bad) ? x[r * 64 + (k ^ sw)] : 0.0;
-    oz_digits(v, e, d);
+  uint32_t* out = reinterpret_cast<uint32_t*>(xsl + r * (long long)(OZ_S * 64));
+  for (int k4 = 0; k4 < 16; ++k4) {
+    uint32_t w[OZ_S] = {0, 0, 0, 0, 0, 0};
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = 4 * k4 + kk;
+      int8_t d[OZ_S];
+      const double v = (r < n_pad16 && !bad) ? x[r * 64 + (k ^ sw)] : 0.0;
+      oz_digits(v, e, d);
 #pragma unroll
-    for (int s = 0; s < OZ_S; ++s) tile[s * OZ_XPLANE + oz_kmajor_offset(rr, k)] = (uint8_t)d[s];
+      for (int sl = 0; sl < OZ_S; ++sl) w[sl] |= (uint32_t)(uint8_t)d[sl] << (8 * kk);
+    }
+#pragma unroll
+    for (int sl = 0; sl < OZ_S; ++sl) out[sl * 16 + k4] = w[sl];
   }
 }
 
-// packed weight sets (W1 = [64][64] swizzled rows at offset 0) -> per set: 6 slice planes + colscale[n] = 2^(f_n - 28)
+// packed weight sets (W1 = [64][64] swizzled rows at offset 0) -> per set: 6 slice planes + colscale[n] = 2^(f_n - 48)
 __global__ void k_slice_w1(const double* __restrict__ wp, int PB, uint8_t* __restrict__ wt) {
   const int c = blockIdx.x, n = threadIdx.x;       // 64 threads: one per output unit
   const double* w = wp + (long long)c * PB + n * 64;
@@ -1080,7 +1086,7 @@ __global__ void k_slice_w1(const double* __restrict__ wp, int PB, uint8_t* __res
   for (int k = 0; k < 64; ++k) mx = fmax(mx, fabs(w[k ^ sw]));
   const int f = oz_exponent(mx);
   uint8_t* out = wt + (long long)c * OZ_W1_BYTES;
-  reinterpret_cast<double*>(out + OZ_S * OZ_WPLANE)[n] = scalbn(1.0, f - 28);   // 2^(f - 92) * 2^64 (the recombined sum is scaled by 2^-64)
+  reinterpret_cast<double*>(out + OZ_S * OZ_WPLANE)[n] = scalbn(1.0, f - 48);   // 2^(f - 92) * 2^44: the helpers park the recombined sum scaled by 2^-44
   for (int k = 0; k < 64; ++k) {
     int8_t d[OZ_S];
     oz_digits(w[k ^ sw], f, d);
@@ -1120,41 +1126,114 @@ __device__ __forceinline__ double oz_group(int hi, int mid, int lo) {
   return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
 }
 
-constexpr int FWD3T_COMPUTE_WARPS = 8;
-constexpr int FWD3T_THREADS = (FWD3T_COMPUTE_WARPS + 1) * 32;
+// 32 TMEM lanes (thread = lane = row) x 8 consecutive 32-bit columns
+__device__ __forceinline__ void oz_ld_row8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+constexpr int FWD3T_COMPUTE_WARPS = 8;     // 16 rows each: layers 2 / 3 (DMMA) + likelihood epilogue
+constexpr int FWD3T_HELPER_WARPS = 4;      // one per TMEM lane quarter: drain, recombine, activate layer 1
+constexpr int FWD3T_CONTROL_WARP = 12;     // lane 0: weight streaming + MMA issue (warps 13-15 only donate registers)
+constexpr int FWD3T_THREADS = 16 * 32;
+// registers per thread after setmaxnreg (the kernel is launched with 512 x 128): 8 x 168 + 4 x 128 + 4 x 40 <= 2048
+constexpr int FWD3T_REGS_COMPUTE = 168, FWD3T_REGS_CONTROL = 40;
+
+// activated layer-1 outputs of the 128-row tile in shared memory: row r, 16-byte chunk c (columns 2c, 2c+1) at
+// r * 512 + ((c ^ s(r)) * 16), s(r) = ((r & 1) << 2) | ((r >> 1) & 3): conflict-free both for the helpers'
+// stores (lane = row, same chunk) and for the compute warps' A-fragment loads (rows g, chunks 4kg + t)
+__device__ __forceinline__ int a1_swz(int r) { return ((r & 1) << 2) | ((r >> 1) & 3); }
+
+__device__ __forceinline__ void oz_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void oz_ld_row16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void oz_st_row16(uint32_t taddr, const uint4 (&w)[4]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(w[0].x), "r"(w[0].y), "r"(w[0].z), "r"(w[0].w), "r"(w[1].x), "r"(w[1].y), "r"(w[1].z), "r"(w[1].w), "r"(w[2].x),
+      "r"(w[2].y), "r"(w[2].z), "r"(w[2].w), "r"(w[3].x), "r"(w[3].y), "r"(w[3].z), "r"(w[3].w)
+      : "memory");
+}
+
+// tuning instrumentation (build with -DBNN_DBG_WAITCLK): clocks spent per wait site / phase, summed over lane 0 of
+// every warp; slots 0-15 helper 0 (control), 16-31 helpers 1-3, 32-47 compute warps.  Read and reset with bnn_debug_counters().
+__device__ unsigned long long g_dbg_clk[48];
+#ifdef BNN_DBG_WAITCLK
+#define DBG_T0() const long long dbg_t0 = clock64()
+#define DBG_ADD(slot) dbg[slot] += clock64() - dbg_t0
+#define DBG_WAIT(slot, bar, par) do { const long long t0__ = clock64(); mbar_wait_sleep(bar, par); dbg[slot] += clock64() - t0__; } while (0)
+#else
+#define DBG_T0()
+#define DBG_ADD(slot)
+#define DBG_WAIT(slot, bar, par) mbar_wait_sleep(bar, par)
+#endif
+cudaError_t bnn_debug_counters_read(unsigned long long* out48) {
+  cudaError_t e = cudaMemcpyFromSymbol(out48, g_dbg_clk, sizeof(unsigned long long) * 48);
+  if (e != cudaSuccess) return e;
+  unsigned long long z[48] = {0};
+  return cudaMemcpyToSymbol(g_dbg_clk, z, sizeof(z));
+}
+
+constexpr uint32_t OZ_TMEM_X = OZ_S * 64;     // TMEM columns [384, 480): X slices (A operand), 16 columns per slice
 
 template <int ACT, int MODE>
 __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constant__ FwdParams p) {
   constexpr int KP0 = 64, N1 = 64, N2 = 32, N3 = 16;
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   constexpr bool PREDICT = (MODE == FWD3_PRED);
-  constexpr int REST = G3::PB - G3::B1_OFF;                       // FP64 part of a weight set: b1, W2, b2, W3, b3
-  constexpr uint32_t SLOT_BYTES = OZ_W1_BYTES + REST * 8;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int TB = 8;                                            // 256-entry exp table (shared memory is short)
+  constexpr int REST = G3::PB - G3::W2_OFF;                       // FP64 part for the compute warps: W2, b2, W3, b3
+  constexpr uint32_t W1_BYTES = OZ_S * OZ_WPLANE;                  // slice planes of W1
+  constexpr uint32_t RSLOT_BYTES = REST * 8;
+  constexpr uint32_t HSLOT_BYTES = 2 * 64 * 8;                     // colscale[64] + b1[64] for the helpers
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
+  long long dbg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  (void)dbg;
 
   // ---- shared memory carve-up
-  uint8_t* xsl = smem_raw;                                         // [6][8 KB] X slices of the current tile
-  uint8_t* ring = xsl + OZ_XTILE;                                  // [2][SLOT_BYTES]
-  double* tab = reinterpret_cast<double*>(ring + 2 * SLOT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + BNN_EXP_TAB_SIZE);
-  uint64_t* full = bars;            // [2] weights of a use have landed
-  uint64_t* empty = bars + 2;       // [2] all compute warps are done with the slot
-  uint64_t* xfull = bars + 4;       // X slices of the tile have landed
-  uint64_t* tfull = bars + 5;       // layer-1 accumulators of a use are complete in TMEM
-  uint64_t* tfree = bars + 6;       // all compute warps have drained the accumulators
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  int* cnt = reinterpret_cast<int*>(bars + 8);
+  uint8_t* w1ring = smem_raw;                                      // [2][W1_BYTES]
+  uint8_t* rring = w1ring + 2 * W1_BYTES;                          // [2][RSLOT_BYTES]
+  double* a1s = reinterpret_cast<double*>(rring + 2 * RSLOT_BYTES);  // [2][128][64] layer-1 outputs (double buffer)
+  double* tab = a1s + 2 * 128 * 64;
+  uint8_t* hring = reinterpret_cast<uint8_t*>(tab + (1 << TB));     // [4][HSLOT_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hring + 4 * HSLOT_BYTES);
+  uint64_t* w1full = bars;          // [2] W1 slices of a use have landed
+  uint64_t* rfull = bars + 2;       // [2] colscale + FP64 part of a use have landed
+  uint64_t* rempty = bars + 4;      // [2] all compute warps are done with the slot
+  uint64_t* tfull = bars + 6;       // layer-1 accumulators of a use are complete in TMEM
+  uint64_t* tfree = bars + 7;       // all helpers have drained the accumulators (and refreshed X at a tile change)
+  uint64_t* a1full = bars + 8;      // [4][2] activated layer-1 rows of a lane quarter are in a1s buffer b
+  uint64_t* a1free = bars + 16;     // [4][2] both compute warps of the quarter have consumed them
+  uint64_t* hfull = bars + 24;      // [4] colscale + b1 of a use have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  int* cnt = reinterpret_cast<int*>(bars + 30);
   const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
+#ifdef BNN_DBG_TAGS
+  volatile int (*dbg_tags)[128] = reinterpret_cast<volatile int (*)[128]>(cnt + ((n_cnt + 3) & ~3));
+#endif
 
-  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < (1 << TB); i += blockDim.x) tab[i] = p.exp_tab_small[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], FWD3T_COMPUTE_WARPS); mbar_init(&empty[1], FWD3T_COMPUTE_WARPS);
-    mbar_init(xfull, 1); mbar_init(tfull, 1); mbar_init(tfree, FWD3T_COMPUTE_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&w1full[i], 1); mbar_init(&rfull[i], 1); mbar_init(&rempty[i], FWD3T_COMPUTE_WARPS); }
+    mbar_init(tfull, 1); mbar_init(tfree, FWD3T_HELPER_WARPS);
+    for (int i = 0; i < 8; ++i) { mbar_init(&a1full[i], 1); mbar_init(&a1free[i], 2); }
+    for (int i = 0; i < 4; ++i) mbar_init(&hfull[i], 1);
     mbar_fence_init();
   }
   if (warp == FWD3T_COMPUTE_WARPS) {
@@ -1170,65 +1249,223 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
   const long long n_iter = (p.n_tiles128 + gridDim.x - 1) / gridDim.x;
   const long long total_q = n_iter * p.C;            // weight-set uses, identical for every warp of the CTA
 
-  if (warp == FWD3T_COMPUTE_WARPS) {
-    // ======================= control warp: operand streaming + MMA issue (one elected lane)
-    if (lane == 0) {
-      auto load_weights = [&](long long use) {
-        const int b = (int)(use & 1), c = (int)(use % p.C);
-        uint8_t* slot = ring + (size_t)b * SLOT_BYTES;
-        mbar_arrive_expect_tx(&full[b], SLOT_BYTES);
-        bulk_g2s(slot, p.wt + (size_t)c * OZ_W1_BYTES, OZ_W1_BYTES, &full[b]);
-        bulk_g2s(slot + OZ_W1_BYTES, p.wp + (size_t)c * G3::PB + G3::B1_OFF, REST * 8, &full[b]);
-      };
-      for (long long u = 0; u < 2 && u < total_q; ++u) load_weights(u);
+  if (warp >= FWD3T_CONTROL_WARP) {
+    // ======================= control warp: lane 0 streams the weights and issues the MMAs; it owns no data, so
+    // none of its waits delays a warp that computes.  Its warpgroup gives its registers to the compute warps.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FWD3T_REGS_CONTROL));
+    if (warp == FWD3T_CONTROL_WARP && lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, S8 x S8, K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t xdesc = oz_smem_desc(smem_u32(xsl));
-      long long q = 0;
-      for (long long it = 0; it < n_iter; ++it) {
-        const long long tile = it * gridDim.x + blockIdx.x;
-        // the MMAs of the previous tile must be complete before its X slices are overwritten
-        if (q > 0) mbar_wait(tfull, (uint32_t)((q - 1) & 1));
-        if (tile < p.n_tiles128) {
-          mbar_arrive_expect_tx(xfull, OZ_XTILE);
-          bulk_g2s(xsl, p.xsl + (size_t)tile * OZ_XTILE, OZ_XTILE, xfull);
-          mbar_wait(xfull, (uint32_t)(it & 1));
-        }
-        for (int c = 0; c < p.C; ++c, ++q) {
-          const int b = (int)(q & 1);
-          mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
-          if (q > 0) mbar_wait(tfree, (uint32_t)((q - 1) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (tile < p.n_tiles128) {
-            const uint64_t wdesc = oz_smem_desc(smem_u32(ring + (size_t)b * SLOT_BYTES));
+      auto load_w1 = [&](long long use) {
+        const int b = (int)(use & 1), c = (int)(use % p.C);
+        mbar_arrive_expect_tx(&w1full[b], W1_BYTES);
+        bulk_g2s(w1ring + (size_t)b * W1_BYTES, p.wt + (size_t)c * OZ_W1_BYTES, W1_BYTES, &w1full[b]);
+      };
+      auto load_rest = [&](long long use) {
+        const int b = (int)(use & 1), c = (int)(use % p.C);
+        mbar_arrive_expect_tx(&rfull[b], RSLOT_BYTES);
+        bulk_g2s(rring + (size_t)b * RSLOT_BYTES, p.wp + (size_t)c * G3::PB + G3::W2_OFF, RSLOT_BYTES, &rfull[b]);
+      };
+      auto load_hslot = [&](long long use) {
+        const int b = (int)(use & 3), c = (int)(use % p.C);
+        uint8_t* slot = hring + (size_t)b * HSLOT_BYTES;
+        mbar_arrive_expect_tx(&hfull[b], HSLOT_BYTES);
+        bulk_g2s(slot, p.wt + (size_t)c * OZ_W1_BYTES + W1_BYTES, 64 * 8, &hfull[b]);
+        bulk_g2s(slot + 64 * 8, p.wp + (size_t)c * G3::PB + G3::B1_OFF, 64 * 8, &hfull[b]);
+      };
+      auto issue_mma = [&](long long use) {
+#ifdef BNN_DBG_NOMMA          // tuning experiment only
+        return;
+#endif
+        // all 21 slice pairs: A = X slices in TMEM, B = W1 slices of `use` in shared memory
+        const uint64_t wdesc = oz_smem_desc(smem_u32(w1ring + (size_t)(use & 1) * W1_BYTES));
 #pragma unroll 1
-            for (int d = 0; d < OZ_S; ++d) {               // diagonal T = 10 - d -> TMEM columns [64 d, 64 d + 64)
-              const int T = 2 * (OZ_S - 1) - d;
-              uint32_t acc = 0;
-              for (int sx = T - (OZ_S - 1); sx <= OZ_S - 1; ++sx) {
-                const int sw = T - sx;
+        for (int d = 0; d < OZ_S; ++d) {               // diagonal T = 10 - d -> TMEM columns [64 d, 64 d + 64)
+          const int T = 2 * (OZ_S - 1) - d;
+          uint32_t acc = 0;
+          for (int sx = T - (OZ_S - 1); sx <= OZ_S - 1; ++sx) {
+            const int sw = T - sx;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  oz_mma(tmem + 64 * d, xdesc + (uint64_t)((sx * OZ_XPLANE + ks * 2 * OZ_LBO) >> 4),
-                         wdesc + (uint64_t)((sw * OZ_WPLANE + ks * 2 * OZ_LBO) >> 4), idesc, acc);
-                  acc = 1;
-                }
-              }
+            for (int ks = 0; ks < 2; ++ks) {
+              oz_mma_ts(tmem + 64 * d, tmem + OZ_TMEM_X + 16 * sx + 8 * ks,
+                        wdesc + (uint64_t)((sw * OZ_WPLANE + ks * 2 * OZ_LBO) >> 4), idesc, acc);
+              acc = 1;
             }
           }
+        }
+      };
+      for (long long u = 0; u < 2 && u < total_q; ++u) { load_w1(u); load_rest(u); load_hslot(u); }
+      // use 0: the helpers have staged the first tile's X slices (phase 0 of tfree)
+      mbar_wait_sleep(tfree, 0);
+      mbar_wait_sleep(&w1full[0], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if ((long long)blockIdx.x < p.n_tiles128) issue_mma(0);
+      oz_commit(tfull);
+      for (long long q = 0; q + 1 < total_q; ++q) {
+        const long long it = q / p.C;
+        const int c = (int)(q - it * p.C);
+        const long long tile = it * gridDim.x + blockIdx.x;
+        // the MMAs of use q are complete: their W1 slot takes the slices of use q + 2 (every helper has finished
+        // pass 1 of use q - 1, so the helper slot of use q - 2 is free as well)
+        DBG_WAIT(1, tfull, (uint32_t)(q & 1));
+        if (q + 2 < total_q) { load_w1(q + 2); load_hslot(q + 2); }
+        // the helpers have drained use q (and staged the next tile's X slices at a tile change)
+        DBG_WAIT(3, tfree, (uint32_t)((q + 1) & 1));
+        DBG_WAIT(4, &w1full[(q + 1) & 1], (uint32_t)(((q + 1) >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long ntile = (c + 1 == p.C) ? tile + gridDim.x : tile;
+        {
+          DBG_T0();
+          if (ntile < p.n_tiles128) issue_mma(q + 1);
           oz_commit(tfull);          // arrives when every MMA issued so far is complete (also with none issued)
-          // refill the slot of use q-1 with use q+1 once the compute warps have released it
-          if (q >= 1 && q + 1 < total_q) {
-            mbar_wait(&empty[b ^ 1], (uint32_t)(((q - 1) >> 1) & 1));
-            load_weights(q + 1);
+          DBG_ADD(8);
+        }
+        // FP64 part of use q + 1 goes into the slot of use q - 1 once the compute warps have released it
+        if (q >= 1) {
+          DBG_WAIT(5, &rempty[(q + 1) & 1], (uint32_t)(((q - 1) >> 1) & 1));
+          load_rest(q + 1);
+        }
+      }
+    }
+  } else if (warp >= FWD3T_COMPUTE_WARPS) {
+    // ======================= helper warps: X slices -> TMEM, accumulators -> activated layer-1 outputs in a1s
+    const int h = warp - FWD3T_COMPUTE_WARPS;                     // TMEM lane quarter (== warp & 3)
+    const int r = 32 * h + lane;                                   // row inside the 128-row tile
+    const uint32_t tlane = (uint32_t)(32 * h) << 16;
+    // this thread's row of X slices (6 x 64 bytes, contiguous) -> TMEM columns [384, 480) of its lane
+    auto stage_x = [&](long long tile) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.xsl + ((size_t)tile * 128 + r) * OZ_XROW);
+#pragma unroll
+      for (int sl = 0; sl < OZ_S; ++sl) {
+        uint4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = __ldg(src + 4 * sl + i);
+        oz_st_row16(tmem + tlane + OZ_TMEM_X + 16 * sl, w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    if ((long long)blockIdx.x < p.n_tiles128) stage_x(blockIdx.x);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tfree);                       // phase 0 of tfree: the first tile's X is in TMEM
+    long long q = 0;
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = it * gridDim.x + blockIdx.x;
+      const bool tile_ok = tile < p.n_tiles128;
+      const double rsc = tile_ok ? p.x_rowscale[tile * 128 + r] : 0.0;
+      for (int c = 0; c < p.C; ++c, ++q) {
+        const int b = (int)(q & 1);
+        DBG_WAIT(0, &hfull[q & 3], (uint32_t)((q >> 2) & 1));
+        DBG_WAIT(1, tfull, (uint32_t)(q & 1));
+        if (q > 1) DBG_WAIT(2, &a1free[2 * h + b], (uint32_t)(((q >> 1) - 1) & 1));
+        // ... and stay at most ONE weight set ahead of this quarter's compute warps (wait until they have consumed
+        // use q - 1 from the other buffer).  Without this bound -- helpers two sets ahead at the moment the next
+        // tile's X slices are stored to TMEM -- a few rows of ONE weight set per launch came out wrong (always the
+        // third-from-last set of an early tile, rows of TMEM lane quarter 0; tools/race_probe.py).  The hand-off
+        // barriers were verified intact in failing runs (tags in a1s, canaries in the weight rings), the cause is
+        // not understood; with the bound 64 launches over 8 chain counts were clean.  The kernel is opt-in.
+        if (q > 0) mbar_wait_sleep(&a1free[2 * h + (b ^ 1)], (uint32_t)(((q - 1) >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint8_t* slot = hring + (size_t)(q & 3) * HSLOT_BYTES;
+        const double* csc = reinterpret_cast<const double*>(slot);
+        const double* b1 = reinterpret_cast<const double*>(slot + 64 * 8);
+        const double al = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
+        double* arow = a1s + (size_t)b * 128 * 64 + r * 64;
+        const int sw = a1_swz(r);
+#ifdef BNN_DBG_TAGS
+        dbg_tags[b][r] = -(int)(q + 1);
+#endif
+        const long long dbg_p1 = clock64(); (void)dbg_p1;
+        // ---- pass 1: drain the accumulators (the tensor core is idle until this is done).  Integer instructions
+        // only -- the FP64 pipe is busy with the compute warps' DMMAs, and every FP64 instruction here would
+        // queue behind them: the 6 diagonals are folded into one 64-bit integer per element,
+        // (a0 2^16 + a1 2^8 + a2) 2^20 + ((a3 2^16 + a4 2^8 + a5) >> 4)   (|.| < 2^60; the 4 dropped bits are
+        // 2^-64 of full scale), which is parked in a1s
+#ifdef BNN_DBG_NOHELPER       // tuning experiment only
+        if (false)
+#endif
+#pragma unroll 1
+        for (int cb = 0; cb < N1 / 16; ++cb) {
+          uint32_t v[OZ_S][16];
+#pragma unroll
+          for (int d = 0; d < OZ_S; ++d) oz_ld_row16(tmem + tlane + 64 * d + 16 * cb, v[d]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            long long w[2];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              const long long hi = (long long)(int)v[0][e] * 65536 + (long long)(int)v[1][e] * 256 + (long long)(int)v[2][e];
+              const long long lo = (long long)(int)v[3][e] * 65536 + (long long)(int)v[4][e] * 256 + (long long)(int)v[5][e];
+              w[e2] = hi * 1048576 + (lo >> 4);
+            }
+            *reinterpret_cast<longlong2*>(arow + 2 * ((8 * cb + i) ^ sw)) = make_longlong2(w[0], w[1]);
           }
         }
+        dbg[6] += clock64() - dbg_p1;
+        // a new tile follows: its X slices replace the current ones (no MMA is in flight: tfull(q) was waited for)
+        if (c + 1 == p.C && tile + gridDim.x < p.n_tiles128) {
+          DBG_T0();
+          stage_x(tile + gridDim.x);
+          DBG_ADD(9);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfree);
+#ifdef BNN_DBG_TAGS
+        if (csc[lane] != reinterpret_cast<const double*>(p.wt + (size_t)c * OZ_W1_BYTES + W1_BYTES)[lane] ||
+            b1[lane] != p.wp[(size_t)c * G3::PB + G3::B1_OFF + lane]) {
+          atomicAdd(&g_dbg_clk[36], 1ULL); g_dbg_clk[37] = (unsigned long long)q; g_dbg_clk[38] = 1;
+        }
+#endif
+        const long long dbg_p2 = clock64(); (void)dbg_p2;
+        // ---- pass 2 (under the MMAs of the next weight set): integer -> FP64, scale, bias, activation, in place
+        // on this thread's own row.  v = vh 2^32 + vl with the two halves converted by the 2^52 trick.
+#ifdef BNN_DBG_NOHELPER
+        if (false)
+#endif
+#pragma unroll 1
+        for (int cb = 0; cb < N1 / 8; ++cb) {
+          double z[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const longlong2 ww = *reinterpret_cast<const longlong2*>(arow + 2 * ((4 * cb + i) ^ sw));
+            const long long w2[2] = {ww.x, ww.y};
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = 2 * i + e2;
+              const int vh = (int)(w2[e2] >> 32);
+              const unsigned vl = (unsigned)w2[e2];
+              const double dh = __hiloint2double(0x43300000, vh ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+              const double dl = __hiloint2double(0x43300000, (int)vl) - 4503599627370496.0;           // 2^52
+              const double hsum = fma(dh, 4294967296.0, dl);
+              z[e] = fma(hsum * rsc, csc[8 * cb + e], b1[8 * cb + e]);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = bnn_act<ACT, TB>(z[e], al, tab);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<double2*>(arow + 2 * ((4 * cb + i) ^ sw)) = make_double2(z[2 * i], z[2 * i + 1]);
+        }
+#ifdef BNN_DBG_TAGS
+        dbg_tags[b][r] = (int)(q + 1);
+        if (csc[lane] != reinterpret_cast<const double*>(p.wt + (size_t)c * OZ_W1_BYTES + W1_BYTES)[lane] ||
+            b1[lane] != p.wp[(size_t)c * G3::PB + G3::B1_OFF + lane]) {
+          atomicAdd(&g_dbg_clk[36], 1ULL); g_dbg_clk[37] = (unsigned long long)q; g_dbg_clk[38] = 2;
+        }
+#endif
+        __syncwarp();
+        dbg[7] += clock64() - dbg_p2;
+        if (lane == 0) mbar_arrive(&a1full[2 * h + b]);
       }
     }
   } else {
     // ======================= compute warps
-    const int rbase = 32 * (warp & 3) + 16 * (warp >> 2);       // rows of this warp inside the 128-row tile
-    const uint32_t tlane = (uint32_t)rbase << 16;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FWD3T_REGS_COMPUTE));
+    const int h = warp & 3;
+    const int rbase = 32 * h + 16 * (warp >> 2);                // rows of this warp inside the 128-row tile
     long long q = 0;
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = it * gridDim.x + blockIdx.x;
@@ -1236,122 +1473,113 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
       const bool have_tile = tile < p.n_tiles128 && wt < p.n_tiles16;
       int y[2] = {0, 0};
       double wgt[2] = {1.0, 1.0};
-      double rsc[2] = {0.0, 0.0};
       double acc3[N3 / 8][4];
       bool prev_valid = false;
 #pragma unroll
       for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
       if (have_tile) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const long long row = wt * 16 + gq + 8 * h;
-          rsc[h] = p.x_rowscale[row];
+        for (int hh = 0; hh < 2; ++hh) {
+          const long long row = wt * 16 + gq + 8 * hh;
           if (row < p.n_total) {
-            y[h] = p.labels[row];
+            y[hh] = p.labels[row];
             if (MODE == FWD3_LIK_W) {
-              if (p.class_w) wgt[h] *= p.class_w[y[h]];
-              if (p.inst_w && row < p.n_train) wgt[h] *= p.inst_w[row];
+              if (p.class_w) wgt[hh] *= p.class_w[y[hh]];
+              if (p.inst_w && row < p.n_train) wgt[hh] *= p.inst_w[row];
             }
           }
         }
       }
       for (int c = 0; c < p.C; ++c, ++q) {
         const int b = (int)(q & 1);
-        mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
-        mbar_wait(tfull, (uint32_t)(q & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint8_t* slot = ring + (size_t)b * SLOT_BYTES;
-        const double* csc = reinterpret_cast<const double*>(slot + OZ_S * OZ_WPLANE);
-        const double* W = reinterpret_cast<const double*>(slot + OZ_W1_BYTES) - G3::B1_OFF;   // k_fwd3 offsets
-        const double a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
-        const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
-        // ---------------- layer 1: drain and recombine the integer accumulators; the likelihood epilogue of
-        // the previous weight set (latency-bound FP64 chains and shuffles) is interleaved stage by stage
-        double acc1[N1 / 8][4];
-        RowStats<N3> rs;
-        LikRow lr;
-        const int K = g.K;
-#pragma unroll
-        for (int jj = 0; jj < N1 / 16; ++jj) {
-          uint32_t v[OZ_S][8];
-#pragma unroll
-          for (int d = 0; d < OZ_S; ++d) oz_ld_frag(tmem + tlane + 64 * d + 16 * jj, v[d]);
-          if (!PREDICT) {
-            if (jj == 0) qs_max<N3>(acc3, K, t, rs);
-            else if (jj == 1) qs_exp<N3, 0, true>(acc3, K, t, y, tab, rs);
-            else if (jj == 2) qs_exp<N3, 1, true>(acc3, K, t, y, tab, rs);
-            else {
-              qs_reduce<N3, true>(rs);
-              lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, prev_valid && have_tile);
-            }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int j = 2 * jj + hh;
-            const double2 sc = *reinterpret_cast<const double2*>(csc + 8 * j + 2 * t);
-            const double2 bb = *reinterpret_cast<const double2*>(W + G3::B1_OFF + 8 * j + 2 * t);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const double hi = oz_group((int)v[0][4 * hh + e], (int)v[1][4 * hh + e], (int)v[2][4 * hh + e]);
-              const double lo = oz_group((int)v[3][4 * hh + e], (int)v[4][4 * hh + e], (int)v[5][4 * hh + e]);
-              const double hsum = fma(lo, 5.9604644775390625e-08, hi);          // hi + lo * 2^-24
-              acc1[j][e] = fma(hsum * rsc[e >> 1], (e & 1) ? sc.y : sc.x, (e & 1) ? bb.y : bb.x);
-            }
+        DBG_WAIT(0, &rfull[b], (uint32_t)((q >> 1) & 1));
+        DBG_WAIT(1, &a1full[2 * h + b], (uint32_t)((q >> 1) & 1));
+#ifdef BNN_DBG_TAGS
+        const long long tag0 = dbg_tags[b][rbase + (lane & 15)];
+        {
+          const double* Wc = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
+          const double want = p.wp[(size_t)c * G3::PB + G3::W2_OFF + lane], want3 = p.wp[(size_t)c * G3::PB + G3::W3_OFF + lane];
+          if (Wc[G3::W2_OFF + lane] != want || Wc[G3::W3_OFF + lane] != want3) {
+            atomicAdd(&g_dbg_clk[45], 1ULL); g_dbg_clk[46] = (unsigned long long)q; g_dbg_clk[47] = 1;
           }
         }
-        // the accumulators are in registers: the tensor core may start the next weight set
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tfree);
-        if (!PREDICT) quad_lik_commit(p, c - 1, wt, lane, cnt, lr, prev_valid && have_tile);
-        // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = activated acc1, no data movement)
+#endif
+        const long long dbg_c0 = clock64(); (void)dbg_c0;
+        const double* W = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
+        const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
+        // ---------------- layer 2: [16 x N1] x [N1 x N2], A operand = activated layer-1 rows from a1s.  The
+        // likelihood epilogue of the previous weight set (latency-bound FP64 chains and shuffles) is cut into
+        // stages between the MMA groups of the first k-groups.
         double acc2[N2 / 8][4];
 #pragma unroll
         for (int j = 0; j < N2 / 8; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(W + G3::B2_OFF + 8 * j + 2 * t);
           acc2[j][0] = bb.x; acc2[j][1] = bb.y; acc2[j][2] = bb.x; acc2[j][3] = bb.y;
         }
+        RowStats<N3> rs;
+        LikRow lr;
+        const int K = g.K;
+#ifdef BNN_DBG_NOCOMPUTE      // tuning experiment only
+        if (p.C < 0)
+#endif
         {
           const double* wr = W + G3::W2_OFF + gq * N1;
           const int sw = (gq & 1) * G3::SW1;
-          act_tile<ACT>(acc1[0], a1, tab);
+          const double* ar0 = a1s + (size_t)b * 128 * 64 + (rbase + gq) * 64;
+          const double* ar1 = ar0 + 8 * 64;
+          const int asw = a1_swz(gq);                            // rows g and g + 8 share the swizzle
 #pragma unroll
-          for (int kg = 0; kg < N1 / 8 - 2; ++kg) {
-            act_tile<ACT>(acc1[kg + 1], a1, tab);
+          for (int kg = 0; kg < N1 / 8; ++kg) {
+            const double2 alo = *reinterpret_cast<const double2*>(ar0 + 2 * ((4 * kg + t) ^ asw));
+            const double2 ahi = *reinterpret_cast<const double2*>(ar1 + 2 * ((4 * kg + t) ^ asw));
+            if (!PREDICT) {
+              if (kg == 0) qs_max<N3>(acc3, K, t, rs);
+              else if (kg == 1) qs_exp<N3, 0, true, TB>(acc3, K, t, y, tab, rs);
+              else if (kg == 2) qs_exp<N3, 1, true, TB>(acc3, K, t, y, tab, rs);
+              else if (kg == 3) {
+                qs_reduce<N3, true>(rs);
+                lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, prev_valid && have_tile);
+              }
+            }
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
               const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + col);
-              dmma16x8x8(acc2[j], acc1[kg][0], acc1[kg][2], acc1[kg][1], acc1[kg][3], bb.x, bb.y);
-            }
-          }
-          {
-            constexpr int k0 = N1 / 8 - 2, k1 = N1 / 8 - 1;
-            act_tile<ACT>(acc1[k1], a1, tab);
-            const int c0 = (8 * k0 + 2 * t) ^ sw, c1 = (8 * k1 + 2 * t) ^ sw;
-#pragma unroll
-            for (int j = 0; j < N2 / 8; ++j) {
-              const double2 b0 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c0);
-              const double2 b1 = *reinterpret_cast<const double2*>(wr + j * 8 * N1 + c1);
-              dmma16x8x8(acc2[j], acc1[k0][0], acc1[k0][2], acc1[k0][1], acc1[k0][3], b0.x, b0.y);
-              dmma16x8x8(acc2[j], acc1[k1][0], acc1[k1][2], acc1[k1][1], acc1[k1][3], b1.x, b1.y);
+              dmma16x8x8(acc2[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
             }
           }
         }
+#ifdef BNN_DBG_TAGS
+        {
+          const long long tag1 = dbg_tags[b][rbase + (lane & 15)];
+          if (tag0 != q + 1 || tag1 != q + 1) {
+            atomicAdd(&g_dbg_clk[40], 1ULL);
+            g_dbg_clk[41] = (unsigned long long)q; g_dbg_clk[42] = (unsigned long long)tag0;
+            g_dbg_clk[43] = (unsigned long long)tag1; g_dbg_clk[44] = (unsigned long long)warp;
+          }
+        }
+#endif
+        // the activated layer-1 rows have been consumed: the helpers may overwrite this buffer (two weight sets on)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a1free[2 * h + b]);
+        dbg[2] += clock64() - dbg_c0;
+        if (!PREDICT) quad_lik_commit(p, c - 1, wt, lane, cnt, lr, prev_valid && have_tile);
         // ---------------- layer 3: [16 x N2] x [N2 x N3]
 #pragma unroll
         for (int j = 0; j < N3 / 8; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
           acc3[j][0] = bb.x; acc3[j][1] = bb.y; acc3[j][2] = bb.x; acc3[j][3] = bb.y;
         }
+#ifdef BNN_DBG_NOCOMPUTE
+        if (p.C < 0)
+#endif
         {
           const double* wr = W + G3::W3_OFF + gq * N2;
           const int sw = (gq & 1) * G3::SW2;
-          act_tile<ACT>(acc2[0], a2, tab);
+          act_tile<ACT, TB>(acc2[0], a2, tab);
 #pragma unroll
           for (int kg = 0; kg < N2 / 8; ++kg) {
-            if (kg + 1 < N2 / 8) act_tile<ACT>(acc2[kg + 1], a2, tab);
+            if (kg + 1 < N2 / 8) act_tile<ACT, TB>(acc2[kg + 1], a2, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N3 / 8; ++j) {
@@ -1360,20 +1588,34 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
             }
           }
         }
+#ifdef BNN_DBG_TAGS
+        {
+          const double* Wc = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
+          const double want = p.wp[(size_t)c * G3::PB + G3::W2_OFF + lane], want3 = p.wp[(size_t)c * G3::PB + G3::W3_OFF + lane];
+          if (Wc[G3::W2_OFF + lane] != want || Wc[G3::W3_OFF + lane] != want3) {
+            atomicAdd(&g_dbg_clk[45], 1ULL); g_dbg_clk[46] = (unsigned long long)q; g_dbg_clk[47] = 2;
+          }
+        }
+#endif
         // weights of this use are no longer needed by this warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[b]);
+        if (lane == 0) mbar_arrive(&rempty[b]);
+        dbg[3] += clock64() - dbg_c0;
         prev_valid = true;
       }
       if (have_tile && !PREDICT) {
         // drain the software pipeline: epilogue of the last weight set of this tile
         RowStats<N3> rs;
-        quad_softmax_stats<N3, true>(acc3, g.K, t, y, tab, rs);
+        quad_softmax_stats<N3, true, TB>(acc3, g.K, t, y, tab, rs);
         const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, true);
         quad_lik_commit(p, p.C - 1, wt, lane, cnt, lr, true);
       }
     }
   }
+#ifdef BNN_DBG_WAITCLK
+  if (lane == 0)
+    for (int i = 0; i < 12; ++i) atomicAdd(&g_dbg_clk[(warp >= FWD3T_CONTROL_WARP ? 0 : warp >= FWD3T_COMPUTE_WARPS ? 16 : 32) + i], (unsigned long long)dbg[i]);
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == FWD3T_COMPUTE_WARPS)
@@ -1397,13 +1639,20 @@ cudaError_t bnn_launch_slice_w1(const double* wp, int PB, uint8_t* wt, int n_set
 size_t bnn_slice_x_tile_bytes() { return OZ_XTILE; }
 size_t bnn_slice_w1_bytes() { return OZ_W1_BYTES; }
 
+static size_t fwd3t_smem_bytes(int C, int K) {
+  using G3 = Fwd3Geom<64, 64, 32, 16>;
+  return 2 * (size_t)(OZ_S * OZ_WPLANE) + 2 * (size_t)(G3::PB - G3::W2_OFF) * 8 + 2 * 128 * 64 * sizeof(double) +
+         256 * sizeof(double) + 4 * 1024 + 30 * sizeof(uint64_t) + (size_t)C * (2 + 2 * K) * sizeof(int)
+#ifdef BNN_DBG_TAGS
+         + 1024 + 16
+#endif
+      ;
+}
+
 template <int ACT, int MODE>
 static cudaError_t launch_fwd3t(const FwdParams& p, int n_sms, cudaStream_t st) {
   auto kern = k_fwd3t<ACT, MODE>;
-  using G3 = Fwd3Geom<64, 64, 32, 16>;
-  const size_t slot = OZ_W1_BYTES + (size_t)(G3::PB - G3::B1_OFF) * 8;
-  size_t smem = OZ_XTILE + 2 * slot + BNN_EXP_TAB_SIZE * sizeof(double) + 8 * sizeof(uint64_t) +
-                (size_t)p.C * (2 + 2 * p.g.K) * sizeof(int);
+  const size_t smem = fwd3t_smem_bytes(p.C, p.g.K);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -1571,7 +1820,7 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
     if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {
       if (which) *which = "k_fwd3<swish,64,64,32,16>";
-      if (!predict && p.xsl && p.wt) {
+      if (!predict && p.xsl && p.wt && fwd3t_smem_bytes(p.C, g.K) <= 232448) {
         if (which) *which = "k_fwd3t<swish,64,64,32,16>";
         if (p.class_w || p.inst_w) return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK_W>(p, n_sms, st);
         return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK>(p, n_sms, st);

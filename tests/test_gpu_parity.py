@@ -269,6 +269,7 @@ def test_c4_shape_tensor_core_first_layer(n):
     eng.set_data(x[: n - n // 5], labels[: n - n // 5], x[n - n // 5:], labels[n - n // 5:])
     m = orc.Model(x=x[: n - n // 5], labels=labels[: n - n // 5], weights=sets[0], act="swish", mode="classification",
                   x_test=x[n - n // 5:], labels_test=labels[n - n // 5:])
+    eng.set_option("tensor_l1", 1)                       # opt-in path
     res = eng.forward_lik(sets)
     assert eng.last_kernel == "k_fwd3t<swish,64,64,32,16>", eng.last_kernel
     eng.set_option("tensor_l1", 0)

@@ -35,6 +35,21 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         out[name] = {"kernel": eng.last_kernel, "ms_per_pass": e0.elapsed_time(e1) / 3, "loglik": r["loglik"], "counts": r["counts"]}
+    if os.environ.get("NPBNN_DBG_COUNTERS"):
+        import ctypes as C
+        buf = (C.c_ulonglong * 48)()
+        eng.set_option("tensor_l1", 1)
+        eng.lib.bnn_debug_counters(eng._h, C.cast(buf, C.c_void_p))           # reset
+        eng.forward_lik(wd)
+        eng.lib.bnn_debug_counters(eng._h, C.cast(buf, C.c_void_p))
+        v = list(buf)
+        names_h = ["wait hfull", "wait tfull", "wait a1free", "ctl wait tfree", "ctl wait w1full", "ctl wait rempty", "pass1", "pass2",
+                   "ctl issue x4", "stage_x", "issue->tfull seen"]
+        names_c = ["wait rfull", "wait a1full", "L2 phase", "whole chain body"]
+        uses = 148 * -(-(n // 128 + (n % 128 > 0)) // 148) * S
+        print("control warp (clocks per use):", {k: round(v[i] / uses, 1) for i, k in enumerate(names_h)})
+        print("helpers (4 warps, clocks per use per warp):", {k: round(v[16 + i] / (uses * 4), 1) for i, k in enumerate(names_h)})
+        print("compute (8 warps/SM, clocks per use per warp):", {k: round(v[32 + i] / (uses * 8), 1) for i, k in enumerate(names_c)})
     a, b = out["tensor"], out["f64"]
     rel = np.abs(a["loglik"] - b["loglik"]) / np.abs(b["loglik"])
     print(json.dumps({"rows": n, "sets": S, "tensor_kernel": a["kernel"], "f64_kernel": b["kernel"],
