@@ -32,6 +32,7 @@ N_ROWS = 1_000_000
 N_CHAINS = 32
 SWAP_FREQUENCY = 100
 CPU_SAMPLE_ROWS = 100_000
+PRED_SAMPLES = 64            # posterior samples of the forward rows/s leg
 
 
 def parse():
@@ -117,7 +118,7 @@ def reference_arm(args, rank, world):
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args):
@@ -128,8 +129,31 @@ def workload_config(args):
             "l2": "inputs larger than L2 (X = %.0f MB streamed once per step)" % (args.rows * 64 * 8 / 1e6)}
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr for the
+    whole run, the JSON line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,6 +275,66 @@ def main():
                 "hbm": {"algorithmic_bytes_per_launch": args.rows * (64 * 8 + 4),
                         "achieved_gbs": args.rows * (64 * 8 + 4) / (fwd_avg_ms * 1e-3) / 1e9 if fwd_n else None}}
 
+    # ------------------------------------------------------------------ forward rows/s (BASELINE metric, second half):
+    # posterior prediction (c5 shape) over this rank's row shard for PRED_SAMPLES posterior samples, summaries
+    # mean + votes; no collective (rows are sharded)
+    import ctypes as C
+    predict = None
+    try:
+        r0, r1 = args.rows * rank // world, args.rows * (rank + 1) // world
+        xd = x_pin[r0:r1].to(dev)
+        rs_p = np.random.default_rng(5)
+        wd = torch.from_numpy(w0[:1].repeat(PRED_SAMPLES, 0) + rs_p.normal(0, 0.05, (PRED_SAMPLES, w0.shape[1]))).to(dev)
+        md = torch.empty((r1 - r0, 10), dtype=torch.float64, device=dev)
+        vd = torch.empty((r1 - r0, 10), dtype=torch.float64, device=dev)
+
+        def run_predict():
+            L.check(eng.lib.bnn_predict(eng._h, C.c_void_p(xd.data_ptr()), r1 - r0, C.c_void_p(wd.data_ptr()), PRED_SAMPLES,
+                                        None, None, None, 0, C.c_void_p(md.data_ptr()), C.c_void_p(vd.data_ptr()), None,
+                                        eng._stream()))
+        run_predict()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        run_predict()
+        p1.record()
+        barrier()
+        pms = max_over_ranks(p0.elapsed_time(p1))
+        predict = {"metric": "forward rows/s (posterior samples x rows / s)", "value": PRED_SAMPLES * args.rows / (pms * 1e-3),
+                   "unit": "row-samples/s", "samples": PRED_SAMPLES, "rows": args.rows, "ms": pms,
+                   "tflops": PRED_SAMPLES * args.rows * wl.C4_FLOP_PER_ROW / (pms * 1e-3) / 1e12,
+                   "frac_of_fp64_peak_per_gpu": PRED_SAMPLES * args.rows * wl.C4_FLOP_PER_ROW / (pms * 1e-3) / 1e12 / world / peak_tf,
+                   "kernel": eng.last_kernel, "rows_sharded_over": world,
+                   "mean_prob_sum": float(md.sum().item()) / max(r1 - r0, 1)}
+        del xd, wd, md, vd
+    except Exception as e:                                 # the headline must not depend on this leg
+        predict = {"error": str(e)}
+
+    # ------------------------------------------------------------------ opt-in kernel: layer 1 on the int8 tensor cores
+    experimental = None
+    try:
+        wl_d = torch.from_numpy(w0).to(dev)
+        t_ms = {}
+        for name, opt in (("f64", 0), ("tensor_l1", 1)):
+            eng.set_option("tensor_l1", opt)
+            ll = eng.forward_lik(wl_d)["loglik"]
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            ll = eng.forward_lik(wl_d)["loglik"]
+            q1.record()
+            torch.cuda.synchronize(dev)
+            t_ms[name] = (q0.elapsed_time(q1), ll, eng.last_kernel)
+        eng.set_option("tensor_l1", 0)
+        experimental = {"tensor_l1": {"what": "one scoring pass of this rank's chains (pack + slice + forward + reduce), "
+                                              "opt-in k_fwd3t vs default k_fwd3",
+                                      "kernel": t_ms["tensor_l1"][2], "ms": t_ms["tensor_l1"][0], "f64_ms": t_ms["f64"][0],
+                                      "speedup": t_ms["f64"][0] / t_ms["tensor_l1"][0],
+                                      "max_rel_diff_loglik": float(np.max(np.abs(t_ms["tensor_l1"][1] - t_ms["f64"][1]) /
+                                                                          np.abs(t_ms["f64"][1])))}}
+        del wl_d
+    except Exception as e:
+        experimental = {"error": str(e)}
+
     # ------------------------------------------------------------------ end-to-end leg (host buffers)
     e2e = None
     if not args.no_e2e:
@@ -306,11 +390,11 @@ def main():
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clk,
+                "gpu_launches": int(launches), "clocks": clk, "predict": predict, "experimental": experimental,
                 "swaps_in_timed_region": n_swaps[0] - swaps_before,
                 "check": {"logLik_finite": bool(np.all(np.isfinite(st.logLik))),
                           "mean_acceptance": float(np.mean(st.n_accepted / np.maximum(st.iteration, 1)))}}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
