@@ -1223,9 +1223,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
   int* cnt = reinterpret_cast<int*>(bars + 30);
   const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
-#ifdef BNN_DBG_TAGS
-  volatile int (*dbg_tags)[128] = reinterpret_cast<volatile int (*)[128]>(cnt + ((n_cnt + 3) & ~3));
-#endif
 
   for (int i = threadIdx.x; i < (1 << TB); i += blockDim.x) tab[i] = p.exp_tab_small[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
@@ -1372,9 +1369,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         const double al = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
         double* arow = a1s + (size_t)b * 128 * 64 + r * 64;
         const int sw = a1_swz(r);
-#ifdef BNN_DBG_TAGS
-        dbg_tags[b][r] = -(int)(q + 1);
-#endif
         const long long dbg_p1 = clock64(); (void)dbg_p1;
         // ---- pass 1: drain the accumulators (the tensor core is idle until this is done).  Integer instructions
         // only -- the FP64 pipe is busy with the compute warps' DMMAs, and every FP64 instruction here would
@@ -1413,12 +1407,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tfree);
-#ifdef BNN_DBG_TAGS
-        if (csc[lane] != reinterpret_cast<const double*>(p.wt + (size_t)c * OZ_W1_BYTES + W1_BYTES)[lane] ||
-            b1[lane] != p.wp[(size_t)c * G3::PB + G3::B1_OFF + lane]) {
-          atomicAdd(&g_dbg_clk[36], 1ULL); g_dbg_clk[37] = (unsigned long long)q; g_dbg_clk[38] = 1;
-        }
-#endif
         const long long dbg_p2 = clock64(); (void)dbg_p2;
         // ---- pass 2 (under the MMAs of the next weight set): integer -> FP64, scale, bias, activation, in place
         // on this thread's own row.  v = vh 2^32 + vl with the two halves converted by the 2^52 trick.
@@ -1449,13 +1437,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<double2*>(arow + 2 * ((4 * cb + i) ^ sw)) = make_double2(z[2 * i], z[2 * i + 1]);
         }
-#ifdef BNN_DBG_TAGS
-        dbg_tags[b][r] = (int)(q + 1);
-        if (csc[lane] != reinterpret_cast<const double*>(p.wt + (size_t)c * OZ_W1_BYTES + W1_BYTES)[lane] ||
-            b1[lane] != p.wp[(size_t)c * G3::PB + G3::B1_OFF + lane]) {
-          atomicAdd(&g_dbg_clk[36], 1ULL); g_dbg_clk[37] = (unsigned long long)q; g_dbg_clk[38] = 2;
-        }
-#endif
         __syncwarp();
         dbg[7] += clock64() - dbg_p2;
         if (lane == 0) mbar_arrive(&a1full[2 * h + b]);
@@ -1494,16 +1475,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         const int b = (int)(q & 1);
         DBG_WAIT(0, &rfull[b], (uint32_t)((q >> 1) & 1));
         DBG_WAIT(1, &a1full[2 * h + b], (uint32_t)((q >> 1) & 1));
-#ifdef BNN_DBG_TAGS
-        const long long tag0 = dbg_tags[b][rbase + (lane & 15)];
-        {
-          const double* Wc = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
-          const double want = p.wp[(size_t)c * G3::PB + G3::W2_OFF + lane], want3 = p.wp[(size_t)c * G3::PB + G3::W3_OFF + lane];
-          if (Wc[G3::W2_OFF + lane] != want || Wc[G3::W3_OFF + lane] != want3) {
-            atomicAdd(&g_dbg_clk[45], 1ULL); g_dbg_clk[46] = (unsigned long long)q; g_dbg_clk[47] = 1;
-          }
-        }
-#endif
         const long long dbg_c0 = clock64(); (void)dbg_c0;
         const double* W = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
         const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
@@ -1549,16 +1520,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
             }
           }
         }
-#ifdef BNN_DBG_TAGS
-        {
-          const long long tag1 = dbg_tags[b][rbase + (lane & 15)];
-          if (tag0 != q + 1 || tag1 != q + 1) {
-            atomicAdd(&g_dbg_clk[40], 1ULL);
-            g_dbg_clk[41] = (unsigned long long)q; g_dbg_clk[42] = (unsigned long long)tag0;
-            g_dbg_clk[43] = (unsigned long long)tag1; g_dbg_clk[44] = (unsigned long long)warp;
-          }
-        }
-#endif
         // the activated layer-1 rows have been consumed: the helpers may overwrite this buffer (two weight sets on)
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1free[2 * h + b]);
@@ -1588,15 +1549,6 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
             }
           }
         }
-#ifdef BNN_DBG_TAGS
-        {
-          const double* Wc = reinterpret_cast<const double*>(rring + (size_t)b * RSLOT_BYTES) - G3::W2_OFF;
-          const double want = p.wp[(size_t)c * G3::PB + G3::W2_OFF + lane], want3 = p.wp[(size_t)c * G3::PB + G3::W3_OFF + lane];
-          if (Wc[G3::W2_OFF + lane] != want || Wc[G3::W3_OFF + lane] != want3) {
-            atomicAdd(&g_dbg_clk[45], 1ULL); g_dbg_clk[46] = (unsigned long long)q; g_dbg_clk[47] = 2;
-          }
-        }
-#endif
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&rempty[b]);
@@ -1643,9 +1595,6 @@ static size_t fwd3t_smem_bytes(int C, int K) {
   using G3 = Fwd3Geom<64, 64, 32, 16>;
   return 2 * (size_t)(OZ_S * OZ_WPLANE) + 2 * (size_t)(G3::PB - G3::W2_OFF) * 8 + 2 * 128 * 64 * sizeof(double) +
          256 * sizeof(double) + 4 * 1024 + 30 * sizeof(uint64_t) + (size_t)C * (2 + 2 * K) * sizeof(int)
-#ifdef BNN_DBG_TAGS
-         + 1024 + 16
-#endif
       ;
 }
 

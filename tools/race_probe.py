@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""Stress probe for the opt-in tensor-core kernel (k_fwd3t): repeated scoring passes compared with the FP64 kernel,
+down to the per-warp-tile partial sums, so that an intermittent corruption is located (weight set, 16-row tile,
+128-row tile, iteration of the persistent loop).  Env: N rows, S weight sets, REPS passes.
+    N=1000000 S=32 REPS=12 python tools/race_probe.py"""
 import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
@@ -24,9 +29,6 @@ dbuf = (C.c_ulonglong * 48)()
 eng.lib.bnn_debug_counters(eng._h, C.cast(dbuf, C.c_void_p))
 for rep in range(int(os.environ.get("REPS", "6"))):
     r = eng.forward_lik(wd)
-    eng.lib.bnn_debug_counters(eng._h, C.cast(dbuf, C.c_void_p))
-    print("tag mismatches:", dbuf[40], "last q/tag0/tag1/warp:", dbuf[41], C.c_longlong(dbuf[42]).value, C.c_longlong(dbuf[43]).value, dbuf[44],
-          "| rring canary fails:", dbuf[45], "q/where:", dbuf[46], dbuf[47], "| hslot canary fails:", dbuf[36], "q/where:", dbuf[37], dbuf[38], flush=True)
     d = r["loglik"] - ref["loglik"]
     cd = (r["counts"] != ref["counts"]).any(axis=1)
     idx = np.nonzero((np.abs(d) > 1e-6) | cd)[0]
