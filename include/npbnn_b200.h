@@ -204,6 +204,17 @@ int bnn_measure_fp64_peak(bnn_ctx* ctx, double* tflops);
 /* Name of the forward kernel variant used by the last call ("k_fwd3<...>" or "k_fwd_generic"). */
 const char* bnn_last_kernel(const bnn_ctx* ctx);
 
+/* Posterior-predictive resampling: sample_from_categorical (BNN_lib.py:682-713), i.e. get_posterior_cat_prob with
+ * post_summary_mode = 2, fused into the prediction pass.  u_dev [n, n_sets] holds the uniforms of the reference
+ * (np.random.random(n_sets) per instance, instance-major); for every (row, set) the class is the first one whose
+ * cumulative softmax probability reaches u (class 0 when none does, as argmin over the clipped differences gives).
+ *   est_dev          [n, K]       share of the n_sets draws per class   ('predictions')
+ *   class_counts_dev [n_sets, K]  int32, instances per class and set     ('class_counts'), may be NULL
+ *   post_pred_dev    [n, n_sets]  the drawn class as f64                 ('post_predictions'), may be NULL */
+int bnn_predict_sample(bnn_ctx* ctx, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                       const double* alpha_dev, const double* u_dev, double* est_dev, int32_t* class_counts_dev,
+                       double* post_pred_dev, void* stream);
+
 /* Debugging / tuning aids (no reference counterpart).
  * bnn_debug_read_part: per-warp-tile partial sums of the last forward pass, [sets in pass][slots][n_tiles16].
  * bnn_debug_counters : 48 clock counters of k_fwd3t, all zero unless the library was built with -DBNN_DBG_WAITCLK. */

@@ -708,12 +708,101 @@ def get_posterior_cat_prob(pred_features, post_samples=None, feature_index_to_sh
         else:
             x[:, feature_index_to_shuffle] = np.random.permutation(x[:, feature_index_to_shuffle])
     weights = [s["weights"] for s in post_samples]
-    if post_summary_mode not in (0, 1):
-        raise NotImplementedError("post_summary_mode 2 (categorical resampling) is not on the device path")
+    if post_summary_mode not in (0, 1, 2):
+        raise ValueError("post_summary_mode must be 0 (argmax votes), 1 (mean softmax) or 2 (categorical resampling)")
     eng = _predict_engine(weights[0], x.shape[1], actFun, output_act_fun)
     al = _alpha_rows([s["alphas"] for s in post_samples], actFun, len(weights[0]))
+    if post_summary_mode == 2:
+        # sample_from_categorical (BNN_lib.py:682-713): the reference draws np.random.random(S) per instance in
+        # instance order; one (N, S) draw consumes the global stream identically.  The draw itself is fused into the
+        # prediction kernel, the [S, N, K] tensor is only produced when the caller wants it back.
+        dense = eng.predict(x, weights, alphas=al, mean=False, dense=True)["dense"] if return_dense else None
+        u = np.random.random((x.shape[0], len(weights)))
+        res = eng.predict_sample(x, weights, u, alphas=al, post_predictions=False)
+        return dense, res["predictions"]
     out = eng.predict(x, weights, alphas=al, mean=(post_summary_mode == 1), votes=(post_summary_mode == 0), dense=return_dense)
     return out.get("dense"), out["votes" if post_summary_mode == 0 else "mean"]
+
+
+def sample_from_categorical(pred_features, post_samples, actFun=None, output_act_fun=None):
+    """Posterior-predictive resampling with the outputs of the reference's sample_from_categorical
+    (BNN_lib.py:682-713: 'predictions', 'class_counts', 'post_predictions'), computed from the features and the
+    posterior samples in one device pass instead of from a materialised [S, N, K] probability tensor."""
+    x = np.ascontiguousarray(pred_features, dtype=np.float64)
+    weights = [s["weights"] for s in post_samples]
+    eng = _predict_engine(weights[0], x.shape[1], actFun, output_act_fun)
+    al = _alpha_rows([s["alphas"] for s in post_samples], actFun, len(weights[0]))
+    u = np.random.random((x.shape[0], len(weights)))
+    return eng.predict_sample(x, weights, u, alphas=al, post_predictions=True)
+
+
+def CalcAccuracy(y, lab):
+    """BNN_lib.py:203-209 on a host summary ([N, K] or [S, N, K]); the per-step accuracies of the sampler come from
+    the fused counters of the forward kernels, this helper only serves the post-processing callers."""
+    y = np.asarray(y)
+    if y.ndim == 3:
+        return np.array([np.sum(i == lab) / len(i) for i in np.argmax(y, axis=2)])
+    prediction = np.argmax(y, axis=1)
+    return np.sum(prediction == lab) / len(prediction)
+
+
+def feature_importance(input_features, weights_pkl=None, weights_posterior=None, true_labels=[], fname_stem="",
+                       feature_names=[], verbose=False, post_summary_mode=0, n_permutations=100, feature_blocks=dict(),
+                       write_to_file=True, predictions_outdir="", unlink_features_within_block=True, actFun=None,
+                       output_act_fun=None):
+    """Permutation feature importance (BNN_lib.py:503-598): accuracy drop when a feature block is shuffled between
+    instances, n_permutations times per block.  Every evaluation is ONE device pass over all posterior samples
+    (get_posterior_cat_prob without the dense tensor); shuffling uses np.random.permutation like the reference, so
+    the permutations are the reference's for the same global seed."""
+    import pandas as pd
+    feature_indices = np.arange(np.asarray(input_features).shape[1])
+    if len(feature_names) == 0:
+        feature_names = feature_indices.astype(str)
+    if type(feature_blocks) is dict:
+        if len(feature_blocks.keys()) > 0:
+            selected_features, feature_block_names = list(feature_blocks.values()), list(feature_blocks.keys())
+        else:
+            selected_features = [[i] for i in feature_indices]
+            feature_block_names = [i for i in feature_names]
+    else:
+        selected_features = feature_blocks
+        feature_block_names = ["block_" + str(i) for i in range(len(feature_blocks))]
+    if weights_pkl:
+        bnn_obj, mcmc_obj, logger_obj = load_obj(weights_pkl)
+        weights_posterior = logger_obj._post_weight_samples
+        actFun, output_act_fun = bnn_obj._act_fun, bnn_obj._output_act_fun
+    kw = dict(post_summary_mode=post_summary_mode, actFun=actFun, output_act_fun=output_act_fun, return_dense=False)
+    _, pred = get_posterior_cat_prob(input_features, weights_posterior, **kw)
+    ref_accuracy = CalcAccuracy(pred, true_labels)
+    if verbose:
+        print("Reference accuracy (mean):", np.mean(ref_accuracy))
+    accuracies_wo_feature = []
+    for block_id, feature_block in enumerate(selected_features):
+        if verbose:
+            print("Processing feature block %i", block_id + 1)
+        accs = []
+        for _ in np.arange(n_permutations):
+            _, pred = get_posterior_cat_prob(input_features, weights_posterior, feature_index_to_shuffle=feature_block,
+                                             unlink_features_within_block=unlink_features_within_block, **kw)
+            accs.append(CalcAccuracy(pred, true_labels))
+        accuracies_wo_feature.append(accs)
+    accuracies_wo_feature = np.array(accuracies_wo_feature)
+    delta_accs = ref_accuracy - accuracies_wo_feature
+    df = pd.DataFrame({"feature_block_index": np.arange(len(selected_features)), "feature_name": list(feature_block_names),
+                       "delta_acc_mean": np.mean(delta_accs, axis=1), "delta_acc_std": np.std(delta_accs, axis=1),
+                       "acc_with_feature_randomized_mean": np.mean(accuracies_wo_feature, axis=1),
+                       "acc_with_feature_randomized_std": np.std(accuracies_wo_feature, axis=1)})
+    df = df.sort_values("delta_acc_mean", ascending=False)
+    if write_to_file:
+        if predictions_outdir == "":
+            predictions_outdir = os.path.dirname(weights_pkl) if weights_pkl else "."
+        if not os.path.exists(predictions_outdir) and predictions_outdir != "":
+            os.makedirs(predictions_outdir)
+        stem = fname_stem + "_" if fname_stem != "" else ""
+        path = os.path.join(predictions_outdir, stem + "feature_importance.txt")
+        df.to_csv(path, sep="\t", index=False, header=True, float_format="%.6f")
+        print("Output saved in: %s" % path)
+    return df
 
 
 def get_posterior_est(pkl_file):

@@ -842,9 +842,10 @@ int bnn_chains_set_temperature(bnn_ctx* c, const double* temperature_host, void*
   return 0;
 }
 
-int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
-                const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
-                int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, void* stream) {
+static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                        const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
+                        int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, const double* u_dev,
+                        int32_t* class_counts_dev, double* post_pred_dev, void* stream) {
   REQUIRE(c && c->have_net, "bnn_predict: call bnn_set_net first");
   REQUIRE(x_dev && w_dev && n >= 1 && n_sets >= 1, "bnn_predict: bad arguments");
   REQUIRE(mean_dev || votes_dev || dense_dev, "bnn_predict: no output requested");
@@ -880,9 +881,28 @@ int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev,
   p.inv_sets = (double)n_sets;   // divisor (np.mean and the vote share divide, BNN_lib.py:390-392)
   p.exp_tab = c->exp_tab.as<double>();
   p.exp_tab_small = c->exp_tab_small.as<double>();
+  p.samp_u = u_dev; p.samp_counts = class_counts_dev; p.samp_dense = post_pred_dev;
+  if (class_counts_dev) CUDA_TRY(cudaMemsetAsync(class_counts_dev, 0, sizeof(int32_t) * (size_t)n_sets * g.K, st));
   CUDA_TRY(timed_forward(c, p, true, st));
   c->launches += 3;
   return 0;
+}
+
+int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
+                int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, void* stream) {
+  return predict_impl(c, x_dev, n, w_dev, n_sets, alpha_dev, override_cols, override_vals, n_override, mean_dev,
+                      votes_dev, dense_dev, nullptr, nullptr, nullptr, stream);
+}
+
+int bnn_predict_sample(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                       const double* alpha_dev, const double* u_dev, double* est_dev, int32_t* class_counts_dev,
+                       double* post_pred_dev, void* stream) {
+  REQUIRE(c && c->have_net && c->g.lik == BNN_LIK_CATEGORICAL, "bnn_predict_sample: needs the categorical likelihood");
+  REQUIRE(u_dev && est_dev, "bnn_predict_sample: u_dev and est_dev are required");
+  // the per-row shares of the drawn classes use the vote accumulator of the prediction kernels
+  return predict_impl(c, x_dev, n, w_dev, n_sets, alpha_dev, nullptr, nullptr, 0, nullptr, est_dev, nullptr, u_dev,
+                      class_counts_dev, post_pred_dev, stream);
 }
 
 }  // extern "C"

@@ -286,6 +286,10 @@ struct FwdParams {
   double* votes_out;        // [n, K] or null
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
+  // posterior-predictive resampling (sample_from_categorical, BNN_lib.py:682-713); samp_u null = off
+  const double* samp_u;     // [n, C] uniforms
+  int* samp_counts;         // [C, K] instances per class and set, or null
+  double* samp_dense;       // [n, C] drawn class, or null   (the per-row shares go to votes_out)
   const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j / BNN_EXP_TAB_SIZE)
   const double* exp_tab_small;   // [256] 2^(j / 256)
   // tensor-core first layer (k_fwd3t): int8 slice tiles of X, per-row scales, per-set slices of W1; null = off

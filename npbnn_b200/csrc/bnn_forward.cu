@@ -98,12 +98,27 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
         for (int k = 0; k < K; ++k) { double e = bnn_exp_neg(z[k] - m, tab); zw[k] = e; S += e; }
         double inv = 1.0 / S;
         double* pa = pacc + (lane & 15) * K;
+        // sample_from_categorical: first class whose running sum (np.cumsum order) reaches u; none => class 0
+        const double u = p.samp_u ? p.samp_u[row * p.C + c] : 0.0;
+        double cum = 0.0;
+        int drawn = -1;
         for (int k = 0; k < K; ++k) {
           double pk = zw[k] * inv;
           pa[k] += pk;
+          cum += pk;
+          if (drawn < 0 && cum - u >= 0.0) drawn = k;
           if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + k] = pk;
         }
+        if (p.samp_u) {
+          arg = drawn < 0 ? 0 : drawn;
+          if (p.samp_dense) p.samp_dense[row * p.C + c] = (double)arg;
+        }
         pvote[(lane & 15) * K + arg] += 1;
+      }
+      if (p.samp_u && p.samp_counts) {
+        // one atomic per distinct class among the 16 rows of the warp tile
+        const unsigned grp = __match_any_sync(FULL_MASK, active ? arg : 64 + lane);
+        if (active && lane == __ffs(grp) - 1) atomicAdd(&p.samp_counts[c * K + arg], __popc(grp));
       }
     }
     return;
@@ -1764,7 +1779,7 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
     if (which) *which = "k_fwd_sparse";
     return launch_sparse(p, n_sms, st);
   }
-  if (!force_generic && g.L == 3) {
+  if (!force_generic && g.L == 3 && !p.samp_u) {
     const int k0 = g.F_pad, n1 = g.l[0].out_pad, n2 = g.l[1].out_pad, n3 = g.l[2].out_pad;
     // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
     if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {

@@ -356,3 +356,22 @@ class Engine:
             if dense:
                 out["dense"] = dd.cpu().numpy()
             return out
+
+    def predict_sample(self, x, weight_sets, u, alphas=None, post_predictions=True):
+        """sample_from_categorical (BNN_lib.py:682-713) fused into the prediction pass.  u [n, S]: the reference's
+        uniforms (np.random.random(S) per instance).  Returns dict(predictions [n,K], class_counts [S,K],
+        post_predictions [n,S] or None)."""
+        w = self._as_sets(weight_sets)
+        with torch.cuda.device(self.device):
+            xd, wd, ad = self._dev(x, torch.float64), self._dev(w, torch.float64), self._dev(alphas, torch.float64)
+            ud = self._dev(u, torch.float64)
+            n, S = xd.shape[0], wd.shape[0]
+            assert tuple(ud.shape) == (n, S)
+            est = torch.empty((n, self.K), dtype=torch.float64, device=self.device)
+            cc = torch.empty((S, self.K), dtype=torch.int32, device=self.device)
+            pp = torch.empty((n, S), dtype=torch.float64, device=self.device) if post_predictions else None
+            L.check(self.lib.bnn_predict_sample(self._h, _ptr(xd), n, _ptr(wd), S, _ptr(ad), _ptr(ud), _ptr(est), _ptr(cc),
+                                                _ptr(pp), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+            return {"predictions": est.cpu().numpy(), "class_counts": cc.cpu().numpy().astype(np.float64),
+                    "post_predictions": None if pp is None else pp.cpu().numpy()}

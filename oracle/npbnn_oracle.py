@@ -482,6 +482,21 @@ def posterior_predict(x: np.ndarray, post_weights: Sequence[Sequence[np.ndarray]
     return dense_out, np.mean(dense_out, axis=0)
 
 
+def resample_categorical(dense: np.ndarray, u: np.ndarray):
+    """sample_from_categorical (BNN_lib.py:682-713) with the uniforms injected: dense [S,N,K] class probabilities,
+    u [N,S] the np.random.random(S) draw of every instance.  For each (instance, sample) the class is the argmin over
+    k of cumsum_k - u with negative entries replaced by 1 (so: the first class whose cumulative probability reaches u;
+    class 0 when none does).  Returns (predictions [N,K], class_counts [S,K], post_predictions [N,S])."""
+    s, n, k = dense.shape
+    q = np.cumsum(dense, axis=2) - np.transpose(u)[:, :, None]
+    q = np.where(q < 0, 1.0, q)
+    drawn = np.argmin(q, axis=2)                               # [S, N]
+    onehot = (drawn[:, :, None] == np.arange(k)[None, None, :])
+    predictions = onehot.sum(axis=0) / float(s)                # share of the S draws per class
+    class_counts = onehot.sum(axis=1).astype(np.float64)       # instances per class and sample
+    return predictions, class_counts, drawn.T.astype(np.float64)
+
+
 def pdp_step(x: np.ndarray, focal: Sequence[int], values: np.ndarray, post_weights, act: str,
              post_alphas=None, out_kind: str = "softmax", classification: bool = True):
     """One grid step of get_pdp (BNN_pdp.py:63-82): overwrite focal columns, predict with all

@@ -330,6 +330,34 @@ def case_predict():
     save("predict", out, meta)
 
 
+def case_sample_cat():
+    """sample_from_categorical (BNN_lib.py:682-713) and get_posterior_cat_prob mode 2: the global numpy stream is
+    seeded, so the uniforms the reference consumed are np.random.random((n, S)) after the same seed."""
+    rng = np.random.default_rng(9)
+    n, f, k, s = 120, 5, 4, 6
+    x = rng.standard_normal((n, f))
+    out = {"x": x}
+    post = []
+    for j in range(s):
+        np.random.seed(500 + j)
+        w = bn.init_weight_prm([6, 5], f, k, init_std=0.1, bias_node=-1)
+        w = [wi + rng.normal(0, 0.8, wi.shape) for wi in w]
+        post.append({"weights": w, "alphas": [0.0]})
+        for li, wi in enumerate(w):
+            out["s%d_w%d" % (j, li)] = wi
+    af = bn.ActFun(fun="swish")
+    dense_out, _ = bn.get_posterior_cat_prob(x, post, post_summary_mode=1, actFun=af, output_act_fun=bn.SoftMax)
+    out["dense"] = dense_out
+    np.random.seed(77)
+    res = bn.sample_from_categorical(posterior_weights=dense_out)
+    np.random.seed(77)
+    out["u"] = np.random.random((n, s))
+    out["predictions"], out["class_counts"], out["post_predictions"] = res["predictions"], res["class_counts"], res["post_predictions"]
+    np.random.seed(78)
+    _, out["mode2"] = bn.get_posterior_cat_prob(x, post, post_summary_mode=2, actFun=af, output_act_fun=bn.SoftMax)
+    save("sample_cat", out, {"S": s, "act": "swish", "use_bias_node": -1, "seed_direct": 77, "seed_mode2": 78})
+
+
 def case_mc3():
     """Reference MC3.run_mcmc (BNN_mc3.py:87-126) on a toy problem: 3 chains, swap every 5 steps.
     The swap RNG (global np.random, BNN_mc3.py:99,109) is recorded by monkeypatching."""
@@ -404,3 +432,4 @@ if __name__ == "__main__":
     case_masks()
     case_predict()
     case_mc3()
+    case_sample_cat()

