@@ -71,6 +71,9 @@ typedef struct {
   double w_bound;                      /* npBNN._w_bound (inf = no reflection) */
   double prior_scale[BNN_MAX_LAYERS];  /* npBNN._prior_scale (one scalar per layer) */
   uint64_t seed;                       /* Philox key for free-running proposals */
+  int32_t n_act_prm;                   /* ActFun(trainable=True): number of activation parameters (len(_acc_prm)); 0 = fixed */
+  int32_t reserved0;
+  double init_additional_prob;         /* MCMC(init_additional_prob=): added to the initial log-prior (BNN_env.py:320) */
 } bnn_sampler_config;
 
 /* Random draws of `n_steps` MH iterations for every chain, recorded from (or generated like) the
@@ -79,7 +82,10 @@ typedef struct {
  *   count    [n_steps, C, L]        number of (ix, iy, dz) triples of that layer (= update_n)
  *   ix, iy   [n_steps, C, cap]      row / column indices, layers concatenated in order
  *   dz       [n_steps, C, cap]      the normal increments (already scaled by update_ws)
- *   log_u    [n_steps, C]           log of the accept uniform */
+ *   log_u    [n_steps, C]           log of the accept uniform
+ * With trainable activation parameters (n_act_prm > 0) alpha_ix / alpha_dz are required: the proposal
+ * prm' = reflect_[0,1](prm + dz e_ix) enters the forward pass (genReLU slopes) and the log-prior through
+ * additional_prob = log(10) * (-sum(prm')) * 10 (BNN_env.py:416-421); it is committed on accept. */
 typedef struct {
   int32_t n_steps;
   int32_t cap;
@@ -89,20 +95,26 @@ typedef struct {
   const int32_t* iy;
   const double* dz;
   const double* log_u;
+  /* optional draws of the branches that precede the layer proposals in mh_step (BNN_env.py:416-444); NULL = absent */
+  const int32_t* alpha_ix;   /* [n_steps, C] index drawn by UpdateNormal1D(_acc_prm, d=0.05, n=1, Mb=1, mb=0) (BNN_mcmc.py:46-56) */
+  const double* alpha_dz;    /* [n_steps, C] its normal increment */
+  const double* add_prob;    /* [n_steps, C] the additional_prob argument of mh_step */
 } bnn_injection;
 
 /* ---- per-chain state export (bnn_chains_read): slot indices ------------------------------------ */
 enum {
   BNN_F_LOGLIK = 0, BNN_F_LOGPRIOR = 1, BNN_F_LOGPOST = 2, BNN_F_TEMPERATURE = 3, BNN_F_ACC_RATE = 4,
   BNN_F_LOGLIK_PROP = 5, BNN_F_LOGPRIOR_PROP = 6, BNN_F_LOG_U = 7,
+  BNN_F_ADD_PROB = 8,            /* additional_prob of the current proposal (part of BNN_F_LOGPRIOR_PROP) */
   BNN_F_UPDATE_F = 16,           /* [BNN_MAX_LAYERS] */
   BNN_F_UPDATE_WS = 24,          /* [BNN_MAX_LAYERS] */
   BNN_F_FREQ_LAYER = 32,         /* [BNN_MAX_LAYERS] */
-  BNN_F_ALPHA = 40,              /* [BNN_MAX_LAYERS] genReLU slopes */
+  BNN_F_ALPHA = 40,              /* [BNN_MAX_LAYERS] genReLU slopes = accepted activation parameters (_acc_prm) */
   BNN_F_SIGMA = 48,              /* [BNN_MAX_OUT] current error_prm */
   BNN_F_SUM_R = 80,              /* [BNN_MAX_OUT] current sum of residuals (train) */
   BNN_F_SUM_R2 = 112,            /* [BNN_MAX_OUT] current sum of squared residuals (train) */
   BNN_F_SUM_R2_TEST = 144,       /* [BNN_MAX_OUT] current sum of squared residuals (test) */
+  BNN_F_ALPHA_PROP = 176,        /* [BNN_MAX_LAYERS] proposed activation parameters (_prm) */
   BNN_F_STRIDE = 192
 };
 enum {

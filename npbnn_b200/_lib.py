@@ -18,7 +18,8 @@ PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_CAUCHY, PRIOR_LAPLACE = 0, 1, 2, 3
 SIGMA_FIXED, SIGMA_EMPIRICAL = 0, 1
 
 # state slots (enum in include/npbnn_b200.h)
-F_LOGLIK, F_LOGPRIOR, F_LOGPOST, F_TEMPERATURE, F_ACC_RATE, F_LOGLIK_PROP, F_LOGPRIOR_PROP, F_LOG_U = range(8)
+F_LOGLIK, F_LOGPRIOR, F_LOGPOST, F_TEMPERATURE, F_ACC_RATE, F_LOGLIK_PROP, F_LOGPRIOR_PROP, F_LOG_U, F_ADD_PROB = range(9)
+F_ALPHA_PROP = 176
 F_UPDATE_F, F_UPDATE_WS, F_FREQ_LAYER, F_ALPHA, F_SIGMA, F_SUM_R, F_SUM_R2, F_SUM_R2_TEST, F_STRIDE = \
     16, 24, 32, 40, 48, 80, 112, 144, 192
 I_ITERATION, I_LAST_ACCEPTED, I_N_ACCEPTED, I_RING_LEN, I_RING_HEAD, I_RING_SUM = range(6)
@@ -35,12 +36,14 @@ class SamplerConfig(C.Structure):
     _fields_ = [("prior", C.c_int32), ("sigma_mode", C.c_int32), ("sample_from_prior", C.c_int32),
                 ("adapt_freq", C.c_int32), ("adapt_stop", C.c_int32), ("use_mask", C.c_int32),
                 ("adapt_f", C.c_double), ("adapt_fM", C.c_double), ("lik_temp", C.c_double),
-                ("w_bound", C.c_double), ("prior_scale", C.c_double * MAX_LAYERS), ("seed", C.c_uint64)]
+                ("w_bound", C.c_double), ("prior_scale", C.c_double * MAX_LAYERS), ("seed", C.c_uint64),
+                ("n_act_prm", C.c_int32), ("reserved0", C.c_int32), ("init_additional_prob", C.c_double)]
 
 
 class Injection(C.Structure):
     _fields_ = [("n_steps", C.c_int32), ("cap", C.c_int32), ("proposed", C.c_void_p), ("count", C.c_void_p),
-                ("ix", C.c_void_p), ("iy", C.c_void_p), ("dz", C.c_void_p), ("log_u", C.c_void_p)]
+                ("ix", C.c_void_p), ("iy", C.c_void_p), ("dz", C.c_void_p), ("log_u", C.c_void_p),
+                ("alpha_ix", C.c_void_p), ("alpha_dz", C.c_void_p), ("add_prob", C.c_void_p)]
 
 
 class NpbnnError(RuntimeError):

@@ -20,10 +20,12 @@ the draws on the device: the chain is then the reference's chain (same accept/re
 log-likelihood differs in the last bits because of the summation order).  `rng="philox"` generates the
 proposals on the device and never leaves it between logging points.
 
-Options of the reference that are not on the device path raise NotImplementedError at construction:
-trainable activation parameters, feature / weight indicators, hyper-priors, user-supplied likelihood /
-proposal / output functions, the regression error-parameter proposal (estimate_error with
-empirical_error=False once the iteration passes `_estimate_error`).
+Trainable activation parameters (ActFun(trainable=True)), init_additional_prob and mh_step(additional_prob=) run
+on the device from host-drawn numbers (rng="host").  Options of the reference that are not on the device path raise
+NotImplementedError: feature / weight indicators, hyper-priors, user-supplied likelihood / proposal / output
+functions, and the regression error-parameter proposal (estimate_error with empirical_error=False once the
+iteration passes `_estimate_error` -- a branch on which the reference itself raises AttributeError as soon as one
+proposal has been accepted before that iteration, BNN_mcmc.py:105).
 """
 import csv
 import os
@@ -80,8 +82,6 @@ class ActFun:
     fun="ReLU" with trainable=True still evaluates as plain ReLU (eval passes prm 0 unless fun=="genReLU")."""
 
     def __init__(self, fun="ReLU", prm=np.zeros(1), trainable=False):
-        if trainable:
-            raise NotImplementedError("trainable activation parameters are not on the device path")
         if fun not in ("ReLU", "genReLU", "swish", "tanh"):
             raise ValueError("unknown activation %r" % (fun,))
         self._prm = prm
@@ -96,12 +96,18 @@ class ActFun:
         self._acc_prm = self._prm + 0
 
     def alphas(self, n_layers):
-        if self._function != "genReLU":
+        """Per-layer slopes for the device state: the parameters matter for the forward pass only with
+        fun == "genReLU" (eval, BNN_lib.py:83-87), but trainable ones are proposed and enter the prior whatever the
+        function is (BNN_env.py:416-421), so they are carried in the chain state in that case too."""
+        if self._function != "genReLU" and not self._trainable:
             return None
         a = np.zeros(n_layers)
-        p = np.atleast_1d(np.asarray(self._prm, dtype=np.float64))
+        p = np.atleast_1d(np.asarray(self._acc_prm if self._trainable else self._prm, dtype=np.float64))
         a[:min(len(p), n_layers)] = p[:n_layers]
         return a
+
+    def n_trainable(self):
+        return len(np.atleast_1d(self._acc_prm)) if self._trainable else 0
 
 
 def init_weight_prm(n_nodes, n_features, size_output, init_std=0.1, bias_node=0):
@@ -290,7 +296,7 @@ class _ChainGroup:
     injection arrays of bnn_mh_steps."""
 
     def __init__(self, bnn, weights_per_chain, temperatures, update_f, update_ws, lik_temp, adapt_f, adapt_fM,
-                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0):
+                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0, init_additional_prob=0.0):
         self.bnn = bnn
         net = _net_of(weights_per_chain[0], bnn._n_features, bnn._act_fun, bnn._estimation_mode)
         self.net = net
@@ -308,12 +314,16 @@ class _ChainGroup:
                              sigma_mode=L.SIGMA_EMPIRICAL if (bnn._estimation_mode == "regression" and bnn._empirical_error)
                              else L.SIGMA_FIXED,
                              lik_temp=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq,
-                             adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed)
+                             adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed,
+                             n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob)
+        self.n_act_prm = bnn._act_fun.n_trainable()
+        if self.n_act_prm > net.n_layers:
+            raise ValueError("more trainable activation parameters than layers")
         self.labels_count = None
         if bnn._estimation_mode == "classification":
             self.labels_count = np.bincount(bnn._labels, minlength=bnn._size_output)
 
-    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None):
+    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None, additional_prob=0):
         """Consume each chain's generator exactly as mh_step + UpdateNormal do (BNN_env.py:446-453,493;
         BNN_mcmc.py:62-65) for n_steps iterations during which no adaptation fires.
         reseed(chain, iteration) -> Generator implements randomize_seed (BNN_env.py:383-384)."""
@@ -323,10 +333,18 @@ class _ChainGroup:
         inj = {"proposed": np.zeros((n_steps, self.n, nl), np.int32), "count": np.zeros((n_steps, self.n, nl), np.int32),
                "ix": np.zeros((n_steps, self.n, cap), np.int32), "iy": np.zeros((n_steps, self.n, cap), np.int32),
                "dz": np.zeros((n_steps, self.n, cap)), "log_u": np.zeros((n_steps, self.n))}
+        if self.n_act_prm:
+            inj["alpha_ix"] = np.zeros((n_steps, self.n), np.int32)
+            inj["alpha_dz"] = np.zeros((n_steps, self.n))
+        if additional_prob:
+            inj["add_prob"] = np.full((n_steps, self.n), float(additional_prob))
         for c in range(self.n):
             flu, un, uws = state.freq_layer_update[c], state.update_n[c], state.update_ws[c]
             for s in range(n_steps):
                 rs = rngs[c] if reseed is None else reseed(chain_ids[c], int(state.iteration[c]) + s)
+                if self.n_act_prm:        # UpdateNormal1D(_acc_prm, d=0.05, n=1, ...) comes first (BNN_env.py:416-417)
+                    inj["alpha_ix"][s, c] = rs.integers(0, self.n_act_prm, 1)[0]
+                    inj["alpha_dz"][s, c] = rs.normal(0, 0.05, 1)[0]
                 rr = rs.random(nl)
                 rr[np.argmin(rr)] = 0
                 o = 0
@@ -367,10 +385,10 @@ class MCMC:
             raise NotImplementedError("only update_function=UpdateNormal runs on the device")
         if likelihood_f is not None or accuracy_f is not None or accuracy_lab_f is not None:
             raise NotImplementedError("user-supplied likelihood / accuracy functions are not on the device path")
-        if init_additional_prob:
-            raise NotImplementedError("init_additional_prob is not on the device path")
         if rng not in ("host", "philox"):
             raise ValueError("rng must be 'host' or 'philox'")
+        if rng == "philox" and bnn_obj._act_fun._trainable:
+            raise NotImplementedError("trainable activation parameters are proposed from host-drawn numbers (rng='host')")
         nl = bnn_obj._n_layers
         if update_ws is None:
             update_ws = [0.075] * nl
@@ -398,7 +416,10 @@ class MCMC:
         if _group is None:
             _group = _ChainGroup(bnn_obj, [bnn_obj._w_layers], [temperature], list(update_f)[:nl], list(update_ws)[:nl],
                                  likelihood_tempering, adapt_f, adapt_fM, adapt_freq, self._adapt_stop, sample_from_prior,
-                                 seed=int(bnn_obj._seed) + 7919 * int(mcmc_id), device=device)
+                                 seed=int(bnn_obj._seed) + 7919 * int(mcmc_id), device=device,
+                                 init_additional_prob=init_additional_prob)
+        elif bnn_obj._act_fun._trainable or init_additional_prob:
+            raise NotImplementedError("trainable activation parameters / init_additional_prob inside an MC3 group")
         self._group, self._slot = _group, _slot
         self._bnn_shapes = [w.shape for w in bnn_obj._w_layers]
         self._sync(bnn_obj, self._group.eng.read_state())
@@ -434,6 +455,10 @@ class MCMC:
             self._test_accuracy = float(np.sum(st.sum_r2_test[c]) / (nt * o)) if nt else 0
             if bnn_obj._estimation_mode == "regression":
                 bnn_obj._error_prm = np.array(st.sigma[c])
+        if bnn_obj._act_fun._trainable:
+            na = bnn_obj._act_fun.n_trainable()
+            bnn_obj._act_fun._acc_prm = np.array(st.alpha[c][:na])          # reset_accepted_prm
+            bnn_obj._act_fun._prm = np.array(st.alpha_prop[c][:na])         # the last proposal (BNN_env.py:421)
         if st.w is not None:
             bnn_obj._w_layers = st.weights(c)        # fresh arrays: logged samples keep their own copies
         self._y_cache = None
@@ -453,13 +478,18 @@ class MCMC:
 
     def _check_supported(self, n_steps):
         if self._regression_error_proposal and self._current_iteration + n_steps - 1 > self._estimate_error:
+            # the reference itself cannot take this branch once any proposal has been accepted: accepts before
+            # _estimate_error reset error_prm to the scalar 1 and multiplier_proposal_vector(1, ...) raises
+            # AttributeError (BNN_mcmc.py:105) -- measured, tests/golden/make_golden.py
             raise NotImplementedError("the regression error-parameter proposal (BNN_env.py:435-442) is not on the device path; "
                                       "use empirical_error=True or estimate_error=False")
 
     # ---------------------------------------------------------------- stepping
-    def run(self, bnn_obj, n_steps):
+    def run(self, bnn_obj, n_steps, additional_prob=0):
         """n_steps MH iterations (BNN_env.py:381-532 each) with as few host round trips as the rng mode allows."""
         self._check_supported(n_steps)
+        if additional_prob and self._rng_mode == "philox":
+            raise NotImplementedError("additional_prob is injected with the host-drawn numbers (rng='host')")
         g = self._group
         if not self._own_group:
             raise RuntimeError("this MCMC belongs to an MC3 group; step the group instead")
@@ -477,15 +507,13 @@ class MCMC:
                                    self._max_n, int(np.sum(self._max_n)))
                 k = min(n_steps - done, _steps_to_adaptation(it, self._adapt_freq, self._adapt_stop))
                 reseed = (lambda cid, i: np.random.default_rng(i + self._mcmc_id)) if self._randomize_seed else None
-                inj = g.draw_steps([self._rs], st, [self._mcmc_id], k, reseed)
+                inj = g.draw_steps([self._rs], st, [self._mcmc_id], k, reseed, additional_prob)
                 g.eng.mh_steps(k, inj)
                 done += k
         self._sync(bnn_obj, g.eng.read_state())
 
     def mh_step(self, bnn_obj, additional_prob=0, return_bnn=False):
-        if additional_prob:
-            raise NotImplementedError("additional_prob is not on the device path")
-        self.run(bnn_obj, 1)
+        self.run(bnn_obj, 1, additional_prob)
         if return_bnn:
             return bnn_obj, self
 

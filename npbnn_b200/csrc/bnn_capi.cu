@@ -70,7 +70,7 @@ struct bnn_ctx {
   bnn_sampler_config cfg{};
   PriorScales ps{};
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
-  DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu;
+  DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu, inj_alpha_ix, inj_alpha_dz, inj_add_prob;
   const char* last_kernel = "";
   // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
   // tensor-core first layer (k_fwd3t): int8 slices of X (made once per data set) and of W1 (per scored batch)
@@ -207,7 +207,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
                     &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -607,6 +607,7 @@ static ChainDev chain_dev(bnn_ctx* c) {
   d.part = c->part.as<double>();
   d.NF = n_slots(c->g);
   d.counts_prop = c->counts_prop.as<int>();
+  d.alpha_fwd = c->alpha_chain.as<double>();
   return d;
 }
 
@@ -643,6 +644,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   REQUIRE(c && c->have_data, "bnn_chains_init: call bnn_set_net and bnn_set_data first");
   REQUIRE(cfg && w0_host && temperature && update_f && update_ws && n_chains >= 1, "bnn_chains_init: bad arguments");
   REQUIRE(cfg->adapt_freq >= 1, "bnn_chains_init: adapt_freq must be >= 1");
+  REQUIRE(cfg->n_act_prm >= 0 && cfg->n_act_prm <= c->g.L, "bnn_chains_init: n_act_prm must be in [0, n_layers]");
   REQUIRE(!cfg->use_mask || mask_host, "bnn_chains_init: use_mask set but mask_host is null");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -767,6 +769,22 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
     d.inj_dz = c->inj_dz.as<double>();
     d.inj_logu = c->inj_logu.as<double>();
     d.inj_cap = inj->cap;
+    const size_t ns = (size_t)n_steps * c->C;
+    if (c->cfg.n_act_prm > 0) {
+      REQUIRE(inj->alpha_ix && inj->alpha_dz, "bnn_mh_steps: trainable activation parameters need alpha_ix / alpha_dz");
+      for (size_t s = 0; s < ns; ++s)
+        REQUIRE(inj->alpha_ix[s] >= 0 && inj->alpha_ix[s] < c->cfg.n_act_prm, "bnn_mh_steps: alpha_ix out of range");
+      if (upload(c->inj_alpha_ix, inj->alpha_ix, ns, st) || upload(c->inj_alpha_dz, inj->alpha_dz, ns, st)) return 1;
+      d.inj_alpha_ix = c->inj_alpha_ix.as<int>();
+      d.inj_alpha_dz = c->inj_alpha_dz.as<double>();
+    }
+    if (inj->add_prob) {
+      if (upload(c->inj_add_prob, inj->add_prob, ns, st)) return 1;
+      d.inj_add_prob = c->inj_add_prob.as<double>();
+    }
+  } else {
+    REQUIRE(c->cfg.n_act_prm == 0, "bnn_mh_steps: trainable activation parameters are proposed from injected draws only "
+                                    "(no on-device generator for that branch)");
   }
   for (int s = 0; s < n_steps; ++s) {
     CUDA_TRY(bnn_launch_mh_update(d, s > 0 ? 1 : 0, 1, s, st));

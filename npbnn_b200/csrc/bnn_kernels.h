@@ -32,6 +32,10 @@ struct ChainDev {
   const double* inj_dz;
   const double* inj_logu;
   int inj_cap;
+  const int* inj_alpha_ix;    // [n_steps, C] or null
+  const double* inj_alpha_dz;
+  const double* inj_add_prob; // [n_steps, C] or null
+  double* alpha_fwd;          // [C, L] slopes the forward kernel reads (= the proposal's)
 };
 
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,

@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
       s_flag = acc;
       if (acc) {
         sf[BNN_F_LOGLIK] = ll; sf[BNN_F_LOGPRIOR] = lp; sf[BNN_F_LOGPOST] = post;
+        // ActFun.reset_accepted_prm (BNN_env.py:502-503)
+        for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA + l] = sf[BNN_F_ALPHA_PROP + l];
       }
       if (accept_mode == 1) {
         si[BNN_I_LAST_ACCEPTED] = acc;
@@ -311,8 +313,30 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
         sf[BNN_F_LOG_U] = log(u53(r.x, r.y));
       }
       for (int l = 0; l < g.L; ++l) si[BNN_I_PROPOSED + l] = s_prop[l];
+      // trainable activation parameters (BNN_env.py:416-421): UpdateNormal1D(_acc_prm, d=0.05, n=1, Mb=1, mb=0) with
+      // the injected draw, both reflections over every entry (BNN_mcmc.py:46-56), Exp(10) term into additional_prob
+      double addp = d.inj_add_prob ? d.inj_add_prob[(long long)step * d.C + c] : 0.0;
+      for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
+      if (d.cfg.n_act_prm > 0 && d.inj_alpha_ix) {
+        const int ix = d.inj_alpha_ix[(long long)step * d.C + c];
+        sf[BNN_F_ALPHA_PROP + ix] = sf[BNN_F_ALPHA + ix] + d.inj_alpha_dz[(long long)step * d.C + c];
+        double sum = 0.0;
+        for (int l = 0; l < d.cfg.n_act_prm; ++l) {
+          double z = sf[BNN_F_ALPHA_PROP + l];
+          if (z > 1.0) z = 1.0 - (z - 1.0);
+          if (z < 0.0) z = 0.0 + (0.0 - z);
+          sf[BNN_F_ALPHA_PROP + l] = z;
+          sum += z;
+        }
+        addp += log(10.0) * (-sum) * 10.0;
+      }
+      sf[BNN_F_ADD_PROB] = addp;
+      for (int l = 0; l < g.L; ++l) d.alpha_fwd[(long long)c * g.L + l] = sf[BNN_F_ALPHA_PROP + l];
     } else {
       for (int l = 0; l < g.L; ++l) { s_prop[l] = 0; s_cnt[l] = 0; s_off[l] = 0; }
+      // initial state (MCMC.__init__, BNN_env.py:313-320): stored parameters, init_additional_prob
+      for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
+      sf[BNN_F_ADD_PROB] = d.cfg.init_additional_prob;
     }
   }
   // zero the proposal's counters (the forward kernel accumulates into them)
@@ -372,7 +396,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     wpk[bnn_packed_index(lg, r, cc)] = z;
   }
   double s = block_sum_fixed(lp, sh);
-  if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s;
+  if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s + sf[BNN_F_ADD_PROB];     // calc_prior(...) + additional_prob (BNN_env.py:481)
 }
 
 // ------------------------------------------------------------------------------------------------

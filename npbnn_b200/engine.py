@@ -87,6 +87,8 @@ class ChainState:
         self.acceptance_rate = f64[:, L.F_ACC_RATE]
         self.logLik_prop = f64[:, L.F_LOGLIK_PROP]
         self.logPrior_prop = f64[:, L.F_LOGPRIOR_PROP]
+        self.alpha = f64[:, L.F_ALPHA:L.F_ALPHA + nl]              # accepted activation parameters per layer
+        self.alpha_prop = f64[:, L.F_ALPHA_PROP:L.F_ALPHA_PROP + nl]
         self.update_f = f64[:, L.F_UPDATE_F:L.F_UPDATE_F + nl]
         self.update_ws = f64[:, L.F_UPDATE_WS:L.F_UPDATE_WS + nl]
         self.freq_layer_update = f64[:, L.F_FREQ_LAYER:L.F_FREQ_LAYER + nl]
@@ -244,7 +246,8 @@ class Engine:
     # ---------------------------------------------------------------- chains
     def chains_init(self, w0, temperature=None, update_f=None, update_ws=None, prior=L.PRIOR_NORMAL, prior_scale=1.0,
                     w_bound=np.inf, mask=None, alphas=None, sigma0=None, sigma_mode=L.SIGMA_FIXED, lik_temp=1.0,
-                    adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=0, sample_from_prior=0, seed=1234):
+                    adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=0, sample_from_prior=0, seed=1234,
+                    n_act_prm=0, init_additional_prob=0.0):
         w = np.ascontiguousarray(self._as_sets(w0), dtype=np.float64)
         n, nl = w.shape[0], self.net.n_layers
 
@@ -267,6 +270,7 @@ class Engine:
         for i in range(nl):
             cfg.prior_scale[i] = float(ps[i])
         cfg.seed = int(seed)
+        cfg.n_act_prm, cfg.init_additional_prob = int(n_act_prm), float(init_additional_prob)
         mk = None
         if mask is not None:
             mk = np.ascontiguousarray(flatten_weights(mask) if not isinstance(mask, np.ndarray) else mask, dtype=np.float64)
@@ -284,6 +288,10 @@ class Engine:
             return
         arrs = {k: np.ascontiguousarray(injection[k], dtype=(np.float64 if k in ("dz", "log_u") else np.int32))
                 for k in ("proposed", "count", "ix", "iy", "dz", "log_u")}
+        for k, dt in (("alpha_ix", np.int32), ("alpha_dz", np.float64), ("add_prob", np.float64)):   # optional branches
+            if injection.get(k) is not None:
+                arrs[k] = np.ascontiguousarray(injection[k], dtype=dt)
+                assert arrs[k].shape[:2] == arrs["log_u"].shape
         T, Cn, cap = arrs["ix"].shape
         assert Cn == self.n_chains and T >= n_steps
         inj = L.Injection()

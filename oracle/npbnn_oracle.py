@@ -245,6 +245,7 @@ class Model:
     error_prm: object = 1.0
     x_test: Optional[np.ndarray] = None
     labels_test: Optional[np.ndarray] = None
+    act_trainable: bool = False         # ActFun(trainable=True): `alphas` are the accepted parameters (_acc_prm)
 
     def __post_init__(self):
         if self.prior_scale is None:
@@ -278,6 +279,7 @@ class Sampler:
     adapt_stop: int = 0
     sample_from_prior: int = 0
     it: int = 0
+    estimate_error: float = np.inf      # MCMC._estimate_error (BNN_env.py:374-377): error_prm is proposed after it
     freq_layer_update: Optional[np.ndarray] = None
     acc_mem: List[int] = field(default_factory=lambda: [1])
     acceptance_rate: float = 0.0
@@ -293,7 +295,7 @@ class Sampler:
 
 def make_sampler(m: Model, update_f=None, update_ws=None, temperature=1.0, n_iteration=100000,
                  lik_temp=1.0, adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=None,
-                 sample_from_prior=0) -> Sampler:
+                 sample_from_prior=0, estimate_error=False, init_additional_prob=0.0) -> Sampler:
     """MCMC.__init__ (BNN_env.py:274-379): update sizes, initial forward / lik / prior / accuracy."""
     nl = len(m.weights)
     if update_ws is None:
@@ -307,10 +309,12 @@ def make_sampler(m: Model, update_f=None, update_ws=None, temperature=1.0, n_ite
                 max_n=sizes.astype(int), temperature=temperature, lik_temp=lik_temp, adapt_f=adapt_f,
                 adapt_fM=adapt_fM, adapt_freq=adapt_freq,
                 adapt_stop=int(n_iteration * 0.05) if adapt_stop is None else adapt_stop,
-                sample_from_prior=sample_from_prior, freq_layer_update=np.ones(nl))
+                sample_from_prior=sample_from_prior, freq_layer_update=np.ones(nl),
+                # BNN_env.py:374-377: min(20000, 0.1 n_iteration) when estimate_error else n_iteration
+                estimate_error=float(min(20000, 0.1 * n_iteration)) if estimate_error else float(n_iteration))
     y = forward(m.x, m.weights, m.act, m.alphas, m.out_kind)
     s.logLik = 0.0 if sample_from_prior else likelihood(m, y, m.error_prm, lik_temp)
-    s.logPrior = log_prior(m.weights, m.prior, m.prior_scale)
+    s.logPrior = log_prior(m.weights, m.prior, m.prior_scale) + init_additional_prob      # BNN_env.py:320
     s.logPost = s.logLik + s.logPrior
     _refresh_accuracy(m, s, y, m.weights)
     return s
@@ -374,6 +378,11 @@ class StepInjection:
     rr: np.ndarray
     layers: List[Optional[tuple]]       # per layer: None (not proposed) or (ix, iy, dz)
     log_u: float
+    # optional proposals drawn BEFORE rr (BNN_env.py:416-444), in this order:
+    alpha_ix: Optional[int] = None      # UpdateNormal1D on ActFun._acc_prm: rs.integers(0, len, 1), rs.normal(0, 0.05, 1)
+    alpha_dz: float = 0.0
+    sigma_mult: Optional[np.ndarray] = None   # multiplier_proposal_vector: rs.binomial(1, .5, S), rs.random(S) -> m
+    add_prob: float = 0.0               # the additional_prob argument of mh_step
 
 
 def layer_is_proposed(rr: np.ndarray, freq_layer_update: np.ndarray, freq_indicator: float = 0.0) -> np.ndarray:
@@ -387,9 +396,39 @@ def layer_is_proposed(rr: np.ndarray, freq_layer_update: np.ndarray, freq_indica
     return ok
 
 
+def error_prm_is_proposed(m: Model, s: Sampler) -> bool:
+    """BNN_env.py:435-444: regression, past _estimate_error, no empirical error."""
+    return m.mode == "regression" and s.it > s.estimate_error and not m.empirical_error
+
+
+def multiplier_from_draws(ff: np.ndarray, u: np.ndarray, d: float = 1.1) -> np.ndarray:
+    """multiplier_proposal_vector (BNN_mcmc.py:101-113): m = exp(2 log(d) (u - 0.5)), 1 where the mask is 0."""
+    mult = np.exp(2 * np.log(d) * (u - .5))
+    mult[ff == 0] = 1.
+    return mult
+
+
+def propose_act_prm(prm, ix: int, dz: float) -> np.ndarray:
+    """UpdateNormal1D(prm, d=0.05, n=1, Mb=1, mb=0) (BNN_mcmc.py:46-56) with the draw injected; both reflections
+    act on every entry."""
+    z = np.zeros(np.shape(prm)) + np.asarray(prm, dtype=np.float64)
+    z[ix] = z[ix] + dz
+    z[z > 1] = 1 - (z[z > 1] - 1)
+    z[z < 0] = 0 + (0 - z[z < 0])
+    return z
+
+
 def draw_injection(m: Model, s: Sampler, rs: np.random.Generator) -> StepInjection:
-    """Consume `rs` exactly as mh_step + UpdateNormal do (BNN_env.py:446-453, BNN_mcmc.py:62-65)."""
+    """Consume `rs` exactly as mh_step + UpdateNormal do (BNN_env.py:416-453, BNN_mcmc.py:46-69,101-113)."""
     nl = len(m.weights)
+    extra = {}
+    if m.act_trainable:
+        extra["alpha_ix"] = int(rs.integers(0, len(m.alphas), 1)[0])
+        extra["alpha_dz"] = float(rs.normal(0, 0.05, 1)[0])
+    if error_prm_is_proposed(m, s):
+        shape = np.shape(m.error_prm)
+        ff = rs.binomial(1, 0.5, shape)
+        extra["sigma_mult"] = multiplier_from_draws(ff, rs.random(shape))
     rr = rs.random(nl)
     ok = layer_is_proposed(rr, s.freq_layer_update)
     layers = []
@@ -403,7 +442,7 @@ def draw_injection(m: Model, s: Sampler, rs: np.random.Generator) -> StepInjecti
         iy = rs.integers(0, w.shape[1], n)
         dz = rs.normal(0, np.full(n, s.update_ws[i]), n)
         layers.append((ix, iy, dz))
-    return StepInjection(rr=rr, layers=layers, log_u=float(np.log(rs.random())))
+    return StepInjection(rr=rr, layers=layers, log_u=float(np.log(rs.random())), **extra)
 
 
 def mh_step(m: Model, s: Sampler, inj: Optional[StepInjection] = None,
@@ -414,6 +453,21 @@ def mh_step(m: Model, s: Sampler, inj: Optional[StepInjection] = None,
     adapt(m, s)
     if inj is None:
         inj = draw_injection(m, s, rs)
+    hastings = 0.0
+    additional_prob = inj.add_prob
+    alphas = m.alphas
+    if m.act_trainable:                                       # BNN_env.py:416-421
+        alphas = propose_act_prm(m.alphas, inj.alpha_ix, inj.alpha_dz)
+        r = 10
+        additional_prob += np.log(r) * -np.sum(alphas) * r    # "aka exponential Exp(r)"
+    # error parameter (BNN_env.py:435-444): multiplier proposal past _estimate_error, else the scalar 1;
+    # regression + empirical_error replaces it by the residual std after the forward pass (:475-476)
+    sig = 1
+    if error_prm_is_proposed(m, s):
+        sig = m.error_prm * inj.sigma_mult
+        hastings += np.sum(np.log(inj.sigma_mult))
+        r = 1
+        additional_prob += np.log(r) * -np.sum(sig) * r
     w_prime = []
     for i, w in enumerate(m.weights):
         upd = inj.layers[i]
@@ -424,19 +478,19 @@ def mh_step(m: Model, s: Sampler, inj: Optional[StepInjection] = None,
         if m.mask is not None:
             z = z * m.mask[i]
         w_prime.append(z)
-    y = forward(m.x, w_prime, m.act, m.alphas, m.out_kind)
-    # error parameter: scalar 1 unless regression+empirical (BNN_env.py:435-444, 475-476)
-    sig = 1
+    y = forward(m.x, w_prime, m.act, alphas, m.out_kind)
     if m.mode == "regression" and m.empirical_error:
         sig = np.std(y - m.labels, axis=0)
-    lp = log_prior(w_prime, m.prior, m.prior_scale)
+    lp = log_prior(w_prime, m.prior, m.prior_scale) + additional_prob
     ll = 0.0 if s.sample_from_prior else likelihood(m, y, sig, s.lik_temp)
     post = ll + lp
-    accept = bool((post - s.logPost) * s.temperature + 0.0 >= inj.log_u)
+    accept = bool((post - s.logPost) * s.temperature + hastings >= inj.log_u)
     if accept:
         m.weights = w_prime
         if m.mode == "regression":
             m.error_prm = sig
+        if m.act_trainable:
+            m.alphas = alphas                                  # reset_accepted_prm
         s.logPost, s.logLik, s.logPrior = post, ll, lp
         _refresh_accuracy(m, s, y, w_prime)
         s.last_accepted = 1
@@ -447,7 +501,8 @@ def mh_step(m: Model, s: Sampler, inj: Optional[StepInjection] = None,
     if len(s.acc_mem) > 100:
         s.acc_mem = s.acc_mem[-100:]
     s.it += 1
-    return {"logLik_prime": ll, "logPrior_prime": lp, "accepted": int(accept)}
+    return {"logLik_prime": ll, "logPrior_prime": lp, "accepted": int(accept), "additional_prob": additional_prob,
+            "hastings": hastings}
 
 
 # --------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CHAIN_CASES = ["c1_classify", "c2_regress_emp1", "c2_regress_emp0", "syn_swish_cauchy", "syn_genrelu_laplace",
                "syn_uniform_bound", "syn_classw_temp", "syn_instw", "syn_adapt", "syn_block_mask",
-               "syn_regress_error"]
+               "syn_regress_error", "syn_trainable_genrelu", "syn_trainable_tanh"]
 
 
 def load(name):
@@ -41,14 +41,15 @@ def build_model(z, meta) -> orc.Model:
         empirical_error=bool(meta.get("empirical_error", False)),
         error_prm=np.ones(labels.shape[1]) if mode == "regression" else 1.0,
         x_test=np.array(z["x_test"]) if len(z["x_test"]) else None,
-        labels_test=labels_test if len(z["x_test"]) else None)
+        labels_test=labels_test if len(z["x_test"]) else None,
+        act_trainable=bool(meta.get("trainable", False)))
 
 
 def build_sampler(m, meta) -> orc.Sampler:
     return orc.make_sampler(m, update_f=meta["update_f"], update_ws=meta["update_ws"],
                             temperature=meta["temperature"], n_iteration=meta["n_iteration"],
                             lik_temp=meta["lik_temp"], adapt_f=meta["adapt_f"], adapt_fM=meta["adapt_fM"],
-                            adapt_freq=meta["adapt_freq"])
+                            adapt_freq=meta["adapt_freq"], init_additional_prob=meta.get("init_additional_prob", 0.0))
 
 
 def injection(z, meta, t) -> orc.StepInjection:
@@ -62,7 +63,10 @@ def injection(z, meta, t) -> orc.StepInjection:
                            z["prop_l%d_dz" % i][a:b]))
         else:
             layers.append(None)
-    return orc.StepInjection(rr=z["steps_rr"][t], layers=layers, log_u=float(z["steps_log_u"][t]))
+    extra = {}
+    if meta.get("trainable"):
+        extra = {"alpha_ix": int(z["steps_alpha_ix"][t]), "alpha_dz": float(z["steps_alpha_dz"][t])}
+    return orc.StepInjection(rr=z["steps_rr"][t], layers=layers, log_u=float(z["steps_log_u"][t]), **extra)
 
 
 def injection_arrays(z, meta, t0, t1, n_chains=1):
@@ -91,4 +95,8 @@ def injection_arrays(z, meta, t0, t1, n_chains=1):
             dz[t - t0, :, o:o + b - a] = z["prop_l%d_dz" % i][a:b]
             o += b - a
         log_u[t - t0, :] = float(z["steps_log_u"][t])
-    return dict(proposed=proposed, count=count, ix=ix, iy=iy, dz=dz, log_u=log_u)
+    out = dict(proposed=proposed, count=count, ix=ix, iy=iy, dz=dz, log_u=log_u)
+    if meta.get("trainable"):
+        out["alpha_ix"] = np.repeat(z["steps_alpha_ix"][t0:t1].astype(np.int32)[:, None], n_chains, 1)
+        out["alpha_dz"] = np.repeat(z["steps_alpha_dz"][t0:t1].astype(np.float64)[:, None], n_chains, 1)
+    return out

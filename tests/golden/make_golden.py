@@ -49,6 +49,11 @@ class RecRNG:
         self.log.append(("random", np.array(v)))
         return v
 
+    def binomial(self, *a, **k):
+        v = self._rng.binomial(*a, **k)
+        self.log.append(("binomial", np.array(v)))
+        return v
+
 
 def quiet(f, *a, **k):
     with contextlib.redirect_stdout(io.StringIO()):
@@ -97,6 +102,17 @@ def record_chain(bnn, mcmc, n_steps, out, prefix=""):
         rec.log.clear(); lik_log.clear(); prior_log.clear()
         quiet(mcmc.mh_step, bnn)
         log = list(rec.log)
+        # optional proposals drawn before rr (BNN_env.py:416-444): activation parameter, error parameter
+        if bnn._act_fun._trainable:
+            assert log[0][0] == "integers" and log[1][0] == "normal", log[:2]
+            put("alpha_ix", int(log[0][1][0])); put("alpha_dz", float(log[1][1][0]))
+            log = log[2:]
+        if bnn._estimation_mode == "regression":
+            if log[0][0] == "binomial":
+                put("sigma_on", 1); put("sigma_ff", log[0][1].astype(np.int32)); put("sigma_u", log[1][1])
+                log = log[2:]
+            else:
+                put("sigma_on", 0); put("sigma_ff", np.zeros(bnn._size_output, np.int32)); put("sigma_u", np.zeros(bnn._size_output))
         assert log[0][0] == "random" and log[0][1].shape == (nl,), log[0]
         assert log[-1][0] == "random" and log[-1][1].shape == ()
         rr = log[0][1]
@@ -142,6 +158,8 @@ def record_chain(bnn, mcmc, n_steps, out, prefix=""):
         put("freq_layer_update", flu)
         if bnn._estimation_mode == "regression":
             put("error_prm", np.asarray(bnn._error_prm, dtype=np.float64) * np.ones(bnn._size_output))
+        if bnn._act_fun._trainable:
+            put("act_prm", np.asarray(bnn._act_fun._acc_prm, dtype=np.float64))
     for k, v in per_step.items():
         out[prefix + "steps_" + k] = np.stack(v)
     for i in range(nl):
@@ -225,13 +243,13 @@ def synth_class(n, f, k, seed, n_test=0):
 def case_synth(name, n=500, f=6, k=3, n_nodes=(4, 3), act="swish", alphas=None, prior=1, p_scale=1.0,
                bias=2, class_w=0, inst_w=False, temperature=1.0, lik_temp=1.0, n_test=64, mask_spec=None,
                n_steps=60, seed=7, adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, update_f=None, update_ws=None,
-               n_iteration=1000, w_bound=np.inf):
+               n_iteration=1000, w_bound=np.inf, trainable=False, init_additional_prob=0):
     dat = synth_class(n, f, k, seed, n_test)
     iw = None
     if inst_w:
         iw = np.random.default_rng(seed + 1).uniform(0.2, 1.5, n)
     np.random.seed(seed)
-    af = bn.ActFun(fun=act, prm=np.array(alphas) if alphas is not None else np.zeros(1))
+    af = bn.ActFun(fun=act, prm=np.array(alphas) if alphas is not None else np.zeros(1), trainable=trainable)
     bnn = quiet(bn.npBNN, dat, n_nodes=list(n_nodes), use_class_weights=class_w, actFun=af, use_bias_node=bias,
                 prior_f=prior, p_scale=p_scale, seed=seed, instance_weights=iw, w_bound=w_bound)
     out = {}
@@ -241,7 +259,8 @@ def case_synth(name, n=500, f=6, k=3, n_nodes=(4, 3), act="swish", alphas=None, 
         for i, mm in enumerate(m):
             out["mask_%d" % i] = mm
     mcmc = bn.MCMC(bnn, update_f=update_f, update_ws=update_ws, temperature=temperature, n_iteration=n_iteration,
-                   likelihood_tempering=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq)
+                   likelihood_tempering=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq,
+                   init_additional_prob=init_additional_prob)
     store_data(out, dat)
     if iw is not None:
         out["inst_w"] = iw
@@ -254,7 +273,7 @@ def case_synth(name, n=500, f=6, k=3, n_nodes=(4, 3), act="swish", alphas=None, 
                 update_f=list(update_f) if update_f else [0.05] * nl,
                 update_ws=list(update_ws) if update_ws else [0.075] * nl, n_iteration=n_iteration, adapt_f=adapt_f,
                 adapt_fM=adapt_fM, adapt_freq=adapt_freq, temperature=temperature, lik_temp=lik_temp,
-                w_bound=float(bnn._w_bound))
+                w_bound=float(bnn._w_bound), trainable=bool(trainable), init_additional_prob=float(init_additional_prob))
     save(name, out, meta)
 
 
@@ -275,6 +294,13 @@ def case_regerr(n_steps=60):
                 update_f=[0.05] * 3, update_ws=[0.075] * 3, n_iteration=1000, adapt_f=0.0, adapt_fM=1.0,
                 adapt_freq=1000, temperature=1.0, lik_temp=1.0, w_bound=float("inf"))
     save("syn_regress_error", out, meta)
+
+
+# NOTE (measured while writing this generator): the error-parameter multiplier proposal of regression mode
+# (BNN_env.py:435-442, estimate_error=True, empirical_error=False) cannot be recorded: every accepted step before
+# _estimate_error resets bnn._error_prm to the scalar 1 (BNN_env.py:443-444,500-501), and the first proposal after it
+# calls multiplier_proposal_vector(1, ...) which raises AttributeError ('int' object has no attribute 'shape',
+# BNN_mcmc.py:105).  The path only survives when no proposal at all is accepted in the first _estimate_error steps.
 
 
 def case_masks():
@@ -433,3 +459,8 @@ if __name__ == "__main__":
     case_predict()
     case_mc3()
     case_sample_cat()
+    # init_additional_prob = the Exp(10) term of the initial parameters, so that proposals are not all rejected
+    case_synth("syn_trainable_genrelu", act="genReLU", alphas=[0.1, 0.3], trainable=True, bias=2,
+               init_additional_prob=float(np.log(10) * -np.sum([0.1, 0.3]) * 10))
+    case_synth("syn_trainable_tanh", act="tanh", alphas=[0.2, 0.9], trainable=True, bias=1,
+               init_additional_prob=float(np.log(10) * -np.sum([0.2, 0.9]) * 10))

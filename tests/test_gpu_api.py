@@ -179,9 +179,10 @@ def test_unsupported_options_raise():
     z, meta = G.load("syn_swish_cauchy")
     dat = _dat(z)
     with pytest.raises(NotImplementedError):
-        bn.ActFun(fun="genReLU", trainable=True)
-    with pytest.raises(NotImplementedError):
         bn.npBNN(dat, n_nodes=[4, 3], freq_indicator=0.1)
+    trainable = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="genReLU", prm=np.array([0.1, 0.2]), trainable=True))
+    with pytest.raises(NotImplementedError):
+        bn.MCMC(trainable, rng="philox")                  # that branch is proposed from host-drawn numbers only
     with pytest.raises(NotImplementedError):
         bn.npBNN(dat, n_nodes=[4, 3], estimation_mode="custom", size_output=3)
     bnn = bn.npBNN(dat, n_nodes=[4, 3])
@@ -242,3 +243,28 @@ def test_feature_importance_flow(tmp_path):
     acc0 = np.mean(np.argmax(orc.posterior_predict(xs, [p["weights"] for p in post], "tanh", None, "softmax", 0)[1], 1) == y)
     assert (tmp_path / "feature_importance.txt").exists()
     assert 0.0 <= acc0 <= ref_acc <= 1.0
+
+
+@pytest.mark.parametrize("name", ["syn_trainable_genrelu", "syn_trainable_tanh"])
+def test_trainable_activation_flow_reproduces_reference_chain(name):
+    """ActFun(trainable=True) + init_additional_prob through the reference-shaped API (BNN_env.py:416-421,502-503):
+    the chain, the accepted activation parameters and the log-prior (with the Exp(10) term) follow the reference."""
+    import npbnn_b200 as bn
+    z, meta = G.load(name)
+    np.random.seed(7)
+    dat = _dat(z)
+    af = bn.ActFun(fun=meta["act"], prm=np.array(meta["alphas"]), trainable=True)
+    bnn = bn.npBNN(dat, n_nodes=meta["n_nodes"], actFun=af, use_bias_node=meta["use_bias_node"], prior_f=meta["prior"],
+                   p_scale=meta["p_scale"], seed=7)
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["w0_%d" % i])
+    mcmc = bn.MCMC(bnn, n_iteration=meta["n_iteration"], init_additional_prob=meta["init_additional_prob"])
+    assert abs(mcmc._logPrior - float(z["init_logPrior"])) <= 1e-9 * abs(float(z["init_logPrior"]))
+    T = int(z["n_steps"])
+    for t in range(T):
+        mcmc.mh_step(bnn)
+        assert mcmc._last_accepted == int(z["steps_accepted"][t]), t
+        assert np.allclose(bnn._act_fun._acc_prm, z["steps_act_prm"][t], rtol=1e-14, atol=0), t
+        assert abs(mcmc._logPrior - float(z["steps_logPrior"][t])) <= 1e-9 * abs(float(z["steps_logPrior"][t]))
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])

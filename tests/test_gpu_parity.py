@@ -11,6 +11,7 @@ from tests import _golden as G
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
+L_ADD_PROB = 8      # BNN_F_ADD_PROB (include/npbnn_b200.h)
 LIK = {"classification": 0, "regression": 1, "regression-error": 2}
 
 
@@ -107,10 +108,11 @@ def _init_chains(eng, m, meta, n_chains):
     n_it = meta["n_iteration"]
     eng.chains_init(w0, temperature=meta["temperature"], update_f=meta["update_f"][:nl], update_ws=meta["update_ws"][:nl],
                     prior=meta["prior"], prior_scale=meta["p_scale"], w_bound=meta["w_bound"], mask=m.mask,
-                    alphas=None if m.alphas is None else np.resize(m.alphas, nl),
+                    alphas=None if m.alphas is None else np.concatenate([m.alphas, np.zeros(nl)])[:nl],
                     sigma_mode=1 if meta.get("empirical_error") else 0, lik_temp=meta["lik_temp"],
                     adapt_f=meta["adapt_f"], adapt_fM=meta["adapt_fM"], adapt_freq=meta["adapt_freq"],
-                    adapt_stop=int(n_it * 0.05))
+                    adapt_stop=int(n_it * 0.05), n_act_prm=len(m.alphas) if m.act_trainable else 0,
+                    init_additional_prob=meta.get("init_additional_prob", 0.0))
 
 
 @pytest.mark.parametrize("name", G.CHAIN_CASES)
@@ -132,8 +134,10 @@ def test_chain_replay_step_by_step(name):
         st = eng.read_state()
         for c in range(2):
             assert rel_close(st.logLik_prop[c], z["steps_logLik_prime"][t]), (t, st.logLik_prop[c], float(z["steps_logLik_prime"][t]))
-            assert rel_close(st.logPrior_prop[c], z["steps_logPrior_prime"][t]), t
-            margin = abs((float(z["steps_logLik_prime"][t]) + float(z["steps_logPrior_prime"][t]) - float(z["steps_logPost"][t - 1] if t else z["init_logLik"] + z["init_logPrior"])) * meta["temperature"] - float(z["steps_log_u"][t]))
+            # the golden holds calc_prior() alone; the proposal's log-prior adds additional_prob (BNN_env.py:481)
+            add = float(st.f64[c, L_ADD_PROB])
+            assert rel_close(st.logPrior_prop[c] - add, z["steps_logPrior_prime"][t]), t
+            margin = abs((float(z["steps_logLik_prime"][t]) + float(z["steps_logPrior_prime"][t]) + add - float(z["steps_logPost"][t - 1] if t else z["init_logLik"] + z["init_logPrior"])) * meta["temperature"] - float(z["steps_log_u"][t]))
             if margin < 1e-8:
                 near_tie += 1       # decision inside the summation-order noise: reported, not asserted
                 continue
@@ -145,6 +149,8 @@ def test_chain_replay_step_by_step(name):
             assert np.allclose(st.update_f[c], z["steps_update_f"][t], rtol=1e-14)
             assert np.allclose(st.update_ws[c], z["steps_update_ws"][t], rtol=1e-14)
             assert np.allclose(st.freq_layer_update[c], z["steps_freq_layer_update"][t], rtol=1e-14)
+            if m.act_trainable:
+                assert np.allclose(st.alpha[c][:len(m.alphas)], z["steps_act_prm"][t], rtol=1e-14, atol=0), t
             if meta["mode"] == "classification":
                 assert st.n_correct[c] / N == float(z["steps_accuracy"][t])
                 assert np.array_equal(st.pred_hist[c] / N, z["steps_label_freq"][t])

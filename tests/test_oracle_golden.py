@@ -32,12 +32,15 @@ def test_chain_replay_matches_reference(name):
         ok = orc.layer_is_proposed(inj.rr, z["steps_freq_layer_update"][t])
         assert np.array_equal(ok.astype(np.int32), z["steps_proposed"][t]), t
         assert close(d["logLik_prime"], z["steps_logLik_prime"][t]), (t, d["logLik_prime"], float(z["steps_logLik_prime"][t]))
-        assert close(d["logPrior_prime"], z["steps_logPrior_prime"][t]), t
+        # the golden records calc_prior() alone; mh_step adds additional_prob to it (BNN_env.py:481)
+        assert close(d["logPrior_prime"] - d["additional_prob"], z["steps_logPrior_prime"][t], rtol=1e-11), t
         assert d["accepted"] == int(z["steps_accepted"][t]), t
         assert close(s.logLik, z["steps_logLik"][t]) and close(s.logPrior, z["steps_logPrior"][t])
         assert close(s.logPost, z["steps_logPost"][t])
         assert close(s.accuracy, z["steps_accuracy"][t]) and close(s.test_accuracy, z["steps_test_accuracy"][t])
         assert close(s.label_acc, z["steps_label_acc"][t])
+        if meta.get("trainable"):
+            assert close(m.alphas, z["steps_act_prm"][t]), t
         if meta["mode"] == "classification":
             assert close(s.label_freq, z["steps_label_freq"][t])
         assert close(s.acceptance_rate, z["steps_acceptance_rate"][t], rtol=1e-15)
