@@ -232,6 +232,8 @@ int bnn_predict_sample(bnn_ctx* ctx, const double* x_dev, int64_t n, const doubl
  * bnn_debug_counters : 48 clock counters of k_fwd3t, all zero unless the library was built with -DBNN_DBG_WAITCLK. */
 int bnn_debug_read_part(bnn_ctx* ctx, double* out_host, int64_t n_doubles);
 int bnn_debug_counters(bnn_ctx* ctx, unsigned long long* out48_host);
+/* bnn_debug_set_trace: device buffer [CTAs][uses][8 warps][2] for the checksums a -DBNN_DBG_CSUM build records. */
+int bnn_debug_set_trace(bnn_ctx* ctx, unsigned long long* trace_dev);
 /* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests);
  * "time_forward" = 1 enables bnn_forward_time; "sparse" = 0 evaluates masked chains with the dense kernels;
  * "tensor_l1" = 1 (default 0, env NPBNN_TENSOR_L1) evaluates layer 1 of the 64-64-32-10 swish network as exact

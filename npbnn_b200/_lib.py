@@ -84,6 +84,7 @@ _SIGNATURES = {
     "bnn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "bnn_debug_read_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "bnn_debug_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bnn_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

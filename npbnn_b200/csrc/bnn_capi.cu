@@ -233,6 +233,15 @@ int bnn_debug_counters(bnn_ctx* c, unsigned long long* out32_host) {
   return 0;
 }
 
+// debugging aid: device buffer for the per-(CTA, use, warp) checksums of a -DBNN_DBG_CSUM build (NULL = off)
+int bnn_debug_set_trace(bnn_ctx* c, unsigned long long* dev_ptr) {
+  REQUIRE(c, "bnn_debug_set_trace: null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(bnn_debug_set_trace_ptr(dev_ptr));
+  return 0;
+}
+
 // debugging aid: per-warp-tile partial sums of the last forward pass, [n_sets_in_pass][NF][n_tiles16]
 int bnn_debug_read_part(bnn_ctx* c, double* out_host, int64_t n_doubles) {
   REQUIRE(c && out_host, "bnn_debug_read_part: null argument");

@@ -1185,6 +1185,8 @@ __device__ __forceinline__ void oz_st_row16(uint32_t taddr, const uint4 (&w)[4])
 // tuning instrumentation (build with -DBNN_DBG_WAITCLK): clocks spent per wait site / phase, summed over lane 0 of
 // every warp; slots 0-15 helper 0 (control), 16-31 helpers 1-3, 32-47 compute warps.  Read and reset with bnn_debug_counters().
 __device__ unsigned long long g_dbg_clk[48];
+__device__ unsigned long long* g_dbg_trace = nullptr;   // BNN_DBG_CSUM: [CTA][use][warp][2] checksums (a1 read, logits)
+cudaError_t bnn_debug_set_trace_ptr(unsigned long long* dev_ptr) { return cudaMemcpyToSymbol(g_dbg_trace, &dev_ptr, sizeof(dev_ptr)); }
 #ifdef BNN_DBG_WAITCLK
 #define DBG_T0() const long long dbg_t0 = clock64()
 #define DBG_ADD(slot) dbg[slot] += clock64() - dbg_t0
@@ -1238,6 +1240,9 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
   int* cnt = reinterpret_cast<int*>(bars + 30);
   const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
+#ifdef BNN_DBG_CSUM            // debugging aid: checksums of the activation hand-off
+  volatile unsigned long long* dbg_cs = reinterpret_cast<volatile unsigned long long*>(cnt + ((n_cnt + 3) & ~3));   // [2][8]
+#endif
 
   for (int i = threadIdx.x; i < (1 << TB); i += blockDim.x) tab[i] = p.exp_tab_small[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
@@ -1373,10 +1378,13 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         // ... and stay at most ONE weight set ahead of this quarter's compute warps (wait until they have consumed
         // use q - 1 from the other buffer).  Without this bound -- helpers two sets ahead at the moment the next
         // tile's X slices are stored to TMEM -- a few rows of ONE weight set per launch came out wrong (always the
-        // third-from-last set of an early tile, rows of TMEM lane quarter 0; tools/race_probe.py).  The hand-off
-        // barriers were verified intact in failing runs (tags in a1s, canaries in the weight rings), the cause is
+        // third-from-last set of an early tile, rows of TMEM lane quarter 0; tools/race_probe.py).  In failing runs
+        // the compute warps read exactly the activations the helper wrote (-DBNN_DBG_CSUM), so the fault is not in
+        // this hand-off; any added delay (trace stores, weights read from global memory) hides it.  The cause is
         // not understood; with the bound 64 launches over 8 chain counts were clean.  The kernel is opt-in.
+#ifndef BNN_DBG_NOLOCKSTEP
         if (q > 0) mbar_wait_sleep(&a1free[2 * h + (b ^ 1)], (uint32_t)(((q - 1) >> 1) & 1));
+#endif
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* slot = hring + (size_t)(q & 3) * HSLOT_BYTES;
         const double* csc = reinterpret_cast<const double*>(slot);
@@ -1428,6 +1436,9 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
 #ifdef BNN_DBG_NOHELPER
         if (false)
 #endif
+#ifdef BNN_DBG_CSUM
+        unsigned long long csum = 0;
+#endif
 #pragma unroll 1
         for (int cb = 0; cb < N1 / 8; ++cb) {
           double z[8];
@@ -1448,10 +1459,18 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) z[e] = bnn_act<ACT, TB>(z[e], al, tab);
+#ifdef BNN_DBG_CSUM
+#pragma unroll
+          for (int e = 0; e < 8; ++e) csum ^= (unsigned long long)__double_as_longlong(z[e]);
+#endif
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<double2*>(arow + 2 * ((4 * cb + i) ^ sw)) = make_double2(z[2 * i], z[2 * i + 1]);
         }
+#ifdef BNN_DBG_CSUM
+        for (int o = 8; o > 0; o >>= 1) csum ^= __shfl_xor_sync(FULL_MASK, csum, o);
+        if ((lane & 15) == 0) dbg_cs[b * 8 + 2 * h + (lane >> 4)] = csum;
+#endif
         __syncwarp();
         dbg[7] += clock64() - dbg_p2;
         if (lane == 0) mbar_arrive(&a1full[2 * h + b]);
@@ -1505,6 +1524,10 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         RowStats<N3> rs;
         LikRow lr;
         const int K = g.K;
+#ifdef BNN_DBG_CSUM
+        unsigned long long ccs = 0;
+        const unsigned long long want_cs = dbg_cs[b * 8 + 2 * h + (warp >> 2)];
+#endif
 #ifdef BNN_DBG_NOCOMPUTE      // tuning experiment only
         if (p.C < 0)
 #endif
@@ -1518,6 +1541,10 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
           for (int kg = 0; kg < N1 / 8; ++kg) {
             const double2 alo = *reinterpret_cast<const double2*>(ar0 + 2 * ((4 * kg + t) ^ asw));
             const double2 ahi = *reinterpret_cast<const double2*>(ar1 + 2 * ((4 * kg + t) ^ asw));
+#ifdef BNN_DBG_CSUM
+            ccs ^= (unsigned long long)__double_as_longlong(alo.x) ^ (unsigned long long)__double_as_longlong(alo.y) ^
+                   (unsigned long long)__double_as_longlong(ahi.x) ^ (unsigned long long)__double_as_longlong(ahi.y);
+#endif
             if (!PREDICT) {
               if (kg == 0) qs_max<N3>(acc3, K, t, rs);
               else if (kg == 1) qs_exp<N3, 0, true, TB>(acc3, K, t, y, tab, rs);
@@ -1535,6 +1562,13 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
             }
           }
         }
+#ifdef BNN_DBG_CSUM
+        for (int o = 16; o > 0; o >>= 1) ccs ^= __shfl_xor_sync(FULL_MASK, ccs, o);
+        if (lane == 0 && ccs != want_cs && have_tile) {
+          atomicAdd(&g_dbg_clk[40], 1ULL);
+          g_dbg_clk[41] = (unsigned long long)q; g_dbg_clk[42] = (unsigned long long)warp; g_dbg_clk[43] = (unsigned long long)it;
+        }
+#endif
         // the activated layer-1 rows have been consumed: the helpers may overwrite this buffer (two weight sets on)
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1free[2 * h + b]);
@@ -1564,6 +1598,20 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
             }
           }
         }
+#ifdef BNN_DBG_CSUM
+        {
+          unsigned long long lcs = 0;
+#pragma unroll
+          for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) lcs ^= (unsigned long long)__double_as_longlong(acc3[j][e]) * (unsigned long long)(2 * (4 * j + e) + 1);
+          for (int o = 16; o > 0; o >>= 1) lcs ^= __shfl_xor_sync(FULL_MASK, lcs, o);
+          if (lane == 0 && g_dbg_trace) {
+            unsigned long long* tr = g_dbg_trace + (((size_t)blockIdx.x * total_q + q) * 8 + warp) * 2;
+            tr[0] = ccs; tr[1] = lcs;
+          }
+        }
+#endif
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&rempty[b]);
@@ -1610,6 +1658,9 @@ static size_t fwd3t_smem_bytes(int C, int K) {
   using G3 = Fwd3Geom<64, 64, 32, 16>;
   return 2 * (size_t)(OZ_S * OZ_WPLANE) + 2 * (size_t)(G3::PB - G3::W2_OFF) * 8 + 2 * 128 * 64 * sizeof(double) +
          256 * sizeof(double) + 4 * 1024 + 30 * sizeof(uint64_t) + (size_t)C * (2 + 2 * K) * sizeof(int)
+#ifdef BNN_DBG_CSUM
+         + 256
+#endif
       ;
 }
 

@@ -48,6 +48,7 @@ cudaError_t bnn_launch_slice_w1(const double* wp, int PB, uint8_t* wt, int n_set
 size_t bnn_slice_x_tile_bytes();
 size_t bnn_slice_w1_bytes();
 cudaError_t bnn_debug_counters_read(unsigned long long* out32);
+cudaError_t bnn_debug_set_trace_ptr(unsigned long long* dev_ptr);
 cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
                               const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st);
 cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st);

@@ -27,8 +27,12 @@ eng.set_option("tensor_l1", 1)
 bad = 0
 dbuf = (C.c_ulonglong * 48)()
 eng.lib.bnn_debug_counters(eng._h, C.cast(dbuf, C.c_void_p))
+dbuf = (C.c_ulonglong * 48)()
+eng.lib.bnn_debug_counters(eng._h, C.cast(dbuf, C.c_void_p))
 for rep in range(int(os.environ.get("REPS", "6"))):
     r = eng.forward_lik(wd)
+    eng.lib.bnn_debug_counters(eng._h, C.cast(dbuf, C.c_void_p))
+    print("csum mismatches:", dbuf[40], "last q/warp/it:", dbuf[41], dbuf[42], dbuf[43], flush=True)
     d = r["loglik"] - ref["loglik"]
     cd = (r["counts"] != ref["counts"]).any(axis=1)
     idx = np.nonzero((np.abs(d) > 1e-6) | cd)[0]
