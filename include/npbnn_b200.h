@@ -216,6 +216,22 @@ int bnn_measure_fp64_peak(bnn_ctx* ctx, double* tflops);
 /* Name of the forward kernel variant used by the last call ("k_fwd3<...>" or "k_fwd_generic"). */
 const char* bnn_last_kernel(const bnn_ctx* ctx);
 
+/* ---- Row sharding (few chains, many rows) ------------------------------------------------------
+ * Every rank stages ITS rows with bnn_set_data, calls bnn_rowshard_config(n_train_global) and then drives the same
+ * chains (same seeds / injected draws) on every rank.  One MH iteration is
+ *     bnn_rowshard_update(accept_mode = 0, propose = 1, inj)   proposal + forward pass over the local rows
+ *     bnn_rowshard_local(red)                                  per-chain sums of the local partials, [C, n_values]
+ *     all-reduce(red, SUM) over the ranks                      (NCCL / gloo: the one exchange step of this mode)
+ *     bnn_rowshard_commit(red)                                 the accept step will see the global sums
+ *     bnn_rowshard_update(accept_mode = 1, propose = 0, NULL)  accept / reject: identical on every rank
+ * After bnn_chains_init the same local / all-reduce / commit sequence is followed by accept_mode = 2 (initial state).
+ * The reductions are fixed-order, so every rank holds bit-identical chain states. */
+int bnn_rowshard_config(bnn_ctx* ctx, int64_t n_train_global);
+int bnn_rowshard_n_values(const bnn_ctx* ctx);                 /* doubles per chain in the exchanged vector */
+int bnn_rowshard_local(bnn_ctx* ctx, double* red_dev, void* stream);
+int bnn_rowshard_commit(bnn_ctx* ctx, const double* red_global_dev, void* stream);
+int bnn_rowshard_update(bnn_ctx* ctx, int32_t accept_mode, int32_t propose, const bnn_injection* inj, void* stream);
+
 /* Posterior-predictive resampling: sample_from_categorical (BNN_lib.py:682-713), i.e. get_posterior_cat_prob with
  * post_summary_mode = 2, fused into the prediction pass.  u_dev [n, n_sets] holds the uniforms of the reference
  * (np.random.random(n_sets) per instance, instance-major); for every (row, set) the class is the first one whose

@@ -82,6 +82,11 @@ _SIGNATURES = {
     "bnn_launch_count": (C.c_int64, [C.c_void_p]),
     "bnn_last_kernel": (C.c_char_p, [C.c_void_p]),
     "bnn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bnn_rowshard_config": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bnn_rowshard_n_values": (C.c_int, [C.c_void_p]),
+    "bnn_rowshard_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_rowshard_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_rowshard_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Injection), C.c_void_p]),
     "bnn_debug_read_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "bnn_debug_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bnn_debug_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -296,14 +296,30 @@ class _ChainGroup:
     injection arrays of bnn_mh_steps."""
 
     def __init__(self, bnn, weights_per_chain, temperatures, update_f, update_ws, lik_temp, adapt_f, adapt_fM,
-                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0, init_additional_prob=0.0):
+                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0, init_additional_prob=0.0, row_shard=False):
         self.bnn = bnn
         net = _net_of(weights_per_chain[0], bnn._n_features, bnn._act_fun, bnn._estimation_mode)
         self.net = net
         self.eng = Engine(net, device=device)
         cw = bnn._class_w if len(bnn._class_w) else None
-        self.eng.set_data(bnn._data, bnn._labels, bnn._test_data if _has_test(bnn) else None,
-                          bnn._test_labels if _has_test(bnn) else None, inst_w=bnn._instance_weights, class_w=cw)
+        import torch.distributed as dist
+        world = dist.get_world_size() if (row_shard and dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            # rows split over the ranks, same chains everywhere, one all-reduce per MH iteration (rowshard.py)
+            from . import rowshard
+            rank = dist.get_rank()
+            a, b = rowshard.row_partition(len(bnn._data), world, rank)
+            iw = None if bnn._instance_weights is None else bnn._instance_weights[a:b]
+            if _has_test(bnn):
+                ta, tb = rowshard.row_partition(len(bnn._test_data), world, rank)
+                self.eng.set_data(bnn._data[a:b], bnn._labels[a:b], bnn._test_data[ta:tb], bnn._test_labels[ta:tb],
+                                  inst_w=iw, class_w=cw)
+            else:
+                self.eng.set_data(bnn._data[a:b], bnn._labels[a:b], inst_w=iw, class_w=cw)
+            self.eng.enable_rowshard(len(bnn._data), rowshard.dist_all_reduce_sum)
+        else:
+            self.eng.set_data(bnn._data, bnn._labels, bnn._test_data if _has_test(bnn) else None,
+                              bnn._test_labels if _has_test(bnn) else None, inst_w=bnn._instance_weights, class_w=cw)
         self.n = len(weights_per_chain)
         sigma0 = None
         if bnn._estimation_mode == "regression":
@@ -380,7 +396,8 @@ class MCMC:
                  print_f=1000, n_post_samples=1000, update_function=UpdateNormal, sample_from_prior=0, run_ID="",
                  init_additional_prob=0, likelihood_tempering=1, mcmc_id=0, randomize_seed=False, adapt_f=0,
                  estimate_error=True, adapt_fM=1, adapt_freq=1000, adapt_stop=None, likelihood_f=None,
-                 adapt_verbose=False, accuracy_f=None, accuracy_lab_f=None, rng="host", device=0, _group=None, _slot=0):
+                 adapt_verbose=False, accuracy_f=None, accuracy_lab_f=None, rng="host", device=0, row_shard=False,
+                 _group=None, _slot=0):
         if update_function is not UpdateNormal:
             raise NotImplementedError("only update_function=UpdateNormal runs on the device")
         if likelihood_f is not None or accuracy_f is not None or accuracy_lab_f is not None:
@@ -417,7 +434,7 @@ class MCMC:
             _group = _ChainGroup(bnn_obj, [bnn_obj._w_layers], [temperature], list(update_f)[:nl], list(update_ws)[:nl],
                                  likelihood_tempering, adapt_f, adapt_fM, adapt_freq, self._adapt_stop, sample_from_prior,
                                  seed=int(bnn_obj._seed) + 7919 * int(mcmc_id), device=device,
-                                 init_additional_prob=init_additional_prob)
+                                 init_additional_prob=init_additional_prob, row_shard=row_shard)
         elif bnn_obj._act_fun._trainable or init_additional_prob:
             raise NotImplementedError("trainable activation parameters / init_additional_prob inside an MC3 group")
         self._group, self._slot = _group, _slot

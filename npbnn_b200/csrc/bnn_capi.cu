@@ -70,6 +70,10 @@ struct bnn_ctx {
   bnn_sampler_config cfg{};
   PriorScales ps{};
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
+  // row sharding: the chains' accept step reads the all-reduced sums from part_red (one pseudo tile)
+  bool rowshard = false;
+  long long n_train_global = 0;
+  DevBuf part_red;
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu, inj_alpha_ix, inj_alpha_dz, inj_add_prob;
   const char* last_kernel = "";
   // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
@@ -207,7 +211,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->part_red, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
                     &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -617,6 +621,11 @@ static ChainDev chain_dev(bnn_ctx* c) {
   d.NF = n_slots(c->g);
   d.counts_prop = c->counts_prop.as<int>();
   d.alpha_fwd = c->alpha_chain.as<double>();
+  if (c->rowshard) {                 // accept step on the sums over all ranks (k_rowshard_commit)
+    d.part = c->part_red.as<double>();
+    d.n_tiles16 = 1;
+    d.n_train = c->n_train_global;
+  }
   return d;
 }
 
@@ -673,6 +682,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   CUDA_TRY(c->counts_prop.ensure(sizeof(int) * (size_t)C * NC, false, st));
   CUDA_TRY(c->alpha_chain.ensure(sizeof(double) * (size_t)C * g.L, false, st));
   CUDA_TRY(c->part.ensure(sizeof(double) * (size_t)n_slots(g) * C * c->n_tiles16, false, st));
+  if (c->rowshard) CUDA_TRY(c->part_red.ensure(sizeof(double) * (size_t)C * n_slots(g), true, st));
   c->use_sparse = false;
   if (cfg->use_mask) {
     CUDA_TRY(c->mask.ensure(sizeof(double) * g.P, false, st));
@@ -732,19 +742,16 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   c->launches++;
   int rc = chains_forward(c, st);
   if (rc) return rc;
+  c->have_chains = true;
+  if (c->rowshard) return 0;          // the caller reduces over the ranks first, then bnn_rowshard_update(accept = 2)
   CUDA_TRY(bnn_launch_mh_update(d, 2, 0, 0, st));
   c->launches++;
-  c->have_chains = true;
   return 0;
 }
 
-int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* stream) {
-  REQUIRE(c && c->have_chains, "bnn_mh_steps: call bnn_chains_init first");
-  REQUIRE(n_steps >= 1, "bnn_mh_steps: n_steps must be >= 1");
-  CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)stream;
+// validate and upload the injected draws of n_steps iterations; fills the injection pointers of d
+static int stage_injection(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, ChainDev& d, cudaStream_t st) {
   const NetGeom& g = c->g;
-  ChainDev d = chain_dev(c);
   if (inj) {
     REQUIRE(inj->n_steps >= n_steps && inj->cap >= 1, "bnn_mh_steps: injection shorter than n_steps");
     REQUIRE(inj->proposed && inj->count && inj->ix && inj->iy && inj->dz && inj->log_u, "bnn_mh_steps: null injection array");
@@ -795,6 +802,17 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
     REQUIRE(c->cfg.n_act_prm == 0, "bnn_mh_steps: trainable activation parameters are proposed from injected draws only "
                                     "(no on-device generator for that branch)");
   }
+  return 0;
+}
+
+int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_mh_steps: call bnn_chains_init first");
+  REQUIRE(n_steps >= 1, "bnn_mh_steps: n_steps must be >= 1");
+  REQUIRE(!c->rowshard, "bnn_mh_steps: row-sharded chains are stepped with bnn_rowshard_update / _local / _commit");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ChainDev d = chain_dev(c);
+  if (int rc = stage_injection(c, n_steps, inj, d, st)) return rc;
   for (int s = 0; s < n_steps; ++s) {
     CUDA_TRY(bnn_launch_mh_update(d, s > 0 ? 1 : 0, 1, s, st));
     c->launches++;
@@ -804,6 +822,57 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
   CUDA_TRY(bnn_launch_mh_update(d, 1, 0, n_steps, st));
   c->launches++;
   if (inj) CUDA_TRY(cudaStreamSynchronize(st));   // the caller may free the host arrays after return
+  return 0;
+}
+
+// ---- row sharding (include/npbnn_b200.h) -------------------------------------------------------------------
+int bnn_rowshard_config(bnn_ctx* c, int64_t n_train_global) {
+  REQUIRE(c && c->have_data, "bnn_rowshard_config: call bnn_set_data (this rank's rows) first");
+  REQUIRE(n_train_global >= c->n_train, "bnn_rowshard_config: n_train_global is smaller than the local shard");
+  c->rowshard = true;
+  c->n_train_global = n_train_global;
+  c->have_chains = false;
+  return 0;
+}
+
+int bnn_rowshard_n_values(const bnn_ctx* c) { return c ? n_slots(c->g) + 2 + 2 * c->g.K : 0; }
+
+int bnn_rowshard_local(bnn_ctx* c, double* red_dev, void* stream) {
+  REQUIRE(c && c->have_chains && c->rowshard && red_dev, "bnn_rowshard_local: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const NetGeom& g = c->g;
+  const int* counts = (g.lik == BNN_LIK_CATEGORICAL) ? c->counts_prop.as<int>() : nullptr;
+  CUDA_TRY(bnn_launch_rowshard_local(c->part.as<double>(), n_slots(g), c->n_tiles16, counts, 2 + 2 * g.K, red_dev, c->C,
+                                     (cudaStream_t)stream));
+  c->launches++;
+  return 0;
+}
+
+int bnn_rowshard_commit(bnn_ctx* c, const double* red_global_dev, void* stream) {
+  REQUIRE(c && c->have_chains && c->rowshard && red_global_dev, "bnn_rowshard_commit: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const NetGeom& g = c->g;
+  int* counts = (g.lik == BNN_LIK_CATEGORICAL) ? c->counts_prop.as<int>() : nullptr;
+  CUDA_TRY(bnn_launch_rowshard_commit(red_global_dev, n_slots(g), 2 + 2 * g.K, c->part_red.as<double>(), counts, c->C,
+                                      (cudaStream_t)stream));
+  c->launches++;
+  return 0;
+}
+
+int bnn_rowshard_update(bnn_ctx* c, int32_t accept_mode, int32_t propose, const bnn_injection* inj, void* stream) {
+  REQUIRE(c && c->have_chains && c->rowshard, "bnn_rowshard_update: call bnn_rowshard_config and bnn_chains_init first");
+  REQUIRE(accept_mode >= 0 && accept_mode <= 2, "bnn_rowshard_update: accept_mode must be 0, 1 or 2");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ChainDev d = chain_dev(c);
+  if (propose)
+    if (int rc = stage_injection(c, 1, inj, d, st)) return rc;
+  CUDA_TRY(bnn_launch_mh_update(d, accept_mode, propose ? 1 : 0, 0, st));
+  c->launches++;
+  if (propose) {
+    if (int rc = chains_forward(c, st)) return rc;
+    if (inj) CUDA_TRY(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 

@@ -58,5 +58,9 @@ cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF
 cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
                                  double* out, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
+cudaError_t bnn_launch_rowshard_local(const double* part, int NF, long long nt, const int* counts, int NC, double* out,
+                                      int n_chains, cudaStream_t st);
+cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double* part_red, int* counts, int n_chains,
+                                       cudaStream_t st);
 // FP64 tensor-pipe peak (back-to-back DMMA, no memory traffic): the roofline denominator of the forward kernel
 cudaError_t bnn_measure_dmma_peak(int n_sms, double* tflops);

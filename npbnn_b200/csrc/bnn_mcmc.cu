@@ -425,6 +425,47 @@ cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, 
   k_log_prior<<<n_sets, UPD_THREADS, 0, st>>>(g, w, prior, ps, out);
   return cudaGetLastError();
 }
+// ------------------------------------------------------------------------------------------------
+// row sharding: the rows of X are split over the ranks, every rank runs the same chains.
+// After the forward pass each rank reduces its per-tile partials to one vector per chain (k_rowshard_local, same
+// fixed order as finalize_loglik); the vectors are summed over the ranks (one all-reduce of C * (NF + 2 + 2K)
+// doubles); k_rowshard_commit stores the sums where k_mh_update expects partials of a single tile, so the accept
+// step runs unchanged and every rank takes the same decision.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPD_THREADS) k_rowshard_local(const double* __restrict__ part, int NF, long long nt,
+                                                                 const int* __restrict__ counts, int NC,
+                                                                 double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x;
+  for (int slot = 0; slot < NF; ++slot) {
+    const double* src = part + ((long long)c * NF + slot) * nt;
+    double v = 0.0;
+    for (long long i = threadIdx.x; i < nt; i += blockDim.x) v += src[i];
+    const double s = block_sum_fixed(v, sh);
+    if (threadIdx.x == 0) out[(long long)c * (NF + NC) + slot] = s;
+  }
+  for (int i = threadIdx.x; i < NC; i += blockDim.x)
+    out[(long long)c * (NF + NC) + NF + i] = counts ? (double)counts[(long long)c * NC + i] : 0.0;
+}
+__global__ void k_rowshard_commit(const double* __restrict__ in, int NF, int NC, double* __restrict__ part_red,
+                                  int* __restrict__ counts) {
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < NF; i += blockDim.x) part_red[(long long)c * NF + i] = in[(long long)c * (NF + NC) + i];
+  if (counts)
+    for (int i = threadIdx.x; i < NC; i += blockDim.x)
+      counts[(long long)c * NC + i] = (int)llrint(in[(long long)c * (NF + NC) + NF + i]);    // exact: integer-valued sums
+}
+cudaError_t bnn_launch_rowshard_local(const double* part, int NF, long long nt, const int* counts, int NC, double* out,
+                                      int n_chains, cudaStream_t st) {
+  k_rowshard_local<<<n_chains, UPD_THREADS, 0, st>>>(part, NF, nt, counts, NC, out);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double* part_red, int* counts, int n_chains,
+                                       cudaStream_t st) {
+  k_rowshard_commit<<<n_chains, 64, 0, st>>>(in, NF, NC, part_red, counts);
+  return cudaGetLastError();
+}
+
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st) {
   k_mh_update<<<d.C, UPD_THREADS, 0, st>>>(d, accept_mode, propose_mode, step);
   return cudaGetLastError();

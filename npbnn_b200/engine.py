@@ -134,6 +134,7 @@ class Engine:
         self.n_train = self.n_test = 0
         self.n_chains = 0
         self._keep = []
+        self._rowshard = None          # callable(tensor) summing a device tensor over the ranks, or None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -279,13 +280,11 @@ class Engine:
         L.check(self.lib.bnn_chains_init(self._h, n, C.byref(cfg), _np_ptr(w), _np_ptr(mk), _np_ptr(temp), _np_ptr(uf),
                                          _np_ptr(uws), _np_ptr(al), _np_ptr(sg), self._stream()))
         self.n_chains = n
+        if callable(self._rowshard):
+            self._rowshard_exchange()
+            self.rowshard_update(2, False)
 
-    def mh_steps(self, n_steps: int, injection: Optional[dict] = None):
-        """Run n_steps MH iterations for all chains on the device.  injection: dict of arrays
-        proposed/count [T,C,L] int32, ix/iy [T,C,cap] int32, dz [T,C,cap] f64, log_u [T,C] f64."""
-        if injection is None:
-            L.check(self.lib.bnn_mh_steps(self._h, int(n_steps), None, self._stream()))
-            return
+    def _pack_injection(self, injection, n_steps):
         arrs = {k: np.ascontiguousarray(injection[k], dtype=(np.float64 if k in ("dz", "log_u") else np.int32))
                 for k in ("proposed", "count", "ix", "iy", "dz", "log_u")}
         for k, dt in (("alpha_ix", np.int32), ("alpha_dz", np.float64), ("add_prob", np.float64)):   # optional branches
@@ -298,7 +297,60 @@ class Engine:
         inj.n_steps, inj.cap = T, cap
         for k, a in arrs.items():
             setattr(inj, k, a.ctypes.data)
+        return inj, arrs
+
+    def mh_steps(self, n_steps: int, injection: Optional[dict] = None):
+        """Run n_steps MH iterations for all chains on the device.  injection: dict of arrays
+        proposed/count [T,C,L] int32, ix/iy [T,C,cap] int32, dz [T,C,cap] f64, log_u [T,C] f64."""
+        if self._rowshard is not None:
+            return self._mh_steps_rowshard(int(n_steps), injection)
+        if injection is None:
+            L.check(self.lib.bnn_mh_steps(self._h, int(n_steps), None, self._stream()))
+            return
+        inj, keep = self._pack_injection(injection, n_steps)
         L.check(self.lib.bnn_mh_steps(self._h, int(n_steps), C.byref(inj), self._stream()))
+
+    # ---------------------------------------------------------------- row sharding (SURVEY.md 8e-2)
+    def enable_rowshard(self, n_train_global: int, all_reduce_sum="manual"):
+        """Rows of X are split over the ranks (set_data was given this rank's rows); all_reduce_sum(t) sums the device
+        tensor t in place over the ranks (rowshard.dist_all_reduce_sum on NCCL / gloo).  "manual": the caller drives
+        rowshard_update / rowshard_local / rowshard_commit itself (chains_init then stops before the initial accept).
+        Call before chains_init.  Every rank must use the same seeds / injected draws."""
+        L.check(self.lib.bnn_rowshard_config(self._h, int(n_train_global)))
+        self._rowshard = all_reduce_sum
+
+    def rowshard_update(self, accept_mode: int, propose: bool, injection: Optional[dict] = None):
+        """accept_mode 0 none / 1 MH accept / 2 initial state; propose: draw (or take the injected) proposal and run the
+        forward pass over the local rows."""
+        if propose and injection is not None:
+            inj, keep = self._pack_injection(injection, 1)
+            L.check(self.lib.bnn_rowshard_update(self._h, int(accept_mode), 1, C.byref(inj), self._stream()))
+            return
+        L.check(self.lib.bnn_rowshard_update(self._h, int(accept_mode), int(bool(propose)), None, self._stream()))
+
+    def rowshard_local(self) -> torch.Tensor:
+        """Per-chain sums of this rank's partials: device tensor [C, n_values], the operand of the all-reduce."""
+        red = torch.empty((self.n_chains, int(self.lib.bnn_rowshard_n_values(self._h))), dtype=torch.float64, device=self.device)
+        L.check(self.lib.bnn_rowshard_local(self._h, _ptr(red), self._stream()))
+        return red
+
+    def rowshard_commit(self, red: torch.Tensor):
+        L.check(self.lib.bnn_rowshard_commit(self._h, _ptr(red), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()      # red may be released by the caller
+
+    def _rowshard_exchange(self):
+        red = self.rowshard_local()
+        self._rowshard(red)                       # the exchange step: C * n_values doubles
+        self.rowshard_commit(red)
+
+    def _mh_steps_rowshard(self, n_steps, injection):
+        if not callable(self._rowshard):
+            raise L.NpbnnError("manual row sharding: drive rowshard_update / rowshard_local / rowshard_commit yourself")
+        for s in range(n_steps):
+            one = None if injection is None else {k: v[s:s + 1] for k, v in injection.items() if v is not None}
+            self.rowshard_update(0, True, one)
+            self._rowshard_exchange()
+            self.rowshard_update(1, False)
 
     def read_state(self, weights=True) -> ChainState:
         n = self.n_chains

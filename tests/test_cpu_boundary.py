@@ -151,3 +151,12 @@ def test_mc3_exchange_two_ranks_gloo(tmp_path):
         temps, _ = mc3.swap_temperatures(lp, temps, j, k, rng.log_uniform())
         assert np.array_equal(temps, t0[it])
     assert sorted(t0[-1]) == sorted(mc3.default_temperatures(n, 0.8))
+
+
+def test_row_partition_covers_all_rows_once():
+    from npbnn_b200 import rowshard
+    for n, w in ((10, 3), (1_000_003, 8), (5, 8), (64, 1)):
+        spans = [rowshard.row_partition(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1

@@ -468,3 +468,65 @@ def test_block_sparse_program_variants(case, n, chains):
     assert np.array_equal(a.n_accepted, b.n_accepted)
     assert np.array_equal(a.w, b.w)
     assert rel_close(a.logLik, b.logLik)
+
+
+def test_row_sharding_matches_unsharded_chains():
+    """Rows split over two "ranks" (two contexts on one GPU, the all-reduce done by hand): the per-chain sums of the
+    shards add up to the unsharded partials, so log-likelihoods agree to rounding, counters exactly, and both shards
+    take the decisions of the unsharded run.  A single shard with the identity as all-reduce is
+    bit-identical to the ordinary path."""
+    from npbnn_b200.engine import Engine, NetShape
+    from npbnn_b200 import rowshard
+    x, labels, sets = _c4_like(3000, 3, seed=21)
+    xt, lt = x[2600:], labels[2600:]
+    x, labels = x[:2600], labels[:2600]
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    kw = dict(temperature=[1.0, 0.9, 0.8], seed=77, adapt_f=0.1, adapt_fM=0.6, adapt_freq=5, adapt_stop=40)
+    full = Engine(net)
+    full.set_data(x, labels, xt, lt)
+    full.chains_init(sets, **kw)
+    one = Engine(net)
+    one.set_data(x, labels, xt, lt)
+    one.enable_rowshard(len(x), lambda t: t)
+    one.chains_init(sets, **kw)
+    shards = []
+    for r in range(2):
+        a, b = rowshard.row_partition(len(x), 2, r)
+        ta, tb = rowshard.row_partition(len(xt), 2, r)
+        e = Engine(net)
+        e.set_data(x[a:b], labels[a:b], xt[ta:tb], lt[ta:tb])
+        e.enable_rowshard(len(x), "manual")
+        e.chains_init(sets, **kw)
+        shards.append(e)
+
+    def exchange(accept_mode):
+        total = shards[0].rowshard_local() + shards[1].rowshard_local()
+        for e in shards:
+            e.rowshard_commit(total.clone())
+            e.rowshard_update(accept_mode, False)
+
+    exchange(2)
+    s0 = full.read_state()
+    for e in shards + [one]:
+        st = e.read_state()
+        assert rel_close(st.logLik, s0.logLik, rtol=1e-12) and np.array_equal(st.n_correct, s0.n_correct)
+        assert np.array_equal(st.n_correct_test, s0.n_correct_test)
+    T = 30
+    full.mh_steps(T)
+    one.mh_steps(T)
+    for _ in range(T):
+        for e in shards:
+            e.rowshard_update(0, True)
+        exchange(1)
+    s0 = full.read_state()
+    st1 = one.read_state()
+    assert np.array_equal(st1.w, s0.w) and np.array_equal(st1.logLik, s0.logLik) and np.array_equal(st1.i32, s0.i32)
+    for e in shards:
+        st = e.read_state()
+        assert np.array_equal(st.n_accepted, s0.n_accepted) and np.array_equal(st.w, s0.w)
+        assert rel_close(st.logLik, s0.logLik, rtol=1e-12) and rel_close(st.logPrior, s0.logPrior, rtol=1e-14)
+        assert np.array_equal(st.n_correct, s0.n_correct) and np.array_equal(st.pred_hist, s0.pred_hist)
+        assert np.array_equal(st.update_n, s0.update_n) and np.all(st.iteration == T)
+    assert np.array_equal(shards[0].read_state().f64, shards[1].read_state().f64)      # ranks stay bit-identical
+    for e in shards + [one, full]:
+        e.close()
