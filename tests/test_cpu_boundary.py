@@ -160,3 +160,42 @@ def test_row_partition_covers_all_rows_once():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+RS_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from npbnn_b200 import rowshard
+rank, world = int(sys.argv[1]), 2
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[2]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+per_row = np.load(sys.argv[3] + "/per_row.npy")            # [C, n_rows, n_values]
+a, b = rowshard.row_partition(per_row.shape[1], world, rank)
+out = []
+for it in range(3):
+    red = torch.from_numpy(per_row[:, a:b].sum(axis=1) * (it + 1))
+    rowshard.dist_all_reduce_sum(red)
+    out.append(red.numpy().copy())
+np.save(sys.argv[3] + "/red_%%d.npy" %% rank, np.array(out))
+dist.destroy_process_group()
+'''
+
+
+def test_rowshard_exchange_two_ranks_gloo(tmp_path):
+    """world_size-2 run of the row-sharding exchange on CPU (gloo): each rank sums its own rows' contributions, the
+    all-reduce leaves the same bits on both ranks (so both take the same accept decision) and they equal the
+    unsharded sums."""
+    rs = np.random.default_rng(5)
+    per_row = rs.normal(size=(3, 1001, 23))
+    np.save(tmp_path / "per_row.npy", per_row)
+    script = tmp_path / "w.py"
+    script.write_text(RS_WORKER % {"root": ROOT})
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port, str(tmp_path)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    r0, r1 = np.load(tmp_path / "red_0.npy"), np.load(tmp_path / "red_1.npy")
+    assert np.array_equal(r0, r1)
+    for it in range(3):
+        np.testing.assert_allclose(r0[it], per_row.sum(axis=1) * (it + 1), rtol=1e-12, atol=1e-12)
