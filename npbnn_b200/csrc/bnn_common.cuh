@@ -81,7 +81,12 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1,
 // ---------------------------------------------------------------------------------------------
 // TB = log2(table entries): 11 (2048 entries + degree 3) or 8 (256 entries + degree 4, one more instruction;
 // used where shared memory is short)
-template <int TB = BNN_EXP_TAB_BITS>
+//
+// ONE_STEP: argument reduction with the single rounded constant ln2/2^TB (one FMA instead of two).  The
+// reduced argument is then off by at most |x| * 3.4e-17, i.e. exp(x) by that relative amount -- harmless where
+// the exponential feeds a sigmoid: d swish / d r = z s (1-s) and d tanh / d r are bounded, so the activation
+// moves by < 1e-16 ABSOLUTE for every z.  Used by the activations only; the softmax keeps the two-step form.
+template <int TB = BNN_EXP_TAB_BITS, bool ONE_STEP = false>
 __device__ __forceinline__ double bnn_exp_core(double x, const double* __restrict__ tab) {
   static_assert(TB == 8 || TB == 11, "exp table: 256 or 2048 entries");
   const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest-integer trick
@@ -92,8 +97,13 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
   double t = fma(x, INV, MAGIC);
   int k = __double2loint(t);
   double kd = t - MAGIC;
-  double r = fma(kd, -C_HI, x);
-  r = fma(kd, -C_LO, r);
+  double r;
+  if (ONE_STEP) {
+    r = fma(kd, (TB == 11) ? -0.0003384507717577858 : -0.0027076061740622863, x);
+  } else {
+    r = fma(kd, -C_HI, x);
+    r = fma(kd, -C_LO, r);
+  }
   double q;
   if (TB == 11) {
     q = fma(r, 1.66666666666666657e-01, 0.5);        // |r| <= ln2/4096: r^4/24 < 4e-17
@@ -133,7 +143,7 @@ __device__ __forceinline__ double bnn_exp_clamped(double x, const double* __rest
   const int hx = __double2hiint(x);
   const bool big = (hx & 0x7fffffff) >= 0x40862000;           // |x| >= 708 (also inf / NaN)
   const double xc = big ? __hiloint2double((hx & 0x80000000) | 0x40862000, 0) : x;
-  return bnn_exp_core<TB>(xc, tab);
+  return bnn_exp_core<TB, true>(xc, tab);
 }
 
 // 1/d for finite d >= 1: MUFU.RCP64H seed (rcp.approx.ftz.f64) + one third-order step
@@ -211,8 +221,8 @@ template <int ACT>
 __device__ __forceinline__ double bnn_act_fast(double z, double alpha, const double* __restrict__ tab) {
   if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
-  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_core(-z, tab));
-  return fma(-2.0, bnn_rcp(bnn_exp_core(z + z, tab) + 1.0), 1.0);
+  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_core<BNN_EXP_TAB_BITS, true>(-z, tab));
+  return fma(-2.0, bnn_rcp(bnn_exp_core<BNN_EXP_TAB_BITS, true>(z + z, tab) + 1.0), 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------

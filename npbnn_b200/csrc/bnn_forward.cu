@@ -769,9 +769,43 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   }
   __syncthreads();
 
+  // Work decomposition.  n_full rounds in which every warp of the grid owns one 16-row tile and runs all C
+  // weight sets over it; the remaining tiles (fewer than one per warp) form `groups` CTA-sized tile groups
+  // whose (group, weight set) pairs are dealt out evenly over the CTAs, so that the last round costs
+  // ceil(groups*C/grid) weight sets per CTA instead of C (c4: 7 instead of 32, 36 rounds -> 35.2).  A CTA's
+  // share is a contiguous range of pairs, i.e. at most two segments (tile group, [lo, hi)).  Every (tile,
+  // weight set) is still computed by exactly one warp with the same instruction sequence, so results do not
+  // depend on the decomposition.  Prediction accumulates over weight sets in registers: no split there.
   const long long total_warps = (long long)gridDim.x * NWARPS;
-  const long long n_iter = (p.n_tiles16 + total_warps - 1) / total_warps;
-  const long long total_q = n_iter * p.C;     // weight-set uses, identical for every warp of the CTA
+  const long long n_full = p.n_tiles16 / total_warps;
+  const long long tail_base = n_full * total_warps;
+  const long long rem = p.n_tiles16 - tail_base;
+  int seg_tg[2] = {0, 0}, seg_lo[2] = {0, 0}, seg_hi[2] = {0, 0};
+  if (rem > 0) {
+    const long long groups = (rem + NWARPS - 1) / NWARPS;
+    if (PREDICT) {
+      if ((long long)blockIdx.x < groups) { seg_tg[0] = blockIdx.x; seg_hi[0] = p.C; }
+    } else {
+      const long long pairs = groups * p.C;
+      const long long per_cta = (pairs + gridDim.x - 1) / gridDim.x;
+      const long long s0 = (long long)blockIdx.x * per_cta;
+      const long long s1 = (s0 + per_cta < pairs) ? s0 + per_cta : pairs;
+      if (s0 < s1) {
+        seg_tg[0] = (int)(s0 / p.C);
+        seg_lo[0] = (int)(s0 % p.C);
+        const long long n0 = ((s1 - s0) < (long long)(p.C - seg_lo[0])) ? (s1 - s0) : (long long)(p.C - seg_lo[0]);
+        seg_hi[0] = seg_lo[0] + (int)n0;
+        if (s1 - s0 > n0) { seg_tg[1] = seg_tg[0] + 1; seg_hi[1] = (int)(s1 - s0 - n0); }
+      }
+    }
+  }
+  const long long q_seg0 = n_full * p.C;                         // first weight-set use of segment 0
+  const long long q_seg1 = q_seg0 + (seg_hi[0] - seg_lo[0]);     // ... of segment 1
+  const long long total_q = q_seg1 + (seg_hi[1] - seg_lo[1]);    // weight-set uses, identical for every warp of the CTA
+  const long long n_iter = n_full + (seg_hi[0] > seg_lo[0] ? 1 : 0) + (seg_hi[1] > seg_lo[1] ? 1 : 0);
+  auto set_of = [&](long long qq) -> long long {                 // weight set consumed by use qq of this CTA
+    return qq < q_seg0 ? qq % p.C : (qq < q_seg1 ? seg_lo[0] + (qq - q_seg0) : seg_lo[1] + (qq - q_seg1));
+  };
   constexpr uint32_t W_BYTES = G3::PB * sizeof(double);
   constexpr uint32_t X_BYTES = 16 * KP0 * sizeof(double);
 
@@ -779,13 +813,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   if (producer) {
     for (int q = 0; q < 2 && q < total_q; ++q) {
       mbar_arrive_expect_tx(&full[q], W_BYTES);
-      bulk_g2s(wbuf + q * G3::PB, p.wp + (long long)(q % p.C) * G3::PB, W_BYTES, &full[q]);
+      bulk_g2s(wbuf + q * G3::PB, p.wp + set_of(q) * G3::PB, W_BYTES, &full[q]);
     }
   }
 
   long long q = 0;
+  uint32_t x_uses = 0;               // X tiles this warp has loaded (parity of its mbarrier)
   for (long long it = 0; it < n_iter; ++it) {
-    const long long wt = it * total_warps + (long long)blockIdx.x * NWARPS + warp;
+    const int sg = (int)(it - n_full);                       // tail segment (>= 0) or full round (< 0)
+    const long long wt = sg < 0 ? it * total_warps + (long long)blockIdx.x * NWARPS + warp
+                                : tail_base + (long long)(sg == 0 ? seg_tg[0] : seg_tg[1]) * NWARPS + warp;
+    const int c_lo = sg < 0 ? 0 : (sg == 0 ? seg_lo[0] : seg_lo[1]);
+    const int c_hi = sg < 0 ? p.C : (sg == 0 ? seg_hi[0] : seg_hi[1]);
     const bool have_tile = wt < p.n_tiles16;
     int y[2] = {0, 0};
     double wgt[2] = {1.0, 1.0};
@@ -815,16 +854,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < N3 / 4; ++i) { pacc[h][i] = 0.0; pvote[h][i] = 0; }
       }
-      mbar_wait(xbar, (uint32_t)(it & 1));
+      mbar_wait(xbar, x_uses & 1);
+      ++x_uses;
     }
-    for (int c = 0; c < p.C; ++c, ++q) {
+    for (int c = c_lo; c < c_hi; ++c, ++q) {
       const int b = (int)(q & 1);
       // producer: refill the other buffer (use q+1) once every warp has released use q-1
       if (producer && q >= 1 && q + 1 < total_q) {
         const int nb = b ^ 1;
         mbar_wait(&empty[nb], (uint32_t)(((q - 1) >> 1) & 1));
         mbar_arrive_expect_tx(&full[nb], W_BYTES);
-        bulk_g2s(wbuf + nb * G3::PB, p.wp + (long long)((q + 1) % p.C) * G3::PB, W_BYTES, &full[nb]);
+        bulk_g2s(wbuf + nb * G3::PB, p.wp + set_of(q + 1) * G3::PB, W_BYTES, &full[nb]);
       }
       __syncwarp();
       mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
@@ -980,7 +1020,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         RowStats<N3> rs;
         quad_softmax_stats<N3, true>(acc3, g.K, t, y, tab, rs);
         const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, true);
-        quad_lik_commit(p, p.C - 1, wt, lane, cnt, lr, true);
+        quad_lik_commit(p, c_hi - 1, wt, lane, cnt, lr, true);
       }
       if (PREDICT) {
 #pragma unroll
@@ -1705,6 +1745,7 @@ static cudaError_t launch_fwd3(const FwdParams& p, int n_sms, cudaStream_t st) {
   }
   if (smem > 232448) return cudaErrorInvalidConfiguration;
   long long ctas = (p.n_tiles16 + NWARPS - 1) / NWARPS;
+  if (MODE != FWD3_PRED) ctas *= p.C;          // likelihood modes deal (tile group, weight set) pairs out over the CTAs
   int grid = (int)(ctas < n_sms ? ctas : n_sms);
   kern<<<grid, NWARPS * 32, smem, st>>>(p);
   return cudaGetLastError();

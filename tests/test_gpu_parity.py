@@ -257,6 +257,96 @@ def test_c4_shape_specialised_kernel(n):
     eng.close()
 
 
+@pytest.mark.parametrize("n,n_sets", [(50000, 5), (30011, 7), (28416 * 2 + 16 * 29, 3)])
+def test_c4_shape_tail_round_split(n, n_sets):
+    """k_fwd3 deals the (tile group, weight set) pairs of the last, partially filled round out over the CTAs
+    (one or two segments per CTA).  Sizes chosen so that CTAs get two segments, an uneven share and a tail
+    behind full rounds (148 SMs x 12 warps x 16 rows = 28,416 rows per full round).  Against the oracle and the
+    generic kernel; the decomposition must not change a single bit between two geometries of the same rows."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(n, n_sets)
+    m = orc.Model(x=x, labels=labels, weights=sets[0], act="swish", mode="classification")
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x, labels)
+    res = eng.forward_lik(sets)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    for i, w in enumerate(sets):
+        ref = oracle_score(m, w)
+        assert rel_close(res["loglik"][i], ref["loglik"]), (i, res["loglik"][i], ref["loglik"])
+        c = res["counts"][i]
+        assert c[0] == ref["n_correct"]
+        assert np.array_equal(c[2:12], ref["class_correct"]) and np.array_equal(c[12:22], ref["pred_hist"])
+    # the same sets scored one at a time (different pair decomposition): identical bits
+    for i in (0, n_sets - 1):
+        one = eng.forward_lik([sets[i]])
+        assert one["loglik"][0] == res["loglik"][i]
+        assert np.array_equal(one["counts"][0], res["counts"][i])
+    eng.close()
+
+
+def test_c4_full_size_properties():
+    """BASELINE config 4 at FULL size (1M x 64, 32 weight sets): the oracle cannot score this in seconds, so
+    parity is carried by size-independent properties of the likelihood pass --
+      * additivity over a row partition (log-likelihood sums to 1e-12 relative, integer counters add exactly),
+      * an oracle check on a random 20k-row subset of the same rows,
+      * duplicate weight sets give identical bits, two runs give identical bits,
+      * invariance under a row permutation (1e-12 relative, counters exactly)."""
+    import torch
+    from npbnn_b200.engine import Engine, NetShape
+    from npbnn_b200 import workloads as wl
+    n, C = 1_000_000, 32
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n, 64, dtype=torch.float64, device="cuda", generator=g)
+    rng = np.random.default_rng(3)
+    shapes = list(wl.C4_SHAPES)
+    teacher = [rng.normal(0, 0.5, s) for s in shapes]
+    sets = [[rng.normal(0, 0.2, s) for s in shapes] for _ in range(C - 1)]
+    sets.append([a.copy() for a in sets[3]])                      # duplicate of set 3
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    lab = torch.as_tensor(eng.predict(x, [teacher], mean=True)["mean"]).argmax(1).to(torch.int32).cuda()
+    eng.set_data(x, lab)
+    full = eng.forward_lik(sets)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    assert np.all(np.isfinite(full["loglik"]))
+    again = eng.forward_lik(sets)
+    assert np.array_equal(full["loglik"], again["loglik"]) and np.array_equal(full["counts"], again["counts"])
+    assert full["loglik"][3] == full["loglik"][C - 1] and np.array_equal(full["counts"][3], full["counts"][C - 1])
+    assert np.all(full["counts"][:, 2:12].sum(1) == full["counts"][:, 0])         # per-class hits add up to hits
+    assert np.all(full["counts"][:, 12:22].sum(1) == n)                           # every row predicted once
+    # additivity over an uneven row partition
+    cuts = [0, 16, 123_457, 500_000, 999_983, n]
+    ll = np.zeros(C)
+    cnt = np.zeros_like(full["counts"])
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        eng.set_data(x[a:b], lab[a:b])
+        part = eng.forward_lik(sets)
+        ll += part["loglik"]
+        cnt += part["counts"]
+    assert np.allclose(ll, full["loglik"], rtol=1e-12, atol=0)
+    assert np.array_equal(cnt, full["counts"])
+    # oracle on a random subset of the same rows
+    idx = torch.as_tensor(np.sort(rng.choice(n, 20_000, replace=False))).cuda()
+    xs, ys = x[idx], lab[idx]
+    eng.set_data(xs, ys)
+    sub = eng.forward_lik(sets[:3])
+    m = orc.Model(x=xs.cpu().numpy(), labels=ys.cpu().numpy().astype(np.int64), weights=sets[0], act="swish",
+                  mode="classification")
+    for i in range(3):
+        ref = oracle_score(m, sets[i])
+        assert rel_close(sub["loglik"][i], ref["loglik"])
+        assert sub["counts"][i][0] == ref["n_correct"]
+        assert np.array_equal(sub["counts"][i][12:22], ref["pred_hist"])
+    # row permutation
+    perm = torch.randperm(n, device="cuda", generator=g)
+    eng.set_data(x[perm], lab[perm])
+    pr = eng.forward_lik(sets)
+    assert np.allclose(pr["loglik"], full["loglik"], rtol=1e-12, atol=0)
+    assert np.array_equal(pr["counts"], full["counts"])
+    eng.close()
+
+
 @pytest.mark.parametrize("n", [16, 130, 1000, 4099, 50000])
 def test_c4_shape_tensor_core_first_layer(n):
     """k_fwd3t: layer 1 as 21 exact int8 tensor-core products (Ozaki slices of X and W1, tcgen05 + TMEM) against
