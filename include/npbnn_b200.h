@@ -170,6 +170,12 @@ int bnn_forward_lik_host(bnn_ctx* ctx, const double* w_host, int32_t n_sets, con
 int bnn_log_prior(bnn_ctx* ctx, const double* w_dev, int32_t n_sets, int32_t prior,
                   const double* prior_scale /* host [n_layers] */, double* logprior_dev, void* stream);
 
+/* The same with one scale per weight entry (host [n_params], canonical layout): calc_prior after
+ * npBNN.sample_prior_scale has replaced the per-layer scalars by a vector per input node or a matrix per weight
+ * (hyper_p = 2, 3; BNN_env.py:180-194,196-219).  Scales must be positive and finite. */
+int bnn_log_prior_entries(bnn_ctx* ctx, const double* w_dev, int32_t n_sets, int32_t prior,
+                          const double* entry_scale_host, double* logprior_dev, void* stream);
+
 /* Create n_chains chains resident on the device.  Replaces MCMC.__init__ (BNN_env.py:274-379) for
  * every chain: initial forward, likelihood, prior and accuracy counters are computed here.
  *   w0_host     [C, n_params]
@@ -187,6 +193,16 @@ int bnn_mh_steps(bnn_ctx* ctx, int32_t n_steps, const bnn_injection* inj, void* 
 /* Export chain state (synchronises the stream).  Any pointer may be NULL.
  *   f64_host [C, BNN_F_STRIDE], i32_host [C, BNN_I_STRIDE], w_host [C, n_params] */
 int bnn_chains_read(bnn_ctx* ctx, double* f64_host, int32_t* i32_host, double* w_host, void* stream);
+/* Write the state arrays back (same layout as bnn_chains_read; synchronises the stream): the host edits what it
+ * read -- MCMC.reset_update_n / reset_update_f / reset_update_ws (BNN_env.py:540-547), the iteration count after
+ * a Gibbs step.  Any pointer may be NULL. */
+int bnn_chains_write(bnn_ctx* ctx, const double* f64_host, const int32_t* i32_host, void* stream);
+/* New prior scales for the chains, one per weight entry (host [C, n_params]; NULL: back to the per-layer scalars
+ * given at bnn_chains_init), then logPrior = calc_prior(), logPost = logLik + logPrior of every chain's current
+ * weights: the device half of MCMC.gibbs_step (BNN_env.py:534-538) once the host has drawn the scales
+ * (npBNN.sample_prior_scale, BNN_env.py:196-219; GibbsSampleNormStdGamma*, BNN_mcmc.py:124-141).  The proposals of
+ * the following bnn_mh_steps are scored with these scales. */
+int bnn_chains_set_prior_scales(bnn_ctx* ctx, const double* entry_scale_host, void* stream);
 /* Device pointers to the live chain state (same layout as bnn_chains_read; e.g. the log-posteriors for
  * the MC3 all-gather are f64_dev[c * BNN_F_STRIDE + BNN_F_LOGPOST]).  Any pointer may be NULL. */
 int bnn_chains_state_dev(bnn_ctx* ctx, double** f64_dev, int32_t** i32_dev, double** w_dev);

@@ -22,8 +22,7 @@ proposals on the device and never leaves it between logging points.
 
 Trainable activation parameters (ActFun(trainable=True)), init_additional_prob and mh_step(additional_prob=) run
 on the device from host-drawn numbers (rng="host").  Options of the reference that are not on the device path raise
-NotImplementedError: feature / weight indicators, hyper-priors, user-supplied likelihood / proposal / output
-functions, and the regression error-parameter proposal (estimate_error with empirical_error=False once the
+NotImplementedError: feature / weight indicators, user-supplied likelihood / proposal / output functions, and the regression error-parameter proposal (estimate_error with empirical_error=False once the
 iteration passes `_estimate_error` -- a branch on which the reference itself raises AttributeError as soon as one
 proposal has been accepted before that iteration, BNN_mcmc.py:105).
 """
@@ -161,8 +160,10 @@ class npBNN:
                  empirical_error=False, size_output=None, output_act_fun=None, feature_indicators=None):
         if actFun is None:
             actFun = ActFun()
-        if hyper_p or freq_indicator or feature_indicators:
-            raise NotImplementedError("hyper-priors / weight indicators / feature indicators are not on the device path")
+        if freq_indicator or feature_indicators:
+            raise NotImplementedError("weight indicators / feature indicators are not on the device path")
+        if hyper_p not in (0, 1, 2, 3):
+            raise ValueError("hyper_p must be 0, 1, 2 or 3")
         if estimation_mode not in _LIK:
             raise NotImplementedError("estimation_mode=%r (custom likelihoods) is not on the device path" % (estimation_mode,))
         if output_act_fun is not None and not (estimation_mode == "regression-error" and output_act_fun is RegressTransformError) \
@@ -251,12 +252,46 @@ class npBNN:
             self._eng = Engine(self._net())
         return self._eng
 
+    def _scales_per_layer(self):
+        """True while _prior_scale holds one scalar per layer (no hyper-prior sample yet)."""
+        return all(np.ndim(s) == 0 for s in self._prior_scale)
+
+    def _entry_scales(self):
+        """_prior_scale broadcast to one scale per weight entry, flattened in the canonical order: a scalar per layer
+        (hyper_p 1), a vector per input node = per weight-matrix column (2), a matrix per weight (3) -- the broadcasting
+        scipy's logpdf(w, 0, scale=...) applies in calc_prior (BNN_env.py:184-189)."""
+        return np.concatenate([np.broadcast_to(np.asarray(s, dtype=np.float64), w.shape).ravel()
+                               for s, w in zip(self._prior_scale, self._w_layers)])
+
     def calc_prior(self, w=0, ind=[]):
         if isinstance(w, int) and w == 0:
             w = self._w_layers
         if self._prior == 0:
             return 0
-        return float(self._engine().log_prior([w], self._prior_kind(), self._prior_scale)[0])
+        ps = self._prior_scale if self._scales_per_layer() else self._entry_scales()
+        return float(self._engine().log_prior([w], self._prior_kind(), ps)[0])
+
+    def sample_prior_scale(self):
+        """Gibbs draw of the prior standard deviations from their conjugate Gamma posteriors on the precision
+        (BNN_env.py:196-219; GibbsSampleNormStdGammaVector / 2D / ONE, BNN_mcmc.py:124-141).  O(n_params) host
+        arithmetic on the host copy of the weights with the reference's global-generator call sequence (one
+        np.random.gamma call per layer), so a seeded run draws the reference's scales."""
+        if self._prior != 1:
+            print("Hyper-priors available only for Normal priors.")
+            quit()
+        if self._hyper_p not in (1, 2, 3):
+            return
+        scales = []
+        for w in self._w_layers:
+            w = np.asarray(w, dtype=np.float64)
+            if self._hyper_p == 1:                                  # one scale per layer: Gamma(2 + n/2, 0.1 + SS/2)
+                tau = np.random.gamma(2 + w.size / 2.0, scale=1.0 / (0.1 + np.sum(w.flatten() ** 2) / 2.0))
+            elif self._hyper_p == 2:                                # per input node (column): Gamma(1 + rows/2, .)
+                tau = np.random.gamma(1 + w.shape[0] / 2.0, scale=1.0 / (0.1 + np.sum(w ** 2, axis=0) / 2.0))
+            else:                                                   # per weight: Gamma(1.5 + 1/2, 0.1 + w^2/2)
+                tau = np.random.gamma(1.5 + 0.5, scale=1.0 / (0.1 + (w ** 2) / 2.0))
+            scales.append(1 / np.sqrt(tau))
+        self._prior_scale = scales
 
     def reset_weights(self, w):
         self._w_layers = w
@@ -324,14 +359,19 @@ class _ChainGroup:
         sigma0 = None
         if bnn._estimation_mode == "regression":
             sigma0 = np.ones(bnn._size_output) * np.asarray(bnn._error_prm, dtype=np.float64)
+        per_layer = bnn._scales_per_layer()
         self.eng.chains_init(weights_per_chain, temperature=temperatures, update_f=update_f, update_ws=update_ws,
-                             prior=bnn._prior_kind(), prior_scale=bnn._prior_scale, w_bound=bnn._w_bound,
+                             prior=bnn._prior_kind(),
+                             prior_scale=bnn._prior_scale if per_layer else np.ones(net.n_layers) * bnn._p_scale,
+                             w_bound=bnn._w_bound,
                              mask=bnn._mask, alphas=bnn._act_fun.alphas(net.n_layers), sigma0=sigma0,
                              sigma_mode=L.SIGMA_EMPIRICAL if (bnn._estimation_mode == "regression" and bnn._empirical_error)
                              else L.SIGMA_FIXED,
                              lik_temp=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq,
                              adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed,
                              n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob)
+        if not per_layer:        # a model that already carries sampled hyper-prior scales
+            self.eng.set_prior_scales(np.tile(bnn._entry_scales(), (self.n, 1)))
         self.n_act_prm = bnn._act_fun.n_trainable()
         if self.n_act_prm > net.n_layers:
             raise ValueError("more trainable activation parameters than layers")
@@ -533,6 +573,49 @@ class MCMC:
         self.run(bnn_obj, 1, additional_prob)
         if return_bnn:
             return bnn_obj, self
+
+    def gibbs_step(self, bnn_obj):
+        """BNN_env.py:534-538: new prior scales from their conditional posterior (host draw, sample_prior_scale), then
+        logPrior / logPost of the current weights under them (device) and one iteration counted."""
+        if not self._own_group:
+            raise RuntimeError("this MCMC belongs to an MC3 group")
+        bnn_obj.sample_prior_scale()
+        eng = self._group.eng
+        eng.set_prior_scales(bnn_obj._entry_scales()[None, :])
+        st = eng.read_state(weights=False)
+        st.i32[:, L.I_ITERATION] += 1
+        eng.write_state(st)
+        self._sync(bnn_obj, eng.read_state())
+
+    def _edit_state(self, edit):
+        if not self._own_group:
+            raise RuntimeError("this MCMC belongs to an MC3 group")
+        eng = self._group.eng
+        st = eng.read_state(weights=False)
+        edit(st)
+        eng.write_state(st)
+
+    # BNN_env.py:540-547.  The reference only rebinds the attribute; here the value also goes to the device state.
+    def reset_update_n(self, n):
+        n = np.asarray(n).astype(int)
+        self._update_n = n
+        self._edit_state(lambda st: st.i32.__setitem__((slice(None), slice(L.I_UPDATE_N, L.I_UPDATE_N + len(n))), n))
+
+    def reset_update_f(self, f):
+        f = np.asarray(f, dtype=np.float64)
+        self._update_f = f
+        self._edit_state(lambda st: st.f64.__setitem__((slice(None), slice(L.F_UPDATE_F, L.F_UPDATE_F + len(f))), f))
+
+    def reset_update_ws(self, w):
+        ws = []
+        for m in w:
+            m = np.asarray(m, dtype=np.float64)
+            if m.size > 1 and not np.all(m == m.flat[0]):
+                raise NotImplementedError("per-weight proposal widths are not on the device path (one width per layer)")
+            ws.append(float(m.flat[0]))
+        self._update_ws = [np.ones(s) * ws[i] for i, s in enumerate(self._bnn_shapes)]
+        ws = np.asarray(ws)
+        self._edit_state(lambda st: st.f64.__setitem__((slice(None), slice(L.F_UPDATE_WS, L.F_UPDATE_WS + len(ws))), ws))
 
     def reset_temperature(self, temp):
         self._temperature = temp

@@ -70,6 +70,8 @@ struct bnn_ctx {
   bnn_sampler_config cfg{};
   PriorScales ps{};
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
+  DevBuf ps_entry, pls_entry, ps_tmp, pls_tmp;   // per-entry prior scales of the chains (hyper-priors) / of a scoring call
+  bool have_ps_entry = false;
   // row sharding: the chains' accept step reads the all-reduced sums from part_red (one pseudo tile)
   bool rowshard = false;
   long long n_train_global = 0;
@@ -454,7 +456,36 @@ int bnn_log_prior(bnn_ctx* c, const double* w_dev, int32_t n_sets, int32_t prior
   CUDA_TRY(cudaSetDevice(c->device));
   PriorScales ps;
   fill_prior_scales(ps, prior_scale, c->g.L);
-  CUDA_TRY(bnn_launch_log_prior(c->g, w_dev, n_sets, prior, ps, logprior_dev, (cudaStream_t)stream));
+  CUDA_TRY(bnn_launch_log_prior(c->g, w_dev, n_sets, prior, ps, nullptr, nullptr, 0, logprior_dev, (cudaStream_t)stream));
+  c->launches++;
+  return 0;
+}
+
+// scales > 0 and finite, logs taken on the host (libm log, as scipy's logpdf does)
+static int upload_entry_scales(DevBuf& sc, DevBuf& lg, const double* scale_host, size_t n, cudaStream_t st, const char* who) {
+  std::vector<double> ls(n);
+  for (size_t i = 0; i < n; ++i) {
+    if (!(scale_host[i] > 0.0) || !std::isfinite(scale_host[i])) {
+      g_last_error = std::string(who) + ": prior scales must be positive and finite";
+      return 1;
+    }
+    ls[i] = std::log(scale_host[i]);
+  }
+  if (upload(sc, scale_host, n, st) || upload(lg, ls.data(), n, st)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(st));     // `ls` leaves scope
+  return 0;
+}
+
+int bnn_log_prior_entries(bnn_ctx* c, const double* w_dev, int32_t n_sets, int32_t prior, const double* entry_scale_host,
+                          double* logprior_dev, void* stream) {
+  REQUIRE(c && c->have_net, "bnn_log_prior_entries: call bnn_set_net first");
+  REQUIRE(w_dev && logprior_dev && entry_scale_host && n_sets >= 1, "bnn_log_prior_entries: bad arguments");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = upload_entry_scales(c->ps_tmp, c->pls_tmp, entry_scale_host, (size_t)c->g.P, st, "bnn_log_prior_entries")) return rc;
+  PriorScales ps{};
+  CUDA_TRY(bnn_launch_log_prior(c->g, w_dev, n_sets, prior, ps, c->ps_tmp.as<double>(), c->pls_tmp.as<double>(), 0,
+                                logprior_dev, st));
   c->launches++;
   return 0;
 }
@@ -614,6 +645,8 @@ static ChainDev chain_dev(bnn_ctx* c) {
   d.w_prop = c->w_prop.as<double>();
   d.wp_prop = c->wp_prop.as<double>();
   d.mask = c->cfg.use_mask ? c->mask.as<double>() : nullptr;
+  d.ps_entry = c->have_ps_entry ? c->ps_entry.as<double>() : nullptr;
+  d.pls_entry = c->have_ps_entry ? c->pls_entry.as<double>() : nullptr;
   d.owner = c->owner.as<int>();
   d.sf = c->sf.as<double>();
   d.si = c->si.as<int>();
@@ -669,6 +702,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   const NetGeom& g = c->g;
   const int C = n_chains, NC = 2 + 2 * g.K;
   c->C = C;
+  c->have_ps_entry = false;          // per-entry prior scales belong to the previous set of chains
   c->cfg = *cfg;
   fill_prior_scales(c->ps, cfg->prior_scale, g.L);
   CUDA_TRY(c->w_cur.ensure(sizeof(double) * (size_t)C * g.P, false, st));
@@ -884,6 +918,33 @@ int bnn_chains_read(bnn_ctx* c, double* f64_host, int32_t* i32_host, double* w_h
   if (i32_host) CUDA_TRY(cudaMemcpyAsync(i32_host, c->si.p, sizeof(int) * (size_t)c->C * BNN_I_STRIDE, cudaMemcpyDeviceToHost, st));
   if (w_host) CUDA_TRY(cudaMemcpyAsync(w_host, c->w_cur.p, sizeof(double) * (size_t)c->C * c->g.P, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bnn_chains_write(bnn_ctx* c, const double* f64_host, const int32_t* i32_host, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_chains_write: call bnn_chains_init first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f64_host) CUDA_TRY(cudaMemcpyAsync(c->sf.p, f64_host, sizeof(double) * (size_t)c->C * BNN_F_STRIDE, cudaMemcpyHostToDevice, st));
+  if (i32_host) CUDA_TRY(cudaMemcpyAsync(c->si.p, i32_host, sizeof(int) * (size_t)c->C * BNN_I_STRIDE, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bnn_chains_set_prior_scales(bnn_ctx* c, const double* entry_scale_host, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_chains_set_prior_scales: call bnn_chains_init first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (entry_scale_host) {
+    if (int rc = upload_entry_scales(c->ps_entry, c->pls_entry, entry_scale_host, (size_t)c->C * c->g.P, st,
+                                     "bnn_chains_set_prior_scales")) return rc;
+    c->have_ps_entry = true;
+  } else {
+    c->have_ps_entry = false;
+  }
+  ChainDev d = chain_dev(c);
+  CUDA_TRY(bnn_launch_prior_refresh(d, st));
+  c->launches++;
   return 0;
 }
 

@@ -18,6 +18,8 @@ struct ChainDev {
   double* w_prop;       // [C, P] canonical proposal
   double* wp_prop;      // [C, PB] packed proposal (input of the forward kernel)
   const double* mask;   // [P] or null
+  const double* ps_entry;   // [C, P] per-entry prior scales (hyper-priors, BNN_env.py:196-219) or null
+  const double* pls_entry;  // [C, P] their logarithms
   int* owner;           // [C, P] scratch for last-write-wins, all -1 between launches
   double* sf;           // [C, BNN_F_STRIDE]
   int* si;              // [C, BNN_I_STRIDE]
@@ -56,7 +58,9 @@ cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF
                                     double lik_temp, int sigma_mode, const double* sigma, double* loglik, double* sums,
                                     int set0, int n_sets, cudaStream_t st);
 cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
-                                 double* out, cudaStream_t st);
+                                 const double* ps_entry, const double* pls_entry, int entry_stride, double* out,
+                                 cudaStream_t st);
+cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
 cudaError_t bnn_launch_rowshard_local(const double* part, int NF, long long nt, const int* counts, int NC, double* out,
                                       int n_chains, cudaStream_t st);

@@ -125,18 +125,44 @@ __global__ void __launch_bounds__(UPD_THREADS) k_finalize_lik(const __grid_const
     for (int i = threadIdx.x; i < 3 * g.K; i += blockDim.x) sums[(long long)(set0 + c) * 3 * g.K + i] = red[1 + i];
 }
 
+// ps_entry / pls_entry: per-entry scales and their logs (hyper-priors: npBNN._prior_scale holds a vector per input
+// node or a matrix per weight after sample_prior_scale, BNN_env.py:196-219), set `entry_stride` doubles apart
+// (0: the same scales for every set); null: one scale per layer.
 __global__ void __launch_bounds__(UPD_THREADS) k_log_prior(const __grid_constant__ NetGeom g, const double* w, int prior,
-                                                            PriorScales ps, double* out) {
+                                                            PriorScales ps, const double* ps_entry,
+                                                            const double* pls_entry, int entry_stride, double* out) {
   __shared__ double sh[32];
   const int c = blockIdx.x;
   double v = 0.0;
   if (prior != BNN_PRIOR_UNIFORM)
     for (int i = threadIdx.x; i < g.P; i += blockDim.x) {
       int l = layer_of(g, i);
-      v += logpdf_prior(w[(long long)c * g.P + i], prior, ps.s[l], ps.ls[l]);
+      const long long e = (long long)c * entry_stride + i;
+      v += logpdf_prior(w[(long long)c * g.P + i], prior, ps_entry ? ps_entry[e] : ps.s[l], ps_entry ? pls_entry[e] : ps.ls[l]);
     }
   double s = block_sum_fixed(v, sh);
   if (threadIdx.x == 0) out[c] = s;
+}
+
+// MCMC.gibbs_step (BNN_env.py:534-538) after new prior scales: logPrior = calc_prior(), logPost = logLik + logPrior
+// of the CURRENT weights of every chain.
+__global__ void __launch_bounds__(UPD_THREADS) k_prior_refresh(const __grid_constant__ ChainDev d) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x;
+  const NetGeom& g = d.g;
+  double v = 0.0;
+  if (d.cfg.prior != BNN_PRIOR_UNIFORM)
+    for (int i = threadIdx.x; i < g.P; i += blockDim.x) {
+      int l = layer_of(g, i);
+      const long long e = (long long)c * g.P + i;
+      v += logpdf_prior(d.w_cur[e], d.cfg.prior, d.ps_entry ? d.ps_entry[e] : d.ps.s[l], d.ps_entry ? d.pls_entry[e] : d.ps.ls[l]);
+    }
+  double s = block_sum_fixed(v, sh);
+  if (threadIdx.x == 0) {
+    double* sf = d.sf + (long long)c * BNN_F_STRIDE;
+    sf[BNN_F_LOGPRIOR] = s;
+    sf[BNN_F_LOGPOST] = sf[BNN_F_LOGLIK] + s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,7 +416,10 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
       if (d.mask) z *= d.mask[i];      // w' *= mask for every layer (BNN_env.py:461-462)
       wn[i] = z;
     }
-    if (d.cfg.prior != BNN_PRIOR_UNIFORM) lp += logpdf_prior(z, d.cfg.prior, d.ps.s[l], d.ps.ls[l]);
+    if (d.cfg.prior != BNN_PRIOR_UNIFORM) {
+      const long long e = (long long)c * g.P + i;
+      lp += logpdf_prior(z, d.cfg.prior, d.ps_entry ? d.ps_entry[e] : d.ps.s[l], d.ps_entry ? d.pls_entry[e] : d.ps.ls[l]);
+    }
     const int cols = lg.in + lg.bias;
     const int r = (i - lg.c_off) / cols, cc = (i - lg.c_off) % cols;
     wpk[bnn_packed_index(lg, r, cc)] = z;
@@ -421,8 +450,13 @@ cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF
   return cudaGetLastError();
 }
 cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
-                                 double* out, cudaStream_t st) {
-  k_log_prior<<<n_sets, UPD_THREADS, 0, st>>>(g, w, prior, ps, out);
+                                 const double* ps_entry, const double* pls_entry, int entry_stride, double* out,
+                                 cudaStream_t st) {
+  k_log_prior<<<n_sets, UPD_THREADS, 0, st>>>(g, w, prior, ps, ps_entry, pls_entry, entry_stride, out);
+  return cudaGetLastError();
+}
+cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st) {
+  k_prior_refresh<<<d.C, UPD_THREADS, 0, st>>>(d);
   return cudaGetLastError();
 }
 // ------------------------------------------------------------------------------------------------

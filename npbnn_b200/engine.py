@@ -230,9 +230,16 @@ class Engine:
         with torch.cuda.device(self.device):
             wd = self._dev(w, torch.float64)
             out = torch.empty(wd.shape[0], dtype=torch.float64, device=self.device)
-            ps = np.ascontiguousarray(np.broadcast_to(np.asarray(prior_scale, dtype=np.float64), (self.net.n_layers,)))
-            L.check(self.lib.bnn_log_prior(self._h, _ptr(wd), wd.shape[0], int(prior), _np_ptr(ps), _ptr(out),
-                                           self._stream()))
+            if isinstance(prior_scale, np.ndarray) and prior_scale.shape == (self.net.n_params,) \
+                    and self.net.n_params != self.net.n_layers:
+                # one scale per weight entry (hyper-priors)
+                ps = np.ascontiguousarray(prior_scale, dtype=np.float64)
+                L.check(self.lib.bnn_log_prior_entries(self._h, _ptr(wd), wd.shape[0], int(prior), _np_ptr(ps), _ptr(out),
+                                                       self._stream()))
+            else:
+                ps = np.ascontiguousarray(np.broadcast_to(np.asarray(prior_scale, dtype=np.float64), (self.net.n_layers,)))
+                L.check(self.lib.bnn_log_prior(self._h, _ptr(wd), wd.shape[0], int(prior), _np_ptr(ps), _ptr(out),
+                                               self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
             return out.cpu().numpy()
 
@@ -359,6 +366,22 @@ class Engine:
         w = np.empty((n, self.net.n_params)) if weights else None
         L.check(self.lib.bnn_chains_read(self._h, _np_ptr(f64), _np_ptr(i32), _np_ptr(w), self._stream()))
         return ChainState(f64, i32, w, self.net, self.K)
+
+    def write_state(self, st: ChainState):
+        """Write an edited host copy of the state arrays back (bnn_chains_write)."""
+        f64 = np.ascontiguousarray(st.f64, dtype=np.float64)
+        i32 = np.ascontiguousarray(st.i32, dtype=np.int32)
+        assert f64.shape == (self.n_chains, L.F_STRIDE) and i32.shape == (self.n_chains, L.I_STRIDE)
+        L.check(self.lib.bnn_chains_write(self._h, _np_ptr(f64), _np_ptr(i32), self._stream()))
+
+    def set_prior_scales(self, entry_scales):
+        """Per-entry prior scales [C, n_params] of the chains (None: back to per-layer scalars) and the refresh of
+        logPrior / logPost that MCMC.gibbs_step does (BNN_env.py:534-538)."""
+        e = None
+        if entry_scales is not None:
+            e = np.ascontiguousarray(entry_scales, dtype=np.float64)
+            assert e.shape == (self.n_chains, self.net.n_params), e.shape
+        L.check(self.lib.bnn_chains_set_prior_scales(self._h, _np_ptr(e), self._stream()))
 
     def set_temperature(self, temps):
         t = np.ascontiguousarray(temps, dtype=np.float64)

@@ -183,6 +183,28 @@ def log_prior(weights: Sequence[np.ndarray], kind: int, scales: Sequence, indica
     return float(lp)
 
 
+def gibbs_prior_scales(weights: Sequence[np.ndarray], hyper_p: int, gamma=None) -> list:
+    """npBNN.sample_prior_scale (BNN_env.py:196-219): one conjugate draw of the Normal prior's standard deviation per
+    layer (hyper_p 1: GibbsSampleNormStdGammaVector, a=2), per input node (2: GibbsSampleNormStdGamma2D, a=1, sums
+    over axis 0) or per weight (3: GibbsSampleNormStdGammaONE, a=1.5 + one observation); b = 0.1, mu = 0
+    (BNN_mcmc.py:124-141).  tau ~ Gamma(a', scale = 1/b'), sd = 1/sqrt(tau).  `gamma(shape, scale=)` defaults to
+    numpy's global generator, which is what the reference draws from; one call per layer."""
+    gamma = np.random.gamma if gamma is None else gamma
+    out = []
+    for w in weights:
+        w = np.asarray(w, dtype=np.float64)
+        if hyper_p == 1:
+            a, b = 2 + w.size / 2.0, 0.1 + np.sum(w.flatten() ** 2) / 2.0
+        elif hyper_p == 2:
+            a, b = 1 + w.shape[0] / 2.0, 0.1 + np.sum(w ** 2, axis=0) / 2.0
+        elif hyper_p == 3:
+            a, b = 1.5 + 0.5, 0.1 + (w ** 2) / 2.0
+        else:
+            raise ValueError("hyper_p must be 1, 2 or 3")
+        out.append(1 / np.sqrt(gamma(a, scale=1.0 / b)))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # proposal  (BNN_mcmc.py:57-69)
 # --------------------------------------------------------------------------------------

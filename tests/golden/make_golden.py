@@ -441,7 +441,46 @@ def case_mc3():
     save("mc3", out, meta)
 
 
+def case_hyper(hyper_p, n_steps=40, seed=11):
+    """Hyper-priors (BNN_env.py:196-219,534-538): MH iterations with a Gibbs step on the prior scales every 4th
+    iteration.  sample_prior_scale draws from numpy's GLOBAL generator (BNN_mcmc.py:124-141), the MH proposals from
+    mcmc._rs, so seeding the global generator before npBNN(...) reproduces both streams."""
+    dat = synth_class(300, 5, 3, seed, 40)
+    np.random.seed(seed)
+    bnn = quiet(bn.npBNN, dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, prior_f=1, p_scale=1,
+                hyper_p=hyper_p, seed=seed)
+    mcmc = bn.MCMC(bnn, n_iteration=1000, update_f=[0.2, 0.2, 0.2])
+    out = {}
+    store_data(out, dat)
+    for i, w in enumerate(bnn._w_layers):
+        out["w0_%d" % i] = np.array(w)
+    out["init_logLik"], out["init_logPrior"] = np.float64(mcmc._logLik), np.float64(mcmc._logPrior)
+    rows = {k: [] for k in ("logLik", "logPrior", "logPost", "accepted", "iteration", "gibbs")}
+    for t in range(n_steps):
+        gibbs = (t % 4 == 3)
+        if gibbs:
+            mcmc.gibbs_step(bnn)
+            for i, sc in enumerate(bnn._prior_scale):
+                out["t%d_scale_%d" % (t, i)] = np.array(sc, dtype=np.float64)
+                out["t%d_w_%d" % (t, i)] = np.array(bnn._w_layers[i])
+        else:
+            quiet(mcmc.mh_step, bnn)
+        rows["logLik"].append(mcmc._logLik); rows["logPrior"].append(mcmc._logPrior); rows["logPost"].append(mcmc._logPost)
+        rows["accepted"].append(mcmc._last_accepted); rows["iteration"].append(mcmc._current_iteration)
+        rows["gibbs"].append(int(gibbs))
+    for k, v in rows.items():
+        out["steps_" + k] = np.array(v)
+    for i, w in enumerate(bnn._w_layers):
+        out["wN_%d" % i] = np.array(w)
+    save("syn_hyper_p%d" % hyper_p, out, dict(hyper_p=hyper_p, seed=seed, n_steps=n_steps, act="tanh", n_nodes=[4, 3],
+                                              use_bias_node=2, update_f=[0.2] * 3, n_iteration=1000))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hyper":          # regenerate only the hyper-prior cases
+        for hp in (1, 2, 3):
+            case_hyper(hp)
+        sys.exit(0)
     case_c1()
     case_c2(True)
     case_c2(False)
@@ -464,3 +503,5 @@ if __name__ == "__main__":
                init_additional_prob=float(np.log(10) * -np.sum([0.1, 0.3]) * 10))
     case_synth("syn_trainable_tanh", act="tanh", alphas=[0.2, 0.9], trainable=True, bias=1,
                init_additional_prob=float(np.log(10) * -np.sum([0.2, 0.9]) * 10))
+    for hp in (1, 2, 3):
+        case_hyper(hp)

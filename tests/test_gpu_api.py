@@ -268,3 +268,55 @@ def test_trainable_activation_flow_reproduces_reference_chain(name):
         assert abs(mcmc._logPrior - float(z["steps_logPrior"][t])) <= 1e-9 * abs(float(z["steps_logPrior"][t]))
     for i in range(3):
         assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])
+
+
+@pytest.mark.parametrize("hp", [1, 2, 3])
+def test_hyper_prior_gibbs_flow_reproduces_reference_chain(hp):
+    """npBNN(hyper_p=1|2|3): MH iterations interleaved with MCMC.gibbs_step (BNN_env.py:196-219,534-538).  The prior
+    scales are drawn on the host with the reference's call sequence, the log-prior of the current weights and of every
+    following proposal is evaluated on the device with one scale per layer / input node / weight.  Scales and weights
+    bit-exact, log-prior / log-posterior to 1e-9, identical accept decisions."""
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_hyper_p%d" % hp)
+    np.random.seed(int(meta["seed"]))
+    bnn = bn.npBNN(_dat(z), n_nodes=[4, 3], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, prior_f=1, p_scale=1,
+                   hyper_p=hp, seed=int(meta["seed"]))
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["w0_%d" % i])
+    mcmc = bn.MCMC(bnn, n_iteration=1000, update_f=[0.2, 0.2, 0.2])
+    assert _close(mcmc._logLik, z["init_logLik"]) and _close(mcmc._logPrior, z["init_logPrior"])
+    for t in range(int(meta["n_steps"])):
+        if int(z["steps_gibbs"][t]):
+            mcmc.gibbs_step(bnn)
+            for i in range(3):
+                assert np.array_equal(np.asarray(bnn._prior_scale[i]), z["t%d_scale_%d" % (t, i)]), (t, i)
+                assert np.array_equal(bnn._w_layers[i], z["t%d_w_%d" % (t, i)])
+            assert _close(bnn.calc_prior(), z["steps_logPrior"][t])
+        else:
+            mcmc.mh_step(bnn)
+            assert mcmc._last_accepted == int(z["steps_accepted"][t]), t
+        assert _close(mcmc._logLik, z["steps_logLik"][t]), t
+        assert _close(mcmc._logPrior, z["steps_logPrior"][t]), (t, mcmc._logPrior, float(z["steps_logPrior"][t]))
+        assert _close(mcmc._logPost, z["steps_logPost"][t]), t
+        assert mcmc._current_iteration == int(z["steps_iteration"][t])
+    for i in range(3):
+        assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])
+
+
+def test_reset_update_parameters_reach_the_device():
+    """MCMC.reset_update_n / _f / _ws (BNN_env.py:540-547) edit the device-resident sampler state."""
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_adapt")
+    np.random.seed(7)
+    bnn = bn.npBNN(_dat(z), n_nodes=[4, 3], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, seed=7)
+    mcmc = bn.MCMC(bnn, n_iteration=1000)
+    mcmc.reset_update_n([3, 2, 1])
+    mcmc.reset_update_f([0.11, 0.12, 0.13])
+    mcmc.reset_update_ws([np.ones(w.shape) * v for w, v in zip(bnn._w_layers, (0.01, 0.02, 0.03))])
+    st = mcmc._group.eng.read_state(weights=False)
+    assert np.array_equal(st.update_n[0], [3, 2, 1])
+    assert np.allclose(st.update_f[0], [0.11, 0.12, 0.13]) and np.allclose(st.update_ws[0], [0.01, 0.02, 0.03])
+    mcmc.mh_step(bnn)
+    assert np.array_equal(mcmc._update_n, [3, 2, 1]) and mcmc._current_iteration == 1
+    with pytest.raises(NotImplementedError):
+        mcmc.reset_update_ws([np.arange(w.size, dtype=float).reshape(w.shape) for w in bnn._w_layers])

@@ -142,3 +142,31 @@ def test_resample_categorical_matches_reference():
     for j in range(s):
         w = [np.array(z["s%d_w%d" % (j, li)]) for li in range(3)]
         assert close(orc.forward(np.array(z["x"]), w, "swish", None, "softmax"), z["dense"][j])
+
+
+@pytest.mark.parametrize("hp", [1, 2, 3])
+def test_hyper_prior_scales_and_prior(hp):
+    """sample_prior_scale / gibbs_step (BNN_env.py:196-219,534-538): the oracle's conjugate draw reproduces the
+    reference's scales when numpy's global generator is in the reference's state, and calc_prior under the sampled
+    scales (scalar / per input node / per weight broadcasting) reproduces the recorded log-priors."""
+    z, meta = G.load("syn_hyper_p%d" % hp)
+    np.random.seed(int(meta["seed"]))
+    w0 = [np.random.normal(0, 0.1, z["w0_%d" % i].shape) for i in range(3)]       # init_weight_prm draws (BNN_mcmc.py:19-24)
+    for i in range(3):
+        assert np.array_equal(w0[i], z["w0_%d" % i])
+    # mh_step draws from mcmc._rs only, so the global generator is now where the first Gibbs step found it
+    n_gibbs = 0
+    for t in range(int(meta["n_steps"])):
+        if not int(z["steps_gibbs"][t]):
+            continue
+        w = [z["t%d_w_%d" % (t, i)] for i in range(3)]
+        scales = orc.gibbs_prior_scales(w, hp)
+        for i in range(3):
+            ref = z["t%d_scale_%d" % (t, i)]
+            assert np.shape(scales[i]) == ref.shape and np.array_equal(np.asarray(scales[i]), ref), (t, i)
+        lp = orc.log_prior(w, 1, scales)
+        assert close(lp, z["steps_logPrior"][t]), (t, lp, float(z["steps_logPrior"][t]))
+        assert close(float(z["steps_logLik"][t]) + lp, z["steps_logPost"][t])
+        assert int(z["steps_iteration"][t]) == t + 1
+        n_gibbs += 1
+    assert n_gibbs == int(meta["n_steps"]) // 4
