@@ -193,6 +193,16 @@ int bnn_mh_steps(bnn_ctx* ctx, int32_t n_steps, const bnn_injection* inj, void* 
 /* Export chain state (synchronises the stream).  Any pointer may be NULL.
  *   f64_host [C, BNN_F_STRIDE], i32_host [C, BNN_I_STRIDE], w_host [C, n_params] */
 int bnn_chains_read(bnn_ctx* ctx, double* f64_host, int32_t* i32_host, double* w_host, void* stream);
+/* Asynchronous export for the logger (replaces the synchronous reads behind
+ * postLogger.log_sample / log_weights, BNN_env.py:600-658, when the chains free-run on the device):
+ * bnn_chains_snapshot copies the state of every chain (same three arrays as bnn_chains_read) into ring slot
+ * `slot` (0..63) in stream order -- device-to-device on `stream`, then device-to-host into pinned memory on the
+ * context's own copy stream -- and returns without waiting, so the caller can queue the next bnn_mh_steps at once.
+ * bnn_snapshot_ready: 1 when the host copy of the slot is complete, 0 when not yet, -1 when the slot is empty.
+ * bnn_snapshot_read waits for the slot, copies it out and frees the slot.  Any output pointer may be NULL. */
+int bnn_chains_snapshot(bnn_ctx* ctx, int32_t slot, void* stream);
+int bnn_snapshot_ready(bnn_ctx* ctx, int32_t slot);
+int bnn_snapshot_read(bnn_ctx* ctx, int32_t slot, double* f64_host, int32_t* i32_host, double* w_host);
 /* Write the state arrays back (same layout as bnn_chains_read; synchronises the stream): the host edits what it
  * read -- MCMC.reset_update_n / reset_update_f / reset_update_ws (BNN_env.py:540-547), the iteration count after
  * a Gibbs step.  Any pointer may be NULL. */

@@ -650,25 +650,73 @@ def _mirror_adaptation(st, c, it, adapt_freq, adapt_stop, adapt_f, adapt_fM, max
             st.update_ws[c] *= 1.2
 
 
-def run_mcmc(bnn, mcmc, logger):
+def _report(bnn, mcmc, logger):
+    """Print / log decisions of the reference's loop for the state just synchronised (BNN_mcmc.py:156-167)."""
+    if mcmc._current_iteration % mcmc._print_f == 0 or mcmc._current_iteration == 1:
+        print(mcmc._current_iteration, np.round([mcmc._logLik, mcmc._accuracy, mcmc._test_accuracy,
+                                                  mcmc._acceptance_rate], 3), flush=True)
+        if bnn._estimation_mode == "regression":
+            print(bnn._error_prm)
+    if mcmc._current_iteration % mcmc._sampling_f == 0:
+        logger.log_sample(bnn, mcmc)
+        logger.log_weights(bnn, mcmc)
+
+
+def _next_stop(mcmc, it):
+    nxt = [mcmc._n_iterations]
+    if it == 0:
+        nxt.append(1)                                  # the reference prints at iteration 1
+    nxt.append((it // mcmc._print_f + 1) * mcmc._print_f)
+    nxt.append((it // mcmc._sampling_f + 1) * mcmc._sampling_f)
+    return max(1, min(nxt) - it)
+
+
+def _run_mcmc_pipelined(bnn, mcmc, logger, depth):
+    """Free-running chains (rng="philox"): the host queues the MH launches up to `depth` logging points ahead and
+    exports each logging point through the asynchronous snapshot ring (bnn_chains_snapshot), so printing, csv rows
+    and pickles are written while the device keeps stepping.  Same decisions, same samples and
+    the same files as the synchronous loop."""
+    from collections import deque
+    eng = mcmc._group.eng
+    it = mcmc._current_iteration
+    pending, free = deque(), list(range(depth))
+    if hasattr(logger, "begin_async"):
+        logger.begin_async()
+
+    def retire():
+        slot = pending.popleft()
+        mcmc._sync(bnn, eng.snapshot_read(slot))
+        free.append(slot)
+        _report(bnn, mcmc, logger)
+
+    while it < mcmc._n_iterations:
+        k = _next_stop(mcmc, it)
+        mcmc._check_supported(k)
+        eng.mh_steps(k)
+        it += k
+        if not free:
+            retire()
+        slot = free.pop()
+        eng.snapshot(slot)
+        pending.append(slot)
+    try:
+        while pending:
+            retire()
+    finally:
+        if hasattr(logger, "end_async"):
+            logger.end_async()
+
+
+def run_mcmc(bnn, mcmc, logger, pipeline_depth=4):
     """The driver loop of BNN_mcmc.py:153-170, batched: the device runs up to the next print / sampling /
-    final iteration without returning to the host."""
+    final iteration without returning to the host; with device-generated proposals (rng="philox") the logging
+    points are exported asynchronously and the loop never waits for the device (pipeline_depth=0: synchronous)."""
+    if mcmc._rng_mode == "philox" and mcmc._own_group and pipeline_depth > 0 and mcmc._current_iteration < mcmc._n_iterations:
+        return _run_mcmc_pipelined(bnn, mcmc, logger, int(pipeline_depth))
     while True:
         it = mcmc._current_iteration
-        nxt = [mcmc._n_iterations]
-        if it == 0:
-            nxt.append(1)                                  # the reference prints at iteration 1
-        nxt.append((it // mcmc._print_f + 1) * mcmc._print_f)
-        nxt.append((it // mcmc._sampling_f + 1) * mcmc._sampling_f)
-        mcmc.run(bnn, max(1, min(nxt) - it))
-        if mcmc._current_iteration % mcmc._print_f == 0 or mcmc._current_iteration == 1:
-            print(mcmc._current_iteration, np.round([mcmc._logLik, mcmc._accuracy, mcmc._test_accuracy,
-                                                      mcmc._acceptance_rate], 3), flush=True)
-            if bnn._estimation_mode == "regression":
-                print(bnn._error_prm)
-        if mcmc._current_iteration % mcmc._sampling_f == 0:
-            logger.log_sample(bnn, mcmc)
-            logger.log_weights(bnn, mcmc)
+        mcmc.run(bnn, _next_stop(mcmc, it))
+        _report(bnn, mcmc, logger)
         if mcmc._current_iteration >= mcmc._n_iterations:
             break
 
@@ -1081,4 +1129,65 @@ class postLogger:
                 post["additional_prm"] = list(add_prms)
             self.update_post_weight_samples(post)
             self.control_weight_sample_length(mcmc_obj._n_post_samples)
-        SaveObject([bnn_obj, mcmc_obj, self] + ([add_obj] if add_obj else []), self._pklfile)
+        self._save([bnn_obj, mcmc_obj, self] + ([add_obj] if add_obj else []))
+
+    # ---- non-blocking pickle.  The reference rewrites the whole [bnn, mcmc, logger] pickle -- X
+    # included -- at every logged sample (BNN_env.py:658); every write replaces the previous one, so only the newest
+    # matters.  Between begin_async() and end_async() the writes go to a worker thread that always pickles the newest
+    # snapshot and skips the ones it was too slow for; end_async() writes the last one and returns when it is on
+    # disk.  Snapshots are shallow copies taken at call time: the drivers rebind attributes (fresh weight arrays per
+    # logging point), they never mutate logged arrays in place.
+    def _save(self, objs):
+        st = self.__dict__.get("_async")
+        if st is None:
+            SaveObject(objs, self._pklfile)
+            return
+        from copy import copy
+        snap = [copy(o) for o in objs]
+        for o in snap:
+            if isinstance(o, postLogger):
+                o.__dict__["_post_weight_samples"] = list(self._post_weight_samples)
+        with st["cv"]:
+            st["job"] = snap
+            st["cv"].notify()
+
+    def begin_async(self):
+        import threading
+        if self.__dict__.get("_async") is not None:
+            return
+        st = {"cv": threading.Condition(), "job": None, "stop": False, "written": 0, "error": None}
+
+        def work():
+            while True:
+                with st["cv"]:
+                    while st["job"] is None and not st["stop"]:
+                        st["cv"].wait()
+                    job, st["job"] = st["job"], None
+                    if job is None and st["stop"]:
+                        return
+                try:
+                    SaveObject(job, self._pklfile)
+                    st["written"] += 1
+                except Exception as e:          # surfaced by end_async
+                    st["error"] = e
+        st["thread"] = threading.Thread(target=work, name="postLogger-pickle", daemon=True)
+        self.__dict__["_async"] = st
+        st["thread"].start()
+
+    def end_async(self):
+        st = self.__dict__.get("_async")
+        if st is None:
+            return 0
+        with st["cv"]:
+            st["stop"] = True
+            st["cv"].notify()
+        st["thread"].join()
+        self.__dict__["_async"] = None
+        if st["error"] is not None:
+            raise st["error"]
+        return st["written"]
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop("_async", None)
+        return d

@@ -95,6 +95,16 @@ struct bnn_ctx {
   size_t ev_used = 0;
   double fwd_ms_sum = 0.0;
   long long fwd_count = 0;
+  // asynchronous state snapshots (logger ring): device staging + pinned host copy per slot, own copy stream
+  struct Snap {
+    DevBuf dev;
+    void* host = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t staged = nullptr, done = nullptr;
+    bool pending = false;
+  };
+  std::vector<Snap> snaps;
+  cudaStream_t copy_stream = nullptr;
 };
 
 // network shapes with a k_fwd3t instantiation (BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 swish, categorical)
@@ -216,6 +226,14 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->part_red, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
                     &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
+  c->ps_entry.release(); c->pls_entry.release(); c->ps_tmp.release(); c->pls_tmp.release();
+  for (auto& sn : c->snaps) {
+    sn.dev.release();
+    if (sn.host) cudaFreeHost(sn.host);
+    if (sn.staged) cudaEventDestroy(sn.staged);
+    if (sn.done) cudaEventDestroy(sn.done);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return 0;
@@ -703,6 +721,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   const int C = n_chains, NC = 2 + 2 * g.K;
   c->C = C;
   c->have_ps_entry = false;          // per-entry prior scales belong to the previous set of chains
+  for (auto& sn : c->snaps) sn.pending = false;
   c->cfg = *cfg;
   fill_prior_scales(c->ps, cfg->prior_scale, g.L);
   CUDA_TRY(c->w_cur.ensure(sizeof(double) * (size_t)C * g.P, false, st));
@@ -918,6 +937,73 @@ int bnn_chains_read(bnn_ctx* c, double* f64_host, int32_t* i32_host, double* w_h
   if (i32_host) CUDA_TRY(cudaMemcpyAsync(i32_host, c->si.p, sizeof(int) * (size_t)c->C * BNN_I_STRIDE, cudaMemcpyDeviceToHost, st));
   if (w_host) CUDA_TRY(cudaMemcpyAsync(w_host, c->w_cur.p, sizeof(double) * (size_t)c->C * c->g.P, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- asynchronous snapshots (include/npbnn_b200.h) ----------------------------------------------------------
+static size_t snap_bytes(const bnn_ctx* c) {
+  return (size_t)c->C * (sizeof(double) * BNN_F_STRIDE + sizeof(int) * BNN_I_STRIDE + sizeof(double) * c->g.P);
+}
+
+int bnn_chains_snapshot(bnn_ctx* c, int32_t slot, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_chains_snapshot: call bnn_chains_init first");
+  REQUIRE(slot >= 0 && slot < 64, "bnn_chains_snapshot: slot must be in [0, 64)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((size_t)slot >= c->snaps.size()) c->snaps.resize(slot + 1);
+  bnn_ctx::Snap& sn = c->snaps[slot];
+  REQUIRE(!sn.pending, "bnn_chains_snapshot: slot still holds an unread snapshot");
+  const size_t nb = snap_bytes(c);
+  if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!sn.staged) {
+    CUDA_TRY(cudaEventCreateWithFlags(&sn.staged, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sn.done, cudaEventDisableTiming));
+  }
+  if (sn.bytes < nb) {
+    if (sn.host) CUDA_TRY(cudaFreeHost(sn.host));
+    sn.host = nullptr;
+    CUDA_TRY(cudaMallocHost(&sn.host, nb));
+    sn.bytes = nb;
+  }
+  CUDA_TRY(sn.dev.ensure(nb, false, st));
+  // device-to-device on the chains' stream (the next launches queue right behind it) ...
+  char* d = sn.dev.as<char>();
+  const size_t nf = sizeof(double) * (size_t)c->C * BNN_F_STRIDE, ni = sizeof(int) * (size_t)c->C * BNN_I_STRIDE;
+  const size_t nw = sizeof(double) * (size_t)c->C * c->g.P;
+  CUDA_TRY(cudaMemcpyAsync(d, c->sf.p, nf, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d + nf, c->si.p, ni, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d + nf + ni, c->w_cur.p, nw, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaEventRecord(sn.staged, st));
+  // ... device-to-host on the copy stream, off the chains' critical path
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, sn.staged, 0));
+  CUDA_TRY(cudaMemcpyAsync(sn.host, d, nb, cudaMemcpyDeviceToHost, c->copy_stream));
+  CUDA_TRY(cudaEventRecord(sn.done, c->copy_stream));
+  sn.pending = true;
+  return 0;
+}
+
+int bnn_snapshot_ready(bnn_ctx* c, int32_t slot) {
+  if (!c || slot < 0 || (size_t)slot >= c->snaps.size() || !c->snaps[slot].pending) return -1;
+  cudaError_t e = cudaEventQuery(c->snaps[slot].done);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  g_last_error = std::string("bnn_snapshot_ready: ") + cudaGetErrorString(e);
+  return -1;
+}
+
+int bnn_snapshot_read(bnn_ctx* c, int32_t slot, double* f64_host, int32_t* i32_host, double* w_host) {
+  REQUIRE(c && slot >= 0 && (size_t)slot < c->snaps.size() && c->snaps[slot].pending,
+          "bnn_snapshot_read: no snapshot pending in this slot");
+  CUDA_TRY(cudaSetDevice(c->device));
+  bnn_ctx::Snap& sn = c->snaps[slot];
+  CUDA_TRY(cudaEventSynchronize(sn.done));
+  const char* h = static_cast<const char*>(sn.host);
+  const size_t nf = sizeof(double) * (size_t)c->C * BNN_F_STRIDE, ni = sizeof(int) * (size_t)c->C * BNN_I_STRIDE;
+  const size_t nw = sizeof(double) * (size_t)c->C * c->g.P;
+  if (f64_host) memcpy(f64_host, h, nf);
+  if (i32_host) memcpy(i32_host, h + nf, ni);
+  if (w_host) memcpy(w_host, h + nf + ni, nw);
+  sn.pending = false;
   return 0;
 }
 

@@ -367,6 +367,22 @@ class Engine:
         L.check(self.lib.bnn_chains_read(self._h, _np_ptr(f64), _np_ptr(i32), _np_ptr(w), self._stream()))
         return ChainState(f64, i32, w, self.net, self.K)
 
+    def snapshot(self, slot: int):
+        """Queue an asynchronous export of the chain state into ring slot `slot` (bnn_chains_snapshot); no wait."""
+        L.check(self.lib.bnn_chains_snapshot(self._h, int(slot), self._stream()))
+
+    def snapshot_ready(self, slot: int) -> bool:
+        return self.lib.bnn_snapshot_ready(self._h, int(slot)) == 1
+
+    def snapshot_read(self, slot: int, weights=True) -> ChainState:
+        """Wait for ring slot `slot`, return it as a ChainState and free the slot."""
+        n = self.n_chains
+        f64 = np.empty((n, L.F_STRIDE))
+        i32 = np.empty((n, L.I_STRIDE), dtype=np.int32)
+        w = np.empty((n, self.net.n_params)) if weights else None
+        L.check(self.lib.bnn_snapshot_read(self._h, int(slot), _np_ptr(f64), _np_ptr(i32), _np_ptr(w)))
+        return ChainState(f64, i32, w, self.net, self.K)
+
     def write_state(self, st: ChainState):
         """Write an edited host copy of the state arrays back (bnn_chains_write)."""
         f64 = np.ascontiguousarray(st.f64, dtype=np.float64)

@@ -320,3 +320,33 @@ def test_reset_update_parameters_reach_the_device():
     assert np.array_equal(mcmc._update_n, [3, 2, 1]) and mcmc._current_iteration == 1
     with pytest.raises(NotImplementedError):
         mcmc.reset_update_ws([np.arange(w.size, dtype=float).reshape(w.shape) for w in bnn._w_layers])
+
+
+def test_pipelined_logger_matches_synchronous_run(tmp_path):
+    """run_mcmc with device-generated proposals: the asynchronous snapshot ring (bnn_chains_snapshot, logging points
+    exported while the device keeps stepping) must log exactly what the synchronous loop logs."""
+    import pickle
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_swish_cauchy")
+    runs = []
+    for tag, depth in (("sync", 0), ("ring", 3)):
+        np.random.seed(5)
+        bnn = bn.npBNN(_dat(z), n_nodes=[4, 3], actFun=bn.ActFun(fun="swish"), use_bias_node=2, seed=5)
+        mcmc = bn.MCMC(bnn, n_iteration=205, sampling_f=10, print_f=50, n_post_samples=8, rng="philox")
+        logger = bn.postLogger(bnn, filename="pl_" + tag, wdir=str(tmp_path), log_all_weights=0)
+        bn.run_mcmc(bnn, mcmc, logger, pipeline_depth=depth)
+        assert mcmc._current_iteration == 205
+        with open(logger._pklfile, "rb") as f:
+            _, _, lg = pickle.load(f)
+        rows = open(logger._logfile).read().splitlines()
+        runs.append((mcmc._logLik, mcmc._logPost, [w.copy() for w in bnn._w_layers], lg._post_weight_samples, rows))
+    a, b = runs
+    assert a[0] == b[0] and a[1] == b[1]
+    for wa, wb in zip(a[2], b[2]):
+        assert np.array_equal(wa, wb)
+    assert len(a[3]) == len(b[3]) == 8
+    for sa, sb in zip(a[3], b[3]):
+        assert sa["mcmc_it"] == sb["mcmc_it"]
+        for wa, wb in zip(sa["weights"], sb["weights"]):
+            assert np.array_equal(wa, wb)
+    assert a[4] == b[4] and len(a[4]) == 1 + 20
