@@ -895,7 +895,7 @@ int bnn_rowshard_local(bnn_ctx* c, double* red_dev, void* stream) {
   CUDA_TRY(cudaSetDevice(c->device));
   const NetGeom& g = c->g;
   const int* counts = (g.lik == BNN_LIK_CATEGORICAL) ? c->counts_prop.as<int>() : nullptr;
-  CUDA_TRY(bnn_launch_rowshard_local(c->part.as<double>(), n_slots(g), c->n_tiles16, counts, 2 + 2 * g.K, red_dev, c->C,
+  CUDA_TRY(bnn_launch_rowshard_local(g, c->part.as<double>(), n_slots(g), c->n_tiles16, counts, 2 + 2 * g.K, red_dev, c->C,
                                      (cudaStream_t)stream));
   c->launches++;
   return 0;

@@ -541,6 +541,9 @@ struct Fwd3Geom {
 #ifndef FWD3_WARPS
 #define FWD3_WARPS 12
 #endif
+#ifndef FWD3_ACT_MODE
+#define FWD3_ACT_MODE 0         // how layer-1 activations interleave with the layer-2 MMAs (tuning variants 1, 2)
+#endif
 
 template <int ACT, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void act_tile(double (&a)[4], double alpha, const double* tab) {
@@ -960,10 +963,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         {
           const double* wr = W + G3::W2_OFF + gq * N1;
           const int sw = (gq & 1) * G3::SW1;
+#if FWD3_ACT_MODE == 2          // tuning: all activations of the layer first, then the MMAs
+#pragma unroll
+          for (int kg = 0; kg < N1 / 8; ++kg) act_tile<ACT>(acc1[kg], a1, tab);
+#elif FWD3_ACT_MODE == 1        // tuning: two fragments (8 independent chains) per two k-groups
           act_tile<ACT>(acc1[0], a1, tab);
+          act_tile<ACT>(acc1[1], a1, tab);
+#else
+          act_tile<ACT>(acc1[0], a1, tab);
+#endif
 #pragma unroll
           for (int kg = 0; kg < N1 / 8 - 2; ++kg) {
+#if FWD3_ACT_MODE == 0
             act_tile<ACT>(acc1[kg + 1], a1, tab);
+#elif FWD3_ACT_MODE == 1
+            if ((kg & 1) == 0) {
+              act_tile<ACT>(acc1[kg + 2], a1, tab);
+              act_tile<ACT>(acc1[kg + 3], a1, tab);
+            }
+#endif
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
@@ -973,7 +991,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           }
           {
             constexpr int k0 = N1 / 8 - 2, k1 = N1 / 8 - 1;
+#if FWD3_ACT_MODE == 0
             act_tile<ACT>(acc1[k1], a1, tab);
+#endif
             const int c0 = (8 * k0 + 2 * t) ^ sw, c1 = (8 * k1 + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {

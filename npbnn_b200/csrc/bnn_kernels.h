@@ -62,8 +62,8 @@ cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, 
                                  cudaStream_t st);
 cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
-cudaError_t bnn_launch_rowshard_local(const double* part, int NF, long long nt, const int* counts, int NC, double* out,
-                                      int n_chains, cudaStream_t st);
+cudaError_t bnn_launch_rowshard_local(const NetGeom& g, const double* part, int NF, long long nt, const int* counts, int NC,
+                                      double* out, int n_chains, cudaStream_t st);
 cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double* part_red, int* counts, int n_chains,
                                        cudaStream_t st);
 // FP64 tensor-pipe peak (back-to-back DMMA, no memory traffic): the roofline denominator of the forward kernel

@@ -10,7 +10,7 @@
 static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
 static constexpr double kLogPi = 1.14472988584940017414;
 static constexpr double kLog2 = 0.69314718055994530942;
-#define UPD_THREADS 256
+#define UPD_THREADS 1024      // upper bound (launch bounds); small networks launch 256 (upd_threads)
 
 // ------------------------------------------------------------------------------------------------
 // layout kernels
@@ -65,6 +65,23 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* sh) {
   return s;
 }
 
+// Sum of src[tid], src[tid + B], src[tid + 2B], ... in exactly that order, with the loads of eight terms issued
+// before the first add: the plain loop is one L2 round trip per term (62,500 partials per chain at 1M rows).
+__device__ __forceinline__ double strided_sum_ordered(const double* __restrict__ src, long long nt) {
+  const long long B = blockDim.x;
+  long long i = threadIdx.x;
+  double v = 0.0;
+  for (; i + 7 * B < nt; i += 8 * B) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = __ldg(src + i + k * B);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += a[k];
+  }
+  for (; i < nt; i += B) v += __ldg(src + i);
+  return v;
+}
+
 __device__ __forceinline__ double logpdf_prior(double w, int kind, double scale, double log_scale) {
   // closed forms of scipy.stats.{norm,cauchy,laplace}.logpdf(w, 0, scale) (BNN_env.py:139-150)
   double x = w / scale;
@@ -80,8 +97,7 @@ __device__ double finalize_loglik(const NetGeom& g, const double* __restrict__ p
                                   const double* __restrict__ sigma_in, double* red, double* sig_out, double* sh) {
   for (int slot = 0; slot < NF; ++slot) {
     const double* src = part + ((long long)c * NF + slot) * nt;
-    double v = 0.0;
-    for (long long i = threadIdx.x; i < nt; i += blockDim.x) v += src[i];
+    const double v = strided_sum_ordered(src, nt);
     double s = block_sum_fixed(v, sh);
     if (threadIdx.x == 0) red[slot] = s;
   }
@@ -212,8 +228,22 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   __shared__ int s_prop[BNN_MAX_LAYERS], s_cnt[BNN_MAX_LAYERS], s_off[BNN_MAX_LAYERS];
   const NetGeom& g = d.g;
   const int c = blockIdx.x, tid = threadIdx.x;
-  double* sf = d.sf + (long long)c * BNN_F_STRIDE;
-  int* si = d.si + (long long)c * BNN_I_STRIDE;
+  // The chain's scalar state is staged in shared memory for the whole launch: the accept / adapt / propose logic is
+  // a serial chain of ~100 reads and writes by one thread, each of which would otherwise be an L2 round trip.
+  __shared__ double ssf[BNN_F_STRIDE];
+  __shared__ int ssi[BNN_I_STRIDE];
+  double* const gsf = d.sf + (long long)c * BNN_F_STRIDE;
+  int* const gsi = d.si + (long long)c * BNN_I_STRIDE;
+  for (int i = tid; i < BNN_F_STRIDE; i += (int)blockDim.x) ssf[i] = gsf[i];
+  for (int i = tid; i < BNN_I_STRIDE; i += (int)blockDim.x) ssi[i] = gsi[i];
+  __syncthreads();
+  double* sf = ssf;
+  int* si = ssi;
+  auto write_back = [&]() {
+    __syncthreads();
+    for (int i = tid; i < BNN_F_STRIDE; i += (int)blockDim.x) gsf[i] = ssf[i];
+    for (int i = tid; i < BNN_I_STRIDE; i += (int)blockDim.x) gsi[i] = ssi[i];
+  };
   double* wc = d.w_cur + (long long)c * g.P;
   double* wn = d.w_prop + (long long)c * g.P;
   const int NC = 2 + 2 * g.K;
@@ -259,16 +289,16 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     }
     __syncthreads();
     if (s_flag) {
-      for (int i = tid; i < g.P; i += UPD_THREADS) wc[i] = wn[i];
+      for (int i = tid; i < g.P; i += (int)blockDim.x) wc[i] = wn[i];
       if (g.lik == BNN_LIK_CATEGORICAL) {
         const int* cp = d.counts_prop + (long long)c * NC;
         if (tid < 2) si[BNN_I_N_CORRECT + tid] = cp[tid];
-        for (int i = tid; i < g.K; i += UPD_THREADS) {
+        for (int i = tid; i < g.K; i += (int)blockDim.x) {
           si[BNN_I_CLASS_CORRECT + i] = cp[2 + i];
           si[BNN_I_PRED_HIST + i] = cp[2 + g.K + i];
         }
       } else {
-        for (int i = tid; i < g.K; i += UPD_THREADS) {
+        for (int i = tid; i < g.K; i += (int)blockDim.x) {
           sf[BNN_F_SUM_R + i] = red[1 + i];
           sf[BNN_F_SUM_R2 + i] = red[1 + g.K + i];
           sf[BNN_F_SUM_R2_TEST + i] = red[1 + 2 * g.K + i];
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     }
     __syncthreads();
   }
-  if (!propose_mode) return;
+  if (!propose_mode) { write_back(); return; }
 
   // ------------------------------------------------------------------ adaptation + which layers
   const int it = si[BNN_I_ITERATION];
@@ -367,8 +397,8 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   }
   // zero the proposal's counters (the forward kernel accumulates into them)
   if (g.lik == BNN_LIK_CATEGORICAL)
-    for (int i = tid; i < NC; i += UPD_THREADS) d.counts_prop[(long long)c * NC + i] = 0;
-  for (int i = tid; i < g.P; i += UPD_THREADS) wn[i] = wc[i];
+    for (int i = tid; i < NC; i += (int)blockDim.x) d.counts_prop[(long long)c * NC + i] = 0;
+  for (int i = tid; i < g.P; i += (int)blockDim.x) wn[i] = wc[i];
   __syncthreads();
 
   // ------------------------------------------------------------------ UpdateNormal (BNN_mcmc.py:57-69)
@@ -382,7 +412,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
       const LayerGeom& lg = g.l[l];
       const int cols = lg.in + lg.bias;
       const double ws = sf[BNN_F_UPDATE_WS + l];
-      for (int k = tid; k < s_cnt[l]; k += UPD_THREADS) {
+      for (int k = tid; k < s_cnt[l]; k += (int)blockDim.x) {
         Draw dr;
         if (d.inj_proposed) {
           dr.ix = d.inj_ix[inj_base + s_off[l] + k];
@@ -404,7 +434,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   const double hi = d.cfg.w_bound, lo = -d.cfg.w_bound;
   double lp = 0.0;
   double* wpk = d.wp_prop + (long long)c * g.PB;
-  for (int i = tid; i < g.P; i += UPD_THREADS) {
+  for (int i = tid; i < g.P; i += (int)blockDim.x) {
     const int l = layer_of(g, i);
     const LayerGeom& lg = g.l[l];
     double z = wn[i];
@@ -426,11 +456,17 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   }
   double s = block_sum_fixed(lp, sh);
   if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s + sf[BNN_F_ADD_PROB];     // calc_prior(...) + additional_prob (BNN_env.py:481)
+  write_back();
 }
 
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (called from bnn_capi.cu)
 // ------------------------------------------------------------------------------------------------
+// threads per CTA of the one-CTA-per-chain kernels: the per-entry loops want the full 1024 at c4 size (6,474 entries,
+// 62,500 partials), while at a few hundred entries the block-wide synchronisations of 32 warps cost more than they save
+// (a function of the network only, so that sharded and unsharded runs of the same chains reduce in the same order)
+static inline int upd_threads(const NetGeom& g) { return g.P > 2048 ? 1024 : 256; }
+
 cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
                               const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st) {
   long long total = n_pad * F_pad;
@@ -446,17 +482,17 @@ cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int
 cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF, long long nt, long long n_train,
                                     double lik_temp, int sigma_mode, const double* sigma, double* loglik, double* sums,
                                     int set0, int n_sets, cudaStream_t st) {
-  k_finalize_lik<<<n_sets, UPD_THREADS, 0, st>>>(g, part, NF, nt, n_train, lik_temp, sigma_mode, sigma, loglik, sums, set0);
+  k_finalize_lik<<<n_sets, upd_threads(g), 0, st>>>(g, part, NF, nt, n_train, lik_temp, sigma_mode, sigma, loglik, sums, set0);
   return cudaGetLastError();
 }
 cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, int prior, const PriorScales& ps,
                                  const double* ps_entry, const double* pls_entry, int entry_stride, double* out,
                                  cudaStream_t st) {
-  k_log_prior<<<n_sets, UPD_THREADS, 0, st>>>(g, w, prior, ps, ps_entry, pls_entry, entry_stride, out);
+  k_log_prior<<<n_sets, upd_threads(g), 0, st>>>(g, w, prior, ps, ps_entry, pls_entry, entry_stride, out);
   return cudaGetLastError();
 }
 cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st) {
-  k_prior_refresh<<<d.C, UPD_THREADS, 0, st>>>(d);
+  k_prior_refresh<<<d.C, upd_threads(d.g), 0, st>>>(d);
   return cudaGetLastError();
 }
 // ------------------------------------------------------------------------------------------------
@@ -473,8 +509,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_rowshard_local(const double* __
   const int c = blockIdx.x;
   for (int slot = 0; slot < NF; ++slot) {
     const double* src = part + ((long long)c * NF + slot) * nt;
-    double v = 0.0;
-    for (long long i = threadIdx.x; i < nt; i += blockDim.x) v += src[i];
+    const double v = strided_sum_ordered(src, nt);
     const double s = block_sum_fixed(v, sh);
     if (threadIdx.x == 0) out[(long long)c * (NF + NC) + slot] = s;
   }
@@ -489,9 +524,9 @@ __global__ void k_rowshard_commit(const double* __restrict__ in, int NF, int NC,
     for (int i = threadIdx.x; i < NC; i += blockDim.x)
       counts[(long long)c * NC + i] = (int)llrint(in[(long long)c * (NF + NC) + NF + i]);    // exact: integer-valued sums
 }
-cudaError_t bnn_launch_rowshard_local(const double* part, int NF, long long nt, const int* counts, int NC, double* out,
-                                      int n_chains, cudaStream_t st) {
-  k_rowshard_local<<<n_chains, UPD_THREADS, 0, st>>>(part, NF, nt, counts, NC, out);
+cudaError_t bnn_launch_rowshard_local(const NetGeom& g, const double* part, int NF, long long nt, const int* counts, int NC,
+                                      double* out, int n_chains, cudaStream_t st) {
+  k_rowshard_local<<<n_chains, upd_threads(g), 0, st>>>(part, NF, nt, counts, NC, out);
   return cudaGetLastError();
 }
 cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double* part_red, int* counts, int n_chains,
@@ -501,7 +536,7 @@ cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double*
 }
 
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st) {
-  k_mh_update<<<d.C, UPD_THREADS, 0, st>>>(d, accept_mode, propose_mode, step);
+  k_mh_update<<<d.C, upd_threads(d.g), 0, st>>>(d, accept_mode, propose_mode, step);
   return cudaGetLastError();
 }
 
