@@ -74,6 +74,14 @@ typedef struct {
   int32_t n_act_prm;                   /* ActFun(trainable=True): number of activation parameters (len(_acc_prm)); 0 = fixed */
   int32_t reserved0;
   double init_additional_prob;         /* MCMC(init_additional_prob=): added to the initial log-prior (BNN_env.py:320) */
+  /* indicators (appended; zero = absent).  Weight indicators: npBNN(freq_indicator > 0): a 0/1 matrix of the shape of
+   * the first weight matrix multiplies it in the forward pass only, and calc_prior adds
+   * sum(ind) log(prior_ind1) + (size - sum(ind)) log(1 - prior_ind1) (BNN_env.py:191-193,458-466).  Feature
+   * indicators: npBNN(feature_indicators=True): features whose indicator is 0 are replaced by their training mean
+   * (data_transform_obj, BNN_env.py:9-17,423-431; means given by bnn_set_feature_means).  Both start as all ones. */
+  double prior_ind1;
+  int32_t use_indicators;
+  int32_t use_feature_indicators;
 } bnn_sampler_config;
 
 /* Random draws of `n_steps` MH iterations for every chain, recorded from (or generated like) the
@@ -99,6 +107,14 @@ typedef struct {
   const int32_t* alpha_ix;   /* [n_steps, C] index drawn by UpdateNormal1D(_acc_prm, d=0.05, n=1, Mb=1, mb=0) (BNN_mcmc.py:46-56) */
   const double* alpha_dz;    /* [n_steps, C] its normal increment */
   const double* add_prob;    /* [n_steps, C] the additional_prob argument of mh_step */
+  /* indicator moves (appended; NULL = none in this call).  UpdateBinomial (BNN_mcmc.py:98-99) is
+   * |ind - binomial(1, u * update_f, shape)|: the host draws the 0/1 flip matrices with the reference's generator, the
+   * device applies them to the chain's current indicators.  ind_move[s, c] = 1: step s of chain c flips the weight
+   * indicators (its layer 0 is then not proposed, BNN_env.py:449-460); fi_move likewise for the feature indicators. */
+  const int32_t* ind_move;   /* [n_steps, C] */
+  const uint8_t* ind_flip;   /* [n_steps, C, size of the first weight matrix] */
+  const int32_t* fi_move;    /* [n_steps, C] */
+  const uint8_t* fi_flip;    /* [n_steps, C, n_features] */
 } bnn_injection;
 
 /* ---- per-chain state export (bnn_chains_read): slot indices ------------------------------------ */
@@ -203,6 +219,12 @@ int bnn_chains_read(bnn_ctx* ctx, double* f64_host, int32_t* i32_host, double* w
 int bnn_chains_snapshot(bnn_ctx* ctx, int32_t slot, void* stream);
 int bnn_snapshot_ready(bnn_ctx* ctx, int32_t slot);
 int bnn_snapshot_read(bnn_ctx* ctx, int32_t slot, double* f64_host, int32_t* i32_host, double* w_host);
+/* Training means of the features (host [n_features]) for the feature-indicator transform; call before
+ * bnn_chains_init with cfg.use_feature_indicators. */
+int bnn_set_feature_means(bnn_ctx* ctx, const double* mean_host, void* stream);
+/* Current indicators of every chain: ind_host [C, size of the first weight matrix], fi_host [C, n_features]
+ * (doubles 0/1; either may be NULL; synchronises). */
+int bnn_chains_read_indicators(bnn_ctx* ctx, double* ind_host, double* fi_host, void* stream);
 /* Write the state arrays back (same layout as bnn_chains_read; synchronises the stream): the host edits what it
  * read -- MCMC.reset_update_n / reset_update_f / reset_update_ws (BNN_env.py:540-547), the iteration count after
  * a Gibbs step.  Any pointer may be NULL. */

@@ -37,13 +37,15 @@ class SamplerConfig(C.Structure):
                 ("adapt_freq", C.c_int32), ("adapt_stop", C.c_int32), ("use_mask", C.c_int32),
                 ("adapt_f", C.c_double), ("adapt_fM", C.c_double), ("lik_temp", C.c_double),
                 ("w_bound", C.c_double), ("prior_scale", C.c_double * MAX_LAYERS), ("seed", C.c_uint64),
-                ("n_act_prm", C.c_int32), ("reserved0", C.c_int32), ("init_additional_prob", C.c_double)]
+                ("n_act_prm", C.c_int32), ("reserved0", C.c_int32), ("init_additional_prob", C.c_double),
+                ("prior_ind1", C.c_double), ("use_indicators", C.c_int32), ("use_feature_indicators", C.c_int32)]
 
 
 class Injection(C.Structure):
     _fields_ = [("n_steps", C.c_int32), ("cap", C.c_int32), ("proposed", C.c_void_p), ("count", C.c_void_p),
                 ("ix", C.c_void_p), ("iy", C.c_void_p), ("dz", C.c_void_p), ("log_u", C.c_void_p),
-                ("alpha_ix", C.c_void_p), ("alpha_dz", C.c_void_p), ("add_prob", C.c_void_p)]
+                ("alpha_ix", C.c_void_p), ("alpha_dz", C.c_void_p), ("add_prob", C.c_void_p),
+                ("ind_move", C.c_void_p), ("ind_flip", C.c_void_p), ("fi_move", C.c_void_p), ("fi_flip", C.c_void_p)]
 
 
 class NpbnnError(RuntimeError):
@@ -70,6 +72,8 @@ _SIGNATURES = {
     "bnn_chains_snapshot": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bnn_snapshot_ready": (C.c_int, [C.c_void_p, C.c_int32]),
     "bnn_snapshot_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_set_feature_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_chains_read_indicators": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_chains_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_chains_set_prior_scales": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_chains_init": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(SamplerConfig), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -20,9 +20,10 @@ the draws on the device: the chain is then the reference's chain (same accept/re
 log-likelihood differs in the last bits because of the summation order).  `rng="philox"` generates the
 proposals on the device and never leaves it between logging points.
 
-Trainable activation parameters (ActFun(trainable=True)), init_additional_prob and mh_step(additional_prob=) run
-on the device from host-drawn numbers (rng="host").  Options of the reference that are not on the device path raise
-NotImplementedError: feature / weight indicators, user-supplied likelihood / proposal / output functions, and the regression error-parameter proposal (estimate_error with empirical_error=False once the
+Trainable activation parameters (ActFun(trainable=True)), init_additional_prob, mh_step(additional_prob=), weight
+indicators (freq_indicator > 0) and feature indicators (feature_indicators=True) run on the device from host-drawn
+numbers (rng="host"); hyper-prior scales (hyper_p) are drawn on the host and evaluated on the device.  Options of the reference that are not on the device path raise
+NotImplementedError: user-supplied likelihood / proposal / output functions, and the regression error-parameter proposal (estimate_error with empirical_error=False once the
 iteration passes `_estimate_error` -- a branch on which the reference itself raises AttributeError as soon as one
 proposal has been accepted before that iteration, BNN_mcmc.py:105).
 """
@@ -160,8 +161,6 @@ class npBNN:
                  empirical_error=False, size_output=None, output_act_fun=None, feature_indicators=None):
         if actFun is None:
             actFun = ActFun()
-        if freq_indicator or feature_indicators:
-            raise NotImplementedError("weight indicators / feature indicators are not on the device path")
         if hyper_p not in (0, 1, 2, 3):
             raise ValueError("hyper_p must be 0, 1, 2 or 3")
         if estimation_mode not in _LIK:
@@ -212,8 +211,13 @@ class npBNN:
         self._prior_ind1 = prior_ind1
         self._estimation_mode = estimation_mode
         self._mask = None
-        self._feature_indicators = None
-        self._feature_means = None
+        # feature indicators (BNN_env.py:169-172): all ones, means of the training features
+        if feature_indicators:
+            self._feature_indicators = np.ones(self._data.shape[1]).astype(int)
+            self._feature_means = np.mean(self._data, axis=0)
+        else:
+            self._feature_indicators = None
+            self._feature_means = None
         if use_class_weights:
             counts = np.unique(self._labels, return_counts=True)[1]
             cw = 1 / (counts / np.max(counts))
@@ -266,10 +270,15 @@ class npBNN:
     def calc_prior(self, w=0, ind=[]):
         if isinstance(w, int) and w == 0:
             w = self._w_layers
-        if self._prior == 0:
-            return 0
-        ps = self._prior_scale if self._scales_per_layer() else self._entry_scales()
-        return float(self._engine().log_prior([w], self._prior_kind(), ps)[0])
+        lp = 0
+        if self._prior != 0:
+            ps = self._prior_scale if self._scales_per_layer() else self._entry_scales()
+            lp = float(self._engine().log_prior([w], self._prior_kind(), ps)[0])
+        if self._freq_indicator:                 # BNN_env.py:191-193 (two scalars; the sums over w are on the device)
+            if len(ind) == 0:
+                ind = self._indicators
+            lp += np.sum(ind) * np.log(self._prior_ind1) + (self._indicators.size - np.sum(ind)) * np.log(1 - self._prior_ind1)
+        return lp
 
     def sample_prior_scale(self):
         """Gibbs draw of the prior standard deviations from their conjugate Gamma posteriors on the precision
@@ -369,7 +378,14 @@ class _ChainGroup:
                              else L.SIGMA_FIXED,
                              lik_temp=lik_temp, adapt_f=adapt_f, adapt_fM=adapt_fM, adapt_freq=adapt_freq,
                              adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed,
-                             n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob)
+                             n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob,
+                             prior_ind1=bnn._prior_ind1 if bnn._freq_indicator else None,
+                             feature_means=bnn._feature_means if bnn._feature_indicators is not None else None)
+        self.freq_indicator = float(bnn._freq_indicator)
+        self.use_fi = bnn._feature_indicators is not None
+        if (self.freq_indicator or self.use_fi) and (np.any(np.asarray(bnn._indicators) != 1) or
+                                                     (self.use_fi and np.any(np.asarray(bnn._feature_indicators) != 1))):
+            raise NotImplementedError("chains start from all-one indicators (as npBNN.__init__ leaves them)")
         if not per_layer:        # a model that already carries sampled hyper-prior scales
             self.eng.set_prior_scales(np.tile(bnn._entry_scales(), (self.n, 1)))
         self.n_act_prm = bnn._act_fun.n_trainable()
@@ -379,7 +395,7 @@ class _ChainGroup:
         if bnn._estimation_mode == "classification":
             self.labels_count = np.bincount(bnn._labels, minlength=bnn._size_output)
 
-    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None, additional_prob=0):
+    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None, additional_prob=0, adapt_stop=0):
         """Consume each chain's generator exactly as mh_step + UpdateNormal do (BNN_env.py:446-453,493;
         BNN_mcmc.py:62-65) for n_steps iterations during which no adaptation fires.
         reseed(chain, iteration) -> Generator implements randomize_seed (BNN_env.py:383-384)."""
@@ -394,6 +410,13 @@ class _ChainGroup:
             inj["alpha_dz"] = np.zeros((n_steps, self.n))
         if additional_prob:
             inj["add_prob"] = np.full((n_steps, self.n), float(additional_prob))
+        p0 = int(np.prod(shapes[0]))
+        if self.freq_indicator:
+            inj["ind_move"] = np.zeros((n_steps, self.n), np.int32)
+            inj["ind_flip"] = np.zeros((n_steps, self.n, p0), np.uint8)
+        if self.use_fi:
+            inj["fi_move"] = np.zeros((n_steps, self.n), np.int32)
+            inj["fi_flip"] = np.zeros((n_steps, self.n, self.net.n_features), np.uint8)
         for c in range(self.n):
             flu, un, uws = state.freq_layer_update[c], state.update_n[c], state.update_ws[c]
             for s in range(n_steps):
@@ -401,10 +424,23 @@ class _ChainGroup:
                 if self.n_act_prm:        # UpdateNormal1D(_acc_prm, d=0.05, n=1, ...) comes first (BNN_env.py:416-417)
                     inj["alpha_ix"][s, c] = rs.integers(0, self.n_act_prm, 1)[0]
                     inj["alpha_dz"][s, c] = rs.normal(0, 0.05, 1)[0]
+                # feature indicators (BNN_env.py:423-431): once past adapt_stop, with probability 0.2 the indicators are
+                # flipped by UpdateBinomial(ind, 0.5, shape) -- numpy's GLOBAL generator (BNN_mcmc.py:98-99)
+                if self.use_fi and int(state.iteration[c]) + s > adapt_stop and rs.random() < 0.2:
+                    inj["fi_move"][s, c] = 1
+                    inj["fi_flip"][s, c] = np.random.binomial(1, np.random.random() * 0.5, self.net.n_features)
                 rr = rs.random(nl)
                 rr[np.argmin(rr)] = 0
                 o = 0
                 for l in range(nl):
+                    if l == 0 and rr[0] < self.freq_indicator:
+                        # the first layer keeps its weights, its indicators move instead (BNN_env.py:449-460)
+                        inj["ind_move"][s, c] = 1
+                        # update_f[3]: the reference indexes its per-layer list here (BNN_env.py:460), so the branch exists
+                        # for networks of at least four layers and raises IndexError otherwise -- as it does here
+                        inj["ind_flip"][s, c] = np.random.binomial(1, np.random.random() * state.update_f[c][3],
+                                                                   shapes[0]).ravel()
+                        continue
                     if rr[l] < flu[l]:
                         n = int(un[l])
                         ix = rs.integers(0, shapes[l][0], n)
@@ -446,6 +482,8 @@ class MCMC:
             raise ValueError("rng must be 'host' or 'philox'")
         if rng == "philox" and bnn_obj._act_fun._trainable:
             raise NotImplementedError("trainable activation parameters are proposed from host-drawn numbers (rng='host')")
+        if rng == "philox" and (bnn_obj._freq_indicator or bnn_obj._feature_indicators is not None):
+            raise NotImplementedError("indicator moves are drawn on the host (rng='host')")
         nl = bnn_obj._n_layers
         if update_ws is None:
             update_ws = [0.075] * nl
@@ -518,12 +556,25 @@ class MCMC:
             bnn_obj._act_fun._prm = np.array(st.alpha_prop[c][:na])         # the last proposal (BNN_env.py:421)
         if st.w is not None:
             bnn_obj._w_layers = st.weights(c)        # fresh arrays: logged samples keep their own copies
+        if g.freq_indicator or g.use_fi:
+            ind, fi = g.eng.read_indicators(weight=bool(g.freq_indicator), feature=g.use_fi)
+            if ind is not None:
+                bnn_obj._indicators = ind[c]
+            if fi is not None:
+                bnn_obj._feature_indicators = fi[c].astype(int)
         self._y_cache = None
 
     def _materialise_y(self, bnn_obj, test=False):
         x = bnn_obj._test_data if test else bnn_obj._data
         al = bnn_obj._act_fun.alphas(bnn_obj._n_layers)
-        out = self._group.eng.predict(x, [bnn_obj._w_layers], alphas=None if al is None else al[None, :], mean=False, dense=True)
+        w = bnn_obj._w_layers
+        if bnn_obj._freq_indicator:
+            w = [w[0] * bnn_obj._indicators] + list(w[1:])
+        ov = None
+        if bnn_obj._feature_indicators is not None:
+            cols, vals = data_transform_obj(bnn_obj._feature_indicators, bnn_obj._feature_means).override()
+            ov = (cols, vals) if len(cols) else None
+        out = self._group.eng.predict(x, [w], alphas=None if al is None else al[None, :], override=ov, mean=False, dense=True)
         return out["dense"][0]
 
     # `_y` / `_y_test` (N x K predictions of the current state, BNN_env.py:299,507) are materialised on demand
@@ -564,7 +615,7 @@ class MCMC:
                                    self._max_n, int(np.sum(self._max_n)))
                 k = min(n_steps - done, _steps_to_adaptation(it, self._adapt_freq, self._adapt_stop))
                 reseed = (lambda cid, i: np.random.default_rng(i + self._mcmc_id)) if self._randomize_seed else None
-                inj = g.draw_steps([self._rs], st, [self._mcmc_id], k, reseed, additional_prob)
+                inj = g.draw_steps([self._rs], st, [self._mcmc_id], k, reseed, additional_prob, adapt_stop=self._adapt_stop)
                 g.eng.mh_steps(k, inj)
                 done += k
         self._sync(bnn_obj, g.eng.read_state())
@@ -785,7 +836,7 @@ class MC3:
             k = min(n - done, _steps_to_adaptation(it, self.adapt_freq, self.adapt_stop))
             # randomize_seed=True: every step reseeds default_rng(iteration + mcmc_id) (BNN_env.py:383-384)
             inj = g.draw_steps([None] * self.n_local, st, [self.start + c for c in range(self.n_local)], k,
-                               reseed=lambda cid, i: np.random.default_rng(i + cid))
+                               reseed=lambda cid, i: np.random.default_rng(i + cid), adapt_stop=self.adapt_stop)
             g.eng.mh_steps(k, inj)
             done += k
 
@@ -848,14 +899,29 @@ def _alpha_rows(post_alphas, actFun, n_layers):
     return np.stack(rows)
 
 
+class data_transform_obj:
+    """BNN_env.py:9-17: features whose indicator is 0 are replaced by their training mean.  On the device the
+    replacement is a column override applied while X is packed (k_pack_x), the same mechanism as the PDP grid."""
+
+    def __init__(self, feature_indicators, feature_means):
+        self.feature_indicators = feature_indicators
+        self.feature_means = feature_means
+
+    def override(self):
+        cols = np.flatnonzero(np.asarray(self.feature_indicators) == 0).astype(np.int32)
+        return cols, np.asarray(self.feature_means, dtype=np.float64)[cols]
+
+
 def RunPredict(data, weights, actFun, output_act_fun, data_transform=None):
     """Forward pass of one weight set (BNN_lib.py:245-256) -> [N, O]."""
-    if data_transform is not None:
-        raise NotImplementedError("data_transform (feature indicators) is not on the device path")
     data = np.ascontiguousarray(data, dtype=np.float64)
     eng = _predict_engine(weights, data.shape[1], actFun, output_act_fun)
     al = _alpha_rows([actFun._prm], actFun, len(weights))
-    return eng.predict(data, [weights], alphas=al, mean=False, dense=True)["dense"][0]
+    ov = None
+    if data_transform is not None:
+        cols, vals = data_transform.override()
+        ov = (cols, vals) if len(cols) else None
+    return eng.predict(data, [weights], alphas=al, override=ov, mean=False, dense=True)["dense"][0]
 
 
 def RunPredictInd(data, weights, ind, actFun, output_act_fun, data_transform=None):
@@ -1018,15 +1084,18 @@ def get_pdp(data, focal_features, estimation_mode, size_output, actFun, output_a
     """Partial dependence (BNN_pdp.py:48-84).  Per grid step the focal columns are overwritten while X is
     staged (no host copy of the data), all posterior samples run in one pass and only the per-row mean over
     samples comes back: cumsum over classes, mean over rows and the 2.5 / 97.5 % row quantiles commute with it."""
-    if data_transform is not None:
-        raise NotImplementedError("data_transform (feature indicators) is not on the device path")
     data = np.ascontiguousarray(data, dtype=np.float64)
     grid = make_pdp_features(data, focal_features)
+    dt_cols, dt_vals = data_transform.override() if data_transform is not None else ([], [])
     out = np.zeros((grid.shape[0], size_output, 3))
     eng = _predict_engine(weights[0], data.shape[1], actFun, output_act_fun)
     al = _alpha_rows(alphas, actFun, len(weights[0]))
     for n in range(grid.shape[0]):
-        smean = eng.predict(data, weights, alphas=al, override=(list(focal_features), grid[n, :]), mean=True)["mean"]
+        # the grid value is written first, the feature-indicator transform inside RunPredict then replaces masked
+        # features by their mean (BNN_pdp.py:65-73, BNN_lib.py:248-249): the transform wins on a shared column
+        ov = dict(zip([int(f) for f in focal_features], [float(v) for v in grid[n, :]]))
+        ov.update(zip([int(cc) for cc in dt_cols], [float(v) for v in dt_vals]))
+        smean = eng.predict(data, weights, alphas=al, override=(list(ov.keys()), list(ov.values())), mean=True)["mean"]
         if estimation_mode == "classification":
             smean = np.cumsum(smean, axis=1)
         out[n, :, 0] = np.mean(smean, axis=0)
@@ -1040,8 +1109,11 @@ def pdp(pickle_file, pdp_features):
     bnn_obj, mcmc_obj, logger_obj = load_obj(pickle_file)
     ps = logger_obj._post_weight_samples
     weights, alphas = [s["weights"] for s in ps], [s["alphas"] for s in ps]
+    dt = None
+    if bnn_obj._feature_indicators is not None:
+        dt = data_transform_obj(bnn_obj._feature_indicators, bnn_obj._feature_means)
     return [get_pdp(bnn_obj._data, f, bnn_obj._estimation_mode, bnn_obj._size_output, bnn_obj._act_fun,
-                    bnn_obj._output_act_fun, weights, alphas, None) for f in pdp_features]
+                    bnn_obj._output_act_fun, weights, alphas, dt) for f in pdp_features]
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -1080,9 +1152,17 @@ class postLogger:
             head += ["MSE", "test_MSE"] + ["MSE_prm%s" % i for i in range(bnn_obj._n_output_prm)]
         for i in range(bnn_obj._n_layers):
             head += ["mean_w%s" % i, "std_w%s" % i]
+            if bnn_obj._hyper_p:                                                   # BNN_files.py:151-155
+                head.append(("prior_std_w%s" if bnn_obj._hyper_p == 1 else "mean_prior_std_w%s") % i)
+        if bnn_obj._freq_indicator:
+            head.append("mean_ind")
         if add_prms:
             head += add_prms
+        if bnn_obj._act_fun._trainable:
+            head += ["alpha_%s" % i for i in range(bnn_obj._n_layers - 1)]
         head += ["sig_%s" % i for i in range(len(bnn_obj._error_prm))]
+        if bnn_obj._feature_indicators is not None:
+            head += ["feature_ind_%s" % i for i in range(bnn_obj._n_features)]
         head += ["acc_prob", "mcmc_id"]
         if not continue_logfile:
             with open(self._logfile, "w", newline="") as f:
@@ -1105,12 +1185,20 @@ class postLogger:
     def log_sample(self, bnn_obj, mcmc_obj, add_prms=None):
         row = [mcmc_obj._current_iteration, mcmc_obj._logPost, mcmc_obj._logLik, mcmc_obj._logPrior, mcmc_obj._accuracy,
                mcmc_obj._test_accuracy] + list(mcmc_obj._label_acc)
-        for w in bnn_obj._w_layers:
+        for i, w in enumerate(bnn_obj._w_layers):                                  # BNN_env.py:594-612
             row += [np.mean(w), np.std(w)]
+            if bnn_obj._hyper_p:
+                row.append(bnn_obj._prior_scale[i] if bnn_obj._hyper_p == 1 else np.mean(bnn_obj._prior_scale[i]))
+        if bnn_obj._freq_indicator > 0:
+            row.append(np.mean(bnn_obj._indicators))
         if add_prms:
             row += add_prms
+        if bnn_obj._act_fun._trainable:
+            row += list(np.atleast_1d(bnn_obj._act_fun._acc_prm))
         if self._estimation_mode == "regression":
             row += list(bnn_obj._error_prm)
+        if bnn_obj._feature_indicators is not None:
+            row += list(bnn_obj._feature_indicators)
         row += [mcmc_obj._acceptance_rate, mcmc_obj._mcmc_id]
         with open(self._logfile, "a", newline="") as f:
             csv.writer(f, delimiter="\t").writerow(row)
@@ -1121,7 +1209,10 @@ class postLogger:
             with open(self._w_file, "a", newline="") as f:
                 csv.writer(f, delimiter="\t").writerow(row)
         else:
-            post = {"weights": bnn_obj._w_layers, "alphas": list(np.atleast_1d(bnn_obj._act_fun._acc_prm)),
+            w = bnn_obj._w_layers
+            if bnn_obj._freq_indicator:                                            # BNN_env.py:635-641
+                w = [w[0] * bnn_obj._indicators] + list(w[1:])
+            post = {"weights": w, "alphas": list(np.atleast_1d(bnn_obj._act_fun._acc_prm)),
                     "mcmc_it": mcmc_obj._current_iteration}
             if len(bnn_obj._error_prm):
                 post["error_prm"] = list(bnn_obj._error_prm)

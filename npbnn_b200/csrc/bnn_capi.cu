@@ -71,6 +71,8 @@ struct bnn_ctx {
   PriorScales ps{};
   DevBuf w_cur, w_prop, wp_prop, mask, owner, sf, si, counts_prop, alpha_chain;
   DevBuf ps_entry, pls_entry, ps_tmp, pls_tmp;   // per-entry prior scales of the chains (hyper-priors) / of a scoring call
+  DevBuf ind_cur, ind_prop, fi_cur, fi_prop, feat_mean, inj_ind_move, inj_ind_flip, inj_fi_move, inj_fi_flip;   // indicators
+  bool have_feat_mean = false;
   bool have_ps_entry = false;
   // row sharding: the chains' accept step reads the all-reduced sums from part_red (one pseudo tile)
   bool rowshard = false;
@@ -227,6 +229,8 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
   c->ps_entry.release(); c->pls_entry.release(); c->ps_tmp.release(); c->pls_tmp.release();
+  for (DevBuf* b : {&c->ind_cur, &c->ind_prop, &c->fi_cur, &c->fi_prop, &c->feat_mean, &c->inj_ind_move, &c->inj_ind_flip,
+                    &c->inj_fi_move, &c->inj_fi_flip}) b->release();
   for (auto& sn : c->snaps) {
     sn.dev.release();
     if (sn.host) cudaFreeHost(sn.host);
@@ -665,6 +669,10 @@ static ChainDev chain_dev(bnn_ctx* c) {
   d.mask = c->cfg.use_mask ? c->mask.as<double>() : nullptr;
   d.ps_entry = c->have_ps_entry ? c->ps_entry.as<double>() : nullptr;
   d.pls_entry = c->have_ps_entry ? c->pls_entry.as<double>() : nullptr;
+  if (c->cfg.use_indicators) { d.ind_cur = c->ind_cur.as<double>(); d.ind_prop = c->ind_prop.as<double>(); }
+  if (c->cfg.use_feature_indicators) {
+    d.fi_cur = c->fi_cur.as<double>(); d.fi_prop = c->fi_prop.as<double>(); d.feat_mean = c->feat_mean.as<double>();
+  }
   d.owner = c->owner.as<int>();
   d.sf = c->sf.as<double>();
   d.si = c->si.as<int>();
@@ -788,6 +796,18 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   CUDA_TRY(cudaMemcpyAsync(c->si.p, si.data(), sizeof(int) * si.size(), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(c->alpha_chain.p, al.data(), sizeof(double) * al.size(), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));   // host staging vectors go out of scope
+  if (cfg->use_indicators || cfg->use_feature_indicators) {
+    // both kinds of indicators start as all ones (BNN_env.py:124,170-171)
+    REQUIRE(!cfg->use_indicators || (cfg->prior_ind1 > 0.0 && cfg->prior_ind1 < 1.0), "bnn_chains_init: prior_ind1 must be in (0, 1)");
+    REQUIRE(!cfg->use_feature_indicators || c->have_feat_mean, "bnn_chains_init: call bnn_set_feature_means first");
+    const size_t P0 = (size_t)g.l[0].out * (g.l[0].in + g.l[0].bias);
+    std::vector<double> ones((size_t)C * (P0 > (size_t)g.F ? P0 : (size_t)g.F), 1.0);
+    if (cfg->use_indicators)
+      if (upload(c->ind_cur, ones.data(), (size_t)C * P0, st) || upload(c->ind_prop, ones.data(), (size_t)C * P0, st)) return 1;
+    if (cfg->use_feature_indicators)
+      if (upload(c->fi_cur, ones.data(), (size_t)C * g.F, st) || upload(c->fi_prop, ones.data(), (size_t)C * g.F, st)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
 
   // initial state: forward + likelihood + prior + counters of w0 (MCMC.__init__, BNN_env.py:299-353)
   ChainDev d = chain_dev(c);
@@ -850,6 +870,19 @@ static int stage_injection(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj
     if (inj->add_prob) {
       if (upload(c->inj_add_prob, inj->add_prob, ns, st)) return 1;
       d.inj_add_prob = c->inj_add_prob.as<double>();
+    }
+    if (inj->ind_move) {
+      REQUIRE(c->cfg.use_indicators && inj->ind_flip, "bnn_mh_steps: ind_move needs cfg.use_indicators and ind_flip");
+      const size_t P0 = (size_t)g.l[0].out * (g.l[0].in + g.l[0].bias);
+      if (upload(c->inj_ind_move, inj->ind_move, ns, st) || upload(c->inj_ind_flip, inj->ind_flip, ns * P0, st)) return 1;
+      d.inj_ind_move = c->inj_ind_move.as<int>();
+      d.inj_ind_flip = c->inj_ind_flip.as<uint8_t>();
+    }
+    if (inj->fi_move) {
+      REQUIRE(c->cfg.use_feature_indicators && inj->fi_flip, "bnn_mh_steps: fi_move needs cfg.use_feature_indicators and fi_flip");
+      if (upload(c->inj_fi_move, inj->fi_move, ns, st) || upload(c->inj_fi_flip, inj->fi_flip, ns * (size_t)g.F, st)) return 1;
+      d.inj_fi_move = c->inj_fi_move.as<int>();
+      d.inj_fi_flip = c->inj_fi_flip.as<uint8_t>();
     }
   } else {
     REQUIRE(c->cfg.n_act_prm == 0, "bnn_mh_steps: trainable activation parameters are proposed from injected draws only "
@@ -1004,6 +1037,33 @@ int bnn_snapshot_read(bnn_ctx* c, int32_t slot, double* f64_host, int32_t* i32_h
   if (i32_host) memcpy(i32_host, h + nf, ni);
   if (w_host) memcpy(w_host, h + nf + ni, nw);
   sn.pending = false;
+  return 0;
+}
+
+int bnn_set_feature_means(bnn_ctx* c, const double* mean_host, void* stream) {
+  REQUIRE(c && c->have_net && mean_host, "bnn_set_feature_means: call bnn_set_net first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upload(c->feat_mean, mean_host, (size_t)c->g.F, st)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  c->have_feat_mean = true;
+  return 0;
+}
+
+int bnn_chains_read_indicators(bnn_ctx* c, double* ind_host, double* fi_host, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_chains_read_indicators: call bnn_chains_init first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P0 = (size_t)c->g.l[0].out * (c->g.l[0].in + c->g.l[0].bias);
+  if (ind_host) {
+    REQUIRE(c->cfg.use_indicators, "bnn_chains_read_indicators: the chains have no weight indicators");
+    CUDA_TRY(cudaMemcpyAsync(ind_host, c->ind_cur.p, sizeof(double) * (size_t)c->C * P0, cudaMemcpyDeviceToHost, st));
+  }
+  if (fi_host) {
+    REQUIRE(c->cfg.use_feature_indicators, "bnn_chains_read_indicators: the chains have no feature indicators");
+    CUDA_TRY(cudaMemcpyAsync(fi_host, c->fi_cur.p, sizeof(double) * (size_t)c->C * c->g.F, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 

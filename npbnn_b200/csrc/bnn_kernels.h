@@ -38,6 +38,16 @@ struct ChainDev {
   const double* inj_alpha_dz;
   const double* inj_add_prob; // [n_steps, C] or null
   double* alpha_fwd;          // [C, L] slopes the forward kernel reads (= the proposal's)
+  // indicators (null = absent): current / proposed weight indicators [C, P0], feature indicators [C, F]
+  double* ind_cur;
+  double* ind_prop;
+  double* fi_cur;
+  double* fi_prop;
+  const double* feat_mean;    // [F]
+  const int* inj_ind_move;    // [n_steps, C] or null
+  const uint8_t* inj_ind_flip;
+  const int* inj_fi_move;
+  const uint8_t* inj_fi_flip;
 };
 
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   double* wc = d.w_cur + (long long)c * g.P;
   double* wn = d.w_prop + (long long)c * g.P;
   const int NC = 2 + 2 * g.K;
+  const int P0 = g.l[0].out * (g.l[0].in + g.l[0].bias);      // size of the first weight matrix (indicator shape)
 
   // ------------------------------------------------------------------ accept / reject
   if (accept_mode) {
@@ -290,6 +291,11 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     __syncthreads();
     if (s_flag) {
       for (int i = tid; i < g.P; i += (int)blockDim.x) wc[i] = wn[i];
+      // reset_indicators / _feature_indicators on accept (BNN_env.py:497-499)
+      if (d.ind_cur)
+        for (int i = tid; i < P0; i += (int)blockDim.x) d.ind_cur[(long long)c * P0 + i] = d.ind_prop[(long long)c * P0 + i];
+      if (d.fi_cur)
+        for (int i = tid; i < g.F; i += (int)blockDim.x) d.fi_cur[(long long)c * g.F + i] = d.fi_prop[(long long)c * g.F + i];
       if (g.lik == BNN_LIK_CATEGORICAL) {
         const int* cp = d.counts_prop + (long long)c * NC;
         if (tid < 2) si[BNN_I_N_CORRECT + tid] = cp[tid];
@@ -399,6 +405,31 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   if (g.lik == BNN_LIK_CATEGORICAL)
     for (int i = tid; i < NC; i += (int)blockDim.x) d.counts_prop[(long long)c * NC + i] = 0;
   for (int i = tid; i < g.P; i += (int)blockDim.x) wn[i] = wc[i];
+  // indicator proposals: UpdateBinomial = |ind - flip| with the injected flips (BNN_mcmc.py:98-99), else unchanged
+  const double* ind_p = nullptr;
+  const double* fi_p = nullptr;
+  if (d.ind_cur) {
+    const long long sc = (long long)step * d.C + c;
+    const bool mv = propose_mode == 1 && d.inj_ind_move && d.inj_ind_move[sc];
+    double* dst = d.ind_prop + (long long)c * P0;
+    for (int i = tid; i < P0; i += (int)blockDim.x) {
+      double v = d.ind_cur[(long long)c * P0 + i];
+      if (mv && d.inj_ind_flip[sc * P0 + i]) v = fabs(v - 1.0);
+      dst[i] = v;
+    }
+    ind_p = dst;
+  }
+  if (d.fi_cur) {
+    const long long sc = (long long)step * d.C + c;
+    const bool mv = propose_mode == 1 && d.inj_fi_move && d.inj_fi_move[sc];
+    double* dst = d.fi_prop + (long long)c * g.F;
+    for (int i = tid; i < g.F; i += (int)blockDim.x) {
+      double v = d.fi_cur[(long long)c * g.F + i];
+      if (mv && d.inj_fi_flip[sc * g.F + i]) v = fabs(v - 1.0);
+      dst[i] = v;
+    }
+    fi_p = dst;
+  }
   __syncthreads();
 
   // ------------------------------------------------------------------ UpdateNormal (BNN_mcmc.py:57-69)
@@ -452,9 +483,37 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     }
     const int cols = lg.in + lg.bias;
     const int r = (i - lg.c_off) / cols, cc = (i - lg.c_off) % cols;
+    // the forward pass sees w0' * indicators' (BNN_env.py:463-466; the prior above does not), and a feature whose
+    // indicator is 0 is replaced by its mean: its weight column leaves the contraction and enters the bias below
+    if (l == 0 && ind_p) z *= ind_p[i];
+    if (l == 0 && fi_p && !(lg.bias && cc == 0) && fi_p[cc - lg.bias] == 0.0) z = 0.0;
     wpk[bnn_packed_index(lg, r, cc)] = z;
   }
   double s = block_sum_fixed(lp, sh);
+  if (ind_p && d.cfg.use_indicators) {
+    // + sum(ind) log(pi1) + (size - sum(ind)) log(1 - pi1)   (BNN_env.py:191-193)
+    double n1 = 0.0;
+    for (int i = tid; i < P0; i += (int)blockDim.x) n1 += ind_p[i];
+    n1 = block_sum_fixed(n1, sh);
+    s += n1 * log(d.cfg.prior_ind1) + ((double)P0 - n1) * log(1.0 - d.cfg.prior_ind1);
+  }
+  if (fi_p) {
+    // data_transform (BNN_env.py:14-17): x'[:, j] = mean_j where the feature indicator is 0, i.e. every first-layer
+    // node gets the constant  sum_j mean_j * w0'[r, j] * ind'[r, j]  on top of its bias
+    __syncthreads();
+    const LayerGeom& l0 = g.l[0];
+    const int cols0 = l0.in + l0.bias;
+    for (int r = tid; r < l0.out; r += (int)blockDim.x) {
+      double adj = 0.0;
+      for (int j = 0; j < l0.in; ++j)
+        if (fi_p[j] == 0.0) {
+          const int e = r * cols0 + l0.bias + j;
+          adj += d.feat_mean[j] * wn[e] * (ind_p ? ind_p[e] : 1.0);
+        }
+      const double b = l0.bias ? wn[r * cols0] * (ind_p ? ind_p[r * cols0] : 1.0) : 0.0;
+      wpk[l0.b_off + r] = b + adj;
+    }
+  }
   if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s + sf[BNN_F_ADD_PROB];     // calc_prior(...) + additional_prob (BNN_env.py:481)
   write_back();
 }

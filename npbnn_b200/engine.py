@@ -255,7 +255,7 @@ class Engine:
     def chains_init(self, w0, temperature=None, update_f=None, update_ws=None, prior=L.PRIOR_NORMAL, prior_scale=1.0,
                     w_bound=np.inf, mask=None, alphas=None, sigma0=None, sigma_mode=L.SIGMA_FIXED, lik_temp=1.0,
                     adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=0, sample_from_prior=0, seed=1234,
-                    n_act_prm=0, init_additional_prob=0.0):
+                    n_act_prm=0, init_additional_prob=0.0, prior_ind1=None, feature_means=None):
         w = np.ascontiguousarray(self._as_sets(w0), dtype=np.float64)
         n, nl = w.shape[0], self.net.n_layers
 
@@ -284,6 +284,15 @@ class Engine:
             mk = np.ascontiguousarray(flatten_weights(mask) if not isinstance(mask, np.ndarray) else mask, dtype=np.float64)
             assert mk.shape == (self.net.n_params,)
         cfg.use_mask = int(mk is not None)
+        # weight indicators (npBNN(freq_indicator > 0)) / feature indicators (npBNN(feature_indicators=True))
+        cfg.use_indicators = int(prior_ind1 is not None)
+        cfg.prior_ind1 = float(prior_ind1) if prior_ind1 is not None else 0.5
+        cfg.use_feature_indicators = int(feature_means is not None)
+        if feature_means is not None:
+            fm = np.ascontiguousarray(feature_means, dtype=np.float64)
+            assert fm.shape == (self.net.n_features,)
+            L.check(self.lib.bnn_set_feature_means(self._h, _np_ptr(fm), self._stream()))
+        self._p0 = int(np.prod(self.net.shapes[0]))
         L.check(self.lib.bnn_chains_init(self._h, n, C.byref(cfg), _np_ptr(w), _np_ptr(mk), _np_ptr(temp), _np_ptr(uf),
                                          _np_ptr(uws), _np_ptr(al), _np_ptr(sg), self._stream()))
         self.n_chains = n
@@ -294,7 +303,8 @@ class Engine:
     def _pack_injection(self, injection, n_steps):
         arrs = {k: np.ascontiguousarray(injection[k], dtype=(np.float64 if k in ("dz", "log_u") else np.int32))
                 for k in ("proposed", "count", "ix", "iy", "dz", "log_u")}
-        for k, dt in (("alpha_ix", np.int32), ("alpha_dz", np.float64), ("add_prob", np.float64)):   # optional branches
+        for k, dt in (("alpha_ix", np.int32), ("alpha_dz", np.float64), ("add_prob", np.float64),
+                      ("ind_move", np.int32), ("ind_flip", np.uint8), ("fi_move", np.int32), ("fi_flip", np.uint8)):   # optional branches
             if injection.get(k) is not None:
                 arrs[k] = np.ascontiguousarray(injection[k], dtype=dt)
                 assert arrs[k].shape[:2] == arrs["log_u"].shape
@@ -382,6 +392,15 @@ class Engine:
         w = np.empty((n, self.net.n_params)) if weights else None
         L.check(self.lib.bnn_snapshot_read(self._h, int(slot), _np_ptr(f64), _np_ptr(i32), _np_ptr(w)))
         return ChainState(f64, i32, w, self.net, self.K)
+
+    def read_indicators(self, weight=True, feature=True):
+        """(weight indicators [C, out0, in0+b0] or None, feature indicators [C, F] or None) of the chains' current state."""
+        ind = np.empty((self.n_chains, self._p0)) if weight else None
+        fi = np.empty((self.n_chains, self.net.n_features)) if feature else None
+        L.check(self.lib.bnn_chains_read_indicators(self._h, _np_ptr(ind), _np_ptr(fi), self._stream()))
+        if ind is not None:
+            ind = ind.reshape((self.n_chains,) + tuple(self.net.shapes[0]))
+        return ind, fi
 
     def write_state(self, st: ChainState):
         """Write an edited host copy of the state arrays back (bnn_chains_write)."""

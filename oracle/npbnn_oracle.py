@@ -183,6 +183,20 @@ def log_prior(weights: Sequence[np.ndarray], kind: int, scales: Sequence, indica
     return float(lp)
 
 
+def feature_transform(x: np.ndarray, feature_indicators, feature_means) -> np.ndarray:
+    """data_transform_obj.transform (BNN_env.py:9-17): columns whose indicator is 0 are replaced by the training mean
+    of that feature."""
+    d = np.array(x, dtype=np.float64, copy=True)
+    off = np.asarray(feature_indicators) == 0
+    d[:, off] = np.asarray(feature_means, dtype=np.float64)[off]
+    return d
+
+
+def update_binomial(ind: np.ndarray, flips: np.ndarray) -> np.ndarray:
+    """UpdateBinomial (BNN_mcmc.py:98-99) with the binomial draw injected: |ind - flips|."""
+    return np.abs(np.asarray(ind) - np.asarray(flips))
+
+
 def gibbs_prior_scales(weights: Sequence[np.ndarray], hyper_p: int, gamma=None) -> list:
     """npBNN.sample_prior_scale (BNN_env.py:196-219): one conjugate draw of the Normal prior's standard deviation per
     layer (hyper_p 1: GibbsSampleNormStdGammaVector, a=2), per input node (2: GibbsSampleNormStdGamma2D, a=1, sums

@@ -476,10 +476,51 @@ def case_hyper(hyper_p, n_steps=40, seed=11):
                                               use_bias_node=2, update_f=[0.2] * 3, n_iteration=1000))
 
 
+def case_indicators(kind, n_steps=80, seed=13):
+    """Indicator moves of mh_step.  kind "weight": npBNN(freq_indicator=0.3) on a FOUR-layer network (the branch reads
+    update_f[3], BNN_env.py:460, so it only exists from four layers on); kind "feature": npBNN(feature_indicators=True)
+    with adapt_stop=5 so that the branch (BNN_env.py:423-431) is live from iteration 6; kind "both".  UpdateBinomial
+    draws from numpy's GLOBAL generator, the rest of the step from mcmc._rs."""
+    dat = synth_class(300, 6, 3, seed, 50)
+    np.random.seed(seed)
+    weight, feature = kind in ("weight", "both"), kind in ("feature", "both")
+    n_nodes = [4, 3, 3] if weight else [4, 3]
+    bnn = quiet(bn.npBNN, dat, n_nodes=n_nodes, actFun=bn.ActFun(fun="tanh"), use_bias_node=2, prior_f=1, p_scale=1,
+                freq_indicator=0.3 if weight else 0, prior_ind1=0.4, seed=seed, feature_indicators=True if feature else None)
+    nl = len(n_nodes) + 1
+    mcmc = bn.MCMC(bnn, n_iteration=1000, update_f=[0.2] * nl, adapt_stop=5)
+    out = {}
+    store_data(out, dat)
+    for i, w in enumerate(bnn._w_layers):
+        out["w0_%d" % i] = np.array(w)
+    out["init_logLik"], out["init_logPrior"] = np.float64(mcmc._logLik), np.float64(mcmc._logPrior)
+    rows = {k: [] for k in ("logLik", "logPrior", "logPost", "accepted", "accuracy", "test_accuracy", "mean_ind", "feature_ind")}
+    for t in range(n_steps):
+        quiet(mcmc.mh_step, bnn)
+        rows["logLik"].append(mcmc._logLik); rows["logPrior"].append(mcmc._logPrior); rows["logPost"].append(mcmc._logPost)
+        rows["accepted"].append(mcmc._last_accepted); rows["accuracy"].append(mcmc._accuracy)
+        rows["test_accuracy"].append(mcmc._test_accuracy)
+        rows["mean_ind"].append(np.mean(bnn._indicators))
+        rows["feature_ind"].append(np.array(bnn._feature_indicators) if feature else np.zeros(0))
+    for k, v in rows.items():
+        out["steps_" + k] = np.array(v)
+    for i, w in enumerate(bnn._w_layers):
+        out["wN_%d" % i] = np.array(w)
+    out["indN"] = np.array(bnn._indicators, dtype=np.float64)
+    out["yN"] = np.array(mcmc._y)
+    save("syn_ind_%s" % kind, out, dict(kind=kind, seed=seed, n_steps=n_steps, act="tanh", n_nodes=n_nodes, use_bias_node=2,
+                                        freq_indicator=0.3 if weight else 0, prior_ind1=0.4, update_f=[0.2] * nl,
+                                        adapt_stop=5, n_iteration=1000))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hyper":          # regenerate only the hyper-prior cases
         for hp in (1, 2, 3):
             case_hyper(hp)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "indicators":
+        for kind in ("weight", "feature", "both"):
+            case_indicators(kind)
         sys.exit(0)
     case_c1()
     case_c2(True)
@@ -505,3 +546,5 @@ if __name__ == "__main__":
                init_additional_prob=float(np.log(10) * -np.sum([0.2, 0.9]) * 10))
     for hp in (1, 2, 3):
         case_hyper(hp)
+    for kind in ("weight", "feature", "both"):
+        case_indicators(kind)

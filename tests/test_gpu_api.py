@@ -179,7 +179,7 @@ def test_unsupported_options_raise():
     z, meta = G.load("syn_swish_cauchy")
     dat = _dat(z)
     with pytest.raises(NotImplementedError):
-        bn.npBNN(dat, n_nodes=[4, 3], freq_indicator=0.1)
+        bn.MCMC(bn.npBNN(dat, n_nodes=[4, 3, 3], freq_indicator=0.1), rng="philox")     # indicator moves are host-drawn
     trainable = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="genReLU", prm=np.array([0.1, 0.2]), trainable=True))
     with pytest.raises(NotImplementedError):
         bn.MCMC(trainable, rng="philox")                  # that branch is proposed from host-drawn numbers only
@@ -393,3 +393,45 @@ def test_philox_chains_agree_statistically_with_reference_chains():
     # predictive probabilities (measured: mean |gap| 0.021, max 0.134 between two sets of 4 chains)
     assert np.abs(ph - pp).mean() < 0.04 and np.abs(ph - pp).max() < 0.25
     assert np.allclose(ph.sum(1), 1.0) and np.allclose(pp.sum(1), 1.0)
+
+
+@pytest.mark.parametrize("kind", ["weight", "feature", "both"])
+def test_indicator_flow_reproduces_reference_chain(kind, tmp_path):
+    """npBNN(freq_indicator=0.3) / npBNN(feature_indicators=True) through mh_step (BNN_env.py:423-431,449-466): the flips
+    are drawn on the host with the reference's generators, the device applies them, multiplies the first layer by the
+    indicators, folds masked features into the first-layer bias and adds the Bernoulli prior term.  Same accept
+    decisions, indicators and weights as the reference's recorded chain; likelihood / prior / accuracies to 1e-9."""
+    import npbnn_b200 as bn
+    z, meta = G.load("syn_ind_%s" % kind)
+    seed, nl = int(meta["seed"]), len(meta["n_nodes"]) + 1
+    np.random.seed(seed)
+    bnn = bn.npBNN(_dat(z), n_nodes=meta["n_nodes"], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, prior_f=1, p_scale=1,
+                   freq_indicator=meta["freq_indicator"], prior_ind1=meta["prior_ind1"], seed=seed,
+                   feature_indicators=True if kind in ("feature", "both") else None)
+    for i in range(nl):
+        assert np.array_equal(bnn._w_layers[i], z["w0_%d" % i])
+    mcmc = bn.MCMC(bnn, n_iteration=1000, update_f=meta["update_f"], adapt_stop=meta["adapt_stop"])
+    assert _close(mcmc._logLik, z["init_logLik"]) and _close(mcmc._logPrior, z["init_logPrior"])
+    assert _close(bnn.calc_prior(), z["init_logPrior"])
+    for t in range(int(meta["n_steps"])):
+        mcmc.mh_step(bnn)
+        assert mcmc._last_accepted == int(z["steps_accepted"][t]), t
+        assert _close(mcmc._logLik, z["steps_logLik"][t]), (t, mcmc._logLik, float(z["steps_logLik"][t]))
+        assert _close(mcmc._logPrior, z["steps_logPrior"][t]), (t, mcmc._logPrior, float(z["steps_logPrior"][t]))
+        assert _close(mcmc._logPost, z["steps_logPost"][t])
+        assert _close(mcmc._accuracy, z["steps_accuracy"][t]) and _close(mcmc._test_accuracy, z["steps_test_accuracy"][t]), t
+        assert abs(np.mean(bnn._indicators) - float(z["steps_mean_ind"][t])) < 1e-15, t
+        if kind in ("feature", "both"):
+            assert np.array_equal(bnn._feature_indicators, z["steps_feature_ind"][t]), t
+    for i in range(nl):
+        assert np.array_equal(bnn._w_layers[i], z["wN_%d" % i])
+    assert np.array_equal(bnn._indicators, z["indN"])
+    assert np.allclose(mcmc.y(bnn), z["yN"], rtol=1e-10, atol=1e-300)
+    # the logger writes the reference's extra columns and the indicated first layer
+    logger = bn.postLogger(bnn, filename="ind", wdir=str(tmp_path))
+    logger.log_sample(bnn, mcmc)
+    logger.log_weights(bnn, mcmc)
+    head, row = [l.split("\t") for l in open(logger._logfile).read().splitlines()]
+    assert len(head) == len(row)
+    assert ("mean_ind" in head) == bool(meta["freq_indicator"]) and ("feature_ind_0" in head) == (kind != "weight")
+    assert np.array_equal(logger._post_weight_samples[-1]["weights"][0], bnn._w_layers[0] * bnn._indicators)

@@ -170,3 +170,30 @@ def test_hyper_prior_scales_and_prior(hp):
         assert int(z["steps_iteration"][t]) == t + 1
         n_gibbs += 1
     assert n_gibbs == int(meta["n_steps"]) // 4
+
+
+@pytest.mark.parametrize("kind", ["weight", "feature", "both"])
+def test_indicator_state_matches_reference(kind):
+    """Weight indicators (first-layer weights times a 0/1 matrix in the forward pass, Bernoulli term in the prior,
+    BNN_env.py:191-193,458-466) and feature indicators (masked features replaced by their training mean,
+    BNN_env.py:9-17,423-431): the oracle's forward pass and prior on the reference's final state reproduce the
+    predictions and the log-prior the reference recorded for it."""
+    z, meta = G.load("syn_ind_%s" % kind)
+    nl = len(meta["n_nodes"]) + 1
+    w = [z["wN_%d" % i] for i in range(nl)]
+    x = z["x"]
+    w_fwd = list(w)
+    if meta["freq_indicator"]:
+        w_fwd[0] = w[0] * z["indN"]
+        assert set(np.unique(z["indN"])) <= {0.0, 1.0} and z["indN"].mean() < 1.0       # the indicators did move
+    if kind in ("feature", "both"):
+        fi = z["steps_feature_ind"][-1]
+        assert fi.min() == 0                                                              # some feature is masked
+        x = orc.feature_transform(x, fi, z["x"].mean(axis=0))
+    y = orc.forward(x, w_fwd, "tanh", None, "softmax")
+    assert close(y, z["yN"], rtol=1e-11)
+    lp = orc.log_prior(w, 1, np.ones(nl), indicators=z["indN"], freq_indicator=meta["freq_indicator"],
+                       prior_ind1=meta["prior_ind1"])
+    assert close(lp, z["steps_logPrior"][-1])
+    assert close(orc.loglik_categorical(y, z["labels"].astype(int), None, None, 1.0), z["steps_logLik"][-1])
+    assert np.array_equal(orc.update_binomial(np.array([1, 0, 1, 0]), np.array([1, 1, 0, 0])), [0, 1, 1, 0])
