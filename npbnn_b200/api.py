@@ -764,12 +764,20 @@ def run_mcmc(bnn, mcmc, logger, pipeline_depth=4):
     points are exported asynchronously and the loop never waits for the device (pipeline_depth=0: synchronous)."""
     if mcmc._rng_mode == "philox" and mcmc._own_group and pipeline_depth > 0 and mcmc._current_iteration < mcmc._n_iterations:
         return _run_mcmc_pipelined(bnn, mcmc, logger, int(pipeline_depth))
-    while True:
-        it = mcmc._current_iteration
-        mcmc.run(bnn, _next_stop(mcmc, it))
-        _report(bnn, mcmc, logger)
-        if mcmc._current_iteration >= mcmc._n_iterations:
-            break
+    # host-drawn proposals: the loop returns to the host at every logging point anyway, but the pickle of
+    # [bnn, mcmc, logger] (X included, rewritten at every sample) still goes to the background writer
+    if pipeline_depth > 0 and hasattr(logger, "begin_async"):
+        logger.begin_async()
+    try:
+        while True:
+            it = mcmc._current_iteration
+            mcmc.run(bnn, _next_stop(mcmc, it))
+            _report(bnn, mcmc, logger)
+            if mcmc._current_iteration >= mcmc._n_iterations:
+                break
+    finally:
+        if pipeline_depth > 0 and hasattr(logger, "end_async"):
+            logger.end_async()
 
 
 class MC3:

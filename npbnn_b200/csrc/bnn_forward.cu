@@ -1821,15 +1821,16 @@ static bool sparse_plan(const FwdParams& p, int C, int nch, int* group, int* nwa
   const size_t per_chain = (size_t)p.sp_wlen * sizeof(double);
   const int c_up = (C + nch - 1) / nch * nch;
   const int max_warps = (nch == 4) ? 10 : 16;
-  for (int min_warps : {8, 4, 2, 1}) {
-    if (fixed + min_warps * per_warp + nch * per_chain > cap) continue;
-    size_t g = (cap - fixed - min_warps * per_warp) / per_chain;
+  // Warps first: the kernel is latency-bound (two to three warps per scheduler), and a smaller resident chain group
+  // only costs another sweep over the tiles (X comes from L2 / HBM at a few percent of the step).  The rest of the
+  // shared memory then takes as many chains' weight streams as fit.
+  for (int w = max_warps; w >= 1; --w) {
+    if (fixed + (size_t)w * per_warp + nch * per_chain > cap) continue;
+    size_t g = (cap - fixed - (size_t)w * per_warp) / per_chain;
     g = g / nch * nch;
     if (g > (size_t)c_up) g = c_up;
-    size_t w = (cap - fixed - g * per_chain) / per_warp;
-    if (w > (size_t)max_warps) w = max_warps;
     *group = (int)g;
-    *nwarps = (int)w;
+    *nwarps = w;
     return true;
   }
   return false;
