@@ -361,26 +361,44 @@ def main():
         def pinned(shape, dtype):
             return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
 
-        # this step's inputs live in pinned host memory; the library copies them to the device inside bnn_mh_steps
-        inj = {"proposed": pinned((1, n_local, 3), torch.int32), "count": pinned((1, n_local, 3), torch.int32),
-               "ix": pinned((1, n_local, cap), torch.int32), "iy": pinned((1, n_local, cap), torch.int32),
-               "dz": pinned((1, n_local, cap), torch.float64), "log_u": pinned((1, n_local), torch.float64)}
-        inj["proposed"][:] = 1
-        inj["count"][:] = np.array(upd_n, np.int32)
+        # this step's inputs live in pinned host memory (two buffers: while the device runs step s, a host thread draws
+        # the proposals of step s+1 -- ctypes releases the GIL while bnn_mh_steps waits for the device); the library
+        # copies them to the device inside bnn_mh_steps
+        def make_inj():
+            b = {"proposed": pinned((1, n_local, 3), torch.int32), "count": pinned((1, n_local, 3), torch.int32),
+                 "ix": pinned((1, n_local, cap), torch.int32), "iy": pinned((1, n_local, cap), torch.int32),
+                 "dz": pinned((1, n_local, cap), torch.float64), "log_u": pinned((1, n_local), torch.float64)}
+            b["proposed"][:] = 1
+            b["count"][:] = np.array(upd_n, np.int32)
+            return b
 
-        def e2e_step():
-            # host side of one MH iteration: draw every chain's proposal (numpy, as the reference does), hand the
-            # host buffers to the library (H2D inside), read the step's result back (D2H, synchronises)
-            inj["dz"][:] = host_rng.normal(0, 0.075, (1, n_local, cap))
-            inj["log_u"][:] = np.log(host_rng.random((1, n_local)))
+        bufs = [make_inj(), make_inj()]
+
+        def draw(b):
+            # host side of one MH iteration: every chain's proposal (numpy, as the reference does)
+            b["dz"][:] = host_rng.normal(0, 0.075, (1, n_local, cap))
+            b["log_u"][:] = np.log(host_rng.random((1, n_local)))
             o = 0
             for l, (r, c) in enumerate(wl.C4_SHAPES):
-                inj["ix"][0, :, o:o + upd_n[l]] = host_rng.integers(0, r, (n_local, upd_n[l]))
-                inj["iy"][0, :, o:o + upd_n[l]] = host_rng.integers(0, c, (n_local, upd_n[l]))
+                b["ix"][0, :, o:o + upd_n[l]] = host_rng.integers(0, r, (n_local, upd_n[l]))
+                b["iy"][0, :, o:o + upd_n[l]] = host_rng.integers(0, c, (n_local, upd_n[l]))
                 o += upd_n[l]
-            eng2.mh_steps(1, inj)
+            return b
+
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(1)
+        nxt = [pool.submit(draw, bufs[0]), 0]
+
+        def e2e_step():
+            # hand the drawn host buffers to the library (H2D inside), start drawing the next step's, read this
+            # step's result back (D2H, synchronises)
+            b = nxt[0].result()
+            nxt[1] ^= 1
+            nxt[0] = pool.submit(draw, bufs[nxt[1]])
+            eng2.mh_steps(1, b)
             return eng2.read_state(weights=False)
 
+        inj = bufs[0]
         for _ in range(max(3, W)):
             st2 = e2e_step()
         h2d = K * sum(a.nbytes for a in inj.values())
@@ -394,12 +412,15 @@ def main():
         t_e2e = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": args.chains * K / t_e2e, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d / K,
                "d2h_bytes_per_step": d2h / K,
-               "includes": "every step, per rank: proposals of all local chains drawn on the host (numpy), copied from "
-                           "pinned host memory inside bnn_mh_steps(1, inj), one MH iteration, chain state read back "
-                           "(bnn_chains_read, synchronises); X is resident (staged once by bnn_set_data from pinned "
+               "includes": "every step, per rank: proposals of all local chains drawn on the host (numpy; a host thread "
+                           "draws step s+1 while the device runs step s), copied from pinned host memory inside "
+                           "bnn_mh_steps(1, inj), one MH iteration, chain state read back (bnn_chains_read, "
+                           "synchronises); X is resident (staged once by bnn_set_data from pinned "
                            "host memory: setup_seconds, not timed)",
                "seconds": t_e2e, "setup_seconds": t_setup, "setup_h2d_bytes": x_pin.numel() * 8 + y_pin.numel() * 4 + w0.nbytes,
                "finite_logLik": bool(np.all(np.isfinite(st2.logLik)))}
+        nxt[0].result()
+        pool.shutdown()
         eng2.close()
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
