@@ -107,7 +107,20 @@ struct bnn_ctx {
   };
   std::vector<Snap> snaps;
   cudaStream_t copy_stream = nullptr;
+  // CUDA graphs of the free-running MH loop (bnn_mh_steps without injection): launch-bound at small N
+  struct StepGraph { int n_steps; cudaGraphExec_t exec; long long launches; };
+  std::vector<StepGraph> graphs;
+  cudaStream_t capture_stream = nullptr;
+  int opt_graphs = 1;               // option "graphs"
+  bool mh_warm = false;             // one eager bnn_mh_steps has run since the last (re)configuration
 };
+
+// every call that changes what a captured launch sequence would contain (pointers, kernel choice, chain count)
+static void invalidate_graphs(bnn_ctx* c) {
+  for (auto& gph : c->graphs) cudaGraphExecDestroy(gph.exec);
+  c->graphs.clear();
+  c->mh_warm = false;
+}
 
 // network shapes with a k_fwd3t instantiation (BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 swish, categorical)
 static bool tensor_shape(const NetGeom& g) {
@@ -238,6 +251,8 @@ int bnn_ctx_destroy(bnn_ctx* c) {
     if (sn.done) cudaEventDestroy(sn.done);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  invalidate_graphs(c);
+  if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return 0;
@@ -245,10 +260,12 @@ int bnn_ctx_destroy(bnn_ctx* c) {
 
 int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   REQUIRE(c && name, "bnn_set_option: null argument");
+  invalidate_graphs(c);
   if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
   if (strcmp(name, "time_forward") == 0) { c->time_forward = value; return 0; }
   if (strcmp(name, "sparse") == 0) { c->opt_sparse = value; return 0; }
   if (strcmp(name, "tensor_l1") == 0) { c->opt_tensor = value; return 0; }
+  if (strcmp(name, "graphs") == 0) { c->opt_graphs = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
 
@@ -340,6 +357,7 @@ int64_t bnn_launch_count(const bnn_ctx* c) { return c ? c->launches : -1; }
 int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_test, const int32_t* labels_dev,
                  const double* targets_dev, const double* inst_w_dev, const double* class_w_dev, void* stream) {
   REQUIRE(c && c->have_net, "bnn_set_data: call bnn_set_net first");
+  invalidate_graphs(c);
   REQUIRE(x_dev != nullptr && n_train >= 1 && n_test >= 0, "bnn_set_data: bad arguments");
   const NetGeom& g = c->g;
   if (g.lik == BNN_LIK_CATEGORICAL) REQUIRE(labels_dev != nullptr, "bnn_set_data: labels_dev required for the categorical likelihood");
@@ -719,6 +737,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
                     const double* mask_host, const double* temperature, const double* update_f,
                     const double* update_ws, const double* alpha, const double* sigma0, void* stream) {
   REQUIRE(c && c->have_data, "bnn_chains_init: call bnn_set_net and bnn_set_data first");
+  invalidate_graphs(c);
   REQUIRE(cfg && w0_host && temperature && update_f && update_ws && n_chains >= 1, "bnn_chains_init: bad arguments");
   REQUIRE(cfg->adapt_freq >= 1, "bnn_chains_init: adapt_freq must be >= 1");
   REQUIRE(cfg->n_act_prm >= 0 && cfg->n_act_prm <= c->g.L, "bnn_chains_init: n_act_prm must be in [0, n_layers]");
@@ -891,14 +910,8 @@ static int stage_injection(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj
   return 0;
 }
 
-int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* stream) {
-  REQUIRE(c && c->have_chains, "bnn_mh_steps: call bnn_chains_init first");
-  REQUIRE(n_steps >= 1, "bnn_mh_steps: n_steps must be >= 1");
-  REQUIRE(!c->rowshard, "bnn_mh_steps: row-sharded chains are stepped with bnn_rowshard_update / _local / _commit");
-  CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  ChainDev d = chain_dev(c);
-  if (int rc = stage_injection(c, n_steps, inj, d, st)) return rc;
+// the launch sequence of n_steps MH iterations: [accept s-1 + propose s] [forward] ... [accept n-1]
+static int launch_mh_sequence(bnn_ctx* c, const ChainDev& d, int32_t n_steps, cudaStream_t st) {
   for (int s = 0; s < n_steps; ++s) {
     CUDA_TRY(bnn_launch_mh_update(d, s > 0 ? 1 : 0, 1, s, st));
     c->launches++;
@@ -907,6 +920,51 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
   }
   CUDA_TRY(bnn_launch_mh_update(d, 1, 0, n_steps, st));
   c->launches++;
+  return 0;
+}
+
+int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* stream) {
+  REQUIRE(c && c->have_chains, "bnn_mh_steps: call bnn_chains_init first");
+  REQUIRE(n_steps >= 1, "bnn_mh_steps: n_steps must be >= 1");
+  REQUIRE(!c->rowshard, "bnn_mh_steps: row-sharded chains are stepped with bnn_rowshard_update / _local / _commit");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ChainDev d = chain_dev(c);
+  if (int rc = stage_injection(c, n_steps, inj, d, st)) return rc;
+  // Free-running chains: the sequence depends on nothing but n_steps (Philox counters come from the chain state), so
+  // it is captured once per n_steps into a CUDA graph and replayed -- at small N the loop is bound by launch latency,
+  // not by the kernels.  The first call after any (re)configuration runs eagerly (function attributes, lazily
+  // allocated workspaces); capture uses a private stream because the caller's may be the legacy default stream.
+  const bool graphable = !inj && c->opt_graphs && c->mh_warm && !c->time_forward && !c->opt_tensor &&
+                         n_steps >= 2 && n_steps <= 512;
+  if (graphable) {
+    cudaGraphExec_t exec = nullptr;
+    long long per_launch = 0;
+    for (auto& gph : c->graphs)
+      if (gph.n_steps == n_steps) { exec = gph.exec; per_launch = gph.launches; }
+    if (!exec) {
+      const long long l0 = c->launches;
+      if (!c->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = launch_mh_sequence(c, d, n_steps, c->capture_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(c->capture_stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CUDA_TRY(e);
+      const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CUDA_TRY(e2);
+      if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+      per_launch = c->launches - l0;          // kernels in the sequence (counted while capturing, launched on replay)
+      c->launches = l0;
+      c->graphs.push_back({n_steps, exec, per_launch});
+    }
+    CUDA_TRY(cudaGraphLaunch(exec, st));
+    c->launches += per_launch;
+    return 0;
+  }
+  if (int rc = launch_mh_sequence(c, d, n_steps, st)) return rc;
+  if (!inj) c->mh_warm = true;
   if (inj) CUDA_TRY(cudaStreamSynchronize(st));   // the caller may free the host arrays after return
   return 0;
 }
@@ -914,6 +972,7 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
 // ---- row sharding (include/npbnn_b200.h) -------------------------------------------------------------------
 int bnn_rowshard_config(bnn_ctx* c, int64_t n_train_global) {
   REQUIRE(c && c->have_data, "bnn_rowshard_config: call bnn_set_data (this rank's rows) first");
+  invalidate_graphs(c);
   REQUIRE(n_train_global >= c->n_train, "bnn_rowshard_config: n_train_global is smaller than the local shard");
   c->rowshard = true;
   c->n_train_global = n_train_global;
@@ -1042,6 +1101,7 @@ int bnn_snapshot_read(bnn_ctx* c, int32_t slot, double* f64_host, int32_t* i32_h
 
 int bnn_set_feature_means(bnn_ctx* c, const double* mean_host, void* stream) {
   REQUIRE(c && c->have_net && mean_host, "bnn_set_feature_means: call bnn_set_net first");
+  invalidate_graphs(c);
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (upload(c->feat_mean, mean_host, (size_t)c->g.F, st)) return 1;
@@ -1079,6 +1139,7 @@ int bnn_chains_write(bnn_ctx* c, const double* f64_host, const int32_t* i32_host
 
 int bnn_chains_set_prior_scales(bnn_ctx* c, const double* entry_scale_host, void* stream) {
   REQUIRE(c && c->have_chains, "bnn_chains_set_prior_scales: call bnn_chains_init first");
+  invalidate_graphs(c);
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (entry_scale_host) {

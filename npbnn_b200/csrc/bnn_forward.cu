@@ -211,6 +211,10 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
 
+  // likelihood mode: when there are fewer row tiles than the GPU has room for, the weight sets are split over
+  // gridDim.y as well (every (tile, set) still has exactly one owner); prediction accumulates over sets per tile
+  const int c_beg = PREDICT ? 0 : (int)((long long)p.C * blockIdx.y / gridDim.y);
+  const int c_end = PREDICT ? p.C : (int)((long long)p.C * (blockIdx.y + 1) / gridDim.y);
   const long long total_warps = (long long)gridDim.x * GEN_WARPS;
   for (long long wt = (long long)blockIdx.x * GEN_WARPS + warp; wt < p.n_tiles16; wt += total_warps) {
     if (PREDICT) {
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
     }
     const double* xrow0 = p.x + (wt * 16 + gq) * (long long)g.F_pad;
     const double* xrow1 = xrow0 + 8LL * g.F_pad;
-    for (int c = 0; c < p.C; ++c) {
+    for (int c = c_beg; c < c_end; ++c) {
       const double* W = p.wp + (long long)c * g.PB;
       const double* src = nullptr;
       double* dst = h0;
@@ -1792,7 +1796,12 @@ static cudaError_t launch_generic_t(const FwdParams& p, int n_sms, cudaStream_t 
   // resident CTAs per SM limited by shared memory; cap the grid at a few waves of resident CTAs
   long long max_grid = (long long)n_sms * 8;
   int grid = (int)(ctas < max_grid ? ctas : max_grid);
-  kern<<<grid, GEN_WARPS * 32, bytes, st>>>(p);
+  int ny = 1;
+  if (!PREDICT && p.C > 1 && grid < n_sms * 4) {
+    const int want = (n_sms * 4 + grid - 1) / grid;
+    ny = want < p.C ? want : p.C;
+  }
+  kern<<<dim3(grid, ny), GEN_WARPS * 32, bytes, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -356,6 +356,35 @@ def case_predict():
     save("predict", out, meta)
 
 
+def case_predict_transform():
+    """RunPredict / RunPredictInd / get_pdp with a feature-indicator data_transform (BNN_env.py:9-17, BNN_lib.py:245-272,
+    BNN_pdp.py:48-84): features 2 and 5 are replaced by their means; the PDP runs over a kept and over a masked feature."""
+    from np_bnn.BNN_env import data_transform_obj
+    rng = np.random.default_rng(8)
+    n, f, k, s = 200, 7, 3, 5
+    x = rng.standard_normal((n, f))
+    fi = np.array([1, 1, 0, 1, 1, 0, 1])
+    dt = data_transform_obj(fi, x.mean(axis=0))
+    post = []
+    out = {"x": x, "fi": fi}
+    for j in range(s):
+        np.random.seed(50 + j)
+        w = [wi + rng.normal(0, 0.5, wi.shape) for wi in bn.init_weight_prm([5, 4], f, k, init_std=0.1, bias_node=2)]
+        post.append(w)
+        for li, wi in enumerate(w):
+            out["s%d_w%d" % (j, li)] = wi
+    af = bn.ActFun(fun="tanh")
+    ind = (rng.random(post[0][0].shape) < 0.7).astype(float)
+    out["ind"] = ind
+    out["y_transform"] = bn.RunPredict(x, post[0], af, bn.SoftMax, data_transform=dt)
+    out["y_transform_ind"] = bn.RunPredictInd(x, post[0], ind, af, bn.SoftMax, data_transform=dt)
+    for focal in ([1], [2]):
+        res = bn.get_pdp(x, focal, "classification", k, af, bn.SoftMax, post, [[0.0]] * s, dt)
+        out["pdp%d_feature" % focal[0]] = res["feature"]
+        out["pdp%d" % focal[0]] = res["pdp"]
+    save("predict_transform", out, {"S": s, "act": "tanh", "use_bias_node": 2})
+
+
 def case_sample_cat():
     """sample_from_categorical (BNN_lib.py:682-713) and get_posterior_cat_prob mode 2: the global numpy stream is
     seeded, so the uniforms the reference consumed are np.random.random((n, S)) after the same seed."""
@@ -521,6 +550,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "indicators":
         for kind in ("weight", "feature", "both"):
             case_indicators(kind)
+        case_predict_transform()
         sys.exit(0)
     case_c1()
     case_c2(True)
@@ -548,3 +578,4 @@ if __name__ == "__main__":
         case_hyper(hp)
     for kind in ("weight", "feature", "both"):
         case_indicators(kind)
+    case_predict_transform()

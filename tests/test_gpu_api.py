@@ -435,3 +435,24 @@ def test_indicator_flow_reproduces_reference_chain(kind, tmp_path):
     assert len(head) == len(row)
     assert ("mean_ind" in head) == bool(meta["freq_indicator"]) and ("feature_ind_0" in head) == (kind != "weight")
     assert np.array_equal(logger._post_weight_samples[-1]["weights"][0], bnn._w_layers[0] * bnn._indicators)
+
+
+def test_predict_and_pdp_with_feature_transform():
+    """RunPredict / RunPredictInd / get_pdp with data_transform (masked features replaced by their training means,
+    BNN_env.py:9-17): the transform is a column override while X is packed; where the PDP's focal feature is itself
+    masked the transform wins, as in the reference (BNN_lib.py:248-249)."""
+    import npbnn_b200 as bn
+    z, meta = G.load("predict_transform")
+    x, fi = z["x"], z["fi"]
+    dt = bn.data_transform_obj(fi, x.mean(axis=0))
+    S = int(meta["S"])
+    post = [[z["s%d_w%d" % (j, li)] for li in range(3)] for j in range(S)]
+    af = bn.ActFun(fun="tanh")
+    y = bn.RunPredict(x, post[0], af, bn.SoftMax, data_transform=dt)
+    assert np.allclose(y, z["y_transform"], rtol=1e-10, atol=1e-300)
+    y = bn.RunPredictInd(x, post[0], z["ind"], af, bn.SoftMax, data_transform=dt)
+    assert np.allclose(y, z["y_transform_ind"], rtol=1e-10, atol=1e-300)
+    for focal in (1, 2):
+        res = bn.get_pdp(x, [focal], "classification", 3, af, bn.SoftMax, post, [[0.0]] * S, dt)
+        assert np.array_equal(res["feature"], z["pdp%d_feature" % focal])
+        assert np.allclose(res["pdp"], z["pdp%d" % focal], rtol=1e-9, atol=1e-12)

@@ -427,6 +427,43 @@ def test_philox_chains_run_and_agree_with_oracle_state():
     eng.close()
 
 
+@pytest.mark.parametrize("shape", ["small", "c4"])
+def test_cuda_graph_replay_matches_eager_launches(shape):
+    """bnn_mh_steps without injection replays a captured CUDA graph of the launch sequence from the second call on
+    (per n_steps, invalidated by every reconfiguration).  Chains stepped through graphs and chains stepped eagerly
+    (option graphs=0) must end in bit-identical states, also across a temperature change and a second chunk length."""
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(4)
+    if shape == "c4":
+        x, labels, sets = _c4_like(3000, 3, seed=5)
+        net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    else:
+        x = rng.standard_normal((700, 9))
+        labels = rng.integers(0, 4, 700)
+        shapes = [(6, 10), (5, 7), (4, 6)]
+        sets = [[rng.normal(0, 0.3, s) for s in shapes] for _ in range(3)]
+        net = NetShape.from_weights(sets[0], 9, act="tanh", lik=0)
+    states = []
+    for graphs in (1, 0):
+        eng = Engine(net)
+        eng.set_data(x, labels)
+        eng.chains_init(sets, temperature=[1.0, 0.9, 0.8], seed=77, adapt_f=0.2, adapt_fM=0.6, adapt_freq=5, adapt_stop=40)
+        eng.set_option("graphs", graphs)
+        for _ in range(4):
+            eng.mh_steps(10)                       # eager, capture, replay, replay
+        eng.set_temperature([0.8, 1.0, 0.9])
+        eng.mh_steps(10)
+        for _ in range(3):
+            eng.mh_steps(7)
+        n_launch = eng.launch_count
+        st = eng.read_state()
+        states.append((st.f64.copy(), st.i32.copy(), st.w.copy(), n_launch))
+        eng.close()
+    a, b = states
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.all(a[1][:, 0] == 71) and a[3] == b[3]
+
+
 def _random_block_net(rng, f, groups_nodes1, groups_nodes2, k):
     """A create_mask-style block network: feature g -> n1 nodes -> n2 nodes -> dense K outputs (bias on the last layer)."""
     h1, h2 = f * groups_nodes1, f * groups_nodes2

@@ -62,7 +62,7 @@ def flop_per_row(shapes, n_features):
 
 
 def mh_rate(name, x, y, xt, yt, shapes, act, lik, chains, steps, mask=None, sigma_mode=L.SIGMA_FIXED, flop_row=None,
-            update_f=None, update_ws=None):
+            update_f=None, update_ws=None, graphs=True):
     F = x.shape[1]
     net = NetShape(F, shapes, act=act, lik=lik)
     eng = Engine(net, device=0)
@@ -75,37 +75,44 @@ def mh_rate(name, x, y, xt, yt, shapes, act, lik, chains, steps, mask=None, sigm
             w = [a * m for a, m in zip(w, mask)]
         w0.append(w)
     eng.chains_init(w0, mask=mask, sigma_mode=sigma_mode, update_f=update_f, update_ws=update_ws, seed=7)
-    eng.mh_steps(max(3, steps // 10))
+    # chunks of at most 100 iterations per call, as run_mcmc / MC3 issue them (sampling_f / swap_frequency); the
+    # first call runs eagerly, the second captures the CUDA graph of the chunk, the timed ones replay it
+    chunk = min(100, steps)
+    if not graphs:
+        eng.set_option("graphs", 0)
+    for _ in range(3):
+        eng.mh_steps(chunk)
     eng.synchronize()
-    ms = timed(lambda: eng.mh_steps(steps))
+    ms = timed(lambda: [eng.mh_steps(chunk) for _ in range(steps // chunk)])
+    steps = steps // chunk * chunk
     st = eng.read_state(weights=False)
     n = x.shape[0] + (0 if xt is None else xt.shape[0])
     fr = flop_row if flop_row is not None else flop_per_row(shapes, F)
     out = {"config": name, "rows": int(n), "features": int(F), "shapes": [list(s) for s in shapes], "act": act, "chains": chains,
            "steps_timed": steps, "ms_per_step": ms / steps, "chain_steps_per_s": chains * steps / (ms * 1e-3),
            "algorithmic_flop_per_row": fr, "tflops": chains * steps * n * fr / (ms * 1e-3) / 1e12,
-           "kernel": eng.last_kernel, "logLik_finite": bool(np.all(np.isfinite(st.logLik))),
+           "cuda_graphs": bool(graphs), "kernel": eng.last_kernel, "logLik_finite": bool(np.all(np.isfinite(st.logLik))),
            "acceptance": float(np.mean(st.n_accepted / np.maximum(st.iteration, 1)))}
     eng.close()
     return out
 
 
-def c1(chains, steps):
+def c1(chains, steps, graphs=True):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((2500, 128))
     y = rng.integers(0, 5, 2500).astype(np.int32)
     sh = shapes_for(128, [5, 5], 5, 2)
     return mh_rate("c1 classify [5,5] tanh (C=%d)" % chains, x[:2250], y[:2250], x[2250:], y[2250:], sh, "tanh",
-                   L.LIK_CATEGORICAL, chains, steps)
+                   L.LIK_CATEGORICAL, chains, steps, graphs=graphs)
 
 
-def c2(chains, steps):
+def c2(chains, steps, graphs=True):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((999, 3))
     y = np.stack([x[:, 0] * 2 + x[:, 1], x[:, 2] - x[:, 0]], 1) + 0.1 * rng.standard_normal((999, 2))
     sh = shapes_for(3, [10, 5], 2, 2)
     return mh_rate("c2 regress [10,5] ReLU empirical sigma (C=%d)" % chains, x[:900], y[:900], x[900:], y[900:], sh, "ReLU",
-                   L.LIK_GAUSSIAN, chains, steps, sigma_mode=L.SIGMA_EMPIRICAL)
+                   L.LIK_GAUSSIAN, chains, steps, sigma_mode=L.SIGMA_EMPIRICAL, graphs=graphs)
 
 
 def c3_mask():
@@ -167,9 +174,9 @@ def main():
     only = set(args.only.split(","))
     res = []
     if "c1" in only:
-        res += [c1(1, 2000), c1(32, 1000)]
+        res += [c1(1, 2000, graphs=False), c1(1, 2000), c1(32, 1000)]
     if "c2" in only:
-        res += [c2(1, 2000), c2(32, 1000)]
+        res += [c2(1, 2000, graphs=False), c2(1, 2000), c2(32, 1000)]
     if "c3" in only:
         res += [c3(8, 40)]
     if "c5" in only:
