@@ -85,7 +85,7 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1,
 // ONE_STEP: argument reduction with the single rounded constant ln2/2^TB (one FMA instead of two).  The
 // reduced argument is then off by at most |x| * 3.4e-17, i.e. exp(x) by that relative amount -- harmless where
 // the exponential feeds a sigmoid: d swish / d r = z s (1-s) and d tanh / d r are bounded, so the activation
-// moves by < 1e-16 ABSOLUTE for every z.  Used by the activations only; the softmax keeps the two-step form.
+// moves by < 1e-16 ABSOLUTE for every z.  The softmax terms (arguments <= 0, see bnn_exp_neg) use it as well.
 template <int TB = BNN_EXP_TAB_BITS, bool ONE_STEP = false>
 __device__ __forceinline__ double bnn_exp_core(double x, const double* __restrict__ tab) {
   static_assert(TB == 8 || TB == 11, "exp table: 256 or 2048 entries");
@@ -119,6 +119,64 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
   return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
 
+// exp(SCALE * z) for SCALE = -1 (swish: exp(-z)) or 2 (tanh: exp(2z)) with the scale folded into the constants, so
+// that neither -z nor 2z is formed in an FP64 instruction (ptxas emits DADD for a negation that feeds an FMA chain).
+// One-step argument reduction as above (activations only); 7 FP64 instructions.
+//   rs = z - k * (C / SCALE)  (= r / SCALE, exact scaling);  exp(r) = 1 + p
+//   SCALE -1:  p = -rs + rs^2 (1/2 - rs/6)
+//   SCALE  2:  p = 2 [rs + rs^2 (1 + 2 rs / 3)], the factor 2 goes into the table value (exponent + 1, integer add)
+template <int TB, int SCALE>
+__device__ __forceinline__ double bnn_exp_scaled(double z, const double* __restrict__ tab) {
+  static_assert(TB == 8 || TB == 11, "exp table: 256 or 2048 entries");
+  static_assert(SCALE == -1 || SCALE == 2, "exp(-z) or exp(2z)");
+  const double MAGIC = 6755399441055744.0;
+  const double INV = (TB == 11) ? 2954.639443740597 : 369.3299304675746271;
+  const double C1 = (TB == 11) ? 0.0003384507717577858 : 0.0027076061740622863;      // ln2 / 2^TB
+  double t = fma(z, (double)SCALE * INV, MAGIC);
+  int k = __double2loint(t);
+  double kd = t - MAGIC;
+#ifdef BNN_DBG_NOTAB          // tuning experiment only: what do the table lookups (random shared-memory reads) cost?
+  double T = 1.0;
+#else
+  double T = tab[k & ((1 << TB) - 1)];
+#endif
+  double res;
+  if (SCALE == -1) {
+    double rs = fma(kd, C1, z);                       // = -r
+    double q = fma(rs, -1.66666666666666657e-01, 0.5);
+    double r2 = rs * rs;
+    double p = fma(r2, q, -rs);
+    res = fma(T, p, T);
+  } else {
+    double rs = fma(kd, -0.5 * C1, z);                // = r / 2
+    double q = fma(rs, 6.66666666666666630e-01, 1.0);
+    double r2 = rs * rs;
+    double p = fma(r2, q, rs);
+    const double T2 = __hiloint2double(__double2hiint(T) + (1 << 20), __double2loint(T));    // 2 T (T in [1, 2))
+    res = fma(T2, p, T);
+  }
+  int n = k >> TB;
+  return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
+}
+
+// the same with z clamped to +-708 / |SCALE| (selects on the integer view of z; NaN handling is the caller's)
+template <int TB, int SCALE>
+__device__ __forceinline__ double bnn_exp_scaled_clamped(double z, const double* __restrict__ tab) {
+  constexpr int THR = (SCALE == 2) ? 0x40762000 : 0x40862000;          // 354.0 / 708.0
+  const int hx = __double2hiint(z);
+  const bool big = (hx & 0x7fffffff) >= THR;                            // also inf / NaN
+  const double zc = big ? __hiloint2double((hx & 0x80000000) | THR, 0) : z;
+  return bnn_exp_scaled<TB, SCALE>(zc, tab);
+}
+
+// x is NaN, as integer instructions only (the 64-bit AND goes through inline PTX: written in C++, ptxas recognises
+// fabs() and materialises it with a DADD on the FP64 pipe)
+__device__ __forceinline__ bool bnn_is_nan_int(double x) {
+  unsigned long long a;
+  asm("and.b64 %0, %1, 0x7fffffffffffffff;" : "=l"(a) : "l"(__double_as_longlong(x)));
+  return a > 0x7ff0000000000000ULL;
+}
+
 // Branch-free range handling (selects on the integer view of x; no BSSY/BSYNC, so ptxas can interleave the
 // FP64 chains of several independent evaluations with the surrounding DMMAs).
 //
@@ -128,11 +186,13 @@ __device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict
   const int hx = __double2hiint(x);
   const int ax = hx & 0x7fffffff;
   const bool big = ax >= 0x4086232c;                  // |x| >= 708.3965 (also inf / NaN): exp(x) < 2^-1022
-  double res = bnn_exp_core<TB>(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
+  // one-step reduction: exp(x) is off by at most |x| * 3.4e-17 relative, i.e. a softmax term e^x <= 1 by at most
+  // 0.37 * 3.4e-17 absolute -- invisible in the row sum (>= 1) and 2e-14 relative in a probability of 1e-300
+  double res = bnn_exp_core<TB, true>(big ? -708.0 : x, tab);   // clamped so the exponent arithmetic stays in range
   res = big ? 0.0 : res;
   // NaN in => NaN out, by OR-ing quiet-NaN bits into the result (an integer op: a select here makes ptxas
   // branch around the whole evaluation, which breaks the interleaving with the surrounding MMAs)
-  const bool is_nan = ((unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL;
+  const bool is_nan = bnn_is_nan_int(x);
   return __hiloint2double(__double2hiint(res) | (is_nan ? 0x7ff80000 : 0), __double2loint(res));
 }
 
@@ -151,7 +211,11 @@ __device__ __forceinline__ double bnn_exp_clamped(double x, const double* __rest
 // BNN_RCP_NEWTON2 selects two Newton steps (4 instructions) instead.
 __device__ __forceinline__ double bnn_rcp(double d) {
   double y;
+#ifdef BNN_DBG_NOMUFU         // tuning experiment only: what does the MUFU seed cost?
+  y = __hiloint2double(0x7fe00000 - __double2hiint(d), 0);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#endif
   double e = fma(-d, y, 1.0);
 #ifndef BNN_RCP_NEWTON2
   e = fma(e, e, e);
@@ -199,12 +263,12 @@ __device__ __forceinline__ double bnn_act(double z, double alpha, const double* 
   if (ACT == BNN_ACT_SWISH) {
     // NaN: z * finite = NaN.  +-inf: inf * 1 = inf, -inf * ~0 -> the reference gives NaN (-inf * 0); here
     // -inf * 3e-308 = -inf.  Both poison the likelihood (NaN or -inf log-posterior => proposal rejected).
-    double e = bnn_exp_clamped<TB>(-z, tab);
+    double e = bnn_exp_scaled_clamped<TB, -1>(z, tab);
     return z * bnn_rcp(1.0 + e);
   }
-  double e = bnn_exp_clamped<TB>(2.0 * z, tab);
+  double e = bnn_exp_scaled_clamped<TB, 2>(z, tab);
   double r = fma(-2.0, bnn_rcp(e + 1.0), 1.0);
-  const bool is_nan = ((unsigned long long)__double_as_longlong(z) & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL;
+  const bool is_nan = bnn_is_nan_int(z);
   return __hiloint2double(__double2hiint(r) | (is_nan ? 0x7ff80000 : 0), __double2loint(r));
 }
 
@@ -221,8 +285,8 @@ template <int ACT>
 __device__ __forceinline__ double bnn_act_fast(double z, double alpha, const double* __restrict__ tab) {
   if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
-  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_core<BNN_EXP_TAB_BITS, true>(-z, tab));
-  return fma(-2.0, bnn_rcp(bnn_exp_core<BNN_EXP_TAB_BITS, true>(z + z, tab) + 1.0), 1.0);
+  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_scaled<BNN_EXP_TAB_BITS, -1>(z, tab));
+  return fma(-2.0, bnn_rcp(bnn_exp_scaled<BNN_EXP_TAB_BITS, 2>(z, tab) + 1.0), 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------
