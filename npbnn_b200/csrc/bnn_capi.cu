@@ -943,25 +943,35 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
     for (auto& gph : c->graphs)
       if (gph.n_steps == n_steps) { exec = gph.exec; per_launch = gph.launches; }
     if (!exec) {
+      // capture; any failure (a launch path that is not capturable on this driver) turns graphs off for this context
+      // and falls through to the eager sequence below -- never an error for the caller
       const long long l0 = c->launches;
-      if (!c->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
-      CUDA_TRY(cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = launch_mh_sequence(c, d, n_steps, c->capture_stream);
-      cudaGraph_t graph = nullptr;
-      const cudaError_t e = cudaStreamEndCapture(c->capture_stream, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      CUDA_TRY(e);
-      const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      CUDA_TRY(e2);
-      if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+      bool ok = true;
+      if (!c->capture_stream) ok = cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int rc = launch_mh_sequence(c, d, n_steps, c->capture_stream);
+        cudaGraph_t graph = nullptr;
+        ok = cudaStreamEndCapture(c->capture_stream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+        ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+      }
       per_launch = c->launches - l0;          // kernels in the sequence (counted while capturing, launched on replay)
       c->launches = l0;
-      c->graphs.push_back({n_steps, exec, per_launch});
+      if (!ok) {
+        cudaGetLastError();
+        c->opt_graphs = 0;
+        exec = nullptr;
+      } else {
+        if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        c->graphs.push_back({n_steps, exec, per_launch});
+      }
     }
-    CUDA_TRY(cudaGraphLaunch(exec, st));
-    c->launches += per_launch;
-    return 0;
+    if (exec) {
+      CUDA_TRY(cudaGraphLaunch(exec, st));
+      c->launches += per_launch;
+      return 0;
+    }
   }
   if (int rc = launch_mh_sequence(c, d, n_steps, st)) return rc;
   if (!inj) c->mh_warm = true;
