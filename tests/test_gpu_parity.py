@@ -347,6 +347,44 @@ def test_c4_full_size_properties():
     eng.close()
 
 
+def test_c5_full_size_prediction_properties():
+    """BASELINE config 5 shape at full row count (1M x 64 rows, 48 posterior samples; the 10k samples of the config are
+    the same kernel looped): size-independent properties of the posterior-prediction pass --
+      * mean probabilities and vote shares are distributions per row (sum to 1, votes are multiples of 1/S),
+      * the mean over all samples is the sample-weighted mean of the means over two disjoint sample batches,
+      * a row block predicted alone equals the same rows of the full pass bit for bit,
+      * an oracle check on 5,000 random rows."""
+    import torch
+    from npbnn_b200.engine import Engine, NetShape
+    from npbnn_b200 import workloads as wl
+    n, S = 1_000_000, 48
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(n, 64, dtype=torch.float64, device="cuda", generator=g)
+    rng = np.random.default_rng(6)
+    shapes = list(wl.C4_SHAPES)
+    sets = [[rng.normal(0, 0.25, s) for s in shapes] for _ in range(S)]
+    eng = Engine(NetShape.from_weights(sets[0], 64, act="swish", lik=0))
+    full = eng.predict(x, sets, mean=True, votes=True)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    mean, votes = full["mean"], full["votes"]
+    assert mean.shape == (n, 10) and np.all(mean >= 0)
+    assert np.allclose(mean.sum(1), 1.0, rtol=0, atol=1e-13) and np.allclose(votes.sum(1), 1.0, rtol=0, atol=1e-13)
+    assert np.allclose(votes * S, np.round(votes * S), rtol=0, atol=1e-9)
+    a = eng.predict(x, sets[:20], mean=True, votes=True)
+    b = eng.predict(x, sets[20:], mean=True, votes=True)
+    assert np.allclose((20 * a["mean"] + 28 * b["mean"]) / S, mean, rtol=1e-13, atol=1e-16)
+    assert np.allclose((20 * a["votes"] + 28 * b["votes"]) / S, votes, rtol=0, atol=1e-13)
+    blk = eng.predict(x[300_016:400_016], sets, mean=True, votes=True)
+    assert np.array_equal(blk["mean"], mean[300_016:400_016]) and np.array_equal(blk["votes"], votes[300_016:400_016])
+    idx = np.sort(rng.choice(n, 5_000, replace=False))
+    xs = x[torch.as_tensor(idx).cuda()].cpu().numpy()
+    _, mean_ref = orc.posterior_predict(xs, sets, "swish", None, "softmax", 1)
+    _, votes_ref = orc.posterior_predict(xs, sets, "swish", None, "softmax", 0)
+    assert np.allclose(mean[idx], mean_ref, rtol=1e-10, atol=1e-300)
+    assert np.array_equal(votes[idx], votes_ref)
+    eng.close()
+
+
 @pytest.mark.parametrize("n", [16, 130, 1000, 4099, 50000])
 def test_c4_shape_tensor_core_first_layer(n):
     """k_fwd3t: layer 1 as 21 exact int8 tensor-core products (Ozaki slices of X and W1, tcgen05 + TMEM) against
