@@ -199,3 +199,104 @@ def test_rowshard_exchange_two_ranks_gloo(tmp_path):
     assert np.array_equal(r0, r1)
     for it in range(3):
         np.testing.assert_allclose(r0[it], per_row.sum(axis=1) * (it + 1), rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-side logic of the Python surface that needs no device
+# ------------------------------------------------------------------------------------------------------
+def _toy_model(hyper_p=0, feature_indicators=None):
+    import npbnn_b200 as bn
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((60, 5))
+    y = rng.integers(0, 3, 60)
+    y[:3] = [0, 1, 2]
+    dat = {"data": x, "labels": y, "test_data": [], "test_labels": []}
+    np.random.seed(3)
+    return bn, bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="tanh"), use_bias_node=2, hyper_p=hyper_p,
+                        feature_indicators=feature_indicators)
+
+
+@pytest.mark.parametrize("hp", [1, 2, 3])
+def test_sample_prior_scale_is_the_oracle_draw(hp):
+    """npBNN.sample_prior_scale (host arithmetic, numpy's global generator) against the oracle's restatement of
+    BNN_mcmc.py:124-141 from the same generator state; the broadcast to one scale per entry follows calc_prior."""
+    from oracle import npbnn_oracle as orc
+    bn, bnn = _toy_model(hyper_p=hp)
+    assert bnn._scales_per_layer()
+    np.random.seed(11)
+    bnn.sample_prior_scale()
+    np.random.seed(11)
+    ref = orc.gibbs_prior_scales(bnn._w_layers, hp)
+    for a, b in zip(bnn._prior_scale, ref):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    e = bnn._entry_scales()
+    assert e.shape == (sum(w.size for w in bnn._w_layers),)
+    off = 0
+    for w, sc in zip(bnn._w_layers, ref):
+        assert np.array_equal(e[off:off + w.size].reshape(w.shape), np.broadcast_to(sc, w.shape))
+        off += w.size
+
+
+def test_data_transform_override_and_feature_means():
+    bn, bnn = _toy_model(feature_indicators=True)
+    assert np.array_equal(bnn._feature_indicators, np.ones(5, dtype=int))
+    assert np.allclose(bnn._feature_means, bnn._data.mean(axis=0))
+    dt = bn.data_transform_obj(np.array([1, 0, 1, 0, 1]), bnn._feature_means)
+    cols, vals = dt.override()
+    assert list(cols) == [1, 3] and np.array_equal(vals, bnn._feature_means[[1, 3]])
+
+
+def test_run_mcmc_stop_points_follow_the_reference_loop():
+    """run_mcmc batches iterations up to the next point at which the reference's loop does something: iteration 1
+    (first print), multiples of print_f and sampling_f, and the last iteration (BNN_mcmc.py:153-170)."""
+    from npbnn_b200 import api
+
+    class M:
+        _n_iterations, _print_f, _sampling_f = 95, 40, 25
+
+    it, stops = 0, []
+    while it < M._n_iterations:
+        it += api._next_stop(M, it)
+        stops.append(it)
+    assert stops == [1, 25, 40, 50, 75, 80, 95]
+
+
+class _FakeMCMC:                          # the attributes log_sample / log_weights read (module level: it is pickled)
+    def __init__(self):
+        self._logPost = self._logLik = self._logPrior = -1.0
+        self._accuracy = self._test_accuracy = 0.5
+        self._label_acc = np.array([0.5, 0.5, 0.5])
+        self._acceptance_rate, self._mcmc_id, self._n_post_samples = 0.3, 0, 5
+        self._current_iteration = 0
+
+
+def test_background_pickle_writer_keeps_the_newest_state(tmp_path):
+    """postLogger.begin_async / end_async: log_weights hands shallow snapshots to a writer thread that always writes the
+    newest one; after end_async the pickle on disk is the last logged state, and the logger pickles without its
+    thread state."""
+    import pickle
+    bn, bnn = _toy_model()
+
+    mc = _FakeMCMC()
+    logger = bn.postLogger(bnn, filename="bg", wdir=str(tmp_path))
+    logger.begin_async()
+    for it in range(1, 41):
+        mc._current_iteration = it
+        bnn._w_layers = [w + 1.0 for w in bnn._w_layers]          # rebinding, as _sync does
+        logger.log_sample(bnn, mc)
+        logger.log_weights(bnn, mc)
+    written = logger.end_async()
+    assert 1 <= written <= 40
+    with open(logger._pklfile, "rb") as f:
+        b2, m2, l2 = pickle.load(f)
+    assert m2._current_iteration == 40 and len(l2._post_weight_samples) == 5
+    assert [s["mcmc_it"] for s in l2._post_weight_samples] == [36, 37, 38, 39, 40]
+    for a, b in zip(b2._w_layers, bnn._w_layers):
+        assert np.array_equal(a, b)
+    assert "_async" not in l2.__dict__ or l2.__dict__["_async"] is None
+    assert len(open(logger._logfile).read().splitlines()) == 41
+    # synchronous mode again after end_async
+    mc._current_iteration = 41
+    logger.log_weights(bnn, mc)
+    with open(logger._pklfile, "rb") as f:
+        assert pickle.load(f)[1]._current_iteration == 41
