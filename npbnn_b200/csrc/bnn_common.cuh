@@ -121,7 +121,7 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
 
 // exp(SCALE * z) for SCALE = -1 (swish: exp(-z)) or 2 (tanh: exp(2z)) with the scale folded into the constants, so
 // that neither -z nor 2z is formed in an FP64 instruction (ptxas emits DADD for a negation that feeds an FMA chain).
-// One-step argument reduction as above (activations only); 7 FP64 instructions.
+// One-step argument reduction as above (activations only); 7 FP64 instructions (8 with the 256-entry table).
 //   rs = z - k * (C / SCALE)  (= r / SCALE, exact scaling);  exp(r) = 1 + p
 //   SCALE -1:  p = -rs + rs^2 (1/2 - rs/6)
 //   SCALE  2:  p = 2 [rs + rs^2 (1 + 2 rs / 3)], the factor 2 goes into the table value (exponent + 1, integer add)
@@ -143,13 +143,25 @@ __device__ __forceinline__ double bnn_exp_scaled(double z, const double* __restr
   double res;
   if (SCALE == -1) {
     double rs = fma(kd, C1, z);                       // = -r
-    double q = fma(rs, -1.66666666666666657e-01, 0.5);
+    double q;
+    if (TB == 11) {
+      q = fma(rs, -1.66666666666666657e-01, 0.5);
+    } else {                                          // 256 entries: |r| <= ln2/512 needs the fourth-order term
+      q = fma(rs, 4.16666666666666644e-02, -1.66666666666666657e-01);
+      q = fma(rs, q, 0.5);
+    }
     double r2 = rs * rs;
     double p = fma(r2, q, -rs);
     res = fma(T, p, T);
   } else {
     double rs = fma(kd, -0.5 * C1, z);                // = r / 2
-    double q = fma(rs, 6.66666666666666630e-01, 1.0);
+    double q;
+    if (TB == 11) {
+      q = fma(rs, 6.66666666666666630e-01, 1.0);
+    } else {
+      q = fma(rs, 3.33333333333333315e-01, 6.66666666666666630e-01);
+      q = fma(rs, q, 1.0);
+    }
     double r2 = rs * rs;
     double p = fma(r2, q, rs);
     const double T2 = __hiloint2double(__double2hiint(T) + (1 << 20), __double2loint(T));    // 2 T (T in [1, 2))
