@@ -1921,7 +1921,7 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
         if (p.class_w || p.inst_w) return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK_W>(p, n_sms, st);
         return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK>(p, n_sms, st);
       }
-      if (predict) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, 8, FWD3_PRED>(p, n_sms, st);
+      if (predict) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_PRED>(p, n_sms, st);
       if (p.class_w || p.inst_w) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK_W>(p, n_sms, st);
       return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK>(p, n_sms, st);
     }
