@@ -456,3 +456,38 @@ def test_predict_and_pdp_with_feature_transform():
         res = bn.get_pdp(x, [focal], "classification", 3, af, bn.SoftMax, post, [[0.0]] * S, dt)
         assert np.array_equal(res["feature"], z["pdp%d_feature" % focal])
         assert np.allclose(res["pdp"], z["pdp%d" % focal], rtol=1e-9, atol=1e-12)
+
+
+def test_philox_chains_agree_statistically_at_the_c4_shape():
+    """The same statistical comparison on the BASELINE config-4 network ([64,32] swish, 64 features, 10 classes, bias on
+    the last layer; 20,000 rows), i.e. through the shape-specialised forward kernel and the 1,024-thread update kernel:
+    3 chains x 1,500 iterations each way (burn-in 700, every 10th state), posterior means of log-likelihood and accuracy
+    within between-chain Monte-Carlo error."""
+    import npbnn_b200 as bn
+    from npbnn_b200 import workloads as wl
+    x, labels = wl.c4_data(22_000, seed=4)
+    dat = {"data": x[:20_000], "labels": labels[:20_000].astype(int), "test_data": x[20_000:], "test_labels": labels[20_000:].astype(int)}
+    out = {}
+    for mode in ("host", "philox"):
+        per_chain = []
+        for ch in range(3):
+            np.random.seed(40 + ch)
+            bnn = bn.npBNN(dat, n_nodes=[64, 32], actFun=bn.ActFun(fun="swish"), use_bias_node=-1, seed=40 + ch)
+            mcmc = bn.MCMC(bnn, n_iteration=1500, rng=mode, mcmc_id=ch)
+            mcmc._rs = np.random.default_rng(900 + ch)
+            rows = []
+            for it in range(150):
+                mcmc.run(bnn, 10)
+                if it >= 70:
+                    rows.append([mcmc._logLik, mcmc._accuracy, mcmc._test_accuracy, mcmc._acceptance_rate])
+            assert mcmc._group.eng.last_kernel.startswith("k_fwd3<")
+            per_chain.append(np.mean(rows, axis=0))
+        per_chain = np.array(per_chain)
+        out[mode] = (per_chain.mean(0), per_chain.std(0, ddof=1) / np.sqrt(3.0))
+    (mh, sh), (mp, sp) = out["host"], out["philox"]
+    se = np.sqrt(sh ** 2 + sp ** 2)
+    gap = np.abs(mh - mp)
+    print("host", mh, "philox", mp, "gap", gap, "se", se)
+    assert gap[0] < max(4 * se[0], 0.01 * abs(mh[0]))            # log-likelihood
+    assert gap[1] < max(4 * se[1], 0.01) and gap[2] < max(4 * se[2], 0.02)
+    assert gap[3] < 0.15
