@@ -834,10 +834,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 
   long long q = 0;
   uint32_t x_uses = 0;               // X tiles this warp has loaded (parity of its mbarrier)
+  bool x_prefetched = false;         // the X tile of this iteration was requested during the previous one
+  auto tile_of = [&](long long i) -> long long {             // 16-row tile of this warp in iteration i
+    const int s2 = (int)(i - n_full);
+    return s2 < 0 ? i * total_warps + (long long)blockIdx.x * NWARPS + warp
+                  : tail_base + (long long)(s2 == 0 ? seg_tg[0] : seg_tg[1]) * NWARPS + warp;
+  };
   for (long long it = 0; it < n_iter; ++it) {
     const int sg = (int)(it - n_full);                       // tail segment (>= 0) or full round (< 0)
-    const long long wt = sg < 0 ? it * total_warps + (long long)blockIdx.x * NWARPS + warp
-                                : tail_base + (long long)(sg == 0 ? seg_tg[0] : seg_tg[1]) * NWARPS + warp;
+    const long long wt = tile_of(it);
     const int c_lo = sg < 0 ? 0 : (sg == 0 ? seg_lo[0] : seg_lo[1]);
     const int c_hi = sg < 0 ? p.C : (sg == 0 ? seg_hi[0] : seg_hi[1]);
     const bool have_tile = wt < p.n_tiles16;
@@ -850,12 +855,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #pragma unroll
     for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
     if (have_tile) {
-      if (lane == 0) {
+      if (lane == 0 && !x_prefetched) {
         // order this warp's earlier generic-proxy reads of xs before the async-proxy overwrite
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(xbar, X_BYTES);
         bulk_g2s(xs, p.x + wt * 16 * KP0, X_BYTES, xbar);
       }
+      x_prefetched = false;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const long long row = wt * 16 + gq + 8 * h;
@@ -963,6 +969,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               dmma16x8x8(acc1[j], alo0.x, ahi0.x, alo0.y, ahi0.y, b0.x, b0.y);
               dmma16x8x8(acc1[j], alo1.x, ahi1.x, alo1.y, ahi1.y, b1.x, b1.y);
             }
+          }
+        }
+        // X is read by layer 1 only: after layer 1 of the tile's LAST weight set the buffer is free, and the next
+        // tile's X (one bulk copy, ~2 us from HBM) arrives under layers 2 / 3 and the epilogue instead of stalling
+        // the start of the next tile -- 0.4 % of a 32-set tile, but 3 % at 4 sets per GPU and 12 % for a single chain.
+        if (c == c_hi - 1 && it + 1 < n_iter) {
+          const long long wt_next = tile_of(it + 1);
+          if (wt_next < p.n_tiles16) {
+            __syncwarp();                                      // every lane's reads of xs are done
+            if (lane == 0) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              mbar_arrive_expect_tx(xbar, X_BYTES);
+              bulk_g2s(xs, p.x + wt_next * 16 * KP0, X_BYTES, xbar);
+            }
+            x_prefetched = true;
           }
         }
         // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = activated acc1, no data movement).
