@@ -840,6 +840,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
     return s2 < 0 ? i * total_warps + (long long)blockIdx.x * NWARPS + warp
                   : tail_base + (long long)(s2 == 0 ? seg_tg[0] : seg_tg[1]) * NWARPS + warp;
   };
+  // Likelihood modes: the epilogue of a (tile, weight set) is software-pipelined into layer 1 of the NEXT weight set
+  // this warp runs -- also across a tile boundary, so that a tile's last set is not finished in a phase of its own
+  // (that phase is 1/32 of a tile at 32 sets per GPU, but a quarter at 4 and everything for a single chain).
+  // acc3 / ep_* describe the pending epilogue: last-layer accumulators, tile, weight set, labels (and weights).
+  double acc3[N3 / 8][4];
+  bool prev_valid = false;
+  long long ep_wt = 0;
+  int ep_c = 0;
+  int ep_y[2] = {0, 0};
+  double ep_wgt[2] = {1.0, 1.0};
+#pragma unroll
+  for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
   for (long long it = 0; it < n_iter; ++it) {
     const int sg = (int)(it - n_full);                       // tail segment (>= 0) or full round (< 0)
     const long long wt = tile_of(it);
@@ -850,10 +862,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
     double wgt[2] = {1.0, 1.0};
     double pacc[2][N3 / 4];
     int pvote[2][N3 / 4];
-    double acc3[N3 / 8][4];          // last-layer accumulators of the previous weight set (likelihood modes)
-    bool prev_valid = false;
-#pragma unroll
-    for (int j = 0; j < N3 / 8; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.0;
     if (have_tile) {
       if (lane == 0 && !x_prefetched) {
         // order this warp's earlier generic-proxy reads of xs before the async-proxy overwrite
@@ -922,7 +930,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
             if (!PREDICT) {
               if (kg == 0) qs_max<N3>(acc3, K, t, rs);
-              else qs_exp<N3, 1, true>(acc3, K, t, y, tab, rs);
+              else qs_exp<N3, 1, true>(acc3, K, t, ep_y, tab, rs);
             }
 #pragma unroll
             for (int j = 0; j < N1 / 16; ++j) {
@@ -930,10 +938,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
             }
             if (!PREDICT) {
-              if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, y, tab, rs);
+              if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, ep_y, tab, rs);
               else {
                 qs_reduce<N3, true>(rs);
-                lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, prev_valid);
+                lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, ep_wt, lane, rs, ep_y, ep_wgt, prev_valid);
               }
             }
 #pragma unroll
@@ -943,7 +951,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
 #ifndef BNN_DBG_NOCOMMIT      // tuning experiment only: counters / partial store of the previous set
-          if (!PREDICT) quad_lik_commit<N3>(p, c - 1, wt, lane, cnt, lr, prev_valid);
+          if (!PREDICT) quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, prev_valid);
 #endif
 #pragma unroll 2
           for (int kg = 2; kg < KP0 / 8 - 2; ++kg) {
@@ -1063,20 +1071,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[b]);
-        prev_valid = true;
+        if (!PREDICT) {
+          prev_valid = true;
+          ep_wt = wt; ep_c = c;
+          ep_y[0] = y[0]; ep_y[1] = y[1];
+          if (MODE == FWD3_LIK_W) { ep_wgt[0] = wgt[0]; ep_wgt[1] = wgt[1]; }
+        }
         if (PREDICT) quad_epilogue_pred<N3>(p, c, wt, lane, acc3, tab, pacc, pvote);
       } else {
         if (lane == 0) mbar_arrive(&empty[b]);
       }
     }
     if (have_tile) {
-      // drain the software pipeline: epilogue of the last weight set of this tile
-      if (!PREDICT) {
-        RowStats<N3> rs;
-        quad_softmax_stats<N3, true>(acc3, g.K, t, y, tab, rs);
-        const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, wt, lane, rs, y, wgt, true);
-        quad_lik_commit<N3>(p, c_hi - 1, wt, lane, cnt, lr, true);
-      }
       if (PREDICT) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1094,6 +1100,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         }
       }
     }
+  }
+  // drain the software pipeline: the epilogue of the last (tile, weight set) this warp ran
+  if (!PREDICT && prev_valid) {
+    RowStats<N3> rs;
+    quad_softmax_stats<N3, true>(acc3, g.K, t, ep_y, tab, rs);
+    const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, ep_wt, lane, rs, ep_y, ep_wgt, true);
+    quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, true);
   }
   if (n_cnt) {
     __syncthreads();
