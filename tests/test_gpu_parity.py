@@ -285,6 +285,35 @@ def test_c4_shape_tail_round_split(n, n_sets):
     eng.close()
 
 
+@pytest.mark.parametrize("kind", ["class", "instance"])
+@pytest.mark.parametrize("n,n_sets", [(4099, 1), (50000, 5)])
+def test_c4_shape_weighted_likelihood(kind, n, n_sets):
+    """The weighted-likelihood instantiation of the shape-specialised kernel (class weights, BNN_env.py:97-100, or
+    instance weights, BNN_lib.py:103-118) at the config-4 shape: sizes with one and with several weight sets per tile,
+    full rounds plus a split tail, so that the epilogue carried across tile boundaries sees the right labels and
+    weights.  Against the oracle and the generic kernel."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(n, n_sets, seed=12)
+    rng = np.random.default_rng(1)
+    cw = rng.uniform(0.5, 2.0, 10) if kind == "class" else None
+    iw = rng.uniform(0.2, 1.8, n) if kind == "instance" else None
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x, labels, inst_w=iw, class_w=cw)
+    res = eng.forward_lik(sets, lik_temp=0.9)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    eng.set_option("force_generic", 1)
+    gen = eng.forward_lik(sets, lik_temp=0.9)
+    assert eng.last_kernel == "k_fwd_generic"
+    for i, w in enumerate(sets):
+        y = orc.forward(x, w, "swish", None, "softmax")
+        ref = orc.loglik_categorical(y, labels, cw, iw, 0.9)
+        assert rel_close(res["loglik"][i], ref), (i, res["loglik"][i], ref)
+        assert rel_close(gen["loglik"][i], ref)
+        assert res["counts"][i][0] == orc.class_counters(y, labels)[0]
+    eng.close()
+
+
 def test_c4_full_size_properties():
     """BASELINE config 4 at FULL size (1M x 64, 32 weight sets): the oracle cannot score this in seconds, so
     parity is carried by size-independent properties of the likelihood pass --
