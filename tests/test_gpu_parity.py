@@ -314,6 +314,27 @@ def test_c4_shape_weighted_likelihood(kind, n, n_sets):
     eng.close()
 
 
+def test_c4_shape_train_and_test_rows_in_one_pass():
+    """Training rows and test rows are staged back to back and scored in one pass (test rows only feed the test-accuracy
+    counter, RunPredictInd on accept, BNN_env.py:511-515).  Config-4 shape with a train / test boundary inside a warp
+    tile and several weight sets: log-likelihood over the training rows only, both accuracy counters exact."""
+    from npbnn_b200.engine import Engine, NetShape
+    x, labels, sets = _c4_like(30_011 + 3_005, 4, seed=14)
+    n_tr = 30_011
+    net = NetShape.from_weights(sets[0], 64, act="swish", lik=0)
+    eng = Engine(net)
+    eng.set_data(x[:n_tr], labels[:n_tr], x[n_tr:], labels[n_tr:])
+    res = eng.forward_lik(sets)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    for i, w in enumerate(sets):
+        y = orc.forward(x, w, "swish", None, "softmax")
+        assert rel_close(res["loglik"][i], orc.loglik_categorical(y[:n_tr], labels[:n_tr]))
+        assert res["counts"][i][0] == orc.class_counters(y[:n_tr], labels[:n_tr])[0]
+        assert res["counts"][i][1] == orc.class_counters(y[n_tr:], labels[n_tr:])[0]
+        assert np.array_equal(res["counts"][i][12:22], orc.class_counters(y[:n_tr], labels[:n_tr])[3])
+    eng.close()
+
+
 def test_c4_full_size_properties():
     """BASELINE config 4 at FULL size (1M x 64, 32 weight sets): the oracle cannot score this in seconds, so
     parity is carried by size-independent properties of the likelihood pass --
