@@ -11,7 +11,34 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CHAIN_CASES = ["c1_classify", "c2_regress_emp1", "c2_regress_emp0", "syn_swish_cauchy", "syn_genrelu_laplace",
                "syn_uniform_bound", "syn_classw_temp", "syn_instw", "syn_adapt", "syn_block_mask",
-               "syn_regress_error", "syn_trainable_genrelu", "syn_trainable_tanh"]
+               "syn_regress_error", "syn_trainable_genrelu", "syn_trainable_tanh", "syn_c4_shape"]
+
+
+class ChainView:
+    """One chain of a multi-chain golden file (syn_c3_shape): keys are looked up as 'c<chain>_<key>' first, then as
+    the shared '<key>' (data, masks), so the single-chain helpers below work on it unchanged."""
+
+    def __init__(self, z, chain):
+        self._z, self._p = z, "c%d_" % chain
+        self.files = [k[len(self._p):] if k.startswith(self._p) else k for k in z.files]
+
+    def __getitem__(self, key):
+        return self._z[self._p + key] if self._p + key in self._z.files else self._z[key]
+
+
+def stack_injections(per_chain):
+    """Injection arrays of several single-chain replays -> one batch with the chains side by side."""
+    cap = max(a["ix"].shape[2] for a in per_chain)
+    out = {}
+    for k in per_chain[0]:
+        parts = []
+        for a in per_chain:
+            v = a[k]
+            if k in ("ix", "iy", "dz") and v.shape[2] < cap:
+                v = np.concatenate([v, np.zeros(v.shape[:2] + (cap - v.shape[2],), v.dtype)], axis=2)
+            parts.append(v)
+        out[k] = np.ascontiguousarray(np.concatenate(parts, axis=1))
+    return out
 
 
 def load(name):

@@ -60,8 +60,11 @@ def quiet(f, *a, **k):
         return f(*a, **k)
 
 
-def record_chain(bnn, mcmc, n_steps, out, prefix=""):
-    """Run n_steps of the reference's mh_step, recording injections and outcomes."""
+def record_chain(bnn, mcmc, n_steps, out, prefix="", rs_seed=None):
+    """Run n_steps of the reference's mh_step, recording injections and outcomes.
+    rs_seed: give this chain its own proposal stream (every MCMC object starts from default_rng(1234), BNN_env.py:362)."""
+    if rs_seed is not None:
+        mcmc._rs = np.random.default_rng(rs_seed)
     rec = RecRNG(mcmc._rs)
     mcmc._rs = rec
     lik_log, prior_log = [], []
@@ -542,10 +545,52 @@ def case_indicators(kind, n_steps=80, seed=13):
                                         adapt_stop=5, n_iteration=1000))
 
 
+C3_MASK_SPEC = ([list(range(40)), sum(([g] * 3 for g in range(40)), []), []], [[3] * 40, [2] * 40, []])
+
+
+def case_c4_shape(n=4000, n_test=500, n_steps=60, seed=41):
+    """BASELINE config 4's network at a size the reference runs in seconds: F=64, [64,32] swish, K=10, bias -1
+    (bnn_runner_MC3.py:28-34) -- the shape k_fwd3 and the 1,024-thread k_mh_update are compiled for."""
+    case_synth("syn_c4_shape", n=n, f=64, k=10, n_nodes=(64, 32), act="swish", bias=-1, n_test=n_test, n_steps=n_steps,
+               seed=seed, n_iteration=10000)
+
+
+def case_c3_shape(n=2000, n_test=200, n_steps=40, n_chains=8, seed=43):
+    """BASELINE config 3's network (block_bnns.py:39-81 pattern at SURVEY.md 8d's size): F=40, [120,80] tanh, K=5,
+    bias -1, each feature -> 3 nodes -> 2 nodes; 8 chains over the same data, chain c initialised after
+    np.random.seed(1000+c) and proposing from its own generator default_rng(1234+c)."""
+    dat = synth_class(n, 40, 5, seed, n_test)
+    out = {}
+    store_data(out, dat)
+    for c in range(n_chains):
+        np.random.seed(1000 + c)
+        bnn = quiet(bn.npBNN, dat, n_nodes=[120, 80], actFun=bn.ActFun(fun="tanh"), use_bias_node=-1, prior_f=1,
+                    p_scale=1, seed=1000 + c)
+        m = bn.create_mask(bnn._w_layers, indx_input_list=C3_MASK_SPEC[0], nodes_per_feature_list=C3_MASK_SPEC[1])
+        quiet(bnn.apply_mask, m)
+        if c == 0:
+            for i, mm in enumerate(m):
+                out["mask_%d" % i] = mm.astype(np.int8)
+        mcmc = bn.MCMC(bnn, n_iteration=10000, mcmc_id=c)
+        record_chain(bnn, mcmc, n_steps, out, prefix="c%d_" % c, rs_seed=1234 + c)
+    meta = dict(act="tanh", alphas=None, mode="classification", prior=1, p_scale=1.0, use_bias_node=-1, n_nodes=[120, 80],
+                update_f=[0.05] * 3, update_ws=[0.075] * 3, n_iteration=10000, adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000,
+                temperature=1.0, lik_temp=1.0, w_bound=float("inf"), n_chains=n_chains)
+    save("syn_c3_shape", out, meta)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hyper":          # regenerate only the hyper-prior cases
         for hp in (1, 2, 3):
             case_hyper(hp)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "shapes":          # the two headline network shapes
+        case_c4_shape()
+        case_c3_shape()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":              # BASELINE config 2 only
+        case_c2(True)
+        case_c2(False)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "indicators":
         for kind in ("weight", "feature", "both"):
@@ -579,3 +624,5 @@ if __name__ == "__main__":
     for kind in ("weight", "feature", "both"):
         case_indicators(kind)
     case_predict_transform()
+    case_c4_shape()
+    case_c3_shape()

@@ -185,6 +185,94 @@ def test_chain_replay_one_launch(name):
     eng.close()
 
 
+def test_headline_shape_goldens_run_on_the_specialised_kernels():
+    """The reference-generated goldens of the two headline network shapes go through the kernels the bench times:
+    syn_c4_shape ([64,32] swish, K=10) -> k_fwd3, syn_c3_shape (block-masked [120,80] tanh) -> k_fwd_sparse."""
+    z, meta = G.load("syn_c4_shape")
+    m = G.build_model(z, meta)
+    eng = make_engine(m)
+    _init_chains(eng, m, meta, 2)
+    eng.mh_steps(2, G.injection_arrays(z, meta, 0, 2, 2))
+    eng.synchronize()
+    assert eng.last_kernel.startswith("k_fwd3"), eng.last_kernel
+    eng.close()
+    z, meta = G.load("syn_c3_shape")
+    v = G.ChainView(z, 0)
+    m = G.build_model(v, meta)
+    eng = make_engine(m)
+    _init_chains(eng, m, meta, 2)
+    eng.mh_steps(2, G.injection_arrays(v, meta, 0, 2, 2))
+    eng.synchronize()
+    assert eng.last_kernel.startswith("k_fwd_sparse"), eng.last_kernel
+    eng.close()
+
+
+def _c3_golden():
+    z, meta = G.load("syn_c3_shape")
+    views = [G.ChainView(z, c) for c in range(meta["n_chains"])]
+    models = [G.build_model(v, meta) for v in views]
+    return z, meta, views, models
+
+
+def test_c3_shape_eight_chains_step_by_step():
+    """BASELINE config 3's network at its real shape (F=40, block-masked [120,80] tanh, K=5, 8 chains batched on one
+    GPU), against the reference's own recorded chains (tests/golden/make_golden.py: case_c3_shape): every chain has
+    its own initial weights and its own proposal stream; all 8 run in ONE k_fwd_sparse pass per iteration."""
+    z, meta, views, models = _c3_golden()
+    nc = len(models)
+    m0 = models[0]
+    eng = make_engine(m0)
+    nl = len(m0.weights)
+    eng.chains_init([m.weights for m in models], temperature=1.0, update_f=meta["update_f"], update_ws=meta["update_ws"],
+                    prior=1, prior_scale=1.0, mask=m0.mask, adapt_stop=int(meta["n_iteration"] * 0.05))
+    st = eng.read_state()
+    N, Nt = m0.x.shape[0], m0.x_test.shape[0]
+    for c, v in enumerate(views):
+        assert rel_close(st.logLik[c], float(v["init_logLik"])) and rel_close(st.logPrior[c], float(v["init_logPrior"]))
+        assert np.array_equal(st.update_n[c], v["init_update_n"])
+        assert st.n_correct[c] / N == float(v["init_accuracy"])
+    T = int(views[0]["n_steps"])
+    for t in range(T):
+        eng.mh_steps(1, G.stack_injections([G.injection_arrays(v, meta, t, t + 1, 1) for v in views]))
+        assert eng.last_kernel.startswith("k_fwd_sparse"), eng.last_kernel
+        st = eng.read_state()
+        for c, v in enumerate(views):
+            assert rel_close(st.logLik_prop[c], v["steps_logLik_prime"][t]), (t, c)
+            assert rel_close(st.logPrior_prop[c], v["steps_logPrior_prime"][t]), (t, c)
+            assert st.last_accepted[c] == int(v["steps_accepted"][t]), (t, c)
+            assert rel_close(st.logLik[c], v["steps_logLik"][t]) and rel_close(st.logPost[c], v["steps_logPost"][t])
+            assert st.n_correct[c] / N == float(v["steps_accuracy"][t])
+            assert st.n_correct_test[c] / Nt == float(v["steps_test_accuracy"][t])
+            assert np.array_equal(st.pred_hist[c] / N, v["steps_label_freq"][t])
+            assert abs(st.acceptance_rate[c] - float(v["steps_acceptance_rate"][t])) < 1e-15
+    for c, v in enumerate(views):
+        for i, w in enumerate(st.weights(c)):
+            assert np.array_equal(w, v["wN_%d" % i]), (c, i)
+            assert np.all(w[m0.mask[i] == 0] == 0)
+    eng.close()
+
+
+def test_c3_shape_eight_chains_one_launch():
+    z, meta, views, models = _c3_golden()
+    m0 = models[0]
+    eng = make_engine(m0)
+    eng.chains_init([m.weights for m in models], update_f=meta["update_f"], update_ws=meta["update_ws"], prior=1,
+                    prior_scale=1.0, mask=m0.mask, adapt_stop=int(meta["n_iteration"] * 0.05))
+    T = int(views[0]["n_steps"])
+    eng.mh_steps(T, G.stack_injections([G.injection_arrays(v, meta, 0, T, 1) for v in views]))
+    st = eng.read_state()
+    assert eng.last_kernel.startswith("k_fwd_sparse"), eng.last_kernel
+    for c, v in enumerate(views):
+        assert st.n_accepted[c] == int(np.sum(v["steps_accepted"]))
+        for i, w in enumerate(st.weights(c)):
+            assert np.array_equal(w, v["wN_%d" % i]), (c, i)
+        assert rel_close(st.logLik[c], v["steps_logLik"][T - 1]) and rel_close(st.logPrior[c], v["steps_logPrior"][T - 1])
+    # the final predictions of chain 0 against the reference's mcmc._y
+    y = eng.predict(m0.x, [st.weights(0)], mean=False, dense=True)["dense"][0]
+    assert np.allclose(y, views[0]["yN"], rtol=1e-10, atol=1e-300)
+    eng.close()
+
+
 def test_predict_matches_reference_goldens():
     from npbnn_b200.engine import Engine, NetShape
     z, meta = G.load("predict")
