@@ -15,7 +15,7 @@ Chains are sharded over ranks (32 / N per GPU, strong scaling); the only exchang
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference algorithm (numpy oracle port) on the host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (oracle/_ref, oracle/make_ref.py) on the host cores
 """
 import argparse
 import json
@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--chains", type=int, default=N_CHAINS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mc3-leg", action="store_true", help="reference arm: skip the np_bnn.MC3.run_mcmc() swap period")
     return ap.parse_args()
 
 
@@ -98,28 +99,62 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def reference_arm(args, rank, world):
-    """The reference's algorithm on the host cores (numpy oracle port): bounded sample per step."""
-    if rank != 0:
-        return
+def run_reference(rows, steps, warmup, chains=N_CHAINS, mc3_period=0, timeout=3000):
+    """The UNMODIFIED reference (oracle/_ref/np_bnn, installed by oracle/make_ref.py) on the host cores, in a
+    subprocess so that `import np_bnn` is the reference and not this repository's drop-in.  Returns the JSON object
+    of oracle/ref_baseline.py, or None when oracle/_ref is absent."""
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "np_bnn", "__init__.py")):
+        return None
+    env = dict(os.environ)
+    for k in ("PYTHONPATH", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_baseline.py"), "--rows", str(rows), "--steps", str(steps),
+           "--warmup", str(warmup), "--chains", str(chains), "--mc3-period", str(mc3_period)]
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr[-2000:])
+        raise RuntimeError("oracle/ref_baseline.py failed (rc %d)" % r.returncode)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def port_baseline(rows, steps, seconds):
+    """Fallback when oracle/_ref is absent: the numpy oracle port on a row sample (kind "port")."""
     from npbnn_b200 import workloads as wl
     from oracle import cpu_baseline
-    x, labels = wl.c4_data(min(args.rows, CPU_SAMPLE_ROWS), seed=0)
-    K = max(1, args.steps)
+    x, labels = wl.c4_data(min(rows, CPU_SAMPLE_ROWS), seed=0)
+    res = cpu_baseline.mh_rate(x, labels.astype(np.int64), wl.C4_SHAPES, "swish", rows, steps_per_proc=steps, seconds=seconds)
+    return {"value": res["value"], "unit": "chain-steps/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]}
+
+
+def reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.
+    A "step" is one np_bnn.MCMC.mh_step of every chain (min(32, cores) forked chains, all 1,000,000 rows)."""
+    if rank != 0:
+        return
+    K, W = max(1, args.steps), max(0, args.warmup)
     t0 = time.perf_counter()
-    # each "step" = one MH iteration of min(32, cores) chains on the row sample
-    res = cpu_baseline.mh_rate(x, labels.astype(np.int64), wl.C4_SHAPES, "swish", args.rows,
-                               steps_per_proc=K, seconds=30.0 + 5.0 * K)
+    ref = run_reference(args.rows, K, W, chains=args.chains, mc3_period=min(K, 5) if not args.no_mc3_leg else 0)
     wall = time.perf_counter() - t0
-    line = {"impl": "reference", "metric": "MH iterations/sec (chains x steps / s)", "value": res["value"],
-            "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
-            "ms_per_step": 1e3 * res["cores"] / res["value"] if res["value"] else None,
+    if ref is None:
+        cpu = port_baseline(args.rows, K, 30.0 + 5.0 * K)
+        value, ms_per_step, extra = cpu["value"], 1e3 * cpu["cores"] / cpu["value"], {}
+    else:
+        value = ref["value"]
+        ms_per_step = 1e3 * ref["chains_leg"]["wall_s"] / K
+        cpu = {"value": value, "unit": "chain-steps/s", "cores": ref["chains"], "kind": "reference", "sample": ref["sample"]}
+        extra = {"reference": {k: ref.get(k) for k in ("reference_version", "cores", "chains", "numpy",
+                                                       "blas_threads_per_process", "chains_leg", "mc3_leg")}}
+    cfg = workload_config(args)
+    line = {"impl": "reference", "metric": "MH iterations/sec (chains x steps / s)", "value": value,
+            "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": res["value"], "unit": "chain-steps/s", "cores": res["cores"], "kind": "port",
-                             "sample": res["sample"]},
-            "e2e": {"value": res["value"], "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": cfg, "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
+    line.update(extra)
     _emit(line)
 
 
@@ -426,11 +461,13 @@ def main():
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline
-        ns = min(args.rows, CPU_SAMPLE_ROWS)
-        cpu = cpu_baseline.mh_rate(x_np[:ns], y_np[:ns].astype(np.int64), wl.C4_SHAPES, "swish", args.rows,
-                                   steps_per_proc=3, seconds=20.0)
-        cpu = {"value": cpu["value"], "unit": "chain-steps/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+        # bounded sample: 3 MH iterations per chain (after 1 warm-up) of the unmodified reference on all rows
+        ref = run_reference(args.rows, 3, 1, chains=args.chains)
+        if ref is None:
+            cpu = port_baseline(args.rows, 3, 20.0)
+        else:
+            cpu = {"value": ref["value"], "unit": "chain-steps/s", "cores": ref["chains"], "kind": "reference",
+                   "sample": ref["sample"], "wall_s": ref["chains_leg"]["wall_s"]}
 
     if rank == 0:
         line = {"metric": "MH iterations/sec (chains x steps / s)", "value": value, "unit": "chain-steps/s",

@@ -1,10 +1,10 @@
 """CPU baseline timing of the hot path with the numpy oracle -- TEST/BENCH INFRASTRUCTURE ONLY.
 
-bench.py's `cpu_baseline` leg and `--impl reference` arm call this.  The reference is pure Python/numpy
-and cannot travel to the GPU box, so its algorithm is timed through the oracle port (same numpy
-operations: np.dot, the `(1+exp(-z))**-1` swish, exp/sum softmax, fancy-index gather + log).  One
-process per chain on its own core, like the reference's MC3 fork pool (BNN_mc3.py:89-96) but without its
-pickling of the data every swap period -- i.e. generous to the reference.
+FALLBACK of bench.py's `cpu_baseline` leg and `--impl reference` arm: they time the unmodified reference
+(oracle/_ref, oracle/ref_baseline.py) and only use this port (kind "port") when oracle/_ref is absent.  Same numpy
+operations as the reference (np.dot, the `(1+exp(-z))**-1` swish, exp/sum softmax, fancy-index gather + log), one
+process per chain on its own core like the reference's MC3 fork pool (BNN_mc3.py:89-96), on a row sample rescaled
+linearly in rows; kept as a cross-check of the reference timing.
 """
 import multiprocessing as mp
 import os
