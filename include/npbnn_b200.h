@@ -72,7 +72,8 @@ typedef struct {
   double prior_scale[BNN_MAX_LAYERS];  /* npBNN._prior_scale (one scalar per layer) */
   uint64_t seed;                       /* Philox key for free-running proposals */
   int32_t n_act_prm;                   /* ActFun(trainable=True): number of activation parameters (len(_acc_prm)); 0 = fixed */
-  int32_t reserved0;
+  int32_t chain_offset;                /* global index of this context's first chain: the Philox key is seed ^ (chain_offset + c),
+                                        * so chain blocks on different ranks (MC3 sharding) draw different streams from one seed */
   double init_additional_prob;         /* MCMC(init_additional_prob=): added to the initial log-prior (BNN_env.py:320) */
   /* indicators (appended; zero = absent).  Weight indicators: npBNN(freq_indicator > 0): a 0/1 matrix of the shape of
    * the first weight matrix multiplies it in the forward pass only, and calc_prior adds

@@ -5,8 +5,8 @@ model / sampler state, the MH drivers, MC3, block masks and the posterior-predic
 """
 __version__ = "0.1.0"
 
-from .api import (ActFun, CalcAccuracy, MC3, MCMC, RegressTransform, RegressTransformError, RunPredict, RunPredictInd, SaveObject,  # noqa: F401
-                  SoftMax, UpdateNormal, calc_likelihood, calc_likelihood_regression, calc_likelihood_regression_error,
-                  create_mask, data_transform_obj, feature_importance, get_pdp, get_posterior_cat_prob, get_posterior_est, init_weight_prm, load_obj,
-                  make_pdp_features, npBNN, pdp, postLogger, predict, run_mcmc, sample_from_categorical)
+from .hostlib import *  # noqa: F401,F403,E402  (file readers, summaries, proposal / Gibbs helpers, BNN_lik functions)
+from .api import (ActFun, MC3, MCMC, RunPredict, RunPredictInd, SaveObject,  # noqa: F401,E402
+                  create_mask, data_transform_obj, feature_importance, get_pdp, get_posterior_cat_prob, get_posterior_est,
+                  init_weight_prm, make_pdp_features, npBNN, pdp, postLogger, predict, run_mcmc, sample_from_categorical)
 from .engine import Engine, NetShape  # noqa: F401

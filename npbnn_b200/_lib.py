@@ -37,7 +37,7 @@ class SamplerConfig(C.Structure):
                 ("adapt_freq", C.c_int32), ("adapt_stop", C.c_int32), ("use_mask", C.c_int32),
                 ("adapt_f", C.c_double), ("adapt_fM", C.c_double), ("lik_temp", C.c_double),
                 ("w_bound", C.c_double), ("prior_scale", C.c_double * MAX_LAYERS), ("seed", C.c_uint64),
-                ("n_act_prm", C.c_int32), ("reserved0", C.c_int32), ("init_additional_prob", C.c_double),
+                ("n_act_prm", C.c_int32), ("chain_offset", C.c_int32), ("init_additional_prob", C.c_double),
                 ("prior_ind1", C.c_double), ("use_indicators", C.c_int32), ("use_feature_indicators", C.c_int32)]
 
 

@@ -41,40 +41,12 @@ from .engine import Engine, NetShape, flatten_weights, unflatten_weights
 small_number = 1e-10
 
 
-# ------------------------------------------------------------------------------------------------------
-# names the reference exports and user code passes around (identity tokens: they select device code)
-# ------------------------------------------------------------------------------------------------------
-def _device_only(name):
-    raise NotImplementedError("%s is evaluated inside the CUDA kernels of npbnn_b200; call RunPredict / MCMC instead" % name)
-
-
-# module-level functions (not closures) so that objects holding them pickle by reference
-def SoftMax(z):                                           # BNN_lib.py:166-168
-    _device_only("SoftMax")
-
-
-def RegressTransform(z):                                  # BNN_lib.py:174-175
-    _device_only("RegressTransform")
-
-
-def RegressTransformError(z, ind=None):                   # BNN_lib.py:177-182
-    _device_only("RegressTransformError")
-
-
-def calc_likelihood(*a, **k):                             # BNN_lib.py:100-121
-    _device_only("calc_likelihood")
-
-
-def calc_likelihood_regression(*a, **k):                  # BNN_lib.py:123-131
-    _device_only("calc_likelihood_regression")
-
-
-def calc_likelihood_regression_error(*a, **k):            # BNN_lib.py:134-143
-    _device_only("calc_likelihood_regression_error")
-
-
-def UpdateNormal(*a, **k):                                # BNN_mcmc.py:57-69
-    _device_only("UpdateNormal")
+# names the reference exports and user code passes around (SoftMax, calc_likelihood, UpdateNormal ...): inside the
+# sampler they are identity tokens that select device code; hostlib holds their host-table forms and the file / summary
+# callers around the path
+from .hostlib import (CalcAccuracy, CalcAccuracyRegression, CalcLabelAccuracy, CalcLabelAccuracyRegression,  # noqa: E402,F401
+                      CalcLabelFreq, RegressTransform, RegressTransformError, SoftMax, UpdateNormal, calc_likelihood,
+                      calc_likelihood_regression, calc_likelihood_regression_error, load_obj, log_header)
 
 
 class ActFun:
@@ -303,6 +275,7 @@ class npBNN:
         self._prior_scale = scales
 
     def reset_weights(self, w):
+        self._data_version = self.__dict__.get("_data_version", 0) + 1     # staged chain state no longer matches
         self._w_layers = w
 
     def reset_indicators(self, ind):
@@ -312,6 +285,8 @@ class npBNN:
         self._error_prm = p
 
     def update_data(self, data_dict):
+        # samplers built before this call hold the previous data on the device: MCMC.run refuses to continue on them
+        self._data_version = self.__dict__.get("_data_version", 0) + 1
         self._data = np.ascontiguousarray(data_dict["data"], dtype=np.float64)
         self._labels = data_dict["labels"]
         self._test_data = data_dict["test_data"]
@@ -340,7 +315,8 @@ class _ChainGroup:
     injection arrays of bnn_mh_steps."""
 
     def __init__(self, bnn, weights_per_chain, temperatures, update_f, update_ws, lik_temp, adapt_f, adapt_fM,
-                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0, init_additional_prob=0.0, row_shard=False):
+                 adapt_freq, adapt_stop, sample_from_prior, seed, device=0, init_additional_prob=0.0, row_shard=False,
+                 chain_offset=0):
         self.bnn = bnn
         net = _net_of(weights_per_chain[0], bnn._n_features, bnn._act_fun, bnn._estimation_mode)
         self.net = net
@@ -380,7 +356,8 @@ class _ChainGroup:
                              adapt_stop=adapt_stop, sample_from_prior=sample_from_prior, seed=seed,
                              n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob,
                              prior_ind1=bnn._prior_ind1 if bnn._freq_indicator else None,
-                             feature_means=bnn._feature_means if bnn._feature_indicators is not None else None)
+                             feature_means=bnn._feature_means if bnn._feature_indicators is not None else None,
+                             chain_offset=chain_offset)
         self.freq_indicator = float(bnn._freq_indicator)
         self.use_fi = bnn._feature_indicators is not None
         if (self.freq_indicator or self.use_fi) and (np.any(np.asarray(bnn._indicators) != 1) or
@@ -516,7 +493,15 @@ class MCMC:
         elif bnn_obj._act_fun._trainable or init_additional_prob:
             raise NotImplementedError("trainable activation parameters / init_additional_prob inside an MC3 group")
         self._group, self._slot = _group, _slot
+        self._seen_version = bnn_obj.__dict__.get("_data_version", 0)
         self._bnn_shapes = [w.shape for w in bnn_obj._w_layers]
+        # the function attributes user scripts call on host tables (bnn_regress.py:55: mcmc._accuracy_lab_f(mcmc._y, ...))
+        cls = bnn_obj._estimation_mode == "classification"
+        self._likelihood_f = {"classification": calc_likelihood, "regression": calc_likelihood_regression,
+                              "regression-error": calc_likelihood_regression_error}[bnn_obj._estimation_mode]
+        self._accuracy_f = CalcAccuracy if cls else CalcAccuracyRegression
+        self._accuracy_lab_f = CalcLabelAccuracy if cls else CalcLabelAccuracyRegression
+        self._bnn_view = bnn_obj
         self._sync(bnn_obj, self._group.eng.read_state())
 
     # ---------------------------------------------------------------- state export
@@ -562,7 +547,23 @@ class MCMC:
                 bnn_obj._indicators = ind[c]
             if fi is not None:
                 bnn_obj._feature_indicators = fi[c].astype(int)
-        self._y_cache = None
+        self._bnn_view = bnn_obj
+        self._y_cache = {}
+
+    # mcmc._y / mcmc._y_test (BNN_env.py:299,343,507,513): the prediction tables of the current state.  The sampler never
+    # needs them on the host (likelihood and accuracies are reduced inside the forward kernel); they are produced by one
+    # prediction pass when a script reads the attribute and cached until the state changes.
+    @property
+    def _y(self):
+        if "y" not in self._y_cache:
+            self._y_cache["y"] = self._materialise_y(self._bnn_view, False)
+        return self._y_cache["y"]
+
+    @property
+    def _y_test(self):
+        if "y_test" not in self._y_cache:
+            self._y_cache["y_test"] = self.y_test(self._bnn_view)
+        return self._y_cache["y_test"]
 
     def _materialise_y(self, bnn_obj, test=False):
         x = bnn_obj._test_data if test else bnn_obj._data
@@ -596,6 +597,9 @@ class MCMC:
     def run(self, bnn_obj, n_steps, additional_prob=0):
         """n_steps MH iterations (BNN_env.py:381-532 each) with as few host round trips as the rng mode allows."""
         self._check_supported(n_steps)
+        if bnn_obj.__dict__.get("_data_version", 0) != self._seen_version:
+            raise RuntimeError("npBNN.update_data / reset_weights was called after this MCMC staged the model on the device; "
+                               "construct a new MCMC (the device state would silently ignore the change)")
         if additional_prob and self._rng_mode == "philox":
             raise NotImplementedError("additional_prob is injected with the host-drawn numbers (rng='host')")
         g = self._group
@@ -678,6 +682,8 @@ class MCMC:
         d["_group"] = None
         d["_rs"] = None
         d["update_function"] = None
+        d["_bnn_view"] = None
+        d["_y_cache"] = {}
         return d
 
 
@@ -703,7 +709,7 @@ def _mirror_adaptation(st, c, it, adapt_freq, adapt_stop, adapt_f, adapt_fM, max
 
 def _report(bnn, mcmc, logger):
     """Print / log decisions of the reference's loop for the state just synchronised (BNN_mcmc.py:156-167)."""
-    if mcmc._current_iteration % mcmc._print_f == 0 or mcmc._current_iteration == 1:
+    if (mcmc._current_iteration % mcmc._print_f == 0 or mcmc._current_iteration == 1) and _is_rank0():
         print(mcmc._current_iteration, np.round([mcmc._logLik, mcmc._accuracy, mcmc._test_accuracy,
                                                   mcmc._acceptance_rate], 3), flush=True)
         if bnn._estimation_mode == "regression":
@@ -800,20 +806,36 @@ class MC3:
         self.adapt_freq, self.adapt_f, self.adapt_fM, self.adapt_stop = adapt_freq, adapt_f, adapt_fM, adapt_stop
         self.n_mc3_iteration = np.round(n_iteration / swap_frequency).astype(int)
         self.rseeds = np.random.choice(range(1000, 9999), n_chains, replace=False)     # BNN_mc3.py:44
+        if data._estimation_mode == "regression" and not data._empirical_error:
+            # MC3 builds its chains with estimate_error=True and n_iteration=swap_frequency (BNN_mc3.py:61-74), so the
+            # error-parameter proposal starts after 0.1 * swap_frequency iterations -- the branch that is not on the device
+            # path (and on which the reference raises AttributeError after the first accept, BNN_mcmc.py:105)
+            raise NotImplementedError("MC3 on a regression model needs empirical_error=True (the error-parameter proposal "
+                                      "of BNN_env.py:435-442 is not on the device path)")
         if temperatures is None:
             temperatures = _mc3.default_temperatures(n_chains, min_temperature)
         self.temperatures = np.array(temperatures, dtype=np.float64)
         self.logger = logger
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
+        if n_chains < self.world:
+            raise ValueError("MC3: n_chains=%d is smaller than the number of ranks (%d); every rank needs a chain"
+                             % (n_chains, self.world))
+        if self.world > 1:
+            # every rank must hold the same chain seeds and swap generator whatever its own numpy state is
+            self.rseeds = np.asarray(_mc3.broadcast_from_rank0(self.rseeds))
         self.start, self.n_local = _mc3.chain_partition(n_chains, self.world, self.rank)
         self._rng_mode = rng
-        self._swap_rng = _mc3.SwapRNG(int(self.rseeds[0]) if swap_seed is None else swap_seed)
+        if swap_seed is None and self.world == 1:
+            self._swap_rng = _mc3.GlobalSwapRNG()      # the reference's own stream (np.random, BNN_mc3.py:99,109)
+        else:
+            self._swap_rng = _mc3.SwapRNG(int(self.rseeds[0]) if swap_seed is None else int(swap_seed))
         nl = data._n_layers
         self._bnn = data
         self._group = _ChainGroup(data, [data._w_layers] * self.n_local,
                                   self.temperatures[self.start:self.start + self.n_local], [0.05] * nl, [0.075] * nl,
-                                  1, adapt_f, adapt_fM, adapt_freq, adapt_stop, 0, seed=int(self.rseeds[0]), device=device)
+                                  1, adapt_f, adapt_fM, adapt_freq, adapt_stop, 0, seed=int(self.rseeds[0]), device=device,
+                                  chain_offset=self.start)
         # per-chain views with the reference's attribute surface (singleChainArgs[i] = [bnn, mcmc])
         self.singleChainArgs = []
         for i in range(self.n_local):
@@ -861,14 +883,57 @@ class MC3:
                     self.current_temperatures = temps
                     g.eng.set_temperature(temps[self.start:self.start + self.n_local])
             st = g.eng.read_state()
+            cold = None
             for i, (b, m) in enumerate(self.singleChainArgs):
                 m._sync(b, st)
                 if m._temperature == 1:                     # the logger follows the cold chain (BNN_mc3.py:118-122)
-                    self.logger.log_sample(b, m)
-                    self.logger.log_weights(b, m)
+                    cold = (b, m)
+            if self.world == 1:
+                if cold is not None:
+                    self.logger.log_sample(*cold)
+                    self.logger.log_weights(*cold)
+            else:
+                self._log_on_rank0(cold)
             if mc3_it % self.print_f == 0 and self.rank == 0 and self.n_local:
                 b0, m0 = self.singleChainArgs[0]
                 print(mc3_it, m0._logPost, b0._w_layers[0][0][0:5])
+
+
+    def _log_on_rank0(self, cold):
+        """Chains sharded over ranks: the cold temperature migrates between ranks with the swaps, the files belong to
+        rank 0.  The rank holding the cold chain sends its exported state (statistics + weights, a few kB) to rank 0,
+        which is the only rank that writes the .log / .pkl and keeps the posterior sample list."""
+        import torch.distributed as dist
+        cold_chain = int(np.flatnonzero(self.current_temperatures == 1)[0]) if np.any(self.current_temperatures == 1) else -1
+        if cold_chain < 0:
+            return
+        owner = _mc3.owner_of(cold_chain, self.n_chains, self.world)
+        box = [None]
+        if self.rank == owner:
+            b, m = cold
+            box[0] = {"bnn": {k: getattr(b, k) for k in ("_w_layers", "_indicators", "_error_prm", "_feature_indicators",
+                                                          "_prior_scale", "_seed")},
+                      "act_prm": (b._act_fun._prm, b._act_fun._acc_prm),
+                      "mcmc": {k: v for k, v in m.__getstate__().items() if k not in ("_likelihood_f", "_accuracy_f",
+                                                                                      "_accuracy_lab_f")}}
+        if owner != 0:
+            dist.broadcast_object_list(box, src=owner)
+        if self.rank != 0:
+            return
+        if owner == 0:
+            b, m = cold
+        else:
+            if getattr(self, "_cold_view", None) is None:
+                b = deepcopy(self._bnn)
+                m = object.__new__(MCMC)
+                self._cold_view = (b, m)
+            b, m = self._cold_view
+            for k, v in box[0]["bnn"].items():
+                setattr(b, k, v)
+            b._act_fun._prm, b._act_fun._acc_prm = box[0]["act_prm"]
+            m.__dict__.update(box[0]["mcmc"])
+        self.logger.log_sample(b, m)
+        self.logger.log_weights(b, m)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -914,6 +979,13 @@ class data_transform_obj:
     def __init__(self, feature_indicators, feature_means):
         self.feature_indicators = feature_indicators
         self.feature_means = feature_means
+
+    def transform(self, x):
+        """Host form (BNN_env.py:14-17) for callers that hand the object to RunHiddenLayer."""
+        cols, vals = self.override()
+        x = np.array(x, dtype=np.float64, copy=True)
+        x[:, cols] = vals
+        return x
 
     def override(self):
         cols = np.flatnonzero(np.asarray(self.feature_indicators) == 0).astype(np.int32)
@@ -984,16 +1056,6 @@ def sample_from_categorical(pred_features, post_samples, actFun=None, output_act
     al = _alpha_rows([s["alphas"] for s in post_samples], actFun, len(weights[0]))
     u = np.random.random((x.shape[0], len(weights)))
     return eng.predict_sample(x, weights, u, alphas=al, post_predictions=True)
-
-
-def CalcAccuracy(y, lab):
-    """BNN_lib.py:203-209 on a host summary ([N, K] or [S, N, K]); the per-step accuracies of the sampler come from
-    the fused counters of the forward kernels, this helper only serves the post-processing callers."""
-    y = np.asarray(y)
-    if y.ndim == 3:
-        return np.array([np.sum(i == lab) / len(i) for i in np.argmax(y, axis=2)])
-    prediction = np.argmax(y, axis=1)
-    return np.sum(prediction == lab) / len(prediction)
 
 
 def feature_importance(input_features, weights_pkl=None, weights_posterior=None, true_labels=[], fname_stem="",
@@ -1127,14 +1189,14 @@ def pdp(pickle_file, pdp_features):
 # ------------------------------------------------------------------------------------------------------
 # logger / pickle helpers the drivers need (I/O, host side; same file formats as BNN_env.py:553-658)
 # ------------------------------------------------------------------------------------------------------
-def load_obj(file_name):
-    with open(file_name, "rb") as f:
-        return pickle.load(f)
-
-
 def SaveObject(obj, filename):
     with open(filename, "wb") as output:
         pickle.dump(obj, output, pickle.HIGHEST_PROTOCOL)
+
+
+def _is_rank0():
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
 
 
 class postLogger:
@@ -1143,8 +1205,9 @@ class postLogger:
 
     def __init__(self, bnn_obj, filename="BNN", wdir="", sample_from_prior=0, add_prms=None, continue_logfile=False,
                  log_all_weights=0):
+        self._writer = _is_rank0()        # under torch.distributed only rank 0 touches the files
         outdir = os.path.dirname(filename)
-        if outdir and not os.path.exists(outdir):
+        if outdir and not os.path.exists(outdir) and self._writer:
             os.makedirs(outdir)
         stem = "%s_l%s" % (filename, "_".join(map(str, bnn_obj._n_nodes)))          # BNN_files.py:127
         self._logfile = os.path.join(wdir, stem + ".log")
@@ -1153,29 +1216,11 @@ class postLogger:
         self._log_all_weights = log_all_weights
         self._post_weight_samples = []
         self._estimation_mode = bnn_obj._estimation_mode
-        head = ["it", "posterior", "likelihood", "prior"]
-        if self._estimation_mode == "classification":
-            head += ["accuracy", "test_accuracy"] + ["acc_C%s" % i for i in range(bnn_obj._n_output_prm)]
-        else:
-            head += ["MSE", "test_MSE"] + ["MSE_prm%s" % i for i in range(bnn_obj._n_output_prm)]
-        for i in range(bnn_obj._n_layers):
-            head += ["mean_w%s" % i, "std_w%s" % i]
-            if bnn_obj._hyper_p:                                                   # BNN_files.py:151-155
-                head.append(("prior_std_w%s" if bnn_obj._hyper_p == 1 else "mean_prior_std_w%s") % i)
-        if bnn_obj._freq_indicator:
-            head.append("mean_ind")
-        if add_prms:
-            head += add_prms
-        if bnn_obj._act_fun._trainable:
-            head += ["alpha_%s" % i for i in range(bnn_obj._n_layers - 1)]
-        head += ["sig_%s" % i for i in range(len(bnn_obj._error_prm))]
-        if bnn_obj._feature_indicators is not None:
-            head += ["feature_ind_%s" % i for i in range(bnn_obj._n_features)]
-        head += ["acc_prob", "mcmc_id"]
-        if not continue_logfile:
+        head = log_header(bnn_obj, add_prms)
+        if not continue_logfile and self._writer:
             with open(self._logfile, "w", newline="") as f:
                 csv.writer(f, delimiter="\t").writerow(head)
-        if log_all_weights:
+        if log_all_weights and self._writer:
             with open(self._w_file, "w", newline="") as f:
                 csv.writer(f, delimiter="\t").writerow(
                     ["it"] + ["w_%s_%s" % (i, j) for i in range(bnn_obj._n_layers) for j in range(bnn_obj._w_layers[i].size)])
@@ -1208,10 +1253,14 @@ class postLogger:
         if bnn_obj._feature_indicators is not None:
             row += list(bnn_obj._feature_indicators)
         row += [mcmc_obj._acceptance_rate, mcmc_obj._mcmc_id]
+        if not self.__dict__.get("_writer", True):
+            return
         with open(self._logfile, "a", newline="") as f:
             csv.writer(f, delimiter="\t").writerow(row)
 
     def log_weights(self, bnn_obj, mcmc_obj, add_prms=None, add_obj=None):
+        if not self.__dict__.get("_writer", True):
+            return
         if self._log_all_weights:
             row = [mcmc_obj._current_iteration] + [v for w in bnn_obj._w_layers for v in w.flatten()]
             with open(self._w_file, "a", newline="") as f:

@@ -359,6 +359,8 @@ int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_tes
   REQUIRE(c && c->have_net, "bnn_set_data: call bnn_set_net first");
   invalidate_graphs(c);
   REQUIRE(x_dev != nullptr && n_train >= 1 && n_test >= 0, "bnn_set_data: bad arguments");
+  c->have_data = false;        // a failed call leaves no half-staged data set behind
+  c->have_chains = false;
   const NetGeom& g = c->g;
   if (g.lik == BNN_LIK_CATEGORICAL) REQUIRE(labels_dev != nullptr, "bnn_set_data: labels_dev required for the categorical likelihood");
   else REQUIRE(targets_dev != nullptr, "bnn_set_data: targets_dev required for the Gaussian likelihoods");
@@ -375,6 +377,15 @@ int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_tes
   if (g.lik == BNN_LIK_CATEGORICAL) {
     CUDA_TRY(c->labels.ensure(sizeof(int) * c->n_total, false, st));
     CUDA_TRY(cudaMemcpyAsync(c->labels.p, labels_dev, sizeof(int) * c->n_total, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(c->oz_flag.ensure(sizeof(int), false, st));
+    CUDA_TRY(cudaMemsetAsync(c->oz_flag.p, 0, sizeof(int), st));
+    CUDA_TRY(bnn_launch_check_labels(c->labels.as<int>(), n_train, c->n_total, g.K, c->oz_flag.as<int>(), st));
+    c->launches++;
+    int bad_label = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad_label, c->oz_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    REQUIRE(bad_label == 0, "bnn_set_data: class labels must lie in [0, K) with K = the output width of the network "
+                            "(the reference raises IndexError at BNN_lib.py:104)");
   } else {
     CUDA_TRY(c->targets.ensure(sizeof(double) * c->n_total * g.K, false, st));
     CUDA_TRY(cudaMemcpyAsync(c->targets.p, targets_dev, sizeof(double) * c->n_total * g.K, cudaMemcpyDeviceToDevice, st));

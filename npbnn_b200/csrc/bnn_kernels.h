@@ -63,6 +63,8 @@ cudaError_t bnn_debug_counters_read(unsigned long long* out32);
 cudaError_t bnn_debug_set_trace_ptr(unsigned long long* dev_ptr);
 cudaError_t bnn_launch_pack_x(const double* x, double* xs, long long n, long long n_pad, int F, int F_pad, int swz,
                               const int* ov_cols, const double* ov_vals, int n_ov, cudaStream_t st);
+// *flag |= 1 if a training label is outside [0, K) or a test label is negative (the reference raises IndexError there)
+cudaError_t bnn_launch_check_labels(const int* labels, long long n_train, long long n_total, int K, int* flag, cudaStream_t st);
 cudaError_t bnn_launch_pack_w(const NetGeom& g, const double* w, double* wp, int n_sets, cudaStream_t st);
 cudaError_t bnn_launch_finalize_lik(const NetGeom& g, const double* part, int NF, long long nt, long long n_train,
                                     double lik_temp, int sigma_mode, const double* sigma, double* loglik, double* sums,

@@ -174,6 +174,15 @@ __global__ void __launch_bounds__(UPD_THREADS) k_prior_refresh(const __grid_cons
       v += logpdf_prior(d.w_cur[e], d.cfg.prior, d.ps_entry ? d.ps_entry[e] : d.ps.s[l], d.ps_entry ? d.pls_entry[e] : d.ps.ls[l]);
     }
   double s = block_sum_fixed(v, sh);
+  if (d.ind_cur && d.cfg.use_indicators) {
+    // calc_prior's indicator term (BNN_env.py:191-193), as in k_mh_update: gibbs_step recomputes the whole log-prior
+    const int P0 = g.l[0].out * (g.l[0].in + g.l[0].bias);
+    const double* ind = d.ind_cur + (long long)c * P0;
+    double n1 = 0.0;
+    for (int i = threadIdx.x; i < P0; i += (int)blockDim.x) n1 += ind[i];
+    n1 = block_sum_fixed(n1, sh);
+    s += n1 * log(d.cfg.prior_ind1) + ((double)P0 - n1) * log(1.0 - d.cfg.prior_ind1);
+  }
   if (threadIdx.x == 0) {
     double* sf = d.sf + (long long)c * BNN_F_STRIDE;
     sf[BNN_F_LOGPRIOR] = s;
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
         sf[BNN_F_LOG_U] = d.inj_logu[(long long)step * d.C + c];
       } else {
         // rr = rs.random(L); rr[argmin] = 0; layer proposed iff rr < freq_layer_update (BNN_env.py:446-451)
-        uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)c, (uint32_t)(d.cfg.seed >> 32));
+        uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
         double rr[BNN_MAX_LAYERS];
         int amin = 0;
         for (int l = 0; l < g.L; ++l) {
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
           dr.iy = d.inj_iy[inj_base + s_off[l] + k];
           dr.dz = d.inj_dz[inj_base + s_off[l] + k];
         } else {
-          dr = philox_draw(d.cfg.seed, c, it, l, k, lg.out, cols, ws);
+          dr = philox_draw(d.cfg.seed, d.cfg.chain_offset + c, it, l, k, lg.out, cols, ws);
         }
         const int idx = lg.c_off + dr.ix * cols + dr.iy;
         if (pass == 0) atomicMax(&owner[idx], k);
@@ -618,6 +627,27 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Labels index the class-probability row, the class weights and the per-class counters inside the forward epilogues
+// (prediction[sample_id, labels], BNN_lib.py:104): a label outside [0, K) is an IndexError in the reference and would be
+// an out-of-bounds access here, so bnn_set_data rejects it.
+__global__ void k_check_labels(const int* __restrict__ labels, long long n_train, long long n_total, int K, int* flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (; i < n_total; i += stride) {
+    const int y = labels[i];
+    bad |= (y < 0) || (y >= K);      // test labels feed the same counters (argmax == label), same range
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+cudaError_t bnn_launch_check_labels(const int* labels, long long n_train, long long n_total, int K, int* flag, cudaStream_t st) {
+  long long blocks = (n_total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_check_labels<<<(int)blocks, 256, 0, st>>>(labels, n_train, n_total, K, flag);
+  return cudaGetLastError();
 }
 
 cudaError_t bnn_measure_dmma_peak(int n_sms, double* tflops) {

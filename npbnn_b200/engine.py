@@ -255,7 +255,7 @@ class Engine:
     def chains_init(self, w0, temperature=None, update_f=None, update_ws=None, prior=L.PRIOR_NORMAL, prior_scale=1.0,
                     w_bound=np.inf, mask=None, alphas=None, sigma0=None, sigma_mode=L.SIGMA_FIXED, lik_temp=1.0,
                     adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=0, sample_from_prior=0, seed=1234,
-                    n_act_prm=0, init_additional_prob=0.0, prior_ind1=None, feature_means=None):
+                    n_act_prm=0, init_additional_prob=0.0, prior_ind1=None, feature_means=None, chain_offset=0):
         w = np.ascontiguousarray(self._as_sets(w0), dtype=np.float64)
         n, nl = w.shape[0], self.net.n_layers
 
@@ -278,6 +278,7 @@ class Engine:
         for i in range(nl):
             cfg.prior_scale[i] = float(ps[i])
         cfg.seed = int(seed)
+        cfg.chain_offset = int(chain_offset)        # device generators are keyed on the GLOBAL chain index
         cfg.n_act_prm, cfg.init_additional_prob = int(n_act_prm), float(init_additional_prob)
         mk = None
         if mask is not None:

@@ -43,6 +43,37 @@ class SwapRNG:
         return float(np.log(self._rs.random_sample()))
 
 
+class GlobalSwapRNG:
+    """Single-process default: the swap step consumes numpy's GLOBAL generator exactly as the reference does
+    (np.random.choice(range(n), 2, replace=False) then np.log(np.random.random()), BNN_mc3.py:99,109), so a script that
+    calls np.random.seed(...) first swaps the same pairs as the reference run."""
+
+    def pair(self, n_chains: int):
+        j, k = np.random.choice(range(n_chains), 2, replace=False)
+        return int(j), int(k)
+
+    def log_uniform(self) -> float:
+        return float(np.log(np.random.random()))
+
+
+def broadcast_from_rank0(obj, group: Optional[dist.ProcessGroup] = None):
+    """Small host object of rank 0 on every rank (seeds); identity without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def owner_of(chain: int, n_chains: int, world_size: int) -> int:
+    """Rank that holds global chain index `chain` under chain_partition."""
+    for r in range(world_size):
+        start, n = chain_partition(n_chains, world_size, r)
+        if start <= chain < start + n:
+            return r
+    raise ValueError("chain %d of %d" % (chain, n_chains))
+
+
 def swap_temperatures(log_post: np.ndarray, temps: np.ndarray, j: int, k: int, log_u: float):
     """r = (lp_k - lp_j) T_j + (lp_j - lp_k) T_k; the two chains exchange temperatures (states stay put)
     iff r >= log u  (BNN_mc3.py:101-112)."""

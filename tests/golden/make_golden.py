@@ -579,10 +579,255 @@ def case_c3_shape(n=2000, n_test=200, n_steps=40, n_chains=8, seed=43):
     save("syn_c3_shape", out, meta)
 
 
+# ---------------------------------------------------------------------------------------
+# host-side callers around the path: file readers, summaries, the script flows
+# ---------------------------------------------------------------------------------------
+sys.path.insert(0, os.path.dirname(OUT))
+import golden_data  # noqa: E402  (tests/golden_data.py: the synthetic example tables)
+
+GET_DATA_CASES = {        # name -> (feature table, label table, kwargs): the calls the five scripts make
+    "classify": ("features", "labels", dict(seed=1234, testsize=0.1, all_class_in_testset=1, header=1, cv=0, instance_id=1)),
+    "mc3": ("features", "labels", dict(seed=1234, testsize=0.1, all_class_in_testset=1, header=1, instance_id=1)),
+    "all": ("features", "labels", dict(testsize=0, header=1, instance_id=1)),
+    "unlabeled": ("unlabeled", None, dict(header=1, instance_id=1)),
+    "tail_split": ("features", "labels", dict(seed=5, testsize=0.2, all_class_in_testset=0, header=1, instance_id=1)),
+    "cv2_subset": ("features", "labels", dict(seed=9, testsize=0.1, header=1, instance_id=1, cv=2, feature_indx=[0, 3, 5],
+                                              batch_training=50)),
+    "regress": ("features_reg", "labels_reg", dict(seed=1234, testsize=0.1, all_class_in_testset=0, cv=0, header=True,
+                                                   from_file=True, instance_id=0, randomize_order=True, label_mode="regression")),
+    "regress_ordered": ("features_reg", "labels_reg", dict(seed=3, testsize=0.1, header=0, instance_id=0,
+                                                           randomize_order=False, label_mode="regression")),
+}
+
+
+def _store_dat(out, prefix, dat):
+    for k, v in dat.items():
+        a = np.asarray(v)
+        if a.dtype.kind in "OU":
+            a = a.astype(str)
+        out[prefix + k] = a
+
+
+def case_hostlib():
+    """Outputs of the reference's host-side helpers (BNN_files.py, BNN_lib.py:195-348,627-679, BNN_mcmc.py:27-150,
+    BNN_lik.py) on seeded inputs."""
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = golden_data.write_example_tables(tmp)
+        for name, (f, l, kw) in GET_DATA_CASES.items():
+            dat = quiet(bn.get_data, paths[f], paths[l] if l else None, **kw)
+            _store_dat(out, "gd_%s_" % name, dat)
+    rng = np.random.default_rng(23)
+    n, k = 400, 5
+    z = rng.normal(0, 2.0, (n, k))
+    probs = bn.SoftMax(z)
+    prior = bn.SoftMax(rng.normal(0, 0.3, (n, k)))
+    lab = rng.integers(0, k - 1, n)                 # class k-1 never appears in the labels
+    lab[:50] = np.argmax(probs[:50], axis=1) % (k - 1)
+    out["probs"], out["prior_probs"], out["lab"], out["z"] = probs, prior, lab, z
+    out["CalcAccuracy"] = bn.CalcAccuracy(probs, lab)
+    out["CalcAccuracy3"] = bn.CalcAccuracy(np.stack([probs, prior]), lab)
+    out["CalcLabelAccuracy"] = bn.CalcLabelAccuracy(probs, lab)
+    out["CalcLabelFreq"] = bn.CalcLabelFreq(probs)
+    out["CalcConfusionMatrix"] = bn.CalcConfusionMatrix(probs, lab).values
+    out["CalcTP"], out["CalcFP"] = bn.CalcTP(probs, lab, threshold=0.8), bn.CalcFP(probs, lab, threshold=0.8)
+    out["CalcTP_BF"], out["CalcFP_BF"] = bn.CalcTP_BF(probs, prior, lab, threshold=20), bn.CalcFP_BF(probs, prior, lab, threshold=20)
+    th = bn.get_accuracy_threshold(probs, lab, threshold=0.75)
+    out["thr_predictions"], out["thr_accuracy"], out["thr_retained"] = th["predictions"], th["accuracy"], th["retained_samples"]
+    out["thr_cm"] = th["confusion_matrix"].values
+    keep = np.where(np.max(probs, axis=1) > 0.9)[0]
+    out["low_pp"] = bn.turn_low_pp_instances_to_nan(probs, keep)
+    out["hpd"] = np.array(bn.calcHPD(z[:, 0], 0.9))
+    yreg, labreg = rng.normal(size=(50, 4)), rng.normal(size=(50, 2))
+    out["yreg"], out["labreg"] = yreg, labreg
+    out["CalcAccuracyRegression"] = bn.CalcAccuracyRegression(yreg, labreg)
+    out["CalcLabelAccuracyRegression"] = bn.CalcLabelAccuracyRegression(yreg, labreg)
+    out["relu"], out["leaky"] = bn.relu_f(z.copy(), 0), bn.leaky_relu_f(z.copy(), 0.2)
+    out["swish"], out["tanh"] = bn.swish_f(z.copy(), 0), bn.tanh_f(z.copy(), 0)
+    out["softplus"], out["regerr"] = bn.SoftPlus(z), bn.RegressTransformError(z.copy())
+    out["lik_cat"] = bn.calc_likelihood(probs, lab, np.arange(n), class_weight=np.linspace(0.5, 1.5, k), lik_temp=0.7)
+    out["lik_cat_iw"] = bn.calc_likelihood(probs, lab, np.arange(n), instance_weight=np.linspace(0.1, 2, n))
+    out["lik_reg"] = bn.calc_likelihood_regression(yreg[:, :2], labreg, None, lik_temp=0.9, sig2=np.array([0.5, 2.0]))
+    out["lik_regerr"] = bn.calc_likelihood_regression_error(bn.RegressTransformError(yreg.copy()), labreg, None)
+    w = rng.normal(size=(7, 6))
+    d = np.full(w.shape, 0.3)
+    out["w"] = w
+    for name in ("UpdateNormal", "UpdateFixedNormal", "UpdateNormalNormalized"):
+        zz, (ix, iy), h = getattr(bn, name)(w, d=d, n=9, Mb=1.0, mb=-1.0, rs=np.random.default_rng(5))
+        out[name + "_z"], out[name + "_ix"], out[name + "_iy"], out[name + "_h"] = zz, ix, iy, h
+    zz, ix, h = bn.UpdateNormal1D(w[0], d=0.05, n=2, rs=np.random.default_rng(5))
+    out["UpdateNormal1D_z"], out["UpdateNormal1D_ix"] = zz, ix
+    np.random.seed(31)
+    out["UpdateUniform_z"] = bn.UpdateUniform(w, d=d, n=4)[0]
+    out["UpdateBinomial"] = bn.UpdateBinomial(np.ones((3, 4)), 0.5, (3, 4))
+    q, _, u = bn.multiplier_proposal_vector(np.array([1.0, 2.0, 3.0]), d=1.2, f=0.6, rs=np.random.default_rng(5))
+    out["mpv_q"], out["mpv_u"] = q, u
+    out["mp"] = np.array(bn.multiplier_proposal(2.0, d=1.1)[::2])
+    out["gibbs_vec"] = bn.GibbsSampleNormStdGammaVector(w.flatten())
+    out["gibbs_2d"], out["gibbs_one"] = bn.GibbsSampleNormStdGamma2D(w), bn.GibbsSampleNormStdGammaONE(w)
+    out["gibbs_rate"] = bn.GibbsSampleGammaRateExp(np.array([0.5, 1.0, 2.0]), 2.0)
+    cnt = rng.integers(0, 20, (50, 2)).astype(float)
+    out["cnt"] = cnt
+    out["poi"], out["negbin"] = bn.poi_likelihood(yreg, cnt), bn.negbin_likelihood(yreg, cnt)
+    out["negbin2d"], out["negbin10"] = bn.negbin_likelihood2d(yreg, cnt), bn.negbin_likelihood_base10(yreg * 0.3, cnt)
+    out["gamma"] = bn.gamma_likelihood(yreg * 0.1, cnt[:, :1] + 3.0)
+    out["negbin_acc"], out["negbin2d_acc"], out["poi_acc"] = bn.negbin_acc(yreg, cnt), bn.negbin2d_acc(yreg, cnt), bn.poi_acc(yreg, cnt)
+    out["negbin_acc10"] = bn.negbin_acc_base10(yreg * 0.3, cnt)
+    out["assign_indx"] = bn.assign_indx(["b", "a", "b", "c", "a"])
+    out["unique_unsorted"] = bn.unique_unsorted(np.array([3, 1, 3, 2, 1]))
+    xs = rng.normal(size=(30, 4))
+    xs[:, 1] = rng.integers(0, 3, 30)
+    out["xs"], out["feature_summary"] = xs, bn.get_feature_summary(xs, [0, 1])
+    mu, var = bn.RecurMeanVar(4, [np.zeros((7, 6)), np.ones((7, 6))], w, (np.array([0, 2]), np.array([1, 3])))
+    out["recur_mu"], out["recur_var"] = mu, var
+    # one hidden layer through the reference's forward helpers (device-side in this repository)
+    x = rng.normal(size=(40, 5))
+    wb = rng.normal(size=(6, 6))
+    out["rh_x"], out["rh_w"] = x, wb
+    out["mmd_bias"], out["mmd_nobias"] = bn.MatrixMultiplicationD(x, wb), bn.MatrixMultiplicationD(x, wb[:, 1:])
+    for fun, prm in (("ReLU", None), ("genReLU", [0.1, 0.3]), ("swish", None), ("tanh", None)):
+        af = bn.ActFun(fun=fun, prm=np.array(prm) if prm else np.zeros(1))
+        out["rh_" + fun] = bn.RunHiddenLayer(x, wb, af, 1 if prm else 0)
+    out["rh_none"] = bn.RunHiddenLayer(x, wb, False, 2)
+    save("hostlib", out, {"get_data_cases": {k: [v[0], v[1], v[2]] for k, v in GET_DATA_CASES.items()}})
+
+
+def _read_rows(path):
+    return [r.split("\t") for r in open(path).read().strip().split("\n")]
+
+
+def case_flow_classify():
+    """bnn_classify.py:15-154 with shortened chains on the synthetic tables: get_data -> npBNN -> MCMC -> postLogger ->
+    run_mcmc -> predictBNN (test set, all data, unlabeled) -> restart from the pickle -> feature_importance."""
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = golden_data.write_example_tables(tmp)
+        os.chdir(tmp)
+        try:
+            dat = quiet(bn.get_data, paths["features"], paths["labels"], seed=1234, testsize=0.1, all_class_in_testset=1,
+                        header=1, cv=0, instance_id=1)
+            np.random.seed(1234)
+            bnn = quiet(bn.npBNN, dat, n_nodes=[5, 5], use_class_weights=0, actFun=bn.ActFun(fun="tanh"), use_bias_node=2,
+                        prior_f=1, p_scale=1, seed=1234, init_std=0.1, instance_weights=None)
+            mcmc = bn.MCMC(bnn, update_f=[0.05, 0.05, 0.07], update_ws=[0.075, 0.075, 0.075], n_iteration=400,
+                           sampling_f=10, print_f=100, n_post_samples=20, sample_from_prior=0, adapt_f=0.3, adapt_fM=0.6)
+            logger = bn.postLogger(bnn, filename="BNN_cv0", log_all_weights=0)
+            quiet(bn.run_mcmc, bnn, mcmc, logger)
+            out["log_rows"] = np.array(_read_rows(logger._logfile)[1:], dtype=np.float64)
+            out["log_head"] = np.array(_read_rows(logger._logfile)[0])
+            pr = quiet(bn.predictBNN, dat["test_data"], pickle_file=logger._pklfile, test_labels=dat["test_labels"],
+                       instance_id=dat["id_test_data"], fname=dat["file_name"], post_summary_mode=0)
+            out["test_pp"], out["test_acc"], out["test_cm"] = pr["post_prob_predictions"], pr["mean_accuracy"], pr["confusion_matrix"]
+            out["test_files"] = np.array(sorted(os.listdir(tmp)))
+            out["test_mean_pr_txt"] = np.array(open(dat["file_name"] + "_BNN_cv0_l5_5_pred_mean_pr.txt").read())
+            out["test_accuracy_txt"] = np.array(open(dat["file_name"] + "_BNN_cv0_l5_5_accuracy.txt").read())
+            dat_all = quiet(bn.get_data, paths["features"], paths["labels"], testsize=0, header=1, instance_id=1)
+            pa = quiet(bn.predictBNN, dat_all["data"], pickle_file=logger._pklfile, test_labels=dat_all["labels"],
+                       instance_id=dat_all["id_data"], fname="all_data", post_summary_mode=1)
+            out["all_pp"], out["all_acc"] = pa["post_prob_predictions"], pa["mean_accuracy"]
+            new = quiet(bn.get_data, paths["unlabeled"], header=1, instance_id=1)
+            pn = quiet(bn.predictBNN, new["data"], pickle_file=logger._pklfile, instance_id=new["id_data"], fname=new["file_name"])
+            out["new_pp"] = pn["post_prob_predictions"]
+            thr = quiet(bn.get_posterior_threshold, logger._pklfile, target_acc=0.5, post_summary_mode=1)
+            out["threshold_row"] = np.asarray(thr)
+            pc = quiet(bn.predictBNN, new["data"], pickle_file=logger._pklfile, post_cutoff=0.6, post_summary_mode=1, fname="cut")
+            out["cut_pp"] = pc["post_prob_predictions"]
+            # restart from the pickle (bnn_classify.py:114-134)
+            bnn2 = quiet(bn.npBNN, dat, n_nodes=[5, 5], use_bias_node=1, prior_f=1, p_scale=1, pickle_file=logger._pklfile,
+                         seed=1234, actFun=bn.ActFun(fun="tanh"))
+            for i, w in enumerate(bnn2._w_layers):
+                out["restart_w%d" % i] = np.array(w)
+            # bn.feature_importance (bnn_classify.py:137-152) cannot be recorded in this container: the reference assigns
+            # float columns into a string-typed frame (BNN_lib.py:580), which pandas 3.0 rejects with TypeError.
+        finally:
+            os.chdir(cwd)
+    save("flow_classify", out, {"n_iteration": 400})
+
+
+def case_flow_mc3():
+    """bnn_runner_MC3.py:17-79 with a shortened run: np.random.seed -> get_data -> npBNN -> postLogger -> MC3.run_mcmc
+    -> predictBNN on the test set."""
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = golden_data.write_example_tables(tmp)
+        os.chdir(tmp)
+        try:
+            np.random.seed(1234)
+            dat = quiet(bn.get_data, paths["features"], paths["labels"], seed=1234, testsize=0.1, all_class_in_testset=1,
+                        header=1, instance_id=1)
+            bnn = quiet(bn.npBNN, dat, n_nodes=[5, 5], use_bias_node=-1, seed=1, init_std=0.1)
+            logger = bn.postLogger(bnn, filename="BNNMC3", log_all_weights=0)
+            mc3 = quiet(bn.MC3, bnn, logger=logger, n_post_samples=100, sampling_f=100, n_iteration=300, n_chains=4,
+                        swap_frequency=20, verbose=1)
+            quiet(mc3.run_mcmc)
+            out["log_rows"] = np.array(_read_rows(logger._logfile)[1:], dtype=np.float64)
+            out["final_logPost"] = np.array([a[1]._logPost for a in mc3.singleChainArgs])
+            out["final_temps"] = np.array([a[1]._temperature for a in mc3.singleChainArgs], dtype=np.float64)
+            pr = quiet(bn.predictBNN, dat["test_data"], pickle_file=logger._pklfile, test_labels=dat["test_labels"],
+                       instance_id=dat["id_test_data"])
+            out["test_pp"], out["test_acc"], out["test_cm"] = pr["post_prob_predictions"], pr["mean_accuracy"], pr["confusion_matrix"]
+            b2, m2, l2 = bn.load_obj(logger._pklfile)
+            out["n_samples"] = len(l2._post_weight_samples)
+            for i, w in enumerate(l2._post_weight_samples[-1]["weights"]):
+                out["last_sample_w%d" % i] = np.array(w)
+        finally:
+            os.chdir(cwd)
+    save("flow_mc3", out, {"n_iteration": 300, "swap_frequency": 20, "n_chains": 4})
+
+
+def case_flow_regress():
+    """bnn_regress.py:19-92 (plots left out) with a shortened chain: the attributes the script reads (mcmc._update_n,
+    mcmc._accuracy_lab_f(mcmc._y, labels), mcmc._y, mcmc._y_test) and its RunPredict loop over the pickled samples."""
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = golden_data.write_example_tables(tmp)
+        os.chdir(tmp)
+        try:
+            np.random.seed(1234)
+            dat = quiet(bn.get_data, paths["features_reg"], paths["labels_reg"], seed=1234, testsize=0.1, all_class_in_testset=0,
+                        cv=0, header=True, from_file=True, instance_id=0, randomize_order=True, label_mode="regression")
+            bnn = quiet(bn.npBNN, dat, n_nodes=[6, 4], estimation_mode="regression", actFun=bn.ActFun(fun="tanh"), p_scale=1,
+                        use_bias_node=2, empirical_error=True)
+            mcmc = bn.MCMC(bnn, update_ws=[0.025, 0.025, 0.05], update_f=[0.005, 0.005, 0.05], n_iteration=300, sampling_f=20,
+                           print_f=100, n_post_samples=10, likelihood_tempering=1, adapt_f=0.3, estimate_error=False)
+            out["update_n"] = np.asarray(mcmc._update_n)
+            out["label_acc0"] = mcmc._accuracy_lab_f(mcmc._y, bnn._labels)
+            logger = bn.postLogger(bnn, filename="testM", log_all_weights=0)
+            quiet(bn.run_mcmc, bnn, mcmc, logger)
+            out["y"], out["y_test"] = np.array(mcmc._y), np.array(mcmc._y_test)
+            out["log_rows"] = np.array(_read_rows(logger._logfile)[1:], dtype=np.float64)
+            b2, m2, l2 = bn.load_obj(logger._pklfile)
+            ps = l2._post_weight_samples
+            preds = []
+            for i in range(len(ps)):
+                af = b2._act_fun
+                af.reset_prm(ps[i]["alphas"])
+                preds.append(bn.RunPredict(b2._data, ps[i]["weights"], actFun=af, output_act_fun=b2._output_act_fun))
+            out["post_preds"] = np.array(preds)
+            est = bn.get_posterior_est(logger._pklfile)
+            out["prm_mean"], out["prm_mean_test"] = est["prm_mean"], est["prm_mean_test"]
+            out["error_prm"] = np.array(est["error_prm"], dtype=np.float64)
+            pd_ = bn.pdp(logger._pklfile, [[0], [1, 2]])
+            out["pdp0_feature"], out["pdp0"], out["pdp1"] = pd_[0]["feature"], pd_[0]["pdp"], pd_[1]["pdp"]
+        finally:
+            os.chdir(cwd)
+    save("flow_regress", out, {"n_iteration": 300})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hyper":          # regenerate only the hyper-prior cases
         for hp in (1, 2, 3):
             case_hyper(hp)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "host":            # host-side helpers and the script flows
+        if "flows" not in sys.argv:
+            case_hostlib()
+        case_flow_classify()
+        case_flow_mc3()
+        case_flow_regress()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "shapes":          # the two headline network shapes
         case_c4_shape()
@@ -626,3 +871,7 @@ if __name__ == "__main__":
     case_predict_transform()
     case_c4_shape()
     case_c3_shape()
+    case_hostlib()
+    case_flow_classify()
+    case_flow_mc3()
+    case_flow_regress()
