@@ -359,31 +359,6 @@ def main():
     except Exception as e:                                 # the headline must not depend on this leg
         predict = {"error": str(e)}
 
-    # ------------------------------------------------------------------ opt-in kernel: layer 1 on the int8 tensor cores
-    experimental = None
-    try:
-        wl_d = torch.from_numpy(w0).to(dev)
-        t_ms = {}
-        for name, opt in (("f64", 0), ("tensor_l1", 1)):
-            eng.set_option("tensor_l1", opt)
-            ll = eng.forward_lik(wl_d)["loglik"]
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            q0.record()
-            ll = eng.forward_lik(wl_d)["loglik"]
-            q1.record()
-            torch.cuda.synchronize(dev)
-            t_ms[name] = (q0.elapsed_time(q1), ll, eng.last_kernel)
-        eng.set_option("tensor_l1", 0)
-        experimental = {"tensor_l1": {"what": "one scoring pass of this rank's chains (pack + slice + forward + reduce), "
-                                              "opt-in k_fwd3t vs default k_fwd3",
-                                      "kernel": t_ms["tensor_l1"][2], "ms": t_ms["tensor_l1"][0], "f64_ms": t_ms["f64"][0],
-                                      "speedup": t_ms["f64"][0] / t_ms["tensor_l1"][0],
-                                      "max_rel_diff_loglik": float(np.max(np.abs(t_ms["tensor_l1"][1] - t_ms["f64"][1]) /
-                                                                          np.abs(t_ms["f64"][1])))}}
-        del wl_d
-    except Exception as e:
-        experimental = {"error": str(e)}
-
     # ------------------------------------------------------------------ end-to-end leg (host buffers)
     e2e = None
     if not args.no_e2e:
@@ -488,7 +463,7 @@ def main():
                 "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clk,
                 "timing": {"blocks": len(blocks_ms), "steps_per_block": K, "blocks_ms": [round(b, 4) for b in blocks_ms],
-                           "reported": "median block", "timed_seconds": sum(blocks_ms) * 1e-3}, "predict": predict, "experimental": experimental,
+                           "reported": "median block", "timed_seconds": sum(blocks_ms) * 1e-3}, "predict": predict,
                 "swaps_in_timed_region": n_swaps[0] - swaps_before,
                 "check": {"logLik_finite": bool(np.all(np.isfinite(st.logLik))),
                           "mean_acceptance": float(np.mean(st.n_accepted / np.maximum(st.iteration, 1)))}}

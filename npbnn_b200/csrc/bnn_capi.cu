@@ -124,6 +124,10 @@ static void invalidate_graphs(bnn_ctx* c) {
 
 // network shapes with a k_fwd3t instantiation (BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 swish, categorical)
 static bool tensor_shape(const NetGeom& g) {
+#ifndef BNN_EXPERIMENTAL_TENSOR_L1
+  (void)g;
+  return false;                      // k_fwd3t is not part of the shipped library (bnn_forward.cu)
+#endif
   return g.L == 3 && g.F_pad == 64 && g.l[0].out_pad == 64 && g.l[1].out_pad == 32 && g.l[2].out_pad == 16 &&
          g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL;
 }
@@ -213,8 +217,10 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   c->n_sms = prop.multiProcessorCount;
   const char* fg = getenv("NPBNN_FORCE_GENERIC");
   c->force_generic = (fg && fg[0] == '1') ? 1 : 0;
+#ifdef BNN_EXPERIMENTAL_TENSOR_L1
   const char* tl = getenv("NPBNN_TENSOR_L1");
   if (tl) c->opt_tensor = (tl[0] != '0');
+#endif
   std::vector<double> tab(BNN_EXP_TAB_SIZE);
   for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = exp2((double)j / BNN_EXP_TAB_SIZE);
   cudaError_t e = c->exp_tab.ensure(sizeof(double) * BNN_EXP_TAB_SIZE, false, 0);
@@ -264,7 +270,14 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   if (strcmp(name, "force_generic") == 0) { c->force_generic = value; return 0; }
   if (strcmp(name, "time_forward") == 0) { c->time_forward = value; return 0; }
   if (strcmp(name, "sparse") == 0) { c->opt_sparse = value; return 0; }
-  if (strcmp(name, "tensor_l1") == 0) { c->opt_tensor = value; return 0; }
+  if (strcmp(name, "tensor_l1") == 0) {
+#ifndef BNN_EXPERIMENTAL_TENSOR_L1
+    REQUIRE(value == 0, "tensor_l1: the experimental tensor-core first layer (k_fwd3t) is not compiled into this library "
+                        "(build with -DBNN_EXPERIMENTAL_TENSOR_L1)");
+#endif
+    c->opt_tensor = value;
+    return 0;
+  }
   if (strcmp(name, "graphs") == 0) { c->opt_graphs = value; return 0; }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
