@@ -57,7 +57,9 @@ struct bnn_ctx {
   bool have_net = false, have_data = false, have_chains = false;
   int force_generic = 0;
   long long launches = 0;
-  NetGeom g{};
+  NetGeom g{};                      // geometry in use: g_base, or padded up to a k_fwd3 width family by bnn_set_data
+  NetGeom g_base{};                 // minimal padding (bnn_set_net)
+  NetGeom wp_geom{};                // layout the zero padding of wp_scratch was prepared for
   // staged data
   DevBuf xs, labels, targets, inst_w, class_w;
   bool has_iw = false, has_cw = false;
@@ -78,6 +80,7 @@ struct bnn_ctx {
   bool rowshard = false;
   long long n_train_global = 0;
   DevBuf part_red;
+  DevBuf part_sl;                   // [C, NF, n_slices]: slice sums of the tile partials (k_reduce_part), read by k_mh_update
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu, inj_alpha_ix, inj_alpha_dz, inj_add_prob;
   const char* last_kernel = "";
   // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
@@ -197,6 +200,70 @@ static int upload(DevBuf& b, const T* src, size_t n, cudaStream_t st) {
   return 0;
 }
 
+// (Re)compute the packed layout of a network for the given padded widths: F_pad for the features, out_pad[l] per layer
+// (each layer's padded input width is the previous layer's padded output width).
+static void geom_layout(NetGeom& g, int f_pad, const int* out_pad) {
+  int off = 0, in_pad = f_pad;
+  g.max_w = 8;
+  for (int l = 0; l < g.L; ++l) {
+    LayerGeom& lg = g.l[l];
+    lg.in_pad = in_pad;
+    lg.out_pad = out_pad[l];
+    lg.stride = lg.in_pad;
+    lg.swz = bnn_swz_for(lg.stride);
+    lg.w_off = off;
+    off += lg.out_pad * lg.stride;
+    lg.b_off = off;
+    off += lg.out_pad;
+    if (l >= 1 && lg.in_pad > g.max_w) g.max_w = lg.in_pad;
+    in_pad = lg.out_pad;
+  }
+  g.F_pad = g.l[0].in_pad;
+  g.x_swz = g.l[0].swz;
+  g.PB = off;
+}
+
+// Three-layer networks that fit one of the two k_fwd3 width families (64 -> 64 -> 32 or 32 -> 32 -> 16, last layer 16
+// columns for classes / 8 for Gaussian outputs) are padded UP to that family when the data set is large enough for the
+// specialised kernel to pay (at least one full round of 148 x 12 warp tiles); padded weights are zero, so the padded
+// hidden units are act(0) = 0 for every supported activation and contribute nothing.  Small data sets keep the
+// minimal padding (rounded up to 8) and the generic kernel.
+static const long long kFwd3PromoteRows = 16LL * 148 * 12;
+static NetGeom geom_for_rows(const NetGeom& base, long long n_rows) {
+  if (base.L != 3 || n_rows < kFwd3PromoteRows || bnn_fwd3_family(base)) return base;
+  const int n3 = (base.lik == BNN_LIK_CATEGORICAL) ? 16 : 8;
+  if (base.l[2].out > n3) return base;
+  NetGeom g = base;
+  if (base.F <= 32 && base.l[0].out <= 32 && base.l[1].out <= 16) {
+    const int pads[3] = {32, 16, n3};
+    geom_layout(g, 32, pads);
+    return g;
+  }
+  if (base.F <= 64 && base.l[0].out <= 64 && base.l[1].out <= 32) {
+    const int pads[3] = {64, 32, n3};
+    geom_layout(g, 64, pads);
+    return g;
+  }
+  return base;
+}
+static bool same_layout(const NetGeom& a, const NetGeom& b) {
+  if (a.L != b.L || a.F_pad != b.F_pad || a.PB != b.PB) return false;
+  for (int l = 0; l < a.L; ++l)
+    if (a.l[l].out_pad != b.l[l].out_pad) return false;
+  return true;
+}
+
+// wp_scratch holds packed weight sets; its padding entries are zeroed when it is (re)allocated and never written, so a
+// change of layout (prediction on a different number of rows may pick another padding) needs a fresh buffer
+static int ensure_wp_scratch(bnn_ctx* c, const NetGeom& g, size_t n_sets, cudaStream_t st) {
+  if (!same_layout(c->wp_geom, g)) {
+    c->wp_scratch.release();
+    c->wp_geom = g;
+  }
+  CUDA_TRY(c->wp_scratch.ensure(sizeof(double) * n_sets * g.PB, true, st));
+  return 0;
+}
+
 extern "C" {
 
 const char* bnn_last_error(void) { return g_last_error.c_str(); }
@@ -244,7 +311,7 @@ int bnn_ctx_destroy(bnn_ctx* c) {
                     &c->counts_scratch, &c->xs_pred, &c->ov_cols, &c->ov_vals, &c->h_w, &c->h_alpha, &c->h_sigma,
                     &c->h_loglik, &c->h_sums, &c->h_counts, &c->w_cur, &c->w_prop, &c->wp_prop, &c->mask, &c->owner,
                     &c->sf, &c->si, &c->counts_prop, &c->alpha_chain, &c->inj_proposed, &c->inj_count, &c->inj_ix,
-                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->part_red, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
+                    &c->inj_iy, &c->inj_dz, &c->inj_logu, &c->inj_alpha_ix, &c->inj_alpha_dz, &c->inj_add_prob, &c->part_red, &c->part_sl, &c->sp_items, &c->sp_widx, &c->xsl, &c->x_rowscale, &c->wt,
                     &c->oz_flag};
   for (DevBuf* b : bufs) b->release();
   c->ps_entry.release(); c->pls_entry.release(); c->ps_tmp.release(); c->pls_tmp.release();
@@ -357,7 +424,9 @@ int bnn_set_net(bnn_ctx* c, const bnn_net_spec* s) {
     g.K = g.O;
   }
   c->g = g;
+  c->g_base = g;
   c->wp_scratch.release();   // packed layout changed: padding entries must be re-zeroed
+  c->wp_geom = g;
   c->have_net = true;
   c->have_data = false;
   c->have_chains = false;
@@ -374,6 +443,7 @@ int bnn_set_data(bnn_ctx* c, const double* x_dev, int64_t n_train, int64_t n_tes
   REQUIRE(x_dev != nullptr && n_train >= 1 && n_test >= 0, "bnn_set_data: bad arguments");
   c->have_data = false;        // a failed call leaves no half-staged data set behind
   c->have_chains = false;
+  c->g = geom_for_rows(c->g_base, n_train + n_test);
   const NetGeom& g = c->g;
   if (g.lik == BNN_LIK_CATEGORICAL) REQUIRE(labels_dev != nullptr, "bnn_set_data: labels_dev required for the categorical likelihood");
   else REQUIRE(targets_dev != nullptr, "bnn_set_data: targets_dev required for the Gaussian likelihoods");
@@ -442,7 +512,7 @@ int bnn_forward_lik(bnn_ctx* c, const double* w_dev, int32_t n_sets, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   const NetGeom& g = c->g;
   const int NC = 2 + 2 * g.K;
-  CUDA_TRY(c->wp_scratch.ensure(sizeof(double) * (size_t)n_sets * g.PB, true, st));
+  if (int rc = ensure_wp_scratch(c, g, (size_t)n_sets, st)) return rc;
   CUDA_TRY(bnn_launch_pack_w(g, w_dev, c->wp_scratch.as<double>(), n_sets, st));
   c->launches++;
   int* counts = counts_dev;
@@ -722,6 +792,10 @@ static ChainDev chain_dev(bnn_ctx* c) {
   d.NF = n_slots(c->g);
   d.counts_prop = c->counts_prop.as<int>();
   d.alpha_fwd = c->alpha_chain.as<double>();
+  if (const int ns = bnn_part_slices(c->n_tiles16)) {     // chains_forward folds the tile partials into ns slices per chain
+    d.part = c->part_sl.as<double>();
+    d.n_tiles16 = ns;
+  }
   if (c->rowshard) {                 // accept step on the sums over all ranks (k_rowshard_commit)
     d.part = c->part_red.as<double>();
     d.n_tiles16 = 1;
@@ -753,6 +827,12 @@ static int chains_forward(bnn_ctx* c, cudaStream_t st) {
     p.counts = c->counts_prop.as<int>() + (size_t)s0 * NC;
     CUDA_TRY(timed_forward(c, p, false, st));
     c->launches++;
+  }
+  if (const int ns = bnn_part_slices(c->n_tiles16)) {
+    if (!c->rowshard) {              // (row-sharded chains fold the full partials in k_rowshard_local)
+      CUDA_TRY(bnn_launch_reduce_part(c->part.as<double>(), c->n_tiles16, ns, c->C * p.NF, c->part_sl.as<double>(), st));
+      c->launches++;
+    }
   }
   return 0;
 }
@@ -787,6 +867,7 @@ int bnn_chains_init(bnn_ctx* c, int32_t n_chains, const bnn_sampler_config* cfg,
   CUDA_TRY(c->alpha_chain.ensure(sizeof(double) * (size_t)C * g.L, false, st));
   CUDA_TRY(c->part.ensure(sizeof(double) * (size_t)n_slots(g) * C * c->n_tiles16, false, st));
   if (c->rowshard) CUDA_TRY(c->part_red.ensure(sizeof(double) * (size_t)C * n_slots(g), true, st));
+  CUDA_TRY(c->part_sl.ensure(sizeof(double) * (size_t)C * n_slots(g) * 64, false, st));
   c->use_sparse = false;
   if (cfg->use_mask) {
     CUDA_TRY(c->mask.ensure(sizeof(double) * g.P, false, st));
@@ -1250,7 +1331,7 @@ static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double
   REQUIRE(n_override >= 0 && (n_override == 0 || (override_cols && override_vals)), "bnn_predict: bad override arguments");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const NetGeom& g = c->g;
+  const NetGeom g = geom_for_rows(c->g_base, n);      // prediction picks its padding from ITS row count
   REQUIRE(!(votes_dev && g.lik != BNN_LIK_CATEGORICAL), "bnn_predict: vote summary needs the categorical likelihood");
   const long long n_pad = (n + 15) / 16 * 16;
   CUDA_TRY(c->xs_pred.ensure(sizeof(double) * (size_t)n_pad * g.F_pad, false, st));
@@ -1265,7 +1346,7 @@ static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double
     ovv = c->ov_vals.as<double>();
   }
   CUDA_TRY(bnn_launch_pack_x(x_dev, c->xs_pred.as<double>(), n, n_pad, g.F, g.F_pad, g.x_swz, ovc, ovv, n_override, st));
-  CUDA_TRY(c->wp_scratch.ensure(sizeof(double) * (size_t)n_sets * g.PB, true, st));
+  if (int rc = ensure_wp_scratch(c, g, (size_t)n_sets, st)) return rc;
   CUDA_TRY(bnn_launch_pack_w(g, w_dev, c->wp_scratch.as<double>(), n_sets, st));
   FwdParams p{};
   p.g = g;

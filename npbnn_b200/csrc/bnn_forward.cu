@@ -751,13 +751,108 @@ __device__ __forceinline__ void quad_epilogue_pred(const FwdParams& p, int c, lo
   }
 }
 
+// Gaussian likelihoods (calc_likelihood_regression / _error, BNN_lib.py:123-143) on the last layer's accumulator
+// fragment (N3 = 8: thread (g, t) holds rows g and g + 8, columns 2t and 2t + 1).  Per (warp tile, weight set) and
+// modelled output j the kernel leaves sum r, sum r^2 over the training rows and sum r^2 over the test rows
+// (r = prediction - target), from which finalize_loglik forms the log-likelihood (fixed or empirical sigma) and the
+// MSE statistics; with the sigma head (columns K..2K-1 through softplus) the per-row log-density is summed here.
+template <int N3>
+__device__ __forceinline__ void quad_gauss_lik(const FwdParams& p, int c, long long wt, int lane,
+                                               const double (&acc)[N3 / 8][4]) {
+  static_assert(N3 == 8, "Gaussian outputs fit one 8-column tile");
+  const int K = p.g.K;
+  const bool head = (p.g.lik == BNN_LIK_GAUSSIAN_HEAD);
+  const int gq = lane >> 2, t = lane & 3;
+  const long long nt = p.n_tiles16;
+  double ll = 0.0, sr[2] = {0.0, 0.0}, sr2[2] = {0.0, 0.0}, st2[2] = {0.0, 0.0};
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int col = 2 * t + e;
+    const int scol = (col + K) & 7;                                // column of this output's sigma parameter (head)
+    const int src = (gq << 2) | (scol >> 1);
+    const double s00 = __shfl_sync(FULL_MASK, acc[0][0], src), s01 = __shfl_sync(FULL_MASK, acc[0][1], src);
+    const double s10 = __shfl_sync(FULL_MASK, acc[0][2], src), s11 = __shfl_sync(FULL_MASK, acc[0][3], src);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long row = wt * 16 + gq + 8 * h;
+      const bool active = row < p.n_total && col < K;
+      const bool train = active && row < p.n_train;
+      double r = 0.0;
+      if (active) {
+        const double tv = p.targets[row * K + col];
+        const double mu = acc[0][2 * h + e];
+        r = mu - tv;
+        if (head && train) {
+          const double zs = (scol & 1) ? (h ? s11 : s01) : (h ? s10 : s00);
+          const double sd = softplus_ref(zs);
+          const double u = (tv - mu) / sd;
+          ll += -0.5 * u * u - kLogSqrt2Pi - log(sd);
+        }
+      }
+      sr[e] += train ? r : 0.0;
+      sr2[e] += train ? r * r : 0.0;
+      st2[e] += (active && !train) ? r * r : 0.0;
+    }
+  }
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1)                                 // rows: fixed xor tree over g => deterministic
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sr[e] += __shfl_xor_sync(FULL_MASK, sr[e], o);
+      sr2[e] += __shfl_xor_sync(FULL_MASK, sr2[e], o);
+      st2[e] += __shfl_xor_sync(FULL_MASK, st2[e], o);
+    }
+#pragma unroll
+  for (int o = 1; o <= 16; o <<= 1) ll += __shfl_xor_sync(FULL_MASK, ll, o);
+  if (gq == 0) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 2 * t + e;
+      if (col < K) {
+        p.part[((long long)c * p.NF + 1 + col) * nt + wt] = sr[e];
+        p.part[((long long)c * p.NF + 1 + K + col) * nt + wt] = sr2[e];
+        p.part[((long long)c * p.NF + 1 + 2 * K + col) * nt + wt] = st2[e];
+      }
+    }
+  }
+  if (lane == 0) p.part[((long long)c * p.NF) * nt + wt] = ll;
+}
+
+// prediction mode: transformed outputs (identity, softplus on the sigma head) accumulated over the weight sets
+template <int N3>
+__device__ __forceinline__ void quad_gauss_pred(const FwdParams& p, int c, long long wt, int lane,
+                                                const double (&acc)[N3 / 8][4], double (&pacc)[2][N3 / 4]) {
+  static_assert(N3 == 8, "Gaussian outputs fit one 8-column tile");
+  const int K = p.g.K, O = p.g.O;
+  const bool head = (p.g.lik == BNN_LIK_GAUSSIAN_HEAD);
+  const int gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long row = wt * 16 + gq + 8 * h;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 2 * t + e;
+      if (row < p.n_total && col < O) {
+        double v = acc[0][2 * h + e];
+        if (head && col >= K) v = softplus_ref(v);
+        pacc[h][e] += v;
+        if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * O + col] = v;
+      }
+    }
+  }
+}
+
 // MODE: 0 likelihood, 1 likelihood with class / instance weights, 2 posterior prediction
 enum { FWD3_LIK = 0, FWD3_LIK_W = 1, FWD3_PRED = 2 };
+// LIKK: 0 categorical (softmax epilogue, software-pipelined into the next weight set), 1 Gaussian (plain or sigma head)
+enum { FWD3_CAT = 0, FWD3_GAUSS = 1 };
 
-template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE, int LIKK = FWD3_CAT>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__ FwdParams p) {
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   constexpr bool PREDICT = (MODE == FWD3_PRED);
+  constexpr bool CAT = (LIKK == FWD3_CAT);
+  constexpr bool DEFER = !PREDICT && CAT;        // categorical likelihood: epilogue pipelined into the next set's layer 1
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -772,7 +867,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   uint64_t* empty = bars + 2;       // [2]
   uint64_t* xbar = bars + 4 + warp; // [NWARPS]
   int* cnt = reinterpret_cast<int*>(bars + 4 + NWARPS);
-  const int n_cnt = PREDICT ? 0 : p.C * (2 + 2 * g.K);
+  const int n_cnt = DEFER ? p.C * (2 + 2 * g.K) : 0;
+  const int PW = CAT ? g.K : g.O;                 // columns of a prediction row
 
   for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
@@ -873,7 +969,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const long long row = wt * 16 + gq + 8 * h;
-        if (!PREDICT && row < p.n_total) {
+        if (DEFER && row < p.n_total) {
           y[h] = p.labels[row];
           if (MODE == FWD3_LIK_W) {
             if (p.class_w) wgt[h] *= p.class_w[y[h]];
@@ -928,7 +1024,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             const int col = (8 * kg + 2 * t) ^ sw;
             const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
-            if (!PREDICT) {
+            if (DEFER) {
               if (kg == 0) qs_max<N3>(acc3, K, t, rs);
               else qs_exp<N3, 1, true>(acc3, K, t, ep_y, tab, rs);
             }
@@ -937,7 +1033,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
               dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
             }
-            if (!PREDICT) {
+            if (DEFER) {
               if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, ep_y, tab, rs);
               else {
                 qs_reduce<N3, true>(rs);
@@ -951,7 +1047,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
 #ifndef BNN_DBG_NOCOMMIT      // tuning experiment only: counters / partial store of the previous set
-          if (!PREDICT) quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, prev_valid);
+          if (DEFER) quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, prev_valid);
 #endif
 #pragma unroll 2
           for (int kg = 2; kg < KP0 / 8 - 2; ++kg) {
@@ -1071,13 +1167,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // weights of this use are no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[b]);
-        if (!PREDICT) {
+        if (DEFER) {
           prev_valid = true;
           ep_wt = wt; ep_c = c;
           ep_y[0] = y[0]; ep_y[1] = y[1];
           if (MODE == FWD3_LIK_W) { ep_wgt[0] = wgt[0]; ep_wgt[1] = wgt[1]; }
         }
-        if (PREDICT) quad_epilogue_pred<N3>(p, c, wt, lane, acc3, tab, pacc, pvote);
+        if constexpr (CAT) {
+          if (PREDICT) quad_epilogue_pred<N3>(p, c, wt, lane, acc3, tab, pacc, pvote);
+        } else {
+          if (PREDICT) quad_gauss_pred<N3>(p, c, wt, lane, acc3, pacc);
+          else quad_gauss_lik<N3>(p, c, wt, lane, acc3);
+        }
       } else {
         if (lane == 0) mbar_arrive(&empty[b]);
       }
@@ -1092,9 +1193,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = 8 * j + 2 * t + e;
-              if (row < p.n_total && col < g.K) {
-                if (p.mean_out) p.mean_out[row * g.K + col] = pacc[h][2 * j + e] / p.inv_sets;
-                if (p.votes_out) p.votes_out[row * g.K + col] = (double)pvote[h][2 * j + e] / p.inv_sets;
+              if (row < p.n_total && col < PW) {
+                if (p.mean_out) p.mean_out[row * PW + col] = pacc[h][2 * j + e] / p.inv_sets;
+                if (CAT && p.votes_out) p.votes_out[row * PW + col] = (double)pvote[h][2 * j + e] / p.inv_sets;
               }
             }
         }
@@ -1102,7 +1203,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
     }
   }
   // drain the software pipeline: the epilogue of the last (tile, weight set) this warp ran
-  if (!PREDICT && prev_valid) {
+  if (DEFER && prev_valid) {
     RowStats<N3> rs;
     quad_softmax_stats<N3, true>(acc3, g.K, t, ep_y, tab, rs);
     const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, ep_wt, lane, rs, ep_y, ep_wgt, true);
@@ -1809,20 +1910,20 @@ static cudaError_t launch_fwd3t(const FwdParams& p, int n_sms, cudaStream_t st) 
 // =============================================================================================
 // host-side launchers
 // =============================================================================================
-template <int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
+template <int KP0, int N1, int N2, int N3, int NWARPS, int MODE, int LIKK>
 static size_t fwd3_smem_bytes(const FwdParams& p) {
-  constexpr bool PREDICT = (MODE == FWD3_PRED);
+  constexpr bool DEFER = (MODE != FWD3_PRED) && (LIKK == FWD3_CAT);
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE;
   size_t bytes = d * sizeof(double) + (4 + NWARPS) * sizeof(uint64_t);
-  size_t ints = PREDICT ? 0 : (size_t)p.C * (2 + 2 * p.g.K);
+  size_t ints = DEFER ? (size_t)p.C * (2 + 2 * p.g.K) : 0;
   return bytes + ints * sizeof(int);
 }
 
-template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE>
+template <int ACT, int KP0, int N1, int N2, int N3, int NWARPS, int MODE, int LIKK>
 static cudaError_t launch_fwd3(const FwdParams& p, int n_sms, cudaStream_t st) {
-  auto kern = k_fwd3<ACT, KP0, N1, N2, N3, NWARPS, MODE>;
-  size_t smem = fwd3_smem_bytes<KP0, N1, N2, N3, NWARPS, MODE>(p);
+  auto kern = k_fwd3<ACT, KP0, N1, N2, N3, NWARPS, MODE, LIKK>;
+  size_t smem = fwd3_smem_bytes<KP0, N1, N2, N3, NWARPS, MODE, LIKK>(p);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -1835,6 +1936,41 @@ static cudaError_t launch_fwd3(const FwdParams& p, int n_sms, cudaStream_t st) {
   int grid = (int)(ctas < n_sms ? ctas : n_sms);
   kern<<<grid, NWARPS * 32, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+// k_fwd3 instantiations: two padded width families x four activations x {categorical (N3 = 16: likelihood, weighted
+// likelihood, prediction), Gaussian / sigma head (N3 = 8: likelihood, prediction)}
+//   family A   64 -> 64 -> 32 -> N3   12 warps per SM (BASELINE config 4 / 5 is its swish / categorical member)
+//   family B   32 -> 32 -> 16 -> N3   16 warps per SM
+template <int ACT, int KP0, int N1, int N2, int NWARPS>
+static cudaError_t launch_fwd3_family(const FwdParams& p, bool predict, int n_sms, cudaStream_t st) {
+  if (p.g.lik == BNN_LIK_CATEGORICAL) {
+    if (predict) return launch_fwd3<ACT, KP0, N1, N2, 16, NWARPS, FWD3_PRED, FWD3_CAT>(p, n_sms, st);
+    if (p.class_w || p.inst_w) return launch_fwd3<ACT, KP0, N1, N2, 16, NWARPS, FWD3_LIK_W, FWD3_CAT>(p, n_sms, st);
+    return launch_fwd3<ACT, KP0, N1, N2, 16, NWARPS, FWD3_LIK, FWD3_CAT>(p, n_sms, st);
+  }
+  if (predict) return launch_fwd3<ACT, KP0, N1, N2, 8, NWARPS, FWD3_PRED, FWD3_GAUSS>(p, n_sms, st);
+  return launch_fwd3<ACT, KP0, N1, N2, 8, NWARPS, FWD3_LIK, FWD3_GAUSS>(p, n_sms, st);
+}
+
+template <int KP0, int N1, int N2, int NWARPS>
+static cudaError_t launch_fwd3_act(const FwdParams& p, bool predict, int n_sms, cudaStream_t st) {
+  switch (p.g.act) {
+    case BNN_ACT_RELU: return launch_fwd3_family<BNN_ACT_RELU, KP0, N1, N2, NWARPS>(p, predict, n_sms, st);
+    case BNN_ACT_LEAKY: return launch_fwd3_family<BNN_ACT_LEAKY, KP0, N1, N2, NWARPS>(p, predict, n_sms, st);
+    case BNN_ACT_SWISH: return launch_fwd3_family<BNN_ACT_SWISH, KP0, N1, N2, NWARPS>(p, predict, n_sms, st);
+    default: return launch_fwd3_family<BNN_ACT_TANH, KP0, N1, N2, NWARPS>(p, predict, n_sms, st);
+  }
+}
+
+// which k_fwd3 family the padded geometry matches exactly: 1 = A, 2 = B, 0 = none
+int bnn_fwd3_family(const NetGeom& g) {
+  if (g.L != 3) return 0;
+  const int n3 = (g.lik == BNN_LIK_CATEGORICAL) ? 16 : 8;
+  if (g.l[2].out_pad != n3) return 0;
+  if (g.F_pad == 64 && g.l[0].out_pad == 64 && g.l[1].out_pad == 32) return 1;
+  if (g.F_pad == 32 && g.l[0].out_pad == 32 && g.l[1].out_pad == 16) return 2;
+  return 0;
 }
 
 template <int ACT, bool PREDICT>
@@ -1963,21 +2099,15 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
     if (which) *which = "k_fwd_sparse";
     return launch_sparse(p, n_sms, st);
   }
-  if (!force_generic && g.L == 3 && !p.samp_u) {
-    const int k0 = g.F_pad, n1 = g.l[0].out_pad, n2 = g.l[1].out_pad, n3 = g.l[2].out_pad;
-    // BASELINE config 4 / 5: 64 -> 64 -> 32 -> 10 (padded 16), swish
-    if (k0 == 64 && n1 == 64 && n2 == 32 && n3 == 16 && g.act == BNN_ACT_SWISH && g.lik == BNN_LIK_CATEGORICAL) {
-      if (which) *which = "k_fwd3<swish,64,64,32,16>";
-#ifdef BNN_EXPERIMENTAL_TENSOR_L1
-      if (!predict && p.xsl && p.wt && fwd3t_smem_bytes(p.C, g.K) <= 232448) {
-        if (which) *which = "k_fwd3t<swish,64,64,32,16>";
-        if (p.class_w || p.inst_w) return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK_W>(p, n_sms, st);
-        return launch_fwd3t<BNN_ACT_SWISH, FWD3_LIK>(p, n_sms, st);
-      }
-#endif
-      if (predict) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_PRED>(p, n_sms, st);
-      if (p.class_w || p.inst_w) return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK_W>(p, n_sms, st);
-      return launch_fwd3<BNN_ACT_SWISH, 64, 64, 32, 16, FWD3_WARPS, FWD3_LIK>(p, n_sms, st);
+  if (!force_generic && !p.samp_u) {
+    static const char* const names[2][4] = {
+        {"k_fwd3<relu,64,64,32>", "k_fwd3<leaky,64,64,32>", "k_fwd3<swish,64,64,32,16>", "k_fwd3<tanh,64,64,32>"},
+        {"k_fwd3<relu,32,32,16>", "k_fwd3<leaky,32,32,16>", "k_fwd3<swish,32,32,16>", "k_fwd3<tanh,32,32,16>"}};
+    const int fam = bnn_fwd3_family(g);
+    if (fam) {
+      if (which) *which = names[fam - 1][g.act];
+      return fam == 1 ? launch_fwd3_act<64, 64, 32, FWD3_WARPS>(p, predict, n_sms, st)
+                      : launch_fwd3_act<32, 32, 16, 16>(p, predict, n_sms, st);
     }
   }
   if (which) *which = "k_fwd_generic";

@@ -53,6 +53,8 @@ struct ChainDev {
 cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int force_generic, cudaStream_t st,
                                const char** which);
 bool bnn_sparse_fits(const FwdParams& p);
+// k_fwd3 width family the padded geometry matches exactly: 1 = 64->64->32, 2 = 32->32->16, 0 = none (generic kernel)
+int bnn_fwd3_family(const NetGeom& g);
 // tensor-core first layer (k_fwd3t): operand slicing
 cudaError_t bnn_launch_slice_x(const double* x, long long n_pad16, uint8_t* xsl, double* rowscale, long long n_tiles128,
                                int* flag, cudaStream_t st);
@@ -73,6 +75,10 @@ cudaError_t bnn_launch_log_prior(const NetGeom& g, const double* w, int n_sets, 
                                  const double* ps_entry, const double* pls_entry, int entry_stride, double* out,
                                  cudaStream_t st);
 cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st);
+// first-level reduction of the per-tile partials: part [n_rows, nt] -> out [n_rows, n_slices]; bnn_part_slices(nt) = 0
+// means "not worth a launch" (k_mh_update reads the tile partials directly)
+int bnn_part_slices(long long nt);
+cudaError_t bnn_launch_reduce_part(const double* part, long long nt, int n_slices, int n_rows, double* out, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
 cudaError_t bnn_launch_rowshard_local(const NetGeom& g, const double* part, int NF, long long nt, const int* counts, int NC,
                                       double* out, int n_chains, cudaStream_t st);

@@ -603,6 +603,40 @@ cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double*
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// First level of the partial-sum reduction.  The forward kernels leave one partial per (chain, slot, 16-row tile):
+// 62,500 per chain at 1M rows, which k_mh_update -- one CTA per chain -- used to fold alone (18.5 MB through 32 SMs,
+// 40 us per step, 2-3 % of a step at 4 chains per GPU).  Here C * NF * n_slices CTAs fold fixed slices of the tile
+// axis in a fixed order (thread-strided terms, then the fixed block tree), so k_mh_update reads n_slices values per
+// chain.  The slice boundaries depend on the tile count only: the result does not depend on how the forward kernel
+// dealt its tiles out, nor on the number of chains in the pass.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce_part(const double* __restrict__ part, long long nt, int n_slices,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int slice = blockIdx.x;
+  const long long cs = blockIdx.y;                       // chain * NF + slot
+  const long long per = (nt + n_slices - 1) / n_slices;
+  const long long a = slice * per;
+  long long b = a + per;
+  if (b > nt) b = nt;
+  const double v = (a < b) ? strided_sum_ordered(part + cs * nt + a, b - a) : 0.0;
+  const double s = block_sum_fixed(v, sh);
+  if (threadIdx.x == 0) out[cs * n_slices + slice] = s;
+}
+
+int bnn_part_slices(long long nt) {
+  if (nt < 4096) return 0;                               // small data sets: k_mh_update reads the tile partials itself
+  long long s = nt / 1024;
+  return (int)(s > 64 ? 64 : s);
+}
+
+cudaError_t bnn_launch_reduce_part(const double* part, long long nt, int n_slices, int n_rows, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)n_slices, (unsigned)n_rows);
+  k_reduce_part<<<grid, 256, 0, st>>>(part, nt, n_slices, out);
+  return cudaGetLastError();
+}
+
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st) {
   k_mh_update<<<d.C, upd_threads(d.g), 0, st>>>(d, accept_mode, propose_mode, step);
   return cudaGetLastError();
