@@ -83,6 +83,9 @@ typedef struct {
   double prior_ind1;
   int32_t use_indicators;
   int32_t use_feature_indicators;
+  /* npBNN(freq_indicator=): probability threshold of the weight-indicator move (BNN_env.py:449-460).  Only read by the
+   * on-device generator (free-running chains); with injected draws the host decides the move (bnn_injection.ind_move). */
+  double freq_indicator;
 } bnn_sampler_config;
 
 /* Random draws of `n_steps` MH iterations for every chain, recorded from (or generated like) the
@@ -291,6 +294,14 @@ int bnn_rowshard_update(bnn_ctx* ctx, int32_t accept_mode, int32_t propose, cons
 int bnn_predict_sample(bnn_ctx* ctx, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
                        const double* alpha_dev, const double* u_dev, double* est_dev, int32_t* class_counts_dev,
                        double* post_pred_dev, void* stream);
+
+/* The same resampling with the uniforms generated inside the kernel (Philox4x32-10, counter = (row, set), key = seed):
+ * nothing of size n x n_sets is ever stored, so get_posterior_cat_prob(post_summary_mode=2) runs at BASELINE config 5
+ * scale (10,000 samples x 1,000,000 rows) in O(n K) memory, on the shape-specialised kernel where one exists.
+ * bnn_predict_sample (injected uniforms) reproduces the reference's draws; this one agrees with it statistically. */
+int bnn_predict_sample_philox(bnn_ctx* ctx, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                              const double* alpha_dev, uint64_t seed, double* est_dev, int32_t* class_counts_dev,
+                              double* post_pred_dev, void* stream);
 
 /* Debugging / tuning aids (no reference counterpart).
  * bnn_debug_read_part: per-warp-tile partial sums of the last forward pass, [sets in pass][slots][n_tiles16].

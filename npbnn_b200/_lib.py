@@ -38,7 +38,8 @@ class SamplerConfig(C.Structure):
                 ("adapt_f", C.c_double), ("adapt_fM", C.c_double), ("lik_temp", C.c_double),
                 ("w_bound", C.c_double), ("prior_scale", C.c_double * MAX_LAYERS), ("seed", C.c_uint64),
                 ("n_act_prm", C.c_int32), ("chain_offset", C.c_int32), ("init_additional_prob", C.c_double),
-                ("prior_ind1", C.c_double), ("use_indicators", C.c_int32), ("use_feature_indicators", C.c_int32)]
+                ("prior_ind1", C.c_double), ("use_indicators", C.c_int32), ("use_feature_indicators", C.c_int32),
+                ("freq_indicator", C.c_double)]
 
 
 class Injection(C.Structure):
@@ -87,6 +88,8 @@ _SIGNATURES = {
     "bnn_chains_set_temperature": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_predict_sample_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_predict_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_launch_count": (C.c_int64, [C.c_void_p]),

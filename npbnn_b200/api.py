@@ -357,7 +357,7 @@ class _ChainGroup:
                              n_act_prm=bnn._act_fun.n_trainable(), init_additional_prob=init_additional_prob,
                              prior_ind1=bnn._prior_ind1 if bnn._freq_indicator else None,
                              feature_means=bnn._feature_means if bnn._feature_indicators is not None else None,
-                             chain_offset=chain_offset)
+                             chain_offset=chain_offset, freq_indicator=float(bnn._freq_indicator))
         self.freq_indicator = float(bnn._freq_indicator)
         self.use_fi = bnn._feature_indicators is not None
         if (self.freq_indicator or self.use_fi) and (np.any(np.asarray(bnn._indicators) != 1) or
@@ -457,10 +457,9 @@ class MCMC:
             raise NotImplementedError("user-supplied likelihood / accuracy functions are not on the device path")
         if rng not in ("host", "philox"):
             raise ValueError("rng must be 'host' or 'philox'")
-        if rng == "philox" and bnn_obj._act_fun._trainable:
-            raise NotImplementedError("trainable activation parameters are proposed from host-drawn numbers (rng='host')")
-        if rng == "philox" and (bnn_obj._freq_indicator or bnn_obj._feature_indicators is not None):
-            raise NotImplementedError("indicator moves are drawn on the host (rng='host')")
+        if rng == "philox" and bnn_obj._freq_indicator and bnn_obj._n_layers < 4:
+            # the reference reads update_f[3] in this branch (BNN_env.py:460): IndexError below four layers
+            raise IndexError("freq_indicator > 0 needs a network of at least four layers (the reference indexes update_f[3])")
         nl = bnn_obj._n_layers
         if update_ws is None:
             update_ws = [0.075] * nl
@@ -1015,8 +1014,26 @@ def predict(bnn_obj, data):
     return RunPredict(data, bnn_obj._w_layers, actFun=bnn_obj._act_fun, output_act_fun=bnn_obj._output_act_fun)
 
 
+_HOST_UNIFORM_LIMIT = 1 << 26       # n x S above which mode 2 draws its uniforms inside the kernel (512 MB of float64)
+
+
+def _sampling_uniforms(n, s, rng):
+    """(u, seed) of the posterior-predictive resampling.  rng="host": the reference's draw -- np.random.random(S) per
+    instance in instance order = one (N, S) draw from the global stream (reproduces the reference for a seeded run).
+    rng="philox": uniforms generated inside the kernel, seeded from the global stream, O(1) extra memory.  rng=None
+    picks "host" while the (N, S) array stays below 512 MB and "philox" beyond (BASELINE config 5: 80 GB)."""
+    if rng is None:
+        rng = "host" if n * s <= _HOST_UNIFORM_LIMIT else "philox"
+    if rng == "host":
+        return np.random.random((n, s)), None
+    if rng != "philox":
+        raise ValueError("rng must be None, 'host' or 'philox'")
+    return None, int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 1
+
+
 def get_posterior_cat_prob(pred_features, post_samples=None, feature_index_to_shuffle=None, post_summary_mode=0,
-                           unlink_features_within_block=False, actFun=None, output_act_fun=None, return_dense=True):
+                           unlink_features_within_block=False, actFun=None, output_act_fun=None, return_dense=True,
+                           rng=None):
     """BNN_lib.py:352-397 with all posterior samples scored in ONE pass over the features.
     return_dense=False skips the [S, N, K] tensor (it is 800 GB at BASELINE config 5) and returns None for it."""
     if len(pred_features) == 0:
@@ -1039,14 +1056,15 @@ def get_posterior_cat_prob(pred_features, post_samples=None, feature_index_to_sh
         # instance order; one (N, S) draw consumes the global stream identically.  The draw itself is fused into the
         # prediction kernel, the [S, N, K] tensor is only produced when the caller wants it back.
         dense = eng.predict(x, weights, alphas=al, mean=False, dense=True)["dense"] if return_dense else None
-        u = np.random.random((x.shape[0], len(weights)))
-        res = eng.predict_sample(x, weights, u, alphas=al, post_predictions=False)
+        u, seed = _sampling_uniforms(x.shape[0], len(weights), rng)
+        res = eng.predict_sample(x, weights, u, alphas=al, post_predictions=False, seed=seed)
         return dense, res["predictions"]
     out = eng.predict(x, weights, alphas=al, mean=(post_summary_mode == 1), votes=(post_summary_mode == 0), dense=return_dense)
     return out.get("dense"), out["votes" if post_summary_mode == 0 else "mean"]
 
 
-def sample_from_categorical(pred_features, post_samples, actFun=None, output_act_fun=None):
+def sample_from_categorical(pred_features, post_samples, actFun=None, output_act_fun=None, rng=None,
+                            post_predictions=True):
     """Posterior-predictive resampling with the outputs of the reference's sample_from_categorical
     (BNN_lib.py:682-713: 'predictions', 'class_counts', 'post_predictions'), computed from the features and the
     posterior samples in one device pass instead of from a materialised [S, N, K] probability tensor."""
@@ -1054,8 +1072,8 @@ def sample_from_categorical(pred_features, post_samples, actFun=None, output_act
     weights = [s["weights"] for s in post_samples]
     eng = _predict_engine(weights[0], x.shape[1], actFun, output_act_fun)
     al = _alpha_rows([s["alphas"] for s in post_samples], actFun, len(weights[0]))
-    u = np.random.random((x.shape[0], len(weights)))
-    return eng.predict_sample(x, weights, u, alphas=al, post_predictions=True)
+    u, seed = _sampling_uniforms(x.shape[0], len(weights), rng)
+    return eng.predict_sample(x, weights, u, alphas=al, post_predictions=post_predictions, seed=seed)
 
 
 def feature_importance(input_features, weights_pkl=None, weights_posterior=None, true_labels=[], fname_stem="",

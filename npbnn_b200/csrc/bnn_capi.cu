@@ -1009,8 +1009,10 @@ static int stage_injection(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj
       d.inj_fi_flip = c->inj_fi_flip.as<uint8_t>();
     }
   } else {
-    REQUIRE(c->cfg.n_act_prm == 0, "bnn_mh_steps: trainable activation parameters are proposed from injected draws only "
-                                    "(no on-device generator for that branch)");
+    // free-running chains: every branch of the proposal is drawn on the device (Philox); the weight-indicator move
+    // reads update_f[3] like the reference (BNN_env.py:460), i.e. it exists from four layers on
+    REQUIRE(!(c->cfg.use_indicators && c->cfg.freq_indicator > 0.0 && g.L < 4),
+            "bnn_mh_steps: weight-indicator moves need a network of at least four layers (update_f[3])");
   }
   return 0;
 }
@@ -1324,7 +1326,8 @@ int bnn_chains_set_temperature(bnn_ctx* c, const double* temperature_host, void*
 static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
                         const double* alpha_dev, const int32_t* override_cols, const double* override_vals,
                         int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, const double* u_dev,
-                        int32_t* class_counts_dev, double* post_pred_dev, void* stream) {
+                        int32_t* class_counts_dev, double* post_pred_dev, void* stream, bool samp_philox = false,
+                        uint64_t samp_seed = 0) {
   REQUIRE(c && c->have_net, "bnn_predict: call bnn_set_net first");
   REQUIRE(x_dev && w_dev && n >= 1 && n_sets >= 1, "bnn_predict: bad arguments");
   REQUIRE(mean_dev || votes_dev || dense_dev, "bnn_predict: no output requested");
@@ -1361,6 +1364,7 @@ static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double
   p.exp_tab = c->exp_tab.as<double>();
   p.exp_tab_small = c->exp_tab_small.as<double>();
   p.samp_u = u_dev; p.samp_counts = class_counts_dev; p.samp_dense = post_pred_dev;
+  p.samp_philox = samp_philox ? 1 : 0; p.samp_seed = samp_seed;
   if (class_counts_dev) CUDA_TRY(cudaMemsetAsync(class_counts_dev, 0, sizeof(int32_t) * (size_t)n_sets * g.K, st));
   CUDA_TRY(timed_forward(c, p, true, st));
   c->launches += 3;
@@ -1372,6 +1376,15 @@ int bnn_predict(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev,
                 int32_t n_override, double* mean_dev, double* votes_dev, double* dense_dev, void* stream) {
   return predict_impl(c, x_dev, n, w_dev, n_sets, alpha_dev, override_cols, override_vals, n_override, mean_dev,
                       votes_dev, dense_dev, nullptr, nullptr, nullptr, stream);
+}
+
+int bnn_predict_sample_philox(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,
+                              const double* alpha_dev, uint64_t seed, double* est_dev, int32_t* class_counts_dev,
+                              double* post_pred_dev, void* stream) {
+  REQUIRE(c && c->have_net && c->g.lik == BNN_LIK_CATEGORICAL, "bnn_predict_sample_philox: needs the categorical likelihood");
+  REQUIRE(est_dev, "bnn_predict_sample_philox: est_dev is required");
+  return predict_impl(c, x_dev, n, w_dev, n_sets, alpha_dev, nullptr, nullptr, 0, nullptr, est_dev, nullptr, nullptr,
+                      class_counts_dev, post_pred_dev, stream, true, seed);
 }
 
 int bnn_predict_sample(bnn_ctx* c, const double* x_dev, int64_t n, const double* w_dev, int32_t n_sets,

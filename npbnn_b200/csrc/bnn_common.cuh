@@ -301,6 +301,31 @@ __device__ __forceinline__ double bnn_act_fast(double z, double alpha, const dou
   return fma(-2.0, bnn_rcp(bnn_exp_scaled<BNN_EXP_TAB_BITS, 2>(z, tab) + 1.0), 1.0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (free-running proposals, posterior-predictive resampling)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // [0,1)
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// uniform of (row, weight set) for the posterior-predictive resampling (sample_from_categorical, BNN_lib.py:682-713)
+__device__ __forceinline__ double bnn_samp_uniform(unsigned long long seed, long long row, int set) {
+  const uint4 r = philox4x32(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)set, 9u),
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return u53(r.x, r.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA 1-D) helpers
 // ---------------------------------------------------------------------------------------------
@@ -373,7 +398,9 @@ struct FwdParams {
   double* dense_out;        // [C, n, K] or null
   double inv_sets;         // number of weight sets as a double: summaries are divided by it
   // posterior-predictive resampling (sample_from_categorical, BNN_lib.py:682-713); samp_u null = off
-  const double* samp_u;     // [n, C] uniforms
+  const double* samp_u;     // [n, C] injected uniforms (parity with the reference's stream), or null
+  int samp_philox;          // 1: uniforms are generated in the kernel, counter (row, set), key samp_seed -- O(1) memory
+  unsigned long long samp_seed;
   int* samp_counts;         // [C, K] instances per class and set, or null
   double* samp_dense;       // [n, C] drawn class, or null   (the per-row shares go to votes_out)
   const double* exp_tab;    // [BNN_EXP_TAB_SIZE] 2^(j / BNN_EXP_TAB_SIZE)

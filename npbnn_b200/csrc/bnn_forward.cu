@@ -99,7 +99,8 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
         double inv = 1.0 / S;
         double* pa = pacc + (lane & 15) * K;
         // sample_from_categorical: first class whose running sum (np.cumsum order) reaches u; none => class 0
-        const double u = p.samp_u ? p.samp_u[row * p.C + c] : 0.0;
+        const bool sampling = p.samp_u || p.samp_philox;
+        const double u = p.samp_u ? p.samp_u[row * p.C + c] : (p.samp_philox ? bnn_samp_uniform(p.samp_seed, row, c) : 0.0);
         double cum = 0.0;
         int drawn = -1;
         for (int k = 0; k < K; ++k) {
@@ -109,13 +110,13 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
           if (drawn < 0 && cum - u >= 0.0) drawn = k;
           if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + k] = pk;
         }
-        if (p.samp_u) {
+        if (sampling) {
           arg = drawn < 0 ? 0 : drawn;
           if (p.samp_dense) p.samp_dense[row * p.C + c] = (double)arg;
         }
         pvote[(lane & 15) * K + arg] += 1;
       }
-      if (p.samp_u && p.samp_counts) {
+      if ((p.samp_u || p.samp_philox) && p.samp_counts) {
         // one atomic per distinct class among the 16 rows of the warp tile
         const unsigned grp = __match_any_sync(FULL_MASK, active ? arg : 64 + lane);
         if (active && lane == __ffs(grp) - 1) atomicAdd(&p.samp_counts[c * K + arg], __popc(grp));
@@ -730,6 +731,53 @@ __device__ __forceinline__ void quad_epilogue_pred(const FwdParams& p, int c, lo
   const int y[2] = {-1, -1};
   RowStats<N3> r;
   quad_softmax_stats<N3, false>(acc, K, t, y, tab, r);
+  if (p.samp_philox) {
+    // Posterior-predictive resampling (sample_from_categorical, BNN_lib.py:682-713) with in-kernel uniforms: the class of
+    // (row, set) is the first one whose cumulative probability reaches u (none: class 0).  The classes of a row are
+    // spread over the 4 lanes of a quad (columns 8j + 2t + e): each lane forms the cumulative sums of its own columns on
+    // top of the quad-exclusive prefix of the 8-column block and the totals of the blocks before it.
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long row = wt * 16 + gq + 8 * h;
+      const bool live = row < p.n_total;
+      const double inv = 1.0 / r.S[h];
+      const double u = live ? bnn_samp_uniform(p.samp_seed, row, c) : 2.0;
+      double base = 0.0;
+      int drawn = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < N3 / 8; ++j) {
+        const int c0 = 8 * j + 2 * t;
+        const double p0 = (c0 < K) ? r.ev[h][2 * j] * inv : 0.0, p1 = (c0 + 1 < K) ? r.ev[h][2 * j + 1] * inv : 0.0;
+        double incl = p0 + p1;                                    // inclusive scan over t (lanes of the quad)
+        const double up1 = __shfl_up_sync(FULL_MASK, incl, 1, 4);
+        if (t >= 1) incl += up1;
+        const double up2 = __shfl_up_sync(FULL_MASK, incl, 2, 4);
+        if (t >= 2) incl += up2;
+        const double excl = base + incl - (p0 + p1);
+        const double cum0 = excl + p0, cum1 = cum0 + p1;
+        if (c0 + 1 < K && cum1 - u >= 0.0 && c0 + 1 < drawn) drawn = c0 + 1;
+        if (c0 < K && cum0 - u >= 0.0 && c0 < drawn) drawn = c0;
+        base += __shfl_sync(FULL_MASK, incl, 3, 4);               // total of this 8-column block
+      }
+      drawn = min(drawn, __shfl_xor_sync(FULL_MASK, drawn, 1));
+      drawn = min(drawn, __shfl_xor_sync(FULL_MASK, drawn, 2));
+      if (drawn == 0x7fffffff) drawn = 0;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < N3 / 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (8 * j + 2 * t + e == drawn) pvote[h][2 * j + e] += 1;
+        if (t == 0 && p.samp_dense) p.samp_dense[row * p.C + c] = (double)drawn;
+      }
+      if (p.samp_counts) {
+        // one atomic per distinct class among the rows of this half tile (lanes t == 0 speak for their row)
+        const unsigned grp = __match_any_sync(FULL_MASK, (live && t == 0) ? drawn : 64 + lane);
+        if (live && t == 0 && lane == __ffs(grp) - 1) atomicAdd(&p.samp_counts[c * K + drawn], __popc(grp));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const long long row = wt * 16 + gq + 8 * h;

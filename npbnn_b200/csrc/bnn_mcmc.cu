@@ -190,24 +190,6 @@ __global__ void __launch_bounds__(UPD_THREADS) k_prior_refresh(const __grid_cons
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG (free-running proposals)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
-}
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // [0,1)
-  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
-}
-
 struct Draw { int ix, iy; double dz; };
 // k-th proposal of layer l of chain c at iteration it
 __device__ __forceinline__ Draw philox_draw(uint64_t seed, int c, int it, int l, int k, int rows, int cols, double ws) {
@@ -235,6 +217,9 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   __shared__ double sh[32];
   __shared__ int s_flag;
   __shared__ int s_prop[BNN_MAX_LAYERS], s_cnt[BNN_MAX_LAYERS], s_off[BNN_MAX_LAYERS];
+  // on-device generator (free-running chains): indicator moves decided by thread 0, flip probabilities for the block
+  __shared__ int s_ind_move, s_fi_move;
+  __shared__ double s_ind_p, s_fi_p;
   const NetGeom& g = d.g;
   const int c = blockIdx.x, tid = threadIdx.x;
   // The chain's scalar state is staged in shared memory for the whole launch: the accept / adapt / propose logic is
@@ -374,8 +359,22 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
           if (rr[l] < rr[amin]) amin = l;
         }
         rr[amin] = 0.0;
+        // weight indicators (BNN_env.py:449-460): the first layer is proposed only if rr[0] >= freq_indicator, otherwise
+        // its indicators move: UpdateBinomial(ind, update_f[3], shape) flips each entry with probability u * update_f[3]
+        s_ind_move = 0;
+        if (d.cfg.use_indicators && rr[0] < d.cfg.freq_indicator) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFCu, 0u, 5u), key);
+          s_ind_move = 1;
+          s_ind_p = u53(r.x, r.y) * sf[BNN_F_UPDATE_F + 3];
+        }
+        // feature indicators (BNN_env.py:423-431): past adapt_stop, with probability 0.2, flips with probability u * 0.5
+        s_fi_move = 0;
+        if (d.cfg.use_feature_indicators && it > d.cfg.adapt_stop) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFBu, 0u, 6u), key);
+          if (u53(r.x, r.y) < 0.2) { s_fi_move = 1; s_fi_p = u53(r.z, r.w) * 0.5; }
+        }
         for (int l = 0; l < g.L; ++l) {
-          s_prop[l] = rr[l] < sf[BNN_F_FREQ_LAYER + l];
+          s_prop[l] = rr[l] < sf[BNN_F_FREQ_LAYER + l] && !(l == 0 && s_ind_move);
           s_cnt[l] = s_prop[l] ? si[BNN_I_UPDATE_N + l] : 0;
           s_off[l] = off;
           off += s_cnt[l];
@@ -388,9 +387,22 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
       // the injected draw, both reflections over every entry (BNN_mcmc.py:46-56), Exp(10) term into additional_prob
       double addp = d.inj_add_prob ? d.inj_add_prob[(long long)step * d.C + c] : 0.0;
       for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
-      if (d.cfg.n_act_prm > 0 && d.inj_alpha_ix) {
-        const int ix = d.inj_alpha_ix[(long long)step * d.C + c];
-        sf[BNN_F_ALPHA_PROP + ix] = sf[BNN_F_ALPHA + ix] + d.inj_alpha_dz[(long long)step * d.C + c];
+      if (d.cfg.n_act_prm > 0 && (d.inj_alpha_ix || !d.inj_proposed)) {
+        int ix;
+        double adz;
+        if (d.inj_alpha_ix) {
+          ix = d.inj_alpha_ix[(long long)step * d.C + c];
+          adz = d.inj_alpha_dz[(long long)step * d.C + c];
+        } else {                                          // rs.integers(0, n, 1), rs.normal(0, 0.05, 1) on the device
+          uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFDu, 0u, 4u), key);
+          ix = (int)__umulhi(r.x, (uint32_t)d.cfg.n_act_prm);
+          double sn, cs;
+          sincospi(2.0 * u53(r.y, r.z), &sn, &cs);
+          uint4 r2 = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFDu, 1u, 4u), key);
+          adz = 0.05 * sqrt(-2.0 * log(1.0 - u53(r2.x, r2.y))) * cs;
+        }
+        sf[BNN_F_ALPHA_PROP + ix] = sf[BNN_F_ALPHA + ix] + adz;
         double sum = 0.0;
         for (int l = 0; l < d.cfg.n_act_prm; ++l) {
           double z = sf[BNN_F_ALPHA_PROP + l];
@@ -404,6 +416,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
       sf[BNN_F_ADD_PROB] = addp;
       for (int l = 0; l < g.L; ++l) d.alpha_fwd[(long long)c * g.L + l] = sf[BNN_F_ALPHA_PROP + l];
     } else {
+      s_ind_move = 0; s_fi_move = 0;
       for (int l = 0; l < g.L; ++l) { s_prop[l] = 0; s_cnt[l] = 0; s_off[l] = 0; }
       // initial state (MCMC.__init__, BNN_env.py:313-320): stored parameters, init_additional_prob
       for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
@@ -417,13 +430,21 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
   // indicator proposals: UpdateBinomial = |ind - flip| with the injected flips (BNN_mcmc.py:98-99), else unchanged
   const double* ind_p = nullptr;
   const double* fi_p = nullptr;
+  __syncthreads();                                   // s_ind_move / s_fi_move and their probabilities are visible
+  const bool gen_moves = propose_mode == 1 && !d.inj_proposed;          // free-running chains draw the flips here
+  const uint2 fkey = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
   if (d.ind_cur) {
     const long long sc = (long long)step * d.C + c;
     const bool mv = propose_mode == 1 && d.inj_ind_move && d.inj_ind_move[sc];
     double* dst = d.ind_prop + (long long)c * P0;
     for (int i = tid; i < P0; i += (int)blockDim.x) {
       double v = d.ind_cur[(long long)c * P0 + i];
-      if (mv && d.inj_ind_flip[sc * P0 + i]) v = fabs(v - 1.0);
+      bool flip = mv && d.inj_ind_flip[sc * P0 + i];
+      if (gen_moves && s_ind_move) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)it, (uint32_t)i, 0u, 7u), fkey);
+        flip = u53(r.x, r.y) < s_ind_p;
+      }
+      if (flip) v = fabs(v - 1.0);
       dst[i] = v;
     }
     ind_p = dst;
@@ -434,7 +455,12 @@ __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant
     double* dst = d.fi_prop + (long long)c * g.F;
     for (int i = tid; i < g.F; i += (int)blockDim.x) {
       double v = d.fi_cur[(long long)c * g.F + i];
-      if (mv && d.inj_fi_flip[sc * g.F + i]) v = fabs(v - 1.0);
+      bool flip = mv && d.inj_fi_flip[sc * g.F + i];
+      if (gen_moves && s_fi_move) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)it, (uint32_t)i, 0u, 8u), fkey);
+        flip = u53(r.x, r.y) < s_fi_p;
+      }
+      if (flip) v = fabs(v - 1.0);
       dst[i] = v;
     }
     fi_p = dst;

@@ -255,7 +255,8 @@ class Engine:
     def chains_init(self, w0, temperature=None, update_f=None, update_ws=None, prior=L.PRIOR_NORMAL, prior_scale=1.0,
                     w_bound=np.inf, mask=None, alphas=None, sigma0=None, sigma_mode=L.SIGMA_FIXED, lik_temp=1.0,
                     adapt_f=0.0, adapt_fM=1.0, adapt_freq=1000, adapt_stop=0, sample_from_prior=0, seed=1234,
-                    n_act_prm=0, init_additional_prob=0.0, prior_ind1=None, feature_means=None, chain_offset=0):
+                    n_act_prm=0, init_additional_prob=0.0, prior_ind1=None, feature_means=None, chain_offset=0,
+                    freq_indicator=0.0):
         w = np.ascontiguousarray(self._as_sets(w0), dtype=np.float64)
         n, nl = w.shape[0], self.net.n_layers
 
@@ -289,6 +290,7 @@ class Engine:
         cfg.use_indicators = int(prior_ind1 is not None)
         cfg.prior_ind1 = float(prior_ind1) if prior_ind1 is not None else 0.5
         cfg.use_feature_indicators = int(feature_means is not None)
+        cfg.freq_indicator = float(freq_indicator) if prior_ind1 is not None else 0.0
         if feature_means is not None:
             fm = np.ascontiguousarray(feature_means, dtype=np.float64)
             assert fm.shape == (self.net.n_features,)
@@ -476,21 +478,27 @@ class Engine:
                 out["dense"] = dd.cpu().numpy()
             return out
 
-    def predict_sample(self, x, weight_sets, u, alphas=None, post_predictions=True):
+    def predict_sample(self, x, weight_sets, u=None, alphas=None, post_predictions=True, seed=None):
         """sample_from_categorical (BNN_lib.py:682-713) fused into the prediction pass.  u [n, S]: the reference's
-        uniforms (np.random.random(S) per instance).  Returns dict(predictions [n,K], class_counts [S,K],
-        post_predictions [n,S] or None)."""
+        uniforms (np.random.random(S) per instance); u=None: uniforms generated in the kernel from `seed` (Philox,
+        nothing of size n x S is stored).  Returns dict(predictions [n,K], class_counts [S,K], post_predictions [n,S]
+        or None)."""
         w = self._as_sets(weight_sets)
         with torch.cuda.device(self.device):
             xd, wd, ad = self._dev(x, torch.float64), self._dev(w, torch.float64), self._dev(alphas, torch.float64)
-            ud = self._dev(u, torch.float64)
             n, S = xd.shape[0], wd.shape[0]
-            assert tuple(ud.shape) == (n, S)
             est = torch.empty((n, self.K), dtype=torch.float64, device=self.device)
             cc = torch.empty((S, self.K), dtype=torch.int32, device=self.device)
             pp = torch.empty((n, S), dtype=torch.float64, device=self.device) if post_predictions else None
-            L.check(self.lib.bnn_predict_sample(self._h, _ptr(xd), n, _ptr(wd), S, _ptr(ad), _ptr(ud), _ptr(est), _ptr(cc),
-                                                _ptr(pp), self._stream()))
+            if u is None:
+                L.check(self.lib.bnn_predict_sample_philox(self._h, _ptr(xd), n, _ptr(wd), S, _ptr(ad),
+                                                           int(0 if seed is None else seed) & (2 ** 64 - 1), _ptr(est), _ptr(cc),
+                                                           _ptr(pp), self._stream()))
+            else:
+                ud = self._dev(u, torch.float64)
+                assert tuple(ud.shape) == (n, S)
+                L.check(self.lib.bnn_predict_sample(self._h, _ptr(xd), n, _ptr(wd), S, _ptr(ad), _ptr(ud), _ptr(est), _ptr(cc),
+                                                    _ptr(pp), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
             return {"predictions": est.cpu().numpy(), "class_counts": cc.cpu().numpy().astype(np.float64),
                     "post_predictions": None if pp is None else pp.cpu().numpy()}

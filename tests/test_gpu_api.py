@@ -179,10 +179,9 @@ def test_unsupported_options_raise():
     z, meta = G.load("syn_swish_cauchy")
     dat = _dat(z)
     with pytest.raises(NotImplementedError):
-        bn.MCMC(bn.npBNN(dat, n_nodes=[4, 3, 3], freq_indicator=0.1), rng="philox")     # indicator moves are host-drawn
-    trainable = bn.npBNN(dat, n_nodes=[4, 3], actFun=bn.ActFun(fun="genReLU", prm=np.array([0.1, 0.2]), trainable=True))
-    with pytest.raises(NotImplementedError):
-        bn.MCMC(trainable, rng="philox")                  # that branch is proposed from host-drawn numbers only
+        bn.MCMC(bn.npBNN(dat, n_nodes=[4, 3]), update_function=bn.UpdateUniform)        # only UpdateNormal is on the device
+    with pytest.raises(IndexError):                       # the reference reads update_f[3] in the indicator branch
+        bn.MCMC(bn.npBNN(dat, n_nodes=[4, 3], freq_indicator=0.1), rng="philox")
     with pytest.raises(NotImplementedError):
         bn.npBNN(dat, n_nodes=[4, 3], estimation_mode="custom", size_output=3)
     bnn = bn.npBNN(dat, n_nodes=[4, 3])
@@ -491,3 +490,87 @@ def test_philox_chains_agree_statistically_at_the_c4_shape():
     assert gap[0] < max(4 * se[0], 0.01 * abs(mh[0]))            # log-likelihood
     assert gap[1] < max(4 * se[1], 0.01) and gap[2] < max(4 * se[2], 0.02)
     assert gap[3] < 0.15
+
+
+def test_mode2_resampling_with_in_kernel_uniforms():
+    """get_posterior_cat_prob(post_summary_mode=2) / sample_from_categorical with the uniforms generated inside the
+    kernel (bnn_predict_sample_philox): O(N K) memory, shape-specialised kernel.  Checked against the injected-uniform
+    path statistically (shares vs mean probabilities) and draw by draw against the generic kernel on the same
+    counters (the two kernels sum the cumulative probabilities in different orders)."""
+    import npbnn_b200 as bn
+    from npbnn_b200 import _lib as L
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(12)
+    n, S, K = 6000, 96, 10
+    shapes = [(64, 64), (32, 64), (K, 33)]
+    x = rng.standard_normal((n, 64))
+    sets = [[rng.normal(0, 0.25, s) for s in shapes] for _ in range(S)]
+    eng = Engine(NetShape.from_weights(sets[0], 64, act="swish", lik=L.LIK_CATEGORICAL))
+    fast = eng.predict_sample(x, sets, u=None, seed=2024)
+    assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+    eng.set_option("force_generic", 1)
+    gen = eng.predict_sample(x, sets, u=None, seed=2024)
+    assert eng.last_kernel == "k_fwd_generic"
+    eng.set_option("force_generic", 0)
+    other = eng.predict_sample(x, sets, u=None, seed=2025)
+    mean = eng.predict(x, sets, mean=True)["mean"]
+    eng.close()
+    pp = fast["post_predictions"]
+    assert pp.shape == (n, S) and pp.min() >= 0 and pp.max() <= K - 1 and np.all(pp == np.round(pp))
+    assert np.mean(pp == gen["post_predictions"]) > 0.9999           # same counters, same draws (up to rounding ties)
+    assert np.mean(pp == other["post_predictions"]) < 0.9            # another seed, other draws
+    # bookkeeping: shares are the per-row histogram of the draws, class_counts the per-set histogram
+    hist = np.stack([(pp == k).mean(1) for k in range(K)], axis=1)
+    assert np.array_equal(fast["predictions"], hist)
+    assert np.array_equal(fast["class_counts"], np.stack([(pp == k).sum(0) for k in range(K)], axis=1))
+    # statistics: E[share] = mean probability; standardised deviations over all (row, class) cells behave like N(0, 1)
+    zs = (fast["predictions"] - mean) / np.sqrt(np.maximum(mean * (1 - mean), 1e-12) / S)
+    sel = (mean > 0.02) & (mean < 0.98)
+    assert abs(zs[sel].mean()) < 0.02 and 0.9 < zs[sel].std() < 1.1
+    # the API picks the in-kernel generator by size (or on request) and seeds it from numpy's global stream
+    post = [{"weights": w, "alphas": [0.0]} for w in sets]
+    af = bn.ActFun(fun="swish")
+    np.random.seed(3)
+    _, a = bn.get_posterior_cat_prob(x, post, post_summary_mode=2, actFun=af, output_act_fun=bn.SoftMax, return_dense=False,
+                                     rng="philox")
+    np.random.seed(3)
+    b = bn.sample_from_categorical(x, post, actFun=af, output_act_fun=bn.SoftMax, rng="philox", post_predictions=False)
+    assert np.array_equal(a, b["predictions"]) and b["post_predictions"] is None
+    assert abs(((a - mean) / np.sqrt(np.maximum(mean * (1 - mean), 1e-12) / S))[sel].mean()) < 0.02
+
+
+def test_free_running_chains_draw_every_proposal_branch_on_the_device(tmp_path):
+    """rng="philox" with trainable activation slopes, weight indicators (four layers) and feature indicators: the
+    secondary proposals (BNN_env.py:416-431,449-460) are generated in k_mh_update.  The chain state must stay coherent:
+    log-prior = calc_prior of the exported weights / indicators (+ the Exp(10) term of the slopes), log-likelihood =
+    the likelihood of a fresh forward pass with the exported indicators, indicators in {0, 1}, slopes in [0, 1]."""
+    import npbnn_b200 as bn
+    from tests import golden_data
+    dat = golden_data.synth_class(800, 6, 3, 13, 100)
+    np.random.seed(13)
+    prm = np.array([0.1, 0.3, 0.2])
+    bnn = bn.npBNN(dat, n_nodes=[5, 4, 4], actFun=bn.ActFun(fun="genReLU", prm=prm, trainable=True), use_bias_node=2,
+                   freq_indicator=0.3, prior_ind1=0.4, feature_indicators=True, seed=13)
+    mcmc = bn.MCMC(bnn, n_iteration=2000, update_f=[0.2] * 4, adapt_stop=5, rng="philox",
+                   init_additional_prob=float(np.log(10) * -np.sum(prm) * 10))
+    mcmc.run(bnn, 400)
+    assert mcmc._current_iteration == 400 and 0.02 < mcmc._acceptance_rate <= 1.0
+    ind, fi = np.asarray(bnn._indicators), np.asarray(bnn._feature_indicators)
+    assert set(np.unique(ind)) <= {0.0, 1.0} and set(np.unique(fi)) <= {0, 1}
+    assert ind.mean() < 1.0 and fi.mean() < 1.0                       # both kinds of move happened and were accepted
+    acc = np.asarray(bnn._act_fun._acc_prm)
+    assert np.all(acc >= 0) and np.all(acc <= 1) and not np.allclose(acc, prm)
+    # coherence of the exported state
+    lp = bnn.calc_prior() + float(np.log(10) * -np.sum(acc) * 10)
+    assert np.isclose(mcmc._logPrior, lp, rtol=1e-9), (mcmc._logPrior, lp)
+    af = bn.ActFun(fun="genReLU", prm=acc)
+    dt = bn.data_transform_obj(fi, bnn._feature_means)
+    y = bn.RunPredictInd(bnn._data, bnn._w_layers, ind, af, bn.SoftMax, data_transform=dt)
+    ll = bn.calc_likelihood(y, bnn._labels, np.arange(len(bnn._labels)))
+    assert np.isclose(mcmc._logLik, ll, rtol=1e-9), (mcmc._logLik, ll)
+    assert np.isclose(mcmc._accuracy, bn.CalcAccuracy(y, bnn._labels))
+    # and through run_mcmc with the pipelined logger
+    logger = bn.postLogger(bnn, filename="sec", wdir=str(tmp_path))
+    bn.run_mcmc(bnn, mcmc, logger)
+    head = open(logger._logfile).read().split("\n")[0].split("\t")
+    assert "mean_ind" in head and "alpha_0" in head and "feature_ind_5" in head

@@ -87,8 +87,10 @@ def test_exact_width_families(family, mode, act):
     out = eng.predict(m.x, sets, alphas=al, mean=True, votes=(mode == "classification"), dense=True)
     assert eng.last_kernel.startswith(prefix), eng.last_kernel
     dense_ref, mean_ref = orc.posterior_predict(m.x, sets, act, None if alphas is None else [alphas] * len(sets), m.out_kind, 1)
-    assert np.allclose(out["dense"], dense_ref, rtol=1e-10, atol=1e-300)
-    assert np.allclose(out["mean"], mean_ref, rtol=1e-10, atol=1e-300)
+    # regression outputs cross zero (cancellation in the last layer): absolute tolerance at the scale of the outputs
+    atol = 1e-300 if mode == "classification" else 1e-11
+    assert np.allclose(out["dense"], dense_ref, rtol=1e-10, atol=atol)
+    assert np.allclose(out["mean"], mean_ref, rtol=1e-10, atol=atol)
     if mode == "classification":
         _, votes_ref = orc.posterior_predict(m.x, sets, act, None if alphas is None else [alphas] * len(sets), "softmax", 0)
         assert np.array_equal(out["votes"], votes_ref)
@@ -147,8 +149,9 @@ def test_smaller_networks_are_padded_up_on_large_data(case):
     assert eng2.last_kernel.startswith(prefix), eng2.last_kernel
     small = eng2.predict(m.x[:999], sets, alphas=al, mean=True)
     assert eng2.last_kernel == "k_fwd_generic"
-    assert np.allclose(big["mean"][:999], small["mean"], rtol=1e-12, atol=1e-300)
+    atol = 1e-300 if mode == "classification" else 1e-11
+    assert np.allclose(big["mean"][:999], small["mean"], rtol=1e-12, atol=atol)
     _, mean_ref = orc.posterior_predict(m.x[:2000], sets, act, None if alphas is None else [alphas] * len(sets), m.out_kind, 1)
-    assert np.allclose(big["mean"][:2000], mean_ref, rtol=1e-10, atol=1e-300)
+    assert np.allclose(big["mean"][:2000], mean_ref, rtol=1e-10, atol=atol)
     eng.close()
     eng2.close()
