@@ -325,39 +325,46 @@ def main():
                         "achieved_gbs": args.rows * (64 * 8 + 4) / (fwd_avg_ms * 1e-3) / 1e9 if fwd_n else None}}
 
     # ------------------------------------------------------------------ forward rows/s (BASELINE metric, second half):
-    # posterior prediction (c5 shape) over this rank's row shard for PRED_SAMPLES posterior samples, summaries
-    # mean + votes; no collective (rows are sharded)
-    import ctypes as C
+    # posterior prediction (c5 shape) for PRED_SAMPLES posterior samples, summaries mean + votes.  The ranks form a
+    # (row groups x sample groups) grid chosen to minimise the rounds of warp tiles per GPU (npbnn_b200/predshard.py):
+    # rows only (no collective) while that is balanced, otherwise the partial sums of a row block are added with one
+    # all-reduce per summary inside the timed region.
+    from npbnn_b200 import predshard
     predict = None
     try:
-        r0, r1 = args.rows * rank // world, args.rows * (rank + 1) // world
-        xd = x_pin[r0:r1].to(dev)
+        rows_p, sets_p, grid_p, _, _ = predshard.partition(args.rows, PRED_SAMPLES, world, rank)
+        xd = x_pin[rows_p[0]:rows_p[1]].to(dev)
         rs_p = np.random.default_rng(5)
-        wd = torch.from_numpy(w0[:1].repeat(PRED_SAMPLES, 0) + rs_p.normal(0, 0.05, (PRED_SAMPLES, w0.shape[1]))).to(dev)
-        md = torch.empty((r1 - r0, 10), dtype=torch.float64, device=dev)
-        vd = torch.empty((r1 - r0, 10), dtype=torch.float64, device=dev)
+        w_all = w0[:1].repeat(PRED_SAMPLES, 0) + rs_p.normal(0, 0.05, (PRED_SAMPLES, w0.shape[1])) if n_local else None
+        if w_all is None:
+            w_all = np.zeros((PRED_SAMPLES, net.n_params))
+        if world > 1:       # every rank must hold the same posterior samples: rank 0's
+            wt_ = torch.from_numpy(w_all).to(dev)
+            dist.broadcast(wt_, 0)
+            w_all = wt_.cpu().numpy()
 
         def run_predict():
-            L.check(eng.lib.bnn_predict(eng._h, C.c_void_p(xd.data_ptr()), r1 - r0, C.c_void_p(wd.data_ptr()), PRED_SAMPLES,
-                                        None, None, None, 0, C.c_void_p(md.data_ptr()), C.c_void_p(vd.data_ptr()), None,
-                                        eng._stream()))
-        run_predict()
+            return predshard.predict_sharded(eng, xd, w_all, args.rows, rank, world, votes=True, grid=grid_p)
+        out_p = run_predict()
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
-        run_predict()
+        out_p = run_predict()
         p1.record()
         barrier()
         pms = max_over_ranks(p0.elapsed_time(p1))
+        tf = PRED_SAMPLES * args.rows * wl.C4_FLOP_PER_ROW / (pms * 1e-3) / 1e12
         predict = {"metric": "forward rows/s (posterior samples x rows / s)", "value": PRED_SAMPLES * args.rows / (pms * 1e-3),
-                   "unit": "row-samples/s", "samples": PRED_SAMPLES, "rows": args.rows, "ms": pms,
-                   "tflops": PRED_SAMPLES * args.rows * wl.C4_FLOP_PER_ROW / (pms * 1e-3) / 1e12,
-                   "frac_of_fp64_peak_per_gpu": PRED_SAMPLES * args.rows * wl.C4_FLOP_PER_ROW / (pms * 1e-3) / 1e12 / world / peak_tf,
-                   "kernel": eng.last_kernel, "rows_sharded_over": world,
-                   "mean_prob_sum": float(md.sum().item()) / max(r1 - r0, 1)}
-        del xd, wd, md, vd
+                   "unit": "row-samples/s", "samples": PRED_SAMPLES, "rows": args.rows, "ms": pms, "tflops": tf,
+                   "frac_of_fp64_peak_per_gpu": tf / world / peak_tf, "kernel": eng.last_kernel,
+                   "grid": {"row_groups": grid_p[0], "sample_groups": grid_p[1],
+                            "rounds_per_gpu": predshard.rounds(rows_p[1] - rows_p[0]),
+                            "collective": "none" if grid_p[1] == 1 else "all-reduce of [rows, 10] partial sums within a row group"},
+                   "includes": "upload + packing of the posterior samples, X row block resident",
+                   "mean_prob_sum": float(out_p["mean"].sum().item()) / max(rows_p[1] - rows_p[0], 1)}
+        del xd, out_p
     except Exception as e:                                 # the headline must not depend on this leg
-        predict = {"error": str(e)}
+        predict = {"error": repr(e)}
 
     # ------------------------------------------------------------------ end-to-end leg (host buffers)
     e2e = None

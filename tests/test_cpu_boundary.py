@@ -300,3 +300,52 @@ def test_background_pickle_writer_keeps_the_newest_state(tmp_path):
     logger.log_weights(bnn, mc)
     with open(logger._pklfile, "rb") as f:
         assert pickle.load(f)[1]._current_iteration == 41
+
+
+PRED_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+import torch.distributed as dist
+rank, port, out = int(sys.argv[1]), sys.argv[2], sys.argv[3]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+dist.init_process_group("gloo", rank=rank, world_size=2)
+from npbnn_b200 import predshard
+n, S, K = 1000, 7, 3
+rng = np.random.default_rng(0)
+probs = rng.random((S, n, K))                            # stands for the per-sample predictions of the kernel
+rows, sets, grid, rg, sg = predshard.partition(n, S, 2, rank, grid=(1, 2))
+local = torch.from_numpy(probs[sets[0]:sets[1], rows[0]:rows[1]].sum(0))
+mean = predshard.combine(local, S, 2, rank, grid)
+np.save(out + "/pred_%%d.npy" %% rank, mean.numpy())
+dist.destroy_process_group()
+'''
+
+
+def test_prediction_grid_and_combine_two_ranks_gloo(tmp_path):
+    """2-D sharding of the posterior prediction (npbnn_b200/predshard.py): grid choice by rounds of warp tiles, exact
+    cover of rows x samples, and the all-reduce of the partial sums over a sample group on two gloo ranks."""
+    from npbnn_b200 import predshard as ps
+    assert ps.grid_for(1_000_000, 10_000, 8) == (4, 2)       # 125k rows: 4.4 rounds executed as 5 -> 250k rows x half the samples
+    assert ps.grid_for(1_000_000, 10_000, 4) == (4, 1) and ps.grid_for(1_000_000, 10_000, 1) == (1, 1)
+    assert ps.grid_for(1_000_000, 1, 8) == (8, 1)            # a single sample cannot be split
+    for n, S, world in ((1_000_003, 77, 8), (999, 5, 4), (50_000, 64, 2)):
+        grid = ps.grid_for(n, S, world)
+        cover = np.zeros((n, S), dtype=np.int8) if n * S < 10 ** 7 else None
+        cells = 0
+        for r in range(world):
+            rows, sets, g, rg, sg = ps.partition(n, S, world, r, grid)
+            assert g == grid and r == rg * grid[1] + sg
+            cells += (rows[1] - rows[0]) * (sets[1] - sets[0])
+            if cover is not None:
+                cover[rows[0]:rows[1], sets[0]:sets[1]] += 1
+        assert cells == n * S and (cover is None or np.all(cover == 1))
+    script = tmp_path / "p.py"
+    script.write_text(PRED_WORKER % {"root": ROOT})
+    port = str(33500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port, str(tmp_path)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    a, b = np.load(tmp_path / "pred_0.npy"), np.load(tmp_path / "pred_1.npy")
+    probs = np.random.default_rng(0).random((7, 1000, 3))
+    assert np.array_equal(a, b) and np.allclose(a, probs.mean(0), rtol=1e-14)

@@ -513,7 +513,8 @@ def test_mode2_resampling_with_in_kernel_uniforms():
     assert eng.last_kernel == "k_fwd_generic"
     eng.set_option("force_generic", 0)
     other = eng.predict_sample(x, sets, u=None, seed=2025)
-    mean = eng.predict(x, sets, mean=True)["mean"]
+    pred = eng.predict(x, sets, mean=True, dense=True)
+    mean, dense = pred["mean"], pred["dense"]
     eng.close()
     pp = fast["post_predictions"]
     assert pp.shape == (n, S) and pp.min() >= 0 and pp.max() <= K - 1 and np.all(pp == np.round(pp))
@@ -523,10 +524,12 @@ def test_mode2_resampling_with_in_kernel_uniforms():
     hist = np.stack([(pp == k).mean(1) for k in range(K)], axis=1)
     assert np.array_equal(fast["predictions"], hist)
     assert np.array_equal(fast["class_counts"], np.stack([(pp == k).sum(0) for k in range(K)], axis=1))
-    # statistics: E[share] = mean probability; standardised deviations over all (row, class) cells behave like N(0, 1)
-    zs = (fast["predictions"] - mean) / np.sqrt(np.maximum(mean * (1 - mean), 1e-12) / S)
+    # statistics: a share is the mean of S independent Bernoulli(p_s) draws: E = mean probability, Var = sum p_s (1 - p_s)
+    # / S^2; the standardised deviations over all (row, class) cells behave like N(0, 1)
+    sd = np.sqrt(np.maximum((dense * (1 - dense)).sum(0), 1e-12)) / S
+    zs = (fast["predictions"] - mean) / sd
     sel = (mean > 0.02) & (mean < 0.98)
-    assert abs(zs[sel].mean()) < 0.02 and 0.9 < zs[sel].std() < 1.1
+    assert abs(zs[sel].mean()) < 0.02 and 0.95 < zs[sel].std() < 1.05
     # the API picks the in-kernel generator by size (or on request) and seeds it from numpy's global stream
     post = [{"weights": w, "alphas": [0.0]} for w in sets]
     af = bn.ActFun(fun="swish")
@@ -536,7 +539,7 @@ def test_mode2_resampling_with_in_kernel_uniforms():
     np.random.seed(3)
     b = bn.sample_from_categorical(x, post, actFun=af, output_act_fun=bn.SoftMax, rng="philox", post_predictions=False)
     assert np.array_equal(a, b["predictions"]) and b["post_predictions"] is None
-    assert abs(((a - mean) / np.sqrt(np.maximum(mean * (1 - mean), 1e-12) / S))[sel].mean()) < 0.02
+    assert abs(((a - mean) / sd)[sel].mean()) < 0.02
 
 
 def test_free_running_chains_draw_every_proposal_branch_on_the_device(tmp_path):
