@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
-  const int ZS = bnn_round_up(g.O, 8) + 1;
+  const int ZS = g.l[g.L - 1].out_pad + 1;        // the last layer may be padded beyond round_up(O, 8) (k_fwd3 width families)
   const int PW = bnn_pred_width(g);
 
   double* tab = reinterpret_cast<double*>(smem_raw);
@@ -2024,7 +2024,7 @@ int bnn_fwd3_family(const NetGeom& g) {
 template <int ACT, bool PREDICT>
 static cudaError_t launch_generic_t(const FwdParams& p, int n_sms, cudaStream_t st) {
   auto kern = k_fwd_generic<ACT, PREDICT>;
-  const int ZS = bnn_round_up(p.g.O, 8) + 1;
+  const int ZS = p.g.l[p.g.L - 1].out_pad + 1;
   const int PW = (p.g.lik == BNN_LIK_CATEGORICAL) ? p.g.K : p.g.O;
   size_t per_warp = 2 * 16 * (size_t)p.g.max_w + 16 * ZS + (PREDICT ? 16 * PW : 0);
   size_t bytes = (BNN_EXP_TAB_SIZE + GEN_WARPS * per_warp) * sizeof(double);

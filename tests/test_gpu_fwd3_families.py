@@ -110,6 +110,10 @@ def test_smaller_networks_are_padded_up_on_large_data(case):
     m, sets, alphas = _problem(mode, n, f, hidden, k, act, bias, seed=5, n_sets=3, n_test=333)
     eng = make_engine(m)
     _check_scores(eng, m, sets, alphas, prefix)
+    # the generic kernel on the padded-up layout (reached through force_generic and by injected-uniform resampling)
+    eng.set_option("force_generic", 1)
+    _check_scores(eng, m, sets, alphas, "k_fwd_generic")
+    eng.set_option("force_generic", 0)
     # a chain on the padded layout: 6 MH iterations replayed against the oracle
     s = orc.make_sampler(m, n_iteration=1000, update_f=[0.1] * 3)
     eng.chains_init([sets[0]], update_f=[0.1] * 3, alphas=None if alphas is None else np.resize(alphas, 3),
