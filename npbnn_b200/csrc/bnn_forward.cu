@@ -14,6 +14,8 @@
 //                 copies + mbarriers, hidden activations never leave registers.
 //   k_fwd_generic any depth/width: hidden activations staged in per-warp shared memory, weights read
 //                 through L1/L2.
+#include <cstdio>
+#include <type_traits>
 #include "bnn_common.cuh"
 
 #define FULL_MASK 0xffffffffu
@@ -550,13 +552,35 @@ struct Fwd3Geom {
 #define FWD3_ACT_MODE 0         // how layer-1 activations interleave with the layer-2 MMAs (tuning variants 1, 2)
 #endif
 
-template <int ACT, int TB = BNN_EXP_TAB_BITS>
+template <int ACT, bool FAST = false, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void act_tile(double (&a)[4], double alpha, const double* tab) {
 #ifdef BNN_DBG_NOACT      // tuning experiment only: how fast is the kernel without activations?
   return;
 #endif
+#ifdef BNN_DBG_ACTCHAIN   // tuning experiment only: N dependent register DFMAs per element instead of the activation
 #pragma unroll
-  for (int e = 0; e < 4; ++e) a[e] = bnn_act<ACT, TB>(a[e], alpha, tab);
+  for (int s = 0; s < BNN_DBG_ACTCHAIN; ++s)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = fma(a[e], 0.999, alpha);
+  return;
+#endif
+#pragma unroll
+  for (int e = 0; e < 4; ++e) a[e] = FAST ? bnn_act_fast<ACT>(a[e], alpha, tab) : bnn_act<ACT, TB>(a[e], alpha, tab);
+}
+
+// Does any pre-activation of this warp's fragments need the guarded evaluation (|z| beyond the exponential's range,
+// inf, NaN)?  One vote per layer: the common case then runs a straight-line copy of the layer without the clamp /
+// NaN fix-up instructions (6 integer instructions per element on the 16-lane ALU pipe, which the activation chains
+// of three warps otherwise keep as busy as the FP64 pipe).
+template <int ACT, int NT>
+__device__ __forceinline__ bool frag_needs_care(const double (&acc)[NT][4]) {
+  if (ACT == BNN_ACT_RELU || ACT == BNN_ACT_LEAKY) return false;
+  int worst = 0;
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) worst = max(worst, __double2hiint(acc[j][e]) & 0x7fffffff);
+  return __any_sync(FULL_MASK, worst >= (ACT == BNN_ACT_SWISH ? 0x40862000 : 0x40762000));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -914,13 +938,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   uint64_t* full = bars;            // [2]
   uint64_t* empty = bars + 2;       // [2]
   uint64_t* xbar = bars + 4 + warp; // [NWARPS]
-  int* cnt = reinterpret_cast<int*>(bars + 4 + NWARPS);
+  int* rel = reinterpret_cast<int*>(bars + 4 + NWARPS);   // [2] warps that released ring slot b (FWD3_RING_LAST), one 8-byte slot
+  int* cnt = reinterpret_cast<int*>(bars + 5 + NWARPS);
   const int n_cnt = DEFER ? p.C * (2 + 2 * g.K) : 0;
   const int PW = CAT ? g.K : g.O;                 // columns of a prediction row
 
   for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   if (threadIdx.x == 0) {
+    rel[0] = rel[1] = 0;
     mbar_init(&full[0], 1); mbar_init(&full[1], 1);
     mbar_init(&empty[0], NWARPS); mbar_init(&empty[1], NWARPS);
     for (int w = 0; w < NWARPS; ++w) mbar_init(&bars[4 + w], 1);
@@ -968,14 +994,38 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   constexpr uint32_t W_BYTES = G3::PB * sizeof(double);
   constexpr uint32_t X_BYTES = 16 * KP0 * sizeof(double);
 
-  const bool producer = (threadIdx.x == 0);
-  if (producer) {
+  if (threadIdx.x == 0) {
     for (int q = 0; q < 2 && q < total_q; ++q) {
       mbar_arrive_expect_tx(&full[q], W_BYTES);
       bulk_g2s(wbuf + q * G3::PB, p.wp + set_of(q) * G3::PB, W_BYTES, &full[q]);
     }
   }
 
+  // Ring slot b is released by every warp when it is done with use qq; the warp whose release is the last one
+  // issues the bulk copy of use qq+2 into the slot itself, so a refill starts the moment the slot is free (a fixed
+  // producer thread would start it only when its own warp next reaches the top of the weight-set loop, and would make
+  // that warp wait for the slowest one before every use: 17.01 -> 16.68 ms at c4).  The warp schedulers prefer the
+  // younger warps (measured ring waits per warp: 0.3 / 2 / 4.5 % of the run for warps 0-3 / 4-7 / 8-11), so the
+  // slowest warp is rarely warp 0.
+  auto release_slot = [&](int b, long long qq) {
+    if (lane == 0) {
+      __threadfence_block();                       // this warp's reads of the slot happen before the release
+      const int old = atomicAdd(&rel[b], 1);
+      if (old == NWARPS - 1) {                     // last warp out refills the slot
+        rel[b] = 0;
+        if (qq + 2 < total_q) {
+          __threadfence_block();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_expect_tx(&full[b], W_BYTES);
+          bulk_g2s(wbuf + b * G3::PB, p.wp + set_of(qq + 2) * G3::PB, W_BYTES, &full[b]);
+        }
+      }
+    }
+  };
+#ifdef BNN_DBG_RINGCLK
+  long long dbg_ring = 0;
+  const long long dbg_start = clock64();
+#endif
   long long q = 0;
   uint32_t x_uses = 0;               // X tiles this warp has loaded (parity of its mbarrier)
   bool x_prefetched = false;         // the X tile of this iteration was requested during the previous one
@@ -1032,15 +1082,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
     }
     for (int c = c_lo; c < c_hi; ++c, ++q) {
       const int b = (int)(q & 1);
-      // producer: refill the other buffer (use q+1) once every warp has released use q-1
-      if (producer && q >= 1 && q + 1 < total_q) {
-        const int nb = b ^ 1;
-        mbar_wait(&empty[nb], (uint32_t)(((q - 1) >> 1) & 1));
-        mbar_arrive_expect_tx(&full[nb], W_BYTES);
-        bulk_g2s(wbuf + nb * G3::PB, p.wp + set_of(q + 1) * G3::PB, W_BYTES, &full[nb]);
-      }
       __syncwarp();
+#ifdef BNN_DBG_RINGCLK      // tuning experiment only: clocks this warp spends waiting for the weight ring
+      const long long dbg_t0 = clock64();
+#endif
       mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
+#ifdef BNN_DBG_RINGCLK
+      dbg_ring += clock64() - dbg_t0;
+#endif
       if (have_tile) {
         const double* W = wbuf + b * G3::PB;
         const double a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
@@ -1141,34 +1190,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // ---------------- layer 2: [16 x N1] x [N1 x N2]   (A operand = activated acc1, no data movement).
         // The activation of k-group kg+1 is independent of the MMAs of k-group kg, so its FP64 chains fill
         // the issue slots between the DMMAs instead of running as a separate latency-bound phase.
+        // Two straight-line copies per layer: one warp vote decides whether any pre-activation needs the guarded
+        // evaluation (frag_needs_care); the common copy carries no clamp / NaN fix-up instructions.
         double acc2[N2 / 8][4];
 #pragma unroll
         for (int j = 0; j < N2 / 8; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(W + G3::B2_OFF + 8 * j + 2 * t);
           acc2[j][0] = bb.x; acc2[j][1] = bb.y; acc2[j][2] = bb.x; acc2[j][3] = bb.y;
         }
-        {
+        auto layer2 = [&](auto fast_tag) {
+          constexpr bool FAST = decltype(fast_tag)::value;
           const double* wr = W + G3::W2_OFF + gq * N1;
           const int sw = (gq & 1) * G3::SW1;
-#if FWD3_ACT_MODE == 2          // tuning: all activations of the layer first, then the MMAs
-#pragma unroll
-          for (int kg = 0; kg < N1 / 8; ++kg) act_tile<ACT>(acc1[kg], a1, tab);
-#elif FWD3_ACT_MODE == 1        // tuning: two fragments (8 independent chains) per two k-groups
-          act_tile<ACT>(acc1[0], a1, tab);
-          act_tile<ACT>(acc1[1], a1, tab);
-#else
-          act_tile<ACT>(acc1[0], a1, tab);
-#endif
+          act_tile<ACT, FAST>(acc1[0], a1, tab);
 #pragma unroll
           for (int kg = 0; kg < N1 / 8 - 2; ++kg) {
-#if FWD3_ACT_MODE == 0
-            act_tile<ACT>(acc1[kg + 1], a1, tab);
-#elif FWD3_ACT_MODE == 1
-            if ((kg & 1) == 0) {
-              act_tile<ACT>(acc1[kg + 2], a1, tab);
-              act_tile<ACT>(acc1[kg + 3], a1, tab);
-            }
-#endif
+            act_tile<ACT, FAST>(acc1[kg + 1], a1, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
@@ -1178,9 +1215,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           }
           {
             constexpr int k0 = N1 / 8 - 2, k1 = N1 / 8 - 1;
-#if FWD3_ACT_MODE == 0
-            act_tile<ACT>(acc1[k1], a1, tab);
-#endif
+            act_tile<ACT, FAST>(acc1[k1], a1, tab);
             const int c0 = (8 * k0 + 2 * t) ^ sw, c1 = (8 * k1 + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N2 / 8; ++j) {
@@ -1190,20 +1225,27 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               dmma16x8x8(acc2[j], acc1[k1][0], acc1[k1][2], acc1[k1][1], acc1[k1][3], b1.x, b1.y);
             }
           }
-        }
+        };
+#ifdef FWD3_NO_FAST_ACT
+        layer2(std::false_type{});
+#else
+        if (frag_needs_care<ACT, N1 / 8>(acc1)) layer2(std::false_type{});
+        else layer2(std::true_type{});
+#endif
         // ---------------- layer 3: [16 x N2] x [N2 x N3]
 #pragma unroll
         for (int j = 0; j < N3 / 8; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
           acc3[j][0] = bb.x; acc3[j][1] = bb.y; acc3[j][2] = bb.x; acc3[j][3] = bb.y;
         }
-        {
+        auto layer3 = [&](auto fast_tag) {
+          constexpr bool FAST = decltype(fast_tag)::value;
           const double* wr = W + G3::W3_OFF + gq * N2;
           const int sw = (gq & 1) * G3::SW2;
-          act_tile<ACT>(acc2[0], a2, tab);
+          act_tile<ACT, FAST>(acc2[0], a2, tab);
 #pragma unroll
           for (int kg = 0; kg < N2 / 8; ++kg) {
-            if (kg + 1 < N2 / 8) act_tile<ACT>(acc2[kg + 1], a2, tab);
+            if (kg + 1 < N2 / 8) act_tile<ACT, FAST>(acc2[kg + 1], a2, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N3 / 8; ++j) {
@@ -1211,10 +1253,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               dmma16x8x8(acc3[j], acc2[kg][0], acc2[kg][2], acc2[kg][1], acc2[kg][3], bb.x, bb.y);
             }
           }
-        }
+        };
+#ifdef FWD3_NO_FAST_ACT
+        layer3(std::false_type{});
+#else
+        if (frag_needs_care<ACT, N2 / 8>(acc2)) layer3(std::false_type{});
+        else layer3(std::true_type{});
+#endif
         // weights of this use are no longer needed by this warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[b]);
+        release_slot(b, q);
         if (DEFER) {
           prev_valid = true;
           ep_wt = wt; ep_c = c;
@@ -1228,7 +1276,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           else quad_gauss_lik<N3>(p, c, wt, lane, acc3);
         }
       } else {
-        if (lane == 0) mbar_arrive(&empty[b]);
+        release_slot(b, q);
       }
     }
     if (have_tile) {
@@ -1250,6 +1298,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
       }
     }
   }
+#ifdef BNN_DBG_RINGCLK
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && p.C >= 32)
+    printf("cta %d warp %2d (smsp %d): ring wait %lld of %lld clk (%.1f%%)\n", blockIdx.x, warp, warp & 3, dbg_ring,
+           clock64() - dbg_start, 100.0 * dbg_ring / (double)(clock64() - dbg_start));
+#endif
   // drain the software pipeline: the epilogue of the last (tile, weight set) this warp ran
   if (DEFER && prev_valid) {
     RowStats<N3> rs;
@@ -1520,6 +1573,7 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
   for (int i = threadIdx.x; i < (1 << TB); i += blockDim.x) tab[i] = p.exp_tab_small[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   if (threadIdx.x == 0) {
+    rel[0] = rel[1] = 0;
     for (int i = 0; i < 2; ++i) { mbar_init(&w1full[i], 1); mbar_init(&rfull[i], 1); mbar_init(&rempty[i], FWD3T_COMPUTE_WARPS); }
     mbar_init(tfull, 1); mbar_init(tfree, FWD3T_HELPER_WARPS);
     for (int i = 0; i < 8; ++i) { mbar_init(&a1full[i], 1); mbar_init(&a1free[i], 2); }
@@ -1859,10 +1913,10 @@ __global__ void __launch_bounds__(FWD3T_THREADS, 1) k_fwd3t(const __grid_constan
         {
           const double* wr = W + G3::W3_OFF + gq * N2;
           const int sw = (gq & 1) * G3::SW2;
-          act_tile<ACT, TB>(acc2[0], a2, tab);
+          act_tile<ACT, false, TB>(acc2[0], a2, tab);
 #pragma unroll
           for (int kg = 0; kg < N2 / 8; ++kg) {
-            if (kg + 1 < N2 / 8) act_tile<ACT, TB>(acc2[kg + 1], a2, tab);
+            if (kg + 1 < N2 / 8) act_tile<ACT, false, TB>(acc2[kg + 1], a2, tab);
             const int col = (8 * kg + 2 * t) ^ sw;
 #pragma unroll
             for (int j = 0; j < N3 / 8; ++j) {
@@ -1963,7 +2017,7 @@ static size_t fwd3_smem_bytes(const FwdParams& p) {
   constexpr bool DEFER = (MODE != FWD3_PRED) && (LIKK == FWD3_CAT);
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE;
-  size_t bytes = d * sizeof(double) + (4 + NWARPS) * sizeof(uint64_t);
+  size_t bytes = d * sizeof(double) + (5 + NWARPS) * sizeof(uint64_t);     // barriers + the ring's release counters
   size_t ints = DEFER ? (size_t)p.C * (2 + 2 * p.g.K) : 0;
   return bytes + ints * sizeof(int);
 }
