@@ -302,6 +302,66 @@ __device__ __forceinline__ double bnn_act_fast(double z, double alpha, const dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same activations for N elements at once, cut into dependency LEVELS ("stages"): stage S of all N elements is
+// N independent instructions, and consecutive stages are what the FP64 latency (8 clk) separates.  The caller places
+// the stages BETWEEN its MMAs in program order; nvcc emits PTX in that order and ptxas largely keeps it, which is
+// the only way to get the activation chains interleaved with the DMMAs instead of scheduled as one long FP64-only
+// stretch (measured: what ptxas does with sequentially written activations).  Fast path only (bnn_act_fast: the
+// caller has voted that no element needs the clamp / NaN fix-up); ReLU / leaky do everything in stage 0.
+// ------------------------------------------------------------------------------------------------
+template <int ACT, int N>
+struct ActPipe {
+  static constexpr int STAGES = (ACT == BNN_ACT_SWISH || ACT == BNN_ACT_TANH) ? 11 : 1;
+  static constexpr int TB = BNN_EXP_TAB_BITS;
+  double z[N], a[N], b[N], T[N];     // a, b: the two live temporaries of the chain
+  int k[N];
+  template <int S>
+  __device__ __forceinline__ void stage(double alpha, const double* __restrict__ tab) {
+    static_assert(TB == 11, "staged activations use the 2048-entry table");
+    constexpr double MAGIC = 6755399441055744.0, INV = 2954.639443740597, C1 = 0.0003384507717577858;
+    constexpr bool SW = (ACT == BNN_ACT_SWISH);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if constexpr (ACT == BNN_ACT_RELU) {
+        if (S == 0) z[i] = z[i] < 0.0 ? 0.0 : z[i];
+      } else if constexpr (ACT == BNN_ACT_LEAKY) {
+        if (S == 0) z[i] = z[i] < 0.0 ? alpha * z[i] : z[i];
+      } else {
+        if (S == 0) a[i] = fma(z[i], SW ? -INV : 2.0 * INV, MAGIC);                  // t
+        if (S == 1) {
+          k[i] = __double2loint(a[i]);
+          T[i] = tab[k[i] & ((1 << TB) - 1)];
+          a[i] = a[i] - MAGIC;                                                        // kd
+        }
+        if (S == 2) a[i] = fma(a[i], SW ? C1 : -0.5 * C1, z[i]);                      // rs = -r (swish) or r/2 (tanh)
+        if (S == 3) {
+          b[i] = SW ? fma(a[i], -1.66666666666666657e-01, 0.5) : fma(a[i], 6.66666666666666630e-01, 1.0);   // q
+          T[i] = T[i];
+        }
+        if (S == 4) {
+          const double r2 = a[i] * a[i];
+          a[i] = SW ? -a[i] : a[i];                                                   // folded into the FMA below by ptxas
+          b[i] = fma(r2, b[i], a[i]);                                                 // p
+        }
+        if (S == 5) {
+          const double T2 = SW ? T[i] : __hiloint2double(__double2hiint(T[i]) + (1 << 20), __double2loint(T[i]));
+          const double res = fma(T2, b[i], T[i]);
+          a[i] = __hiloint2double(__double2hiint(res) + ((k[i] >> TB) << 20), __double2loint(res));   // exp(..)
+        }
+        if (S == 6) {
+          a[i] = a[i] + 1.0;                                                          // d
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(b[i]) : "d"(a[i]));                 // y0
+        }
+        if (S == 7) a[i] = fma(-a[i], b[i], 1.0);                                     // e
+        if (S == 8) a[i] = fma(a[i], a[i], a[i]);
+        if (S == 9) b[i] = fma(b[i], a[i], b[i]);                                     // y
+        if (S == 10) z[i] = SW ? z[i] * b[i] : fma(-2.0, b[i], 1.0);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (free-running proposals, posterior-predictive resampling)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {

@@ -925,30 +925,40 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   constexpr bool PREDICT = (MODE == FWD3_PRED);
   constexpr bool CAT = (LIKK == FWD3_CAT);
   constexpr bool DEFER = !PREDICT && CAT;        // categorical likelihood: epilogue pipelined into the next set's layer 1
+#ifdef BNN_DBG_NOEPI      // tuning experiment only: no likelihood epilogue at all (results are garbage)
+  constexpr bool EPI = false;
+#else
+  constexpr bool EPI = DEFER;
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
 
   // ---- shared memory carve-up
-  double* wbuf = reinterpret_cast<double*>(smem_raw);                  // [2][PB]   weight-set ring
-  double* xs = wbuf + 2 * G3::PB + warp * 16 * KP0;                     // [NWARPS][16*KP0] X warp tiles
-  double* tab = wbuf + 2 * G3::PB + NWARPS * 16 * KP0;                  // exp table
+  // Weight ring, two slots per part: part 0 = first-layer matrix + bias (W1_D doubles), part 1 = the rest of the
+  // packed weight set (W23_D doubles).  The parts are released separately: the first layer is 61 % of a use, so its
+  // slot is free (and its refill under way) long before the warp is done with the use.
+  constexpr int W1_D = G3::W2_OFF, W23_D = G3::PB - G3::W2_OFF;
+  double* w1buf = reinterpret_cast<double*>(smem_raw);                  // [2][W1_D]
+  double* w23buf = w1buf + 2 * W1_D;                                    // [2][W23_D]
+  double* xs = w23buf + 2 * W23_D + warp * 16 * KP0;                    // [NWARPS][16*KP0] X warp tiles
+  double* tab = w23buf + 2 * W23_D + NWARPS * 16 * KP0;                 // exp table
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab + BNN_EXP_TAB_SIZE);
-  uint64_t* full = bars;            // [2]
-  uint64_t* empty = bars + 2;       // [2]
+  uint64_t* full1 = bars;           // [2]
+  uint64_t* full23 = bars + 2;      // [2]
   uint64_t* xbar = bars + 4 + warp; // [NWARPS]
-  int* rel = reinterpret_cast<int*>(bars + 4 + NWARPS);   // [2] warps that released ring slot b (FWD3_RING_LAST), one 8-byte slot
-  int* cnt = reinterpret_cast<int*>(bars + 5 + NWARPS);
+  int* rel = reinterpret_cast<int*>(bars + 4 + NWARPS);   // [4] warps that released slot b of part 0 / part 1
+  int* cnt = reinterpret_cast<int*>(bars + 6 + NWARPS);
   const int n_cnt = DEFER ? p.C * (2 + 2 * g.K) : 0;
   const int PW = CAT ? g.K : g.O;                 // columns of a prediction row
 
   for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   if (threadIdx.x == 0) {
-    rel[0] = rel[1] = 0;
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], NWARPS); mbar_init(&empty[1], NWARPS);
+    rel[0] = rel[1] = rel[2] = rel[3] = 0;
+    mbar_init(&full1[0], 1); mbar_init(&full1[1], 1);
+    mbar_init(&full23[0], 1); mbar_init(&full23[1], 1);
     for (int w = 0; w < NWARPS; ++w) mbar_init(&bars[4 + w], 1);
     mbar_fence_init();
   }
@@ -991,33 +1001,42 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   auto set_of = [&](long long qq) -> long long {                 // weight set consumed by use qq of this CTA
     return qq < q_seg0 ? qq % p.C : (qq < q_seg1 ? seg_lo[0] + (qq - q_seg0) : seg_lo[1] + (qq - q_seg1));
   };
-  constexpr uint32_t W_BYTES = G3::PB * sizeof(double);
+  constexpr uint32_t W1_BYTES = W1_D * sizeof(double), W23_BYTES = W23_D * sizeof(double);
   constexpr uint32_t X_BYTES = 16 * KP0 * sizeof(double);
+  static_assert(W1_BYTES % 16 == 0 && W23_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < 2 && q < total_q; ++q) {
-      mbar_arrive_expect_tx(&full[q], W_BYTES);
-      bulk_g2s(wbuf + q * G3::PB, p.wp + set_of(q) * G3::PB, W_BYTES, &full[q]);
+  auto load_part = [&](int part, long long qq) {
+    const int b = (int)(qq & 1);
+    const double* src = p.wp + set_of(qq) * G3::PB;
+    if (part == 0) {
+      mbar_arrive_expect_tx(&full1[b], W1_BYTES);
+      bulk_g2s(w1buf + b * W1_D, src, W1_BYTES, &full1[b]);
+    } else {
+      mbar_arrive_expect_tx(&full23[b], W23_BYTES);
+      bulk_g2s(w23buf + b * W23_D, src + W1_D, W23_BYTES, &full23[b]);
     }
+  };
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 2 && q < total_q; ++q) { load_part(0, q); load_part(1, q); }
   }
 
-  // Ring slot b is released by every warp when it is done with use qq; the warp whose release is the last one
-  // issues the bulk copy of use qq+2 into the slot itself, so a refill starts the moment the slot is free (a fixed
+  // A slot is released by every warp when it is done with use qq of that part; the warp whose release is the last
+  // one issues the bulk copy of use qq+2 into the slot itself, so a refill starts the moment the slot is free (a fixed
   // producer thread would start it only when its own warp next reaches the top of the weight-set loop, and would make
   // that warp wait for the slowest one before every use: 17.01 -> 16.68 ms at c4).  The warp schedulers prefer the
   // younger warps (measured ring waits per warp: 0.3 / 2 / 4.5 % of the run for warps 0-3 / 4-7 / 8-11), so the
   // slowest warp is rarely warp 0.
-  auto release_slot = [&](int b, long long qq) {
+  auto release_part = [&](int part, long long qq) {
     if (lane == 0) {
+      int* r = &rel[2 * part + (int)(qq & 1)];
       __threadfence_block();                       // this warp's reads of the slot happen before the release
-      const int old = atomicAdd(&rel[b], 1);
+      const int old = atomicAdd(r, 1);
       if (old == NWARPS - 1) {                     // last warp out refills the slot
-        rel[b] = 0;
+        *r = 0;
         if (qq + 2 < total_q) {
           __threadfence_block();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive_expect_tx(&full[b], W_BYTES);
-          bulk_g2s(wbuf + b * G3::PB, p.wp + set_of(qq + 2) * G3::PB, W_BYTES, &full[b]);
+          load_part(part, qq + 2);
         }
       }
     }
@@ -1086,12 +1105,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #ifdef BNN_DBG_RINGCLK      // tuning experiment only: clocks this warp spends waiting for the weight ring
       const long long dbg_t0 = clock64();
 #endif
-      mbar_wait(&full[b], (uint32_t)((q >> 1) & 1));
+      mbar_wait(&full1[b], (uint32_t)((q >> 1) & 1));
 #ifdef BNN_DBG_RINGCLK
       dbg_ring += clock64() - dbg_t0;
 #endif
       if (have_tile) {
-        const double* W = wbuf + b * G3::PB;
+        const double* W = w1buf + b * W1_D;                          // part 0; layers 2 / 3 index W23 with the same offsets
+        const double* W23 = w23buf + b * W23_D - G3::W2_OFF;
         const double a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 0] : 0.0;
         const double a2 = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * 3 + 1] : 0.0;
         // ---------------- layer 1: [16 x KP0] x [KP0 x N1]
@@ -1121,7 +1141,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             const int col = (8 * kg + 2 * t) ^ sw;
             const double2 alo = *reinterpret_cast<const double2*>(xr0 + col);
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
-            if (DEFER) {
+            if (EPI) {
               if (kg == 0) qs_max<N3>(acc3, K, t, rs);
               else qs_exp<N3, 1, true>(acc3, K, t, ep_y, tab, rs);
             }
@@ -1130,7 +1150,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               const double2 bb = *reinterpret_cast<const double2*>(wr + j * 8 * KP0 + col);
               dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
             }
-            if (DEFER) {
+            if (EPI) {
               if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, ep_y, tab, rs);
               else {
                 qs_reduce<N3, true>(rs);
@@ -1144,7 +1164,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
 #ifndef BNN_DBG_NOCOMMIT      // tuning experiment only: counters / partial store of the previous set
-          if (DEFER) quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, prev_valid);
+          if (EPI) quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, prev_valid);
 #endif
 #pragma unroll 2
           for (int kg = 2; kg < KP0 / 8 - 2; ++kg) {
@@ -1172,6 +1192,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             }
           }
         }
+        // the first-layer weights of this use are no longer needed by this warp; layers 2 / 3 need part 1
+        __syncwarp();
+        release_part(0, q);
+        mbar_wait(&full23[b], (uint32_t)((q >> 1) & 1));
         // X is read by layer 1 only: after layer 1 of the tile's LAST weight set the buffer is free, and the next
         // tile's X (one bulk copy, ~2 us from HBM) arrives under layers 2 / 3 and the epilogue instead of stalling
         // the start of the next tile -- 0.4 % of a 32-set tile, but 3 % at 4 sets per GPU and 12 % for a single chain.
@@ -1195,12 +1219,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         double acc2[N2 / 8][4];
 #pragma unroll
         for (int j = 0; j < N2 / 8; ++j) {
-          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B2_OFF + 8 * j + 2 * t);
+          const double2 bb = *reinterpret_cast<const double2*>(W23 + G3::B2_OFF + 8 * j + 2 * t);
           acc2[j][0] = bb.x; acc2[j][1] = bb.y; acc2[j][2] = bb.x; acc2[j][3] = bb.y;
         }
         auto layer2 = [&](auto fast_tag) {
           constexpr bool FAST = decltype(fast_tag)::value;
-          const double* wr = W + G3::W2_OFF + gq * N1;
+          const double* wr = W23 + G3::W2_OFF + gq * N1;
           const int sw = (gq & 1) * G3::SW1;
           act_tile<ACT, FAST>(acc1[0], a1, tab);
 #pragma unroll
@@ -1235,12 +1259,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         // ---------------- layer 3: [16 x N2] x [N2 x N3]
 #pragma unroll
         for (int j = 0; j < N3 / 8; ++j) {
-          const double2 bb = *reinterpret_cast<const double2*>(W + G3::B3_OFF + 8 * j + 2 * t);
+          const double2 bb = *reinterpret_cast<const double2*>(W23 + G3::B3_OFF + 8 * j + 2 * t);
           acc3[j][0] = bb.x; acc3[j][1] = bb.y; acc3[j][2] = bb.x; acc3[j][3] = bb.y;
         }
         auto layer3 = [&](auto fast_tag) {
           constexpr bool FAST = decltype(fast_tag)::value;
-          const double* wr = W + G3::W3_OFF + gq * N2;
+          const double* wr = W23 + G3::W3_OFF + gq * N2;
           const int sw = (gq & 1) * G3::SW2;
           act_tile<ACT, FAST>(acc2[0], a2, tab);
 #pragma unroll
@@ -1262,7 +1286,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
 #endif
         // weights of this use are no longer needed by this warp
         __syncwarp();
-        release_slot(b, q);
+        release_part(1, q);
         if (DEFER) {
           prev_valid = true;
           ep_wt = wt; ep_c = c;
@@ -1276,7 +1300,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
           else quad_gauss_lik<N3>(p, c, wt, lane, acc3);
         }
       } else {
-        release_slot(b, q);
+        // (a warp without a tile waits for both parts before releasing them, so that its releases cannot run ahead)
+        mbar_wait(&full23[b], (uint32_t)((q >> 1) & 1));
+        release_part(0, q);
+        release_part(1, q);
       }
     }
     if (have_tile) {
@@ -2017,7 +2044,7 @@ static size_t fwd3_smem_bytes(const FwdParams& p) {
   constexpr bool DEFER = (MODE != FWD3_PRED) && (LIKK == FWD3_CAT);
   using G3 = Fwd3Geom<KP0, N1, N2, N3>;
   size_t d = 2 * (size_t)G3::PB + (size_t)NWARPS * 16 * KP0 + BNN_EXP_TAB_SIZE;
-  size_t bytes = d * sizeof(double) + (5 + NWARPS) * sizeof(uint64_t);     // barriers + the ring's release counters
+  size_t bytes = d * sizeof(double) + (6 + NWARPS) * sizeof(uint64_t);     // barriers + the ring's release counters
   size_t ints = DEFER ? (size_t)p.C * (2 + 2 * p.g.K) : 0;
   return bytes + ints * sizeof(int);
 }
