@@ -91,6 +91,7 @@ struct bnn_ctx {
   int opt_tensor = 0;               // option "tensor_l1" (env NPBNN_TENSOR_L1): 1 = layer 1 on the int8 tensor cores (opt-in)
   DevBuf sp_items, sp_widx;
   int sp_prog_len = 0, sp_n_items = 0, sp_slots = 1, sp_wlen = 0;
+  int sp_pair_nc1 = 0, sp_pair_nr1 = 0, sp_pair_nr2 = 0;   // uniform block pairs (k_fwd_sparse's fused path); nc1 == 0: none
   bool use_sparse = false;
   int opt_sparse = 1;               // option "sparse": 0 forces the dense kernels for masked chains
   long long sp_fma = 0, dense_fma = 0;
@@ -764,6 +765,26 @@ static bool build_sparse_program(bnn_ctx* c, const double* mask_host, std::vecto
     }
   }
   c->sp_slots = n_slots < 1 ? 1 : n_slots;
+  // Uniform block pairs: two hidden layers, and the program is (first-layer item, the second-layer item that reads
+  // exactly its units) repeated with the same shape -- then k_fwd_sparse keeps the hidden units in registers.
+  c->sp_pair_nc1 = c->sp_pair_nr1 = c->sp_pair_nr2 = 0;
+  if (H == 2 && c->sp_n_items >= 2 && c->sp_n_items % 2 == 0) {
+    bool uniform = true;
+    int nc1 = 0, nr1 = 0, nr2 = 0;
+    size_t pos = 0;
+    for (int n = 0; n < c->sp_n_items && uniform; n += 2) {
+      const int* a = prog.data() + pos;
+      const int a_nr = (a[0] >> 8) & 0xff, a_nc = a[1];
+      const int* b = a + 8 + ((a_nc + 3) & ~3);
+      const int b_nr = (b[0] >> 8) & 0xff, b_nc = b[1];
+      uniform = (a[0] & 0xff) == 0 && !((a[0] >> 16) & 1) && (b[0] & 0xff) == 1 && ((b[0] >> 16) & 1) && b_nc == a_nr;
+      for (int i = 0; i < a_nr && uniform; ++i) uniform = (b[8 + i] == a[4 + i]);     // reads the slots the first item wrote, in order
+      if (n == 0) { nc1 = a_nc; nr1 = a_nr; nr2 = b_nr; }
+      uniform = uniform && a_nc == nc1 && a_nr == nr1 && b_nr == nr2;
+      pos += 16 + ((a_nc + 3) & ~3) + ((b_nc + 3) & ~3);
+    }
+    if (uniform && nc1 > 0) { c->sp_pair_nc1 = nc1; c->sp_pair_nr1 = nr1; c->sp_pair_nr2 = nr2; }
+  }
   return true;
 }
 
@@ -817,6 +838,7 @@ static int chains_forward(bnn_ctx* c, cudaStream_t st) {
     p.sp_prog_len = c->sp_prog_len;
     p.sp_n_items = c->sp_n_items;
     p.sp_slots = c->sp_slots;
+    p.sp_pair_nc1 = c->sp_pair_nc1; p.sp_pair_nr1 = c->sp_pair_nr1; p.sp_pair_nr2 = c->sp_pair_nr2;
   }
   for (int s0 = 0; s0 < c->C; s0 += per) {
     const int n = (c->C - s0 < per) ? c->C - s0 : per;

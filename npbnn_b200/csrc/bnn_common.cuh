@@ -316,12 +316,16 @@ struct ActPipe {
   double z[N], a[N], b[N], T[N];     // a, b: the two live temporaries of the chain
   int k[N];
   template <int S>
-  __device__ __forceinline__ void stage(double alpha, const double* __restrict__ tab) {
+  __device__ __forceinline__ void stage(double alpha, const double* __restrict__ tab) { stage_range<S>(0, N, alpha, tab); }
+  // elements [i0, i1) only (compile-time bounds after unrolling): per-chain slopes of the leaky ReLU
+  template <int S>
+  __device__ __forceinline__ void stage_range(int i0, int i1, double alpha, const double* __restrict__ tab) {
     static_assert(TB == 11, "staged activations use the 2048-entry table");
     constexpr double MAGIC = 6755399441055744.0, INV = 2954.639443740597, C1 = 0.0003384507717577858;
     constexpr bool SW = (ACT == BNN_ACT_SWISH);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+      if (i < i0 || i >= i1) continue;
       if constexpr (ACT == BNN_ACT_RELU) {
         if (S == 0) z[i] = z[i] < 0.0 ? 0.0 : z[i];
       } else if constexpr (ACT == BNN_ACT_LEAKY) {
@@ -477,4 +481,6 @@ struct FwdParams {
   int sp_prog_len, sp_n_items, sp_wlen;
   int sp_slots;             // scratch slots (hidden units alive at the same time) per row and chain
   int sp_group;             // chains whose weight streams are resident in shared memory (set by the launcher)
+  int sp_share;             // k_fwd_pairs: warps that share one X tile (set by the launcher)
+  int sp_pair_nc1, sp_pair_nr1, sp_pair_nr2;   // uniform block pairs (sparse_pair): features / units / units per pair; nc1 == 0: not uniform
 };

@@ -19,6 +19,15 @@
 #include "bnn_common.cuh"
 
 #define FULL_MASK 0xffffffffu
+
+// compile-time loop: f(std::integral_constant<int, I>{}) for I in [I0, N)
+template <int I0, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I0 < N) {
+    f(std::integral_constant<int, I0>{});
+    static_for<I0 + 1, N>(f);
+  }
+}
 static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
 
 __device__ __forceinline__ double warp16_sum(double v) {
@@ -408,7 +417,149 @@ __device__ __forceinline__ void sparse_item(const int* it, int nc, int qs, int s
   for (int q = 0; q < NCH; ++q) w[q] += adv;
 }
 
-// NCH chains per work unit: 4 (at most 10 warps, <= 204 registers) or 2 (at most 16 warps, <= 128 registers)
+// Fused evaluation of one "block pair" for networks whose program is a uniform sequence of pairs (what create_mask
+// produces when every feature group has the same node counts, BASELINE config 3: 40 x [1 feature -> 3 nodes -> 2
+// nodes]): a first-layer item (NR1 units reading nc1 features) directly followed by the second-layer item that reads
+// exactly those units (NR2 units, feeding the output layer).  Same program, same weight stream as the interpreter
+// (sparse_item), but the hidden units stay in registers (no scratch slots), the item headers are not decoded and
+// there is no dispatch on the item height -- the interpreter spends two thirds of its instructions on those.
+template <int ACT, int NCH, int NR1, int NR2, int NC1 = 0>
+__device__ __forceinline__ void sparse_pair(const int* it, int nc1_rt, int O, const double* (&w)[NCH], const double* bufl,
+                                            const double (&alpha1)[NCH], const double (&alpha2)[NCH], const double* tab,
+                                            double (&out)[NCH][SP_MAX_O]) {
+  constexpr int P1 = (NR1 + 1) & ~1, P2 = (NR2 + 1) & ~1;
+  double h1[NCH][P1], h2[NCH][P2];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int i = 0; i < P1; i += 2) {
+      const double2 b = *reinterpret_cast<const double2*>(w[q] + i);
+      h1[q][i] = b.x; h1[q][i + 1] = b.y;
+    }
+  const int nc1 = NC1 > 0 ? NC1 : nc1_rt;                    // NC1 > 0: features per pair known at compile time
+#pragma unroll
+  for (int k = 0; k < nc1; ++k) {
+    const double a = bufl[it[SP_HDR + k]];                   // the feature is shared by the chains
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < P1; i += 2) {
+        const double2 ww = *reinterpret_cast<const double2*>(w[q] + (k + 1) * P1 + i);
+        h1[q][i] = fma(ww.x, a, h1[q][i]);
+        if (i + 1 < NR1) h1[q][i + 1] = fma(ww.y, a, h1[q][i + 1]);
+      }
+  }
+  const int adv1 = (nc1 + 1) * P1;
+  bool care = false;
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int i = 0; i < NR1; ++i) care |= bnn_act_needs_care<ACT>(h1[q][i]);
+  if (!__any_sync(FULL_MASK, care)) {
+#ifndef SPARSE_STAGED_ACT
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR1; ++i) h1[q][i] = bnn_act_fast<ACT>(h1[q][i], alpha1[q], tab);
+#else
+    // all NCH * NR1 evaluations level by level (ActPipe): the program order ptxas gets is already interleaved
+    ActPipe<ACT, NCH * NR1> ap;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR1; ++i) ap.z[q * NR1 + i] = h1[q][i];
+    static_for<0, ActPipe<ACT, NCH * NR1>::STAGES>([&](auto st) {
+      if constexpr (ACT == BNN_ACT_LEAKY) {
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) ap.template stage_range<decltype(st)::value>(q * NR1, (q + 1) * NR1, alpha1[q], tab);
+      } else {
+        ap.template stage<decltype(st)::value>(0.0, tab);
+      }
+    });
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR1; ++i) h1[q][i] = ap.z[q * NR1 + i];
+#endif
+  } else {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int i = 0; i < NR1; ++i) h1[q][i] = bnn_act<ACT>(h1[q][i], alpha1[q], tab);
+  }
+  // second-layer item: bias[P2], then one column of P2 weights per first-layer unit
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int j = 0; j < P2; j += 2) {
+      const double2 b = *reinterpret_cast<const double2*>(w[q] + adv1 + j);
+      h2[q][j] = b.x; h2[q][j + 1] = b.y;
+    }
+#pragma unroll
+  for (int i = 0; i < NR1; ++i)
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int j = 0; j < P2; j += 2) {
+        const double2 ww = *reinterpret_cast<const double2*>(w[q] + adv1 + (i + 1) * P2 + j);
+        h2[q][j] = fma(ww.x, h1[q][i], h2[q][j]);
+        if (j + 1 < NR2) h2[q][j + 1] = fma(ww.y, h1[q][i], h2[q][j + 1]);
+      }
+  care = false;
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int j = 0; j < NR2; ++j) care |= bnn_act_needs_care<ACT>(h2[q][j]);
+  if (!__any_sync(FULL_MASK, care)) {
+#ifndef SPARSE_STAGED_ACT
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int j = 0; j < NR2; ++j) h2[q][j] = bnn_act_fast<ACT>(h2[q][j], alpha2[q], tab);
+#else
+    ActPipe<ACT, NCH * NR2> ap;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int j = 0; j < NR2; ++j) ap.z[q * NR2 + j] = h2[q][j];
+    static_for<0, ActPipe<ACT, NCH * NR2>::STAGES>([&](auto st) {
+      if constexpr (ACT == BNN_ACT_LEAKY) {
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) ap.template stage_range<decltype(st)::value>(q * NR2, (q + 1) * NR2, alpha2[q], tab);
+      } else {
+        ap.template stage<decltype(st)::value>(0.0, tab);
+      }
+    });
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int j = 0; j < NR2; ++j) h2[q][j] = ap.z[q * NR2 + j];
+#endif
+  } else {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+      for (int j = 0; j < NR2; ++j) h2[q][j] = bnn_act<ACT>(h2[q][j], alpha2[q], tab);
+  }
+  const int adv2 = adv1 + (NR1 + 1) * P2;
+  const int op = (O + 1) & ~1;
+#pragma unroll
+  for (int j = 0; j < NR2; ++j)
+#pragma unroll
+    for (int o = 0; o < SP_MAX_O / 2; ++o)
+      if (2 * o < O) {
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          const double2 ww = *reinterpret_cast<const double2*>(w[q] + adv2 + j * op + 2 * o);
+          out[q][2 * o] = fma(ww.x, h2[q][j], out[q][2 * o]);
+          out[q][2 * o + 1] = fma(ww.y, h2[q][j], out[q][2 * o + 1]);
+        }
+      }
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) w[q] += adv2 + NR2 * op;
+}
+
+// NCH chains per work unit: 4 (at most 10 warps, <= 204 registers) or 2 (at most 16 warps, <= 128 registers).
 template <int ACT, int NCH>
 __global__ void __launch_bounds__(NCH == 4 ? 320 : 512, 1) k_fwd_sparse(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -520,6 +671,114 @@ __global__ void __launch_bounds__(NCH == 4 ? 320 : 512, 1) k_fwd_sparse(const __
           for (int o = 0; o < SP_MAX_O; ++o) zs[lane * ZS + o] = out[q][o];
           __syncwarp();
           bnn_epilogue<false, true>(p, c0 + ch[q], w32 * 2, lane, zs, ZS, tab, cnt, nullptr, nullptr);
+        }
+      }
+    }
+  }
+  if (n_cnt) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
+      if (cnt[i]) atomicAdd(&p.counts[i], cnt[i]);
+  }
+}
+
+// Uniform block pairs (sparse_pair) for all chains of the pass.  Thread = row as in k_fwd_sparse, but the in-flight
+// work comes from MANY warps with few chains each instead of few warps with four chains each: groups of GW warps
+// share one transposed X tile (the tile's rows are the same for every chain subset), so a warp's private shared
+// memory is only the 32 x 9 staging area of the likelihood epilogue and 16-24 warps fit next to the weight streams.
+//   NCH 1: up to 24 warps (<= 80 registers), 2: up to 16 warps (<= 128 registers)
+// Measured at BASELINE config 3 (8 chains, 200k rows): interpreter 0.90 ms per step, pairs with 4 chains x 10 warps
+// 0.69, 1 chain x 24 warps 0.67, 2 chains x 16 warps 0.63 (issue slots 65 % busy, FP64 pipe 52 %).
+template <int ACT, int NCH, int NR1, int NR2, int NC1>
+__global__ void __launch_bounds__(NCH == 1 ? 768 : 512, 1) k_fwd_pairs(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const NetGeom& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int ZS = SP_MAX_O + 1;
+  const int O = g.O;
+  const int G = p.sp_group;                                   // chains whose weight streams are resident
+  const int GW = p.sp_share;                                   // warps per group (share one X tile)
+  const int n_groups = nwarps / GW, grp = warp / GW, wi = warp - grp * GW;
+
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  double* wsm = tab + BNN_EXP_TAB_SIZE;                       // [G][sp_wlen]
+  double* tile = wsm + (size_t)G * p.sp_wlen + (size_t)grp * g.F * SP_US;       // [n_groups][F][33]
+  double* zs = wsm + (size_t)G * p.sp_wlen + (size_t)n_groups * g.F * SP_US + (size_t)warp * 32 * ZS;
+  int* cnt = reinterpret_cast<int*>(wsm + (size_t)G * p.sp_wlen + (size_t)n_groups * g.F * SP_US + (size_t)nwarps * 32 * ZS);
+  const int n_cnt = (g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
+  int* prog = cnt + ((n_cnt + 3) & ~3);                        // 16-byte aligned: the areas before it are
+
+  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
+  for (int i = threadIdx.x; i < p.sp_prog_len; i += blockDim.x) prog[i] = p.sp_prog[i];
+
+  const long long n_tiles32 = (p.n_tiles16 + 1) >> 1;
+  const long long n_pad = p.n_tiles16 * 16;
+  const long long t0 = n_tiles32 * blockIdx.x / gridDim.x, t1 = n_tiles32 * (blockIdx.x + 1) / gridDim.x;
+  const double* bufl = tile + lane;
+  const int nc1 = p.sp_pair_nc1;
+  const int stride = 2 * SP_HDR + ((nc1 + 3) & ~3) + ((NR1 + 3) & ~3);          // two padded items per pair
+  const int gthreads = GW * 32, gtid = wi * 32 + lane;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory"); };
+
+  for (int c0 = 0; c0 < p.C; c0 += G) {
+    const int gc = min(G, p.C - c0);                          // chains of this group
+    const int n_sub = (gc + NCH - 1) / NCH;                   // chain subsets of NCH
+    __syncthreads();                                           // previous group's readers are done
+    for (int i = threadIdx.x; i < gc * p.sp_wlen; i += blockDim.x) {
+      const int c = i / p.sp_wlen, j = i - c * p.sp_wlen;
+      const int idx = __ldg(p.sp_widx + j);
+      wsm[i] = idx < 0 ? 0.0 : __ldg(p.wp + (long long)(c0 + c) * g.PB + idx);
+    }
+    __syncthreads();
+    if (grp >= n_groups) continue;                             // (left-over warps when nwarps is not a multiple of GW)
+    for (long long w32 = t0 + grp; w32 < t1; w32 += n_groups) {
+      // X tile -> [feature][row], loaded by the whole group; global reads are contiguous (32 * F_pad doubles)
+      const double* xt = p.x + w32 * 32 * (long long)g.F_pad;
+      group_sync();                                            // the previous tile's readers are done
+      for (int e0 = gtid; e0 < 32 * g.F_pad; e0 += 4 * gthreads) {
+        double v[4];
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int idx = e0 + uu * gthreads;
+          v[uu] = (idx < 32 * g.F_pad && w32 * 32 + idx / g.F_pad < n_pad) ? __ldg(xt + idx) : 0.0;
+        }
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int idx = e0 + uu * gthreads;
+          const int r = idx / g.F_pad, cp = idx - r * g.F_pad;
+          const int cidx = cp ^ ((r & 1) * g.x_swz);
+          if (idx < 32 * g.F_pad && cidx < g.F) tile[cidx * SP_US + r] = v[uu];
+        }
+      }
+      group_sync();
+      for (int sub = wi; sub < n_sub; sub += GW) {
+        int ch[NCH];
+        const double* w[NCH];
+        double out[NCH][SP_MAX_O];
+        double alpha1[NCH], alpha2[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          ch[q] = min(NCH * sub + q, gc - 1);
+          w[q] = wsm + (size_t)ch[q] * p.sp_wlen;
+#pragma unroll
+          for (int o = 0; o < SP_MAX_O; ++o) out[q][o] = w[q][o];
+          w[q] += SP_MAX_O;
+          alpha1[q] = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[(c0 + ch[q]) * g.L + 0] : 0.0;
+          alpha2[q] = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[(c0 + ch[q]) * g.L + 1] : 0.0;
+        }
+        const int* it = prog;
+        for (int n = 0; n < p.sp_n_items; n += 2, it += stride)
+          sparse_pair<ACT, NCH, NR1, NR2, NC1>(it, nc1, O, w, bufl, alpha1, alpha2, tab, out);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          if (NCH * sub + q < gc) {
+            __syncwarp();
+#pragma unroll
+            for (int o = 0; o < SP_MAX_O; ++o) zs[lane * ZS + o] = out[q][o];
+            __syncwarp();
+            bnn_epilogue<false, true>(p, c0 + ch[q], w32 * 2, lane, zs, ZS, tab, cnt, nullptr, nullptr);
+          }
         }
       }
     }
@@ -2196,8 +2455,85 @@ static cudaError_t launch_sparse_n(const FwdParams& p0, int n_sms, cudaStream_t 
   return cudaGetLastError();
 }
 
+// the (units, units) shapes of uniform block pairs with a compiled instantiation of k_fwd_pairs
+static int sparse_pair_shape(const FwdParams& p) {
+  const int pr = p.sp_pair_nc1 > 0 ? p.sp_pair_nr1 * 16 + p.sp_pair_nr2 : 0;
+  return (pr == 3 * 16 + 2 || pr == 2 * 16 + 1 || pr == 2 * 16 + 2 || pr == 4 * 16 + 2) ? pr : 0;
+}
+#ifndef SPARSE_PAIR_NCH
+#define SPARSE_PAIR_NCH 2
+#endif
+// shared-memory plan of k_fwd_pairs: resident chains, warps per group, warps
+static bool pairs_plan(const FwdParams& p, int nch, int* group, int* share, int* nwarps, size_t* bytes) {
+  const size_t cap = 232448;
+  const size_t n_cnt = (p.g.lik == BNN_LIK_CATEGORICAL) ? (size_t)p.C * (2 + 2 * p.g.K) : 0;
+  const size_t fixed = BNN_EXP_TAB_SIZE * sizeof(double) + (((n_cnt + 3) & ~(size_t)3) + p.sp_prog_len + 4) * sizeof(int);
+  const size_t per_chain = (size_t)p.sp_wlen * sizeof(double), tile_b = (size_t)p.g.F * SP_US * sizeof(double);
+  const size_t zs_b = 32 * (SP_MAX_O + 1) * sizeof(double);
+  const int max_warps = (nch == 1) ? 24 : 16;
+  const int c_up = (p.C + nch - 1) / nch * nch;
+  // all chains resident if they fit next to a useful number of warps, else as many as fit with the full set of warps
+  for (int gch = c_up; gch >= nch; gch -= nch) {
+    const int n_sub = gch / nch;
+    int gw = n_sub < 8 ? n_sub : 8;
+    while (max_warps % gw) --gw;                       // groups tile the CTA exactly
+    for (int w = max_warps; w >= gw; w -= gw) {
+      const size_t need = fixed + (size_t)gch * per_chain + (size_t)(w / gw) * tile_b + (size_t)w * zs_b;
+      if (need <= cap && (w >= max_warps / 2 || gch == nch)) {
+        *group = gch; *share = gw; *nwarps = w; *bytes = need;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+static bool sparse_uses_pairs(const FwdParams& p) {
+  int group, share, nwarps;
+  size_t bytes;
+  return p.C >= 2 && sparse_pair_shape(p) && pairs_plan(p, SPARSE_PAIR_NCH, &group, &share, &nwarps, &bytes);
+}
+template <int ACT, int NR1, int NR2, int NC1 = 0>
+static cudaError_t launch_pairs(const FwdParams& p0, int n_sms, cudaStream_t st) {
+  if (NC1 == 0 && p0.sp_pair_nc1 == 1) return launch_pairs<ACT, NR1, NR2, 1>(p0, n_sms, st);
+  auto kern = k_fwd_pairs<ACT, SPARSE_PAIR_NCH, NR1, NR2, NC1>;
+  FwdParams p = p0;
+  int group = 0, share = 1, nwarps = 0;
+  size_t bytes = 0;
+  if (!pairs_plan(p, SPARSE_PAIR_NCH, &group, &share, &nwarps, &bytes)) return cudaErrorInvalidConfiguration;
+  p.sp_group = group;
+  p.sp_share = share;
+  const long long n_tiles32 = (p.n_tiles16 + 1) >> 1;
+  int grid = (int)(n_tiles32 < n_sms ? n_tiles32 : n_sms);
+  // small problems: no more groups than tiles per CTA
+  const long long tiles_per_cta = (n_tiles32 + grid - 1) / grid;
+  if (tiles_per_cta * share < nwarps) {
+    nwarps = (int)tiles_per_cta * share;
+    const size_t n_cnt = (p.g.lik == BNN_LIK_CATEGORICAL) ? (size_t)p.C * (2 + 2 * p.g.K) : 0;
+    bytes = BNN_EXP_TAB_SIZE * sizeof(double) + (((n_cnt + 3) & ~(size_t)3) + p.sp_prog_len + 4) * sizeof(int) +
+            (size_t)group * p.sp_wlen * sizeof(double) + (size_t)(nwarps / share) * p.g.F * SP_US * sizeof(double) +
+            (size_t)nwarps * 32 * (SP_MAX_O + 1) * sizeof(double);
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  kern<<<grid, nwarps * 32, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int ACT>
 static cudaError_t launch_sparse_t(const FwdParams& p, int n_sms, cudaStream_t st) {
+  if (sparse_uses_pairs(p)) {
+    // uniform block pairs (create_mask with equal node counts per feature group): fused, register-resident path
+    switch (sparse_pair_shape(p)) {
+      case 3 * 16 + 2: return launch_pairs<ACT, 3, 2>(p, n_sms, st);
+      case 2 * 16 + 1: return launch_pairs<ACT, 2, 1>(p, n_sms, st);
+      case 2 * 16 + 2: return launch_pairs<ACT, 2, 2>(p, n_sms, st);
+      default: return launch_pairs<ACT, 4, 2>(p, n_sms, st);
+    }
+  }
   int group, nwarps;
   if (p.C >= 3 && sparse_plan(p, p.C, 4, &group, &nwarps)) return launch_sparse_n<ACT, 4>(p, n_sms, st);
   return launch_sparse_n<ACT, 2>(p, n_sms, st);
@@ -2225,7 +2561,7 @@ cudaError_t bnn_launch_forward(const FwdParams& p, bool predict, int n_sms, int 
                                const char** which) {
   const NetGeom& g = p.g;
   if (p.sp_prog && !predict) {
-    if (which) *which = "k_fwd_sparse";
+    if (which) *which = sparse_uses_pairs(p) ? "k_fwd_sparse<pairs>" : "k_fwd_sparse";
     return launch_sparse(p, n_sms, st);
   }
   if (!force_generic && !p.samp_u) {

@@ -677,7 +677,7 @@ def test_block_sparse_kernel_matches_dense_and_oracle(act, n):
         eng.set_data(x, labels)
         sets = [w, [a + rng.normal(0, 0.2, a.shape) * m for a, m in zip(w, mask)]] if sparse else sets
         eng.chains_init(sets, mask=mask, seed=5)
-        assert eng.last_kernel == ("k_fwd_sparse" if sparse else "k_fwd_generic")
+        assert eng.last_kernel == "k_fwd_generic" if not sparse else eng.last_kernel.startswith("k_fwd_sparse")
         st = eng.read_state()
         for c, ws in enumerate(sets):
             y = orc.forward(x, ws, act, None, "softmax")
@@ -756,7 +756,7 @@ def test_block_sparse_program_variants(case, n, chains):
         eng.set_option("sparse", sparse)
         eng.set_data(x, labels)
         eng.chains_init(sets, mask=mask, seed=9)
-        assert eng.last_kernel == ("k_fwd_sparse" if sparse else "k_fwd_generic")
+        assert eng.last_kernel == "k_fwd_generic" if not sparse else eng.last_kernel.startswith("k_fwd_sparse")
         st = eng.read_state()
         for c, ws in enumerate(sets):
             y = orc.forward(x, ws, act, None, out_kind)
