@@ -14,7 +14,7 @@ __device__ __forceinline__ void mma1688(double (&c)[4], const double (&a)[4], co
 
 enum { P_NONE, P_DFMA_RRR, P_DFMA_RIR, P_DFMA_RRI, P_DADD_RR, P_DADD_RI, P_DMUL_RR, P_DMUL_RI, P_LOP3, P_IADD, P_IMAD,
        P_FSEL, P_FFMA, P_MUFU_RCP64H, P_MUFU_EX2, P_LDS64, P_LDS128, P_SHFL, P_F2F_64_32, P_F2F_32_64, P_I2F64, P_ISETP_SEL,
-       P_F2I64, P_DSETP };
+       P_F2I64, P_DSETP, P_IMAD_HI, P_IMAD_HI_C, P_IMAD_WIDE, P_SHF, P_LEA, P_IADD3 };
 
 template <int KIND>
 __device__ __forceinline__ void payload(double (&f)[8], int (&x)[8], float (&s)[8], int i, double u, double v, int k1, int k2,
@@ -30,6 +30,16 @@ __device__ __forceinline__ void payload(double (&f)[8], int (&x)[8], float (&s)[
   if (KIND == P_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(k1), "r"(k2));
   if (KIND == P_IADD) asm volatile("add.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(k1));
   if (KIND == P_IMAD) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(k1), "r"(k2));
+  if (KIND == P_IMAD_HI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(k1));
+  if (KIND == P_IMAD_HI_C) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(k1), "r"(k2));
+  if (KIND == P_IMAD_WIDE) {
+    unsigned long long w;
+    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[j]), "r"(k1));
+    asm volatile("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %1; xor.b32 %0, lo, hi;}" : "=r"(x[j]) : "l"(w));
+  }
+  if (KIND == P_SHF) asm volatile("shf.l.wrap.b32 %0, %0, %1, 9;" : "+r"(x[j]) : "r"(k1));
+  if (KIND == P_LEA) asm volatile("{.reg .u32 t; shl.b32 t, %0, 9; add.u32 %0, t, %1;}" : "+r"(x[j]) : "r"(k1));
+  if (KIND == P_IADD3) asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(x[j]) : "r"(k1), "r"(k2));
   if (KIND == P_FSEL) asm volatile("{.reg .pred p; setp.gt.s32 p, %1, 0; selp.b32 %0, %0, %2, p;}" : "+r"(x[j]) : "r"(k1), "r"(k2));
   if (KIND == P_ISETP_SEL) asm volatile("{.reg .pred p; setp.gt.s32 p, %0, %1; selp.b32 %0, %0, %2, p;}" : "+r"(x[j]) : "r"(k1), "r"(k2));
   if (KIND == P_FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(s[j]) : "f"(0.999f), "f"(s[(j + 1) & 7]));
@@ -172,7 +182,7 @@ double run(int sms, double* out, const char* what, double base_per_it) {
   run<K, 4, 32>(sms, out, name " (4 mma + 32)", base4);                \
   run<K, 0, 32>(sms, out, name " (no mma, 32)", 0.0);
 
-int main(int argc, char**) {   // no args: throughput table; 1 arg: conversions; 2 args: latencies
+int main(int argc, char**) {   // no args: throughput table; 1 arg: conversions; 2 args: latencies; 3 args: integer multiplies / shifts
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   const int sms = prop.multiProcessorCount;
@@ -180,7 +190,7 @@ int main(int argc, char**) {   // no args: throughput table; 1 arg: conversions;
   cudaMalloc(&out, sizeof(double) * sms * 384);
   printf("%s, %d SMs, 12 warps/SM\n", prop.name, sms);
   const double base4 = run<P_NONE, 4, 0>(sms, out, "4 mma", 0.0);
-  if (argc > 2) {
+  if (argc == 3) {
     lat<P_DFMA_RRR, 32>(sms, out, "DFMA");
     lat<P_DADD_RR, 32>(sms, out, "DADD");
     lat<P_DMUL_RR, 32>(sms, out, "DMUL");
@@ -194,8 +204,18 @@ int main(int argc, char**) {   // no args: throughput table; 1 arg: conversions;
     lat<P_F2I64, 32>(sms, out, "F2I.F64+LOP3");
     return 0;
   }
-  if (argc > 1) {
+  if (argc > 3) {
+    ROW(P_IMAD, "IMAD")
+    ROW(P_IMAD_HI, "IMAD.HI")
+    ROW(P_IMAD_HI_C, "IMAD.HI + c")
+    ROW(P_IMAD_WIDE, "IMAD.WIDE + LOP3")
+    ROW(P_SHF, "SHF")
+    ROW(P_LEA, "SHL+ADD")
+    ROW(P_IADD3, "ADD+ADD")
     ROW(P_LOP3, "LOP3")
+    return 0;
+  }
+  if (argc > 1) {
     ROW(P_F2F_64_32, "F2F.64.32+LOP3+F2F.32.64")
     ROW(P_F2F_32_64, "F2F.F32.F64+LOP3")
     ROW(P_I2F64, "I2F.F64.S32+LOP3")
