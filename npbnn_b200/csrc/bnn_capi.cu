@@ -290,8 +290,7 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   if (tl) c->opt_tensor = (tl[0] != '0');
 #endif
   std::vector<double> tab(BNN_EXP_TAB_SIZE);
-  // pre-scaled by 2^-BNN_EXP_TAB_BIAS (exact): see bnn_exp_split
-  for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = ldexp(exp2((double)j / BNN_EXP_TAB_SIZE), -BNN_EXP_TAB_BIAS);
+  for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = exp2((double)j / BNN_EXP_TAB_SIZE);
   cudaError_t e = c->exp_tab.ensure(sizeof(double) * BNN_EXP_TAB_SIZE, false, 0);
   if (e == cudaSuccess) e = cudaMemcpy(c->exp_tab.p, tab.data(), sizeof(double) * BNN_EXP_TAB_SIZE, cudaMemcpyHostToDevice);
   for (int j = 0; j < 256; ++j) tab[j] = exp2((double)j / 256.0);

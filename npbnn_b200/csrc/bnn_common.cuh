@@ -17,9 +17,6 @@
 #define BNN_EXP_TAB_BITS 11      // 2048-entry table of 2^(j/2048) (16 KB of shared memory) + degree-3 polynomial
 #endif
 #define BNN_EXP_TAB_SIZE (1 << BNN_EXP_TAB_BITS)
-// The 2048-entry table is stored pre-scaled: tab[j] = 2^(j/2048 - BNN_EXP_TAB_BIAS), so that the exponent the
-// fixed-point evaluation (bnn_exp_split) adds is a non-negative bit field of the reduced argument (no constant to subtract).
-#define BNN_EXP_TAB_BIAS 64
 
 struct LayerGeom {
   int in, out, bias;        // canonical: W is [out, in + bias]
@@ -79,8 +76,6 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], double a0, double a1,
 // FP64 transcendentals tuned for the shared FP64 pipe (DMMA and DFMA issue to the same pipe on B200,
 // profiles/r01_fp64_peaks.log), i.e. as few FP64 instructions as possible:
 //   exp : 2048-entry table of 2^(j/2048) + degree-3 polynomial, 8 FP64 instructions, |rel err| < 3e-16
-//         (guarded paths, prediction outputs); fast paths: fixed-point reduction + FP32 second-order terms,
-//         3 FP64 instructions, |rel err| < 2.2e-14 (bnn_exp_split)
 //         (BNN_EXP_TAB_BITS=8: 256 entries + degree 4, 9 instructions)
 //   rcp : MUFU.RCP64H seed + one third-order step, 3 FP64 instructions
 // ---------------------------------------------------------------------------------------------
@@ -120,7 +115,7 @@ __device__ __forceinline__ double bnn_exp_core(double x, const double* __restric
   double p = fma(r2, q, r);
   double T = tab[k & ((1 << TB) - 1)];
   double res = fma(T, p, T);
-  int n = (k >> TB) + (TB == 11 ? BNN_EXP_TAB_BIAS : 0);
+  int n = k >> TB;
   return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
 
@@ -172,7 +167,7 @@ __device__ __forceinline__ double bnn_exp_scaled(double z, const double* __restr
     const double T2 = __hiloint2double(__double2hiint(T) + (1 << 20), __double2loint(T));    // 2 T (T in [1, 2))
     res = fma(T2, p, T);
   }
-  int n = (k >> TB) + (TB == 11 ? BNN_EXP_TAB_BIAS : 0);
+  int n = k >> TB;
   return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
 
@@ -184,50 +179,6 @@ __device__ __forceinline__ double bnn_exp_scaled_clamped(double z, const double*
   const bool big = (hx & 0x7fffffff) >= THR;                            // also inf / NaN
   const double zc = big ? __hiloint2double((hx & 0x80000000) | THR, 0) : z;
   return bnn_exp_scaled<TB, SCALE>(zc, tab);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fixed-point evaluation of the exponential (2048-entry table only) for the fast paths: 3 FP64 instructions.
-//
-// Every non-MMA FP64 instruction costs 2.5 clk of the FP64 pipe the DMMAs need, FP32 and 32-bit integer instructions
-// 0.2 clk (tools/pipe_cost.cu; IMAD.HI / IMAD.WIDE cost 3.7 clk -- 64-bit integer products are no way out), and the
-// table scheme above spends 7 FP64 instructions per exponential.  Here ONE FMA does the whole argument reduction
-//     t = z * (SCALE * 2^11 / ln 2) + 1.5 * 2^18          |SCALE * z| < 2^17 ln2 / 2^11 = 44.36
-// t lies in [2^18, 2^19), its unit in the last place is 2^-34: with u = the scaled argument, the low 20 bits of the
-// high word hold 4 * (2^17 + floor(u)) + (the two leading fraction bits), the low word holds the next 32 fraction
-// bits.  exp(SCALE z) = 2^(u / 2^11) = 2^n * tab[j] * D1 with j = floor(u) mod 2^11, n = floor(u) >> 11 and
-//     D1 = 2^(f / 2^11) = 1 + c f + (c^2 f^2 / 2 + c^3 f^3 / 6),   c = ln2 / 2^11,  f = frac(u) in [0, 1).
-// The bracket (< 5.8e-8) is evaluated in FP32 from the 23 leading bits of f and rounded to an integer g in units of
-// c 2^-34 by the 2^23 trick; the 34 fraction bits plus g, placed under the exponent of 2^52, ARE the double
-// 2^52 + (f + g) 2^34, and one FMA with c'' = Q 2^-98, K0 = 1 - Q 2^-46 (Q = round(c 2^64), 53 bits, so that both
-// constants are exact and the 2^52 offset cancels exactly inside the FMA) gives D1.  2^n goes into the exponent of the
-// pre-scaled table value with a mask and a shift-add.  The caller folds Ts * D1 into the FMA that forms 1 + exp.
-// Accuracy: the rounding of t leaves f off by <= 2^-35, g by <= 0.6 units: exp is off by <= 2.2e-14 relative
-// (rms 8e-15, unbiased; tools/exp_fix_check.cu) -- the log-likelihood by ~1e-14 relative against a tolerance of 1e-9.
-// Arguments outside the range (and inf / NaN) take the callers' guarded path with the table scheme above.
-// ------------------------------------------------------------------------------------------------
-#define BNN_FIX_THR_1 0x40460000     // 44.0: |z| below it keeps exp(+-z) inside the fixed-point range
-#define BNN_FIX_THR_2 0x40360000     // 22.0: the same for exp(2z)
-template <int SCALE>
-__device__ __forceinline__ void bnn_exp_split(double z, const double* __restrict__ tab, double& Ts, double& D1) {
-  static_assert(BNN_EXP_TAB_BITS == 11, "fixed-point exponential: 2048-entry table");
-  static_assert(SCALE == -1 || SCALE == 1 || SCALE == 2, "exp(-z), exp(z) or exp(2z)");
-  const double t = fma(z, (double)SCALE * 2954.639443740597, 393216.0);
-  const unsigned hi = (unsigned)__double2hiint(t), F = (unsigned)__double2loint(t);
-#ifdef BNN_DBG_NOTAB          // tuning experiment only: what do the table lookups (random shared-memory reads) cost?
-  const double T = 1.0;
-#else
-  const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + ((hi << 1) & 0x3FF8u));
-#endif
-  Ts = __hiloint2double(__double2hiint(T) + (int)((hi & 0x000FE000u) << 7), __double2loint(T));
-  // second-order terms in FP32: y = 1 + (23 leading bits of f); f re-centred on its truncation interval
-  const float y = __uint_as_float((__funnelshift_r(F, hi, 11) & 0x007FFFFFu) | 0x3F800000u);
-  const float ff = y - 0.99999994f;
-  const float h = fmaf(327.98926f, ff, 2907270.0f);                  // 2^34 (c^2 / 2 + c^3 f / 6) / c
-  const float gm = fmaf(ff * ff, h, 8388608.0f);                     // 2^23 + g
-  const unsigned long long w = (((unsigned long long)(0x43300000u | (hi & 3u))) << 32 | F) +
-                               (unsigned long long)(__float_as_uint(gm) - 0x4B000000u);
-  D1 = fma(__longlong_as_double((long long)w), 1.9700427758378546e-14, -87.722839111673);
 }
 
 // x is NaN, as integer instructions only (the 64-bit AND goes through inline PTX: written in C++, ptxas recognises
@@ -253,21 +204,6 @@ __device__ __forceinline__ double bnn_exp_neg(double x, const double* __restrict
   res = big ? 0.0 : res;
   // NaN in => NaN out, by OR-ing quiet-NaN bits into the result (an integer op: a select here makes ptxas
   // branch around the whole evaluation, which breaks the interleaving with the surrounding MMAs)
-  const bool is_nan = bnn_is_nan_int(x);
-  return __hiloint2double(__double2hiint(res) | (is_nan ? 0x7ff80000 : 0), __double2loint(res));
-}
-
-// Softmax terms of the likelihood epilogue, exp(x) for x <= 0, through the fixed-point evaluation: arguments below -44
-// give 0, i.e. a term below 8e-20 of a sum that is >= 1 -- less than half a unit in the last place of the sum
-// (NaN propagates).  Only the SUM is used in likelihood mode (the -inf of an underflowing log-softmax is decided on z_y - max, not on this value);
-// prediction mode reports the individual terms and keeps bnn_exp_neg.
-__device__ __forceinline__ double bnn_exp_neg_fast(double x, const double* __restrict__ tab) {
-  const int hx = __double2hiint(x);
-  const bool big = (hx & 0x7fffffff) >= BNN_FIX_THR_1;                // also inf / NaN
-  double Ts, D1;
-  bnn_exp_split<1>(__hiloint2double(big ? 0 : hx, big ? 0 : __double2loint(x)), tab, Ts, D1);
-  double res = Ts * D1;
-  res = big ? 0.0 : res;
   const bool is_nan = bnn_is_nan_int(x);
   return __hiloint2double(__double2hiint(res) | (is_nan ? 0x7ff80000 : 0), __double2loint(res));
 }
@@ -349,42 +285,43 @@ __device__ __forceinline__ double bnn_act(double z, double alpha, const double* 
 }
 
 // Fast-path activation for callers that have established (e.g. by a warp vote on bnn_act_needs_care) that the
-// argument of the exponential is finite and inside the range of the fixed-point evaluation (bnn_exp_split):
-// 7 FP64 instructions per swish / tanh instead of 12, no clamp, no NaN fix-up
-//   t ; D1 ; d = Ts * D1 + 1 ; e = 1 - d y0 ; e + e^2 ; y ; z * y  (tanh: 1 - 2 y)
+// argument of the exponential is finite and below 708 in magnitude: no clamp, no NaN fix-up -- the integer
+// instructions of those two are a third of the slow path's issue slots.
 template <int ACT>
 __device__ __forceinline__ bool bnn_act_needs_care(double z) {
   if (ACT == BNN_ACT_RELU || ACT == BNN_ACT_LEAKY) return false;
-  // swish: exp(-z), |z| < 44 ; tanh: exp(2z), |z| < 22 (inf / NaN compare as large)
-  return (__double2hiint(z) & 0x7fffffff) >= (ACT == BNN_ACT_SWISH ? BNN_FIX_THR_1 : BNN_FIX_THR_2);
+  // swish: exp(-z), |z| < 708 ; tanh: exp(2z), |z| < 354 (inf / NaN compare as large)
+  return (__double2hiint(z) & 0x7fffffff) >= (ACT == BNN_ACT_SWISH ? 0x40862000 : 0x40762000);
 }
 template <int ACT>
 __device__ __forceinline__ double bnn_act_fast(double z, double alpha, const double* __restrict__ tab) {
   if (ACT == BNN_ACT_RELU) return z < 0.0 ? 0.0 : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.0 ? alpha * z : z;
-  double Ts, D1;
-  bnn_exp_split<(ACT == BNN_ACT_SWISH) ? -1 : 2>(z, tab, Ts, D1);
-  const double y = bnn_rcp(fma(Ts, D1, 1.0));
-  return (ACT == BNN_ACT_SWISH) ? z * y : fma(-2.0, y, 1.0);
+  if (ACT == BNN_ACT_SWISH) return z * bnn_rcp(1.0 + bnn_exp_scaled<BNN_EXP_TAB_BITS, -1>(z, tab));
+  return fma(-2.0, bnn_rcp(bnn_exp_scaled<BNN_EXP_TAB_BITS, 2>(z, tab) + 1.0), 1.0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // The same activations for N elements at once, cut into dependency LEVELS ("stages"): stage S of all N elements is
 // N independent instructions, and consecutive stages are what the FP64 latency (8 clk) separates.  The caller places
-// the stages BETWEEN its other work in program order; nvcc emits PTX in that order and ptxas largely keeps it, which
-// is the only way to get the activation chains interleaved instead of scheduled as one long FP64-only stretch.
-// Fast path only (bnn_act_fast: the caller has voted that no element needs the guarded evaluation); ReLU / leaky do
-// everything in stage 0.
+// the stages BETWEEN its MMAs in program order; nvcc emits PTX in that order and ptxas largely keeps it, which is
+// the only way to get the activation chains interleaved with the DMMAs instead of scheduled as one long FP64-only
+// stretch (measured: what ptxas does with sequentially written activations).  Fast path only (bnn_act_fast: the
+// caller has voted that no element needs the clamp / NaN fix-up); ReLU / leaky do everything in stage 0.
 // ------------------------------------------------------------------------------------------------
 template <int ACT, int N>
 struct ActPipe {
-  static constexpr int STAGES = (ACT == BNN_ACT_SWISH || ACT == BNN_ACT_TANH) ? 6 : 1;
-  double z[N], a[N], b[N];           // a, b: the two live temporaries of the chain
+  static constexpr int STAGES = (ACT == BNN_ACT_SWISH || ACT == BNN_ACT_TANH) ? 11 : 1;
+  static constexpr int TB = BNN_EXP_TAB_BITS;
+  double z[N], a[N], b[N], T[N];     // a, b: the two live temporaries of the chain
+  int k[N];
   template <int S>
   __device__ __forceinline__ void stage(double alpha, const double* __restrict__ tab) { stage_range<S>(0, N, alpha, tab); }
   // elements [i0, i1) only (compile-time bounds after unrolling): per-chain slopes of the leaky ReLU
   template <int S>
   __device__ __forceinline__ void stage_range(int i0, int i1, double alpha, const double* __restrict__ tab) {
+    static_assert(TB == 11, "staged activations use the 2048-entry table");
+    constexpr double MAGIC = 6755399441055744.0, INV = 2954.639443740597, C1 = 0.0003384507717577858;
     constexpr bool SW = (ACT == BNN_ACT_SWISH);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -394,15 +331,35 @@ struct ActPipe {
       } else if constexpr (ACT == BNN_ACT_LEAKY) {
         if (S == 0) z[i] = z[i] < 0.0 ? alpha * z[i] : z[i];
       } else {
-        if (S == 0) bnn_exp_split<SW ? -1 : 2>(z[i], tab, a[i], b[i]);                // t, FP32 polynomial: Ts, D1
+        if (S == 0) a[i] = fma(z[i], SW ? -INV : 2.0 * INV, MAGIC);                  // t
         if (S == 1) {
-          a[i] = fma(a[i], b[i], 1.0);                                                // d
+          k[i] = __double2loint(a[i]);
+          T[i] = tab[k[i] & ((1 << TB) - 1)];
+          a[i] = a[i] - MAGIC;                                                        // kd
+        }
+        if (S == 2) a[i] = fma(a[i], SW ? C1 : -0.5 * C1, z[i]);                      // rs = -r (swish) or r/2 (tanh)
+        if (S == 3) {
+          b[i] = SW ? fma(a[i], -1.66666666666666657e-01, 0.5) : fma(a[i], 6.66666666666666630e-01, 1.0);   // q
+          T[i] = T[i];
+        }
+        if (S == 4) {
+          const double r2 = a[i] * a[i];
+          a[i] = SW ? -a[i] : a[i];                                                   // folded into the FMA below by ptxas
+          b[i] = fma(r2, b[i], a[i]);                                                 // p
+        }
+        if (S == 5) {
+          const double T2 = SW ? T[i] : __hiloint2double(__double2hiint(T[i]) + (1 << 20), __double2loint(T[i]));
+          const double res = fma(T2, b[i], T[i]);
+          a[i] = __hiloint2double(__double2hiint(res) + ((k[i] >> TB) << 20), __double2loint(res));   // exp(..)
+        }
+        if (S == 6) {
+          a[i] = a[i] + 1.0;                                                          // d
           asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(b[i]) : "d"(a[i]));                 // y0
         }
-        if (S == 2) a[i] = fma(-a[i], b[i], 1.0);                                     // e
-        if (S == 3) a[i] = fma(a[i], a[i], a[i]);
-        if (S == 4) b[i] = fma(b[i], a[i], b[i]);                                     // y
-        if (S == 5) z[i] = SW ? z[i] * b[i] : fma(-2.0, b[i], 1.0);
+        if (S == 7) a[i] = fma(-a[i], b[i], 1.0);                                     // e
+        if (S == 8) a[i] = fma(a[i], a[i], a[i]);
+        if (S == 9) b[i] = fma(b[i], a[i], b[i]);                                     // y
+        if (S == 10) z[i] = SW ? z[i] * b[i] : fma(-2.0, b[i], 1.0);
       }
     }
   }

@@ -839,7 +839,7 @@ __device__ __forceinline__ bool frag_needs_care(const double (&acc)[NT][4]) {
   for (int j = 0; j < NT; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) worst = max(worst, __double2hiint(acc[j][e]) & 0x7fffffff);
-  return __any_sync(FULL_MASK, worst >= (ACT == BNN_ACT_SWISH ? BNN_FIX_THR_1 : BNN_FIX_THR_2));
+  return __any_sync(FULL_MASK, worst >= (ACT == BNN_ACT_SWISH ? 0x40862000 : 0x40762000));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -885,8 +885,7 @@ __device__ __forceinline__ void qs_max(const double (&acc)[N3 / 8][4], int K, in
 }
 
 // stage 2: exp(z - max) of this thread's columns of row h, local sums
-// FASTEXP (likelihood modes: only the row sums are used): fixed-point exponential, terms below e^-44 flush to 0
-template <int N3, int H, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS, bool FASTEXP = false>
+template <int N3, int H, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void qs_exp(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
                                        const double* tab, RowStats<N3>& r) {
   double S = 0.0, zy = 0.0;
@@ -897,8 +896,7 @@ __device__ __forceinline__ void qs_exp(const double (&acc)[N3 / 8][4], int K, in
       const int col = 8 * j + 2 * t + e;
       const double v = acc[j][2 * H + e];
       // padded columns: argument -1000 => exp flushes to exactly 0 (no branch around the evaluation)
-      const double xa = (col < K) ? v - r.m[H] : -1000.0;
-      const double ex = FASTEXP ? bnn_exp_neg_fast(xa, tab) : bnn_exp_neg<TB>(xa, tab);
+      const double ex = bnn_exp_neg<TB>((col < K) ? v - r.m[H] : -1000.0, tab);
       r.ev[H][2 * j + e] = ex;
       S += ex;
       if (NEED_ZY) zy = (col == y[H]) ? v : zy;
@@ -921,12 +919,12 @@ __device__ __forceinline__ void qs_reduce(RowStats<N3>& r) {
   }
 }
 
-template <int N3, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS, bool FASTEXP = false>
+template <int N3, bool NEED_ZY, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void quad_softmax_stats(const double (&acc)[N3 / 8][4], int K, int t, const int (&y)[2],
                                                    const double* tab, RowStats<N3>& r) {
   qs_max<N3>(acc, K, t, r);
-  qs_exp<N3, 0, NEED_ZY, TB, FASTEXP>(acc, K, t, y, tab, r);
-  qs_exp<N3, 1, NEED_ZY, TB, FASTEXP>(acc, K, t, y, tab, r);
+  qs_exp<N3, 0, NEED_ZY, TB>(acc, K, t, y, tab, r);
+  qs_exp<N3, 1, NEED_ZY, TB>(acc, K, t, y, tab, r);
   qs_reduce<N3, NEED_ZY>(r);
 }
 
@@ -1404,7 +1402,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
             const double2 ahi = *reinterpret_cast<const double2*>(xr1 + col);
             if (EPI) {
               if (kg == 0) qs_max<N3>(acc3, K, t, rs);
-              else qs_exp<N3, 1, true, BNN_EXP_TAB_BITS, true>(acc3, K, t, ep_y, tab, rs);
+              else qs_exp<N3, 1, true>(acc3, K, t, ep_y, tab, rs);
             }
 #pragma unroll
             for (int j = 0; j < N1 / 16; ++j) {
@@ -1412,7 +1410,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
               dmma16x8x8(acc1[j], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
             }
             if (EPI) {
-              if (kg == 0) qs_exp<N3, 0, true, BNN_EXP_TAB_BITS, true>(acc3, K, t, ep_y, tab, rs);
+              if (kg == 0) qs_exp<N3, 0, true>(acc3, K, t, ep_y, tab, rs);
               else {
                 qs_reduce<N3, true>(rs);
                 lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, ep_wt, lane, rs, ep_y, ep_wgt, prev_valid);
@@ -1594,7 +1592,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
   // drain the software pipeline: the epilogue of the last (tile, weight set) this warp ran
   if (DEFER && prev_valid) {
     RowStats<N3> rs;
-    quad_softmax_stats<N3, true, BNN_EXP_TAB_BITS, true>(acc3, g.K, t, ep_y, tab, rs);
+    quad_softmax_stats<N3, true>(acc3, g.K, t, ep_y, tab, rs);
     const LikRow lr = quad_lik_finish<N3, MODE == FWD3_LIK_W>(p, ep_wt, lane, rs, ep_y, ep_wgt, true);
     quad_lik_commit<N3>(p, ep_c, ep_wt, lane, cnt, lr, true);
   }

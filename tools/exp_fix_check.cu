@@ -4,7 +4,7 @@
 #include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../npbnn_b200/csrc/bnn_common.cuh"
+#include "exp_fixed_point.cuh"
 
 __global__ void k_eval(const double* __restrict__ x, int n, const double* __restrict__ gtab, double* o_exp, double* o_sw,
                        double* o_th, double* o_swf, double* o_thf) {
@@ -14,18 +14,20 @@ __global__ void k_eval(const double* __restrict__ x, int n, const double* __rest
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double v = x[i];
     o_exp[i] = bnn_exp_neg_fast(-fabs(v), tab);
-    o_sw[i] = bnn_act<BNN_ACT_SWISH>(v, 0.0, tab);
-    o_th[i] = bnn_act<BNN_ACT_TANH>(v, 0.0, tab);
-    const bool ok1 = !bnn_act_needs_care<BNN_ACT_SWISH>(v), ok2 = !bnn_act_needs_care<BNN_ACT_TANH>(v);
-    o_swf[i] = ok1 ? bnn_act_fast<BNN_ACT_SWISH>(v, 0.0, tab) : o_sw[i];
-    o_thf[i] = ok2 ? bnn_act_fast<BNN_ACT_TANH>(v, 0.0, tab) : o_th[i];
+    // reference columns: the library's table + polynomial activations need the UNSCALED table -> evaluated in double
+    // precision library calls here (the host compares everything with long double anyway)
+    o_sw[i] = v / (1.0 + exp(-v));
+    o_th[i] = tanh(v);
+    const bool ok1 = !expfix_needs_care<BNN_ACT_SWISH>(v), ok2 = !expfix_needs_care<BNN_ACT_TANH>(v);
+    o_swf[i] = ok1 ? expfix_act_fast<BNN_ACT_SWISH>(v, tab) : o_sw[i];
+    o_thf[i] = ok2 ? expfix_act_fast<BNN_ACT_TANH>(v, tab) : o_th[i];
   }
 }
 
 int main() {
   const int n = 1 << 22;
   std::vector<double> x(n), tab(BNN_EXP_TAB_SIZE);
-  for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = ldexp(exp2((double)j / BNN_EXP_TAB_SIZE), -BNN_EXP_TAB_BIAS);
+  for (int j = 0; j < BNN_EXP_TAB_SIZE; ++j) tab[j] = ldexp(exp2((double)j / BNN_EXP_TAB_SIZE), -EXPFIX_TAB_BIAS);
   unsigned long long s = 88172645463325252ULL;
   auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) / 9007199254740992.0; };
   for (int i = 0; i < n; ++i) {
@@ -43,7 +45,7 @@ int main() {
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed\n"); return 1; }
   std::vector<double> r[5];
   for (int k = 0; k < 5; ++k) { r[k].resize(n); cudaMemcpy(r[k].data(), o[k], n * 8, cudaMemcpyDeviceToHost); }
-  const char* names[5] = {"exp(-|x|)", "swish", "tanh", "swish fast", "tanh fast"};
+  const char* names[5] = {"exp(-|x|) fix", "swish libm", "tanh libm", "swish fix", "tanh fix"};
   for (int k = 0; k < 5; ++k) {
     double worst_rel = 0, worst_abs = 0, wx = 0, sum2 = 0; long cnt = 0;
     for (int i = 16; i < n; ++i) {
