@@ -116,6 +116,8 @@ struct bnn_ctx {
   std::vector<StepGraph> graphs;
   cudaStream_t capture_stream = nullptr;
   int opt_graphs = 1;               // option "graphs"
+  int opt_chain_loop = 1;           // option "chain_loop": small data sets step inside one persistent launch (k_chain_loop)
+  int opt_chain_cluster = 16;       // option "chain_loop_cluster": largest thread-block cluster per chain
   bool mh_warm = false;             // one eager bnn_mh_steps has run since the last (re)configuration
 };
 
@@ -347,6 +349,12 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
     return 0;
   }
   if (strcmp(name, "graphs") == 0) { c->opt_graphs = value; return 0; }
+  if (strcmp(name, "chain_loop") == 0) { c->opt_chain_loop = value; return 0; }
+  if (strcmp(name, "chain_loop_cluster") == 0) {
+    REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "bnn_set_option: chain_loop_cluster must be 1, 2, 4, 8 or 16");
+    c->opt_chain_cluster = value;
+    return 0;
+  }
   return fail(std::string("bnn_set_option: unknown option ") + name);
 }
 
@@ -1060,6 +1068,29 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
   cudaStream_t st = (cudaStream_t)stream;
   ChainDev d = chain_dev(c);
   if (int rc = stage_injection(c, n_steps, inj, d, st)) return rc;
+  // Small data sets (a few thousand rows, <= 2048 weights, dense generic forward path): all n_steps iterations run
+  // inside ONE persistent launch, a thread-block cluster per chain (bnn_chainloop.cu) -- injected or device-generated
+  // proposals alike.  Same update / forward bodies and reduction order as the launch sequence below: identical chains.
+  if (c->opt_chain_loop && !c->time_forward && !c->opt_tensor && !(c->use_sparse && c->opt_sparse) &&
+      (c->force_generic || !bnn_fwd3_family(c->g)) && !bnn_part_slices(c->n_tiles16) &&
+      bnn_chain_loop_fits(c->g, d.NF, d.n_tiles16, c->C, c->n_sms)) {
+    FwdParams p = base_params(c);
+    p.C = 1;
+    int cl = 0;
+    cudaError_t e = bnn_launch_chain_loop(d, p, n_steps, c->n_sms, c->opt_chain_cluster, st, &cl);
+    if (e == cudaSuccess) {
+      c->launches++;
+      c->last_kernel = "k_chain_loop";
+      if (inj) CUDA_TRY(cudaStreamSynchronize(st));
+      return 0;
+    }
+    cudaGetLastError();
+    if (e != cudaErrorNotSupported) {
+      // a cluster shape this GPU cannot schedule (MIG slices, non-portable size): halve it once, then give the path up
+      if (c->opt_chain_cluster > 8) c->opt_chain_cluster = 8; else c->opt_chain_loop = 0;
+      return bnn_mh_steps(c, n_steps, inj, stream);
+    }
+  }
   // Free-running chains: the sequence depends on nothing but n_steps (Philox counters come from the chain state), so
   // it is captured once per n_steps into a CUDA graph and replayed -- at small N the loop is bound by launch latency,
   // not by the kernels.  The first call after any (re)configuration runs eagerly (function attributes, lazily

@@ -17,181 +17,7 @@
 #include <cstdio>
 #include <type_traits>
 #include "bnn_common.cuh"
-
-#define FULL_MASK 0xffffffffu
-
-// compile-time loop: f(std::integral_constant<int, I>{}) for I in [I0, N)
-template <int I0, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I0 < N) {
-    f(std::integral_constant<int, I0>{});
-    static_for<I0 + 1, N>(f);
-  }
-}
-static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
-
-__device__ __forceinline__ double warp16_sum(double v) {
-  // lanes 0..15 hold values; fixed xor tree => deterministic
-  v += __shfl_xor_sync(FULL_MASK, v, 8);
-  v += __shfl_xor_sync(FULL_MASK, v, 4);
-  v += __shfl_xor_sync(FULL_MASK, v, 2);
-  v += __shfl_xor_sync(FULL_MASK, v, 1);
-  return v;
-}
-
-__device__ __forceinline__ double softplus_ref(double z) {
-  // np.logaddexp(0, z) (BNN_lib.py:170-172)
-  return fmax(z, 0.0) + log1p(exp(-fabs(z)));
-}
-
-// Per-warp epilogue on the staged outputs of one (warp tile, weight set).
-//   zs  : [16][ZS] pre-transform outputs of the last layer (row-major, per warp)
-//   lane r < 16 owns row r of the tile.
-// Likelihood mode (PREDICT=false): writes part[(c*NF+slot)*n_tiles16 + wt] and bumps the CTA counters.
-// Prediction mode: accumulates transformed outputs into pacc/pvote (per warp, [16][K_out]) and
-// optionally writes the dense tensor.
-// R32 (likelihood mode only): the warp owns 32 rows = warp tiles wt and wt + 1, lane r owns row r; the xor
-// trees of warp16_sum stay inside each half-warp, so lanes 0 and 16 hold the two warp-tile sums.
-template <bool PREDICT, bool R32 = false>
-__device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long long wt, int lane, const double* zs,
-                                             int ZS, const double* tab, int* cnt_smem, double* pacc, int* pvote) {
-  const NetGeom& g = p.g;
-  const int rl = R32 ? lane : (lane & 15);
-  const long long row = wt * 16 + rl;
-  const bool active = (R32 || lane < 16) && row < p.n_total;
-  const bool is_train = active && row < p.n_train;
-  const bool is_test = active && !is_train;
-  const double* z = zs + rl * ZS;
-  const long long nt = p.n_tiles16;
-  // lane that stores the warp-tile partial sums, and the tile it stores them for
-  const bool writer = (lane == 0) || (R32 && lane == 16 && wt + 1 < nt);
-  const long long wts = wt + (R32 ? (lane >> 4) : 0);
-
-  if (g.lik == BNN_LIK_CATEGORICAL) {
-    const int K = g.K;
-    double m = -INFINITY;
-    int arg = 0;
-    double S = 0.0, ll = 0.0;
-    if (active) {
-      m = z[0];
-      for (int k = 1; k < K; ++k) {
-        double v = z[k];
-        if (v > m) { m = v; arg = k; }   // first maximum wins, as np.argmax
-      }
-      if (!PREDICT && is_train) {
-        for (int k = 0; k < K; ++k) S += bnn_exp_neg(z[k] - m, tab);
-      }
-    }
-    if (!PREDICT) {
-      int y = 0;
-      if (active) {
-        y = p.labels[row];
-        bool ok = (arg == y);
-        if (is_train) {
-          double d = z[y] - m;
-          // log(softmax) of the reference is -inf once exp(d) underflows to 0 (BNN_lib.py:121,168)
-          ll = (d < -745.1332191019412) ? -INFINITY : d - log(S);
-          if (p.class_w) ll *= p.class_w[y];
-          if (p.inst_w) ll *= p.inst_w[row];
-          int* cc = cnt_smem + c * (2 + 2 * K);
-          if (ok) atomicAdd(&cc[2 + y], 1);
-          atomicAdd(&cc[2 + K + arg], 1);
-          if (ok) atomicAdd(&cc[0], 1);
-        } else if (ok) {
-          atomicAdd(&cnt_smem[c * (2 + 2 * K) + 1], 1);
-        }
-      }
-      double s = warp16_sum(is_train ? ll : 0.0);
-      if (writer) p.part[((long long)c * p.NF) * nt + wts] = s;
-    } else {
-      if (active) {
-        double* zw = const_cast<double*>(z);     // the staged row is private to this lane: reuse as scratch
-        for (int k = 0; k < K; ++k) { double e = bnn_exp_neg(z[k] - m, tab); zw[k] = e; S += e; }
-        double inv = 1.0 / S;
-        double* pa = pacc + (lane & 15) * K;
-        // sample_from_categorical: first class whose running sum (np.cumsum order) reaches u; none => class 0
-        const bool sampling = p.samp_u || p.samp_philox;
-        const double u = p.samp_u ? p.samp_u[row * p.C + c] : (p.samp_philox ? bnn_samp_uniform(p.samp_seed, row, c) : 0.0);
-        double cum = 0.0;
-        int drawn = -1;
-        for (int k = 0; k < K; ++k) {
-          double pk = zw[k] * inv;
-          pa[k] += pk;
-          cum += pk;
-          if (drawn < 0 && cum - u >= 0.0) drawn = k;
-          if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * K + k] = pk;
-        }
-        if (sampling) {
-          arg = drawn < 0 ? 0 : drawn;
-          if (p.samp_dense) p.samp_dense[row * p.C + c] = (double)arg;
-        }
-        pvote[(lane & 15) * K + arg] += 1;
-      }
-      if ((p.samp_u || p.samp_philox) && p.samp_counts) {
-        // one atomic per distinct class among the 16 rows of the warp tile
-        const unsigned grp = __match_any_sync(FULL_MASK, active ? arg : 64 + lane);
-        if (active && lane == __ffs(grp) - 1) atomicAdd(&p.samp_counts[c * K + arg], __popc(grp));
-      }
-    }
-    return;
-  }
-
-  // Gaussian likelihoods: K modelled outputs, targets [n_total, K]
-  const int K = g.K;
-  const bool head = (g.lik == BNN_LIK_GAUSSIAN_HEAD);
-  if (!PREDICT) {
-    double ll = 0.0;
-    for (int j = 0; j < K; ++j) {
-      double r = 0.0;
-      if (active) {
-        double t = p.targets[row * K + j];
-        r = z[j] - t;
-        if (head && is_train) {
-          double s = softplus_ref(z[K + j]);
-          double u = (t - z[j]) / s;
-          ll += -0.5 * u * u - kLogSqrt2Pi - log(s);
-        }
-      }
-      double sr = warp16_sum(is_train ? r : 0.0);
-      double sr2 = warp16_sum(is_train ? r * r : 0.0);
-      double st2 = warp16_sum(is_test ? r * r : 0.0);
-      if (writer) {
-        p.part[((long long)c * p.NF + 1 + j) * nt + wts] = sr;
-        p.part[((long long)c * p.NF + 1 + K + j) * nt + wts] = sr2;
-        p.part[((long long)c * p.NF + 1 + 2 * K + j) * nt + wts] = st2;
-      }
-    }
-    double s = warp16_sum(ll);
-    if (writer) p.part[((long long)c * p.NF) * nt + wts] = s;
-  } else {
-    if (active) {
-      const int O = g.O;
-      double* pa = pacc + (lane & 15) * O;
-      for (int j = 0; j < O; ++j) {
-        double v = z[j];
-        if (head && j >= K) v = softplus_ref(v);
-        pa[j] += v;
-        if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * O + j] = v;
-      }
-    }
-  }
-}
-
-// number of output columns per row in prediction mode
-__device__ __forceinline__ int bnn_pred_width(const NetGeom& g) { return g.lik == BNN_LIK_CATEGORICAL ? g.K : g.O; }
-
-template <bool PREDICT>
-__device__ __forceinline__ void bnn_pred_flush(const FwdParams& p, long long wt, int lane, double* pacc, int* pvote) {
-  if (!PREDICT) return;
-  const int W = bnn_pred_width(p.g);
-  for (int i = lane; i < 16 * W; i += 32) {
-    long long row = wt * 16 + i / W;
-    if (row < p.n_total) {
-      if (p.mean_out) p.mean_out[row * W + (i % W)] = pacc[i] / p.inv_sets;
-      if (p.votes_out) p.votes_out[row * W + (i % W)] = (double)pvote[i] / p.inv_sets;
-    }
-  }
-}
+#include "bnn_generic_body.cuh"
 
 // =============================================================================================
 // generic kernel
@@ -203,7 +29,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const NetGeom& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gq = lane >> 2, t = lane & 3;
+  const int gq = lane >> 2;
   const int ZS = g.l[g.L - 1].out_pad + 1;        // the last layer may be padded beyond round_up(O, 8) (k_fwd3 width families)
   const int PW = bnn_pred_width(g);
 
@@ -236,69 +62,9 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
     const double* xrow0 = p.x + (wt * 16 + gq) * (long long)g.F_pad;
     const double* xrow1 = xrow0 + 8LL * g.F_pad;
     for (int c = c_beg; c < c_end; ++c) {
-      const double* W = p.wp + (long long)c * g.PB;
-      const double* src = nullptr;
-      double* dst = h0;
-      for (int l = 0; l < g.L; ++l) {
-        const LayerGeom& lg = g.l[l];
-        const bool last = (l == g.L - 1);
-        const double alpha = (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha[c * g.L + l] : 0.0;
-        const int sw = (gq & 1) * lg.swz;
-        const int nkg = lg.in_pad >> 3;
-        // destination geometry = next layer's A operand
-        const int dstride = last ? ZS : g.l[l + 1].stride;
-        const int dsw = last ? 0 : (gq & 1) * g.l[l + 1].swz;
-        for (int n0 = 0; n0 < lg.out_pad; n0 += 32) {
-          const int ntile = min(4, (lg.out_pad - n0) >> 3);
-          double acc[4][4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double b0 = 0.0, b1 = 0.0;
-            if (j < ntile) {
-              const double2 bb = *reinterpret_cast<const double2*>(W + lg.b_off + n0 + 8 * j + 2 * t);
-              b0 = bb.x; b1 = bb.y;
-            }
-            acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
-          }
-          for (int kg = 0; kg < nkg; ++kg) {
-            const int col = (8 * kg + 2 * t) ^ sw;
-            double2 a_lo, a_hi;
-            if (l == 0) {
-              a_lo = __ldg(reinterpret_cast<const double2*>(xrow0 + col));
-              a_hi = __ldg(reinterpret_cast<const double2*>(xrow1 + col));
-            } else {
-              a_lo = *reinterpret_cast<const double2*>(src + gq * lg.stride + col);
-              a_hi = *reinterpret_cast<const double2*>(src + (gq + 8) * lg.stride + col);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < ntile) {
-                const double2 bb =
-                    __ldg(reinterpret_cast<const double2*>(W + lg.w_off + (long long)(n0 + 8 * j + gq) * lg.stride + col));
-                dmma16x8x8(acc[j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bb.x, bb.y);
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < ntile) {
-              const int cn = n0 + 8 * j + 2 * t;
-              if (!last) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[j][e] = bnn_act<ACT>(acc[j][e], alpha, tab);
-                *reinterpret_cast<double2*>(dst + gq * dstride + (cn ^ dsw)) = make_double2(acc[j][0], acc[j][1]);
-                *reinterpret_cast<double2*>(dst + (gq + 8) * dstride + (cn ^ dsw)) = make_double2(acc[j][2], acc[j][3]);
-              } else {
-                zs[gq * ZS + cn] = acc[j][0]; zs[gq * ZS + cn + 1] = acc[j][1];
-                zs[(gq + 8) * ZS + cn] = acc[j][2]; zs[(gq + 8) * ZS + cn + 1] = acc[j][3];
-              }
-            }
-          }
-        }
-        __syncwarp();
-        src = dst;
-        dst = (dst == h0) ? h1 : h0;
-      }
+      fwd_generic_layers<ACT, true, true>(g, xrow0, xrow1, p.wp + (long long)c * g.PB,
+                                    (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha + (long long)c * g.L : nullptr, h0, h1, zs, ZS,
+                                    tab, lane);
       bnn_epilogue<PREDICT>(p, c, wt, lane, zs, ZS, tab, cnt, pacc, pvote);
       __syncwarp();
     }

@@ -80,6 +80,11 @@ cudaError_t bnn_launch_prior_refresh(const ChainDev& d, cudaStream_t st);
 int bnn_part_slices(long long nt);
 cudaError_t bnn_launch_reduce_part(const double* part, long long nt, int n_slices, int n_rows, double* out, cudaStream_t st);
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
+// persistent small-data MH loop (bnn_chainloop.cu): n_steps iterations of every chain in one launch, one thread-block
+// cluster per chain; cudaErrorNotSupported when the problem does not fit (bnn_chain_loop_fits)
+bool bnn_chain_loop_fits(const NetGeom& g, int NF, long long nt, int C, int n_sms);
+cudaError_t bnn_launch_chain_loop(const ChainDev& d, const FwdParams& p, int n_steps, int n_sms, int max_cluster,
+                                  cudaStream_t st, int* cluster_out);
 cudaError_t bnn_launch_rowshard_local(const NetGeom& g, const double* part, int NF, long long nt, const int* counts, int NC,
                                       double* out, int n_chains, cudaStream_t st);
 cudaError_t bnn_launch_rowshard_commit(const double* in, int NF, int NC, double* part_red, int* counts, int n_chains,

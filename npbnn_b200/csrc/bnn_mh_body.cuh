@@ -1,0 +1,476 @@
+// Device-side body of the Metropolis-Hastings update (accept / adapt / propose / prior / pack) and the deterministic
+// reduction of the forward partials, shared by k_mh_update (bnn_mcmc.cu, one launch per step) and the persistent
+// small-data chain loop (k_chain_loop, bnn_chainloop.cu).
+//
+// COH = true: the data another CTA of the same launch produced (tile partials, proposal counters) is read with
+// ld.global.cg / plain loads instead of the read-only path, which is only valid for data that no thread of the
+// launch writes.
+#pragma once
+#include "bnn_common.cuh"
+#include "bnn_kernels.h"
+
+#ifndef BNN_HAVE_LOGSQRT2PI
+#define BNN_HAVE_LOGSQRT2PI
+static constexpr double kLogSqrt2Pi = 0.91893853320467274178;
+#endif
+static constexpr double kLogPi = 1.14472988584940017414;
+static constexpr double kLog2 = 0.69314718055994530942;
+#define UPD_THREADS 1024      // upper bound (launch bounds); small networks launch 256 (upd_threads)
+
+__device__ __forceinline__ int layer_of(const NetGeom& g, int i) {
+  int l = 0;
+#pragma unroll 1
+  for (int k = 1; k < g.L; ++k)
+    if (i >= g.l[k].c_off) l = k;
+  return l;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// deterministic block reductions (fixed order: per-thread strided sum -> xor tree -> warps in order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_fixed(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+  return s;
+}
+
+// Sum of src[tid], src[tid + B], src[tid + 2B], ... in exactly that order, with the loads of eight terms issued
+// before the first add: the plain loop is one L2 round trip per term (62,500 partials per chain at 1M rows).
+template <bool COH>
+__device__ __forceinline__ double ld_part(const double* p) {
+  // COH: written by other CTAs of this launch -- plain (generic) load, valid for global and (distributed) shared memory
+  if (COH) return *reinterpret_cast<const volatile double*>(p);
+  return __ldg(p);
+}
+template <bool COH = false>
+__device__ __forceinline__ double strided_sum_ordered(const double* src, long long nt) {
+  const long long B = blockDim.x;
+  long long i = threadIdx.x;
+  double v = 0.0;
+  for (; i + 7 * B < nt; i += 8 * B) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = ld_part<COH>(src + i + k * B);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += a[k];
+  }
+  for (; i < nt; i += B) v += ld_part<COH>(src + i);
+  return v;
+}
+
+__device__ __forceinline__ double logpdf_prior(double w, int kind, double scale, double log_scale) {
+  // closed forms of scipy.stats.{norm,cauchy,laplace}.logpdf(w, 0, scale) (BNN_env.py:139-150)
+  double x = w / scale;
+  if (kind == BNN_PRIOR_CAUCHY) return -kLogPi - log1p(x * x) - log_scale;
+  if (kind == BNN_PRIOR_LAPLACE) return -kLog2 - fabs(x) - log_scale;
+  return -0.5 * x * x - kLogSqrt2Pi - log_scale;
+}
+
+// Reduce the per-warp-tile partials of chain `c` and turn them into the log-likelihood.
+//   red : shared [1 + 3*BNN_MAX_OUT] receives the reduced slots; sig_out [K] the sigma that was used
+template <bool COH = false>
+__device__ double finalize_loglik(const NetGeom& g, const double* part, int NF, long long nt, int c,
+                                  long long n_train, double lik_temp, int sigma_mode,
+                                  const double* __restrict__ sigma_in, double* red, double* sig_out, double* sh) {
+  for (int slot = 0; slot < NF; ++slot) {
+    const double* src = part + ((long long)c * NF + slot) * nt;
+    const double v = strided_sum_ordered<COH>(src, nt);
+    double s = block_sum_fixed(v, sh);
+    if (threadIdx.x == 0) red[slot] = s;
+  }
+  __syncthreads();
+  double ll = red[0];
+  if (g.lik == BNN_LIK_GAUSSIAN) {
+    // calc_likelihood_regression (BNN_lib.py:123-131) from sum r, sum r^2:
+    //   sum_i logN(y_i; mu_i, s) = -SSR/(2 s^2) - N log s - N log sqrt(2 pi)
+    ll = 0.0;
+    const double N = (double)n_train;
+    for (int j = 0; j < g.K; ++j) {
+      double sr = red[1 + j], ssr = red[1 + g.K + j];
+      double s;
+      if (sigma_mode == BNN_SIGMA_EMPIRICAL) {
+        double mu = sr / N;                       // np.std(y' - labels, axis=0) (BNN_env.py:475-476)
+        s = sqrt(fmax(ssr / N - mu * mu, 0.0));
+      } else {
+        s = sigma_in ? sigma_in[j] : 1.0;
+      }
+      if (threadIdx.x == 0) sig_out[j] = s;
+      ll += -ssr / (2.0 * s * s) - N * log(s) - N * kLogSqrt2Pi;
+    }
+  }
+  __syncthreads();
+  return lik_temp * ll;
+}
+
+struct Draw { int ix, iy; double dz; };
+// k-th proposal of layer l of chain c at iteration it
+__device__ __forceinline__ Draw philox_draw(uint64_t seed, int c, int it, int l, int k, int rows, int cols, double ws) {
+  uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)c, (uint32_t)(seed >> 32));
+  uint4 a = philox4x32(make_uint4((uint32_t)it, (uint32_t)k, (uint32_t)l, 0u), key);
+  uint4 b = philox4x32(make_uint4((uint32_t)it, (uint32_t)k, (uint32_t)l, 1u), key);
+  Draw d;
+  d.ix = (int)__umulhi(a.x, (uint32_t)rows);
+  d.iy = (int)__umulhi(a.y, (uint32_t)cols);
+  double u1 = 1.0 - u53(a.z, a.w);            // (0,1]
+  double u2 = u53(b.x, b.y);
+  double s, co;
+  sincospi(2.0 * u2, &s, &co);
+  d.dz = ws * sqrt(-2.0 * log(u1)) * co;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per chain: [accept previous proposal] + [adapt, propose, prior, pack]
+// ------------------------------------------------------------------------------------------------
+//   part_c / counts_c (COH only): this chain's tile partials [NF, n_tiles16] and proposal counters [2 + 2K] when they
+//   do not live in d.part / d.counts_prop (k_chain_loop keeps them in the leader CTA's shared memory); null otherwise
+template <bool COH>
+__device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, int propose_mode, int step,
+                               const double* part_c = nullptr, int* counts_c = nullptr) {
+  __shared__ double red[1 + 3 * BNN_MAX_OUT];
+  __shared__ double sig[BNN_MAX_OUT];
+  __shared__ double sh[32];
+  __shared__ int s_flag;
+  __shared__ int s_prop[BNN_MAX_LAYERS], s_cnt[BNN_MAX_LAYERS], s_off[BNN_MAX_LAYERS];
+  // on-device generator (free-running chains): indicator moves decided by thread 0, flip probabilities for the block
+  __shared__ int s_ind_move, s_fi_move;
+  __shared__ double s_ind_p, s_fi_p;
+  const NetGeom& g = d.g;
+  const int tid = threadIdx.x;
+  // The chain's scalar state is staged in shared memory for the whole launch: the accept / adapt / propose logic is
+  // a serial chain of ~100 reads and writes by one thread, each of which would otherwise be an L2 round trip.
+  __shared__ double ssf[BNN_F_STRIDE];
+  __shared__ int ssi[BNN_I_STRIDE];
+  double* const gsf = d.sf + (long long)c * BNN_F_STRIDE;
+  int* const gsi = d.si + (long long)c * BNN_I_STRIDE;
+  for (int i = tid; i < BNN_F_STRIDE; i += (int)blockDim.x) ssf[i] = gsf[i];
+  for (int i = tid; i < BNN_I_STRIDE; i += (int)blockDim.x) ssi[i] = gsi[i];
+  __syncthreads();
+  double* sf = ssf;
+  int* si = ssi;
+  auto write_back = [&]() {
+    __syncthreads();
+    for (int i = tid; i < BNN_F_STRIDE; i += (int)blockDim.x) gsf[i] = ssf[i];
+    for (int i = tid; i < BNN_I_STRIDE; i += (int)blockDim.x) gsi[i] = ssi[i];
+  };
+  double* wc = d.w_cur + (long long)c * g.P;
+  double* wn = d.w_prop + (long long)c * g.P;
+  const int NC = 2 + 2 * g.K;
+  const int P0 = g.l[0].out * (g.l[0].in + g.l[0].bias);      // size of the first weight matrix (indicator shape)
+
+  // ------------------------------------------------------------------ accept / reject
+  if (accept_mode) {
+    const bool smode_is_empirical = (accept_mode != 2) && d.cfg.sigma_mode == BNN_SIGMA_EMPIRICAL;
+    // the initial likelihood of MCMC.__init__ always uses the stored error_prm (ones), even with
+    // empirical_error=True (BNN_env.py:313-319); the empirical std only enters in mh_step (:475-476)
+    const int smode = (accept_mode == 2) ? BNN_SIGMA_FIXED : d.cfg.sigma_mode;
+    const double* sg_in = (g.lik == BNN_LIK_GAUSSIAN && smode == BNN_SIGMA_FIXED) ? sf + BNN_F_SIGMA : nullptr;
+    const double* part_chain = part_c ? part_c : d.part + (long long)c * d.NF * d.n_tiles16;
+    double ll = finalize_loglik<COH>(g, part_chain, d.NF, d.n_tiles16, 0, d.n_train, d.cfg.lik_temp, smode, sg_in, red, sig, sh);
+    if (d.cfg.sample_from_prior) ll = 0.0;
+    if (tid == 0) {
+      double lp = sf[BNN_F_LOGPRIOR_PROP];
+      double post = ll + lp;
+      sf[BNN_F_LOGLIK_PROP] = ll;
+      // accept iff (logPost' - logPost) * T + hastings >= log u   (BNN_env.py:493-494); NaN compares false
+      int acc = (accept_mode == 2) ? 1 : (((post - sf[BNN_F_LOGPOST]) * sf[BNN_F_TEMPERATURE] + 0.0 >= sf[BNN_F_LOG_U]) ? 1 : 0);
+      s_flag = acc;
+      if (acc) {
+        sf[BNN_F_LOGLIK] = ll; sf[BNN_F_LOGPRIOR] = lp; sf[BNN_F_LOGPOST] = post;
+        // ActFun.reset_accepted_prm (BNN_env.py:502-503)
+        for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA + l] = sf[BNN_F_ALPHA_PROP + l];
+      }
+      if (accept_mode == 1) {
+        si[BNN_I_LAST_ACCEPTED] = acc;
+        si[BNN_I_N_ACCEPTED] += acc;
+        // acceptance window (BNN_env.py:523-529): mean over the stored outcomes + the new one, then keep 100
+        int len = si[BNN_I_RING_LEN], head = si[BNN_I_RING_HEAD], sum = si[BNN_I_RING_SUM];
+        sf[BNN_F_ACC_RATE] = (double)(sum + acc) / (double)(len + 1);
+        if (len < 100) {
+          si[BNN_I_RING + (head + len) % 100] = acc;
+          si[BNN_I_RING_LEN] = len + 1;
+          si[BNN_I_RING_SUM] = sum + acc;
+        } else {
+          si[BNN_I_RING_SUM] = sum + acc - si[BNN_I_RING + head];
+          si[BNN_I_RING + head] = acc;
+          si[BNN_I_RING_HEAD] = (head + 1) % 100;
+        }
+        si[BNN_I_ITERATION] += 1;
+      }
+    }
+    __syncthreads();
+    if (s_flag) {
+      for (int i = tid; i < g.P; i += (int)blockDim.x) wc[i] = wn[i];
+      // reset_indicators / _feature_indicators on accept (BNN_env.py:497-499)
+      if (d.ind_cur)
+        for (int i = tid; i < P0; i += (int)blockDim.x) d.ind_cur[(long long)c * P0 + i] = d.ind_prop[(long long)c * P0 + i];
+      if (d.fi_cur)
+        for (int i = tid; i < g.F; i += (int)blockDim.x) d.fi_cur[(long long)c * g.F + i] = d.fi_prop[(long long)c * g.F + i];
+      if (g.lik == BNN_LIK_CATEGORICAL) {
+        // (COH: the counters were accumulated by other CTAs of this launch -- volatile generic loads)
+        const volatile int* cp = counts_c ? counts_c : d.counts_prop + (long long)c * NC;
+        if (tid < 2) si[BNN_I_N_CORRECT + tid] = cp[tid];
+        for (int i = tid; i < g.K; i += (int)blockDim.x) {
+          si[BNN_I_CLASS_CORRECT + i] = cp[2 + i];
+          si[BNN_I_PRED_HIST + i] = cp[2 + g.K + i];
+        }
+      } else {
+        for (int i = tid; i < g.K; i += (int)blockDim.x) {
+          sf[BNN_F_SUM_R + i] = red[1 + i];
+          sf[BNN_F_SUM_R2 + i] = red[1 + g.K + i];
+          sf[BNN_F_SUM_R2_TEST + i] = red[1 + 2 * g.K + i];
+          // reset_error_prm on accept, regression mode only (BNN_env.py:500-501)
+          if (g.lik == BNN_LIK_GAUSSIAN && smode_is_empirical) sf[BNN_F_SIGMA + i] = sig[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!propose_mode) { write_back(); return; }
+
+  // ------------------------------------------------------------------ adaptation + which layers
+  const int it = si[BNN_I_ITERATION];
+  if (tid == 0) {
+    if (propose_mode == 1) {
+      // BNN_env.py:392-413
+      if (it % d.cfg.adapt_freq == 0 && it < d.cfg.adapt_stop) {
+        double ar = sf[BNN_F_ACC_RATE];
+        if (ar < d.cfg.adapt_f) {
+          for (int l = 0; l < g.L; ++l) {
+            sf[BNN_F_FREQ_LAYER + l] *= 0.8;
+            sf[BNN_F_UPDATE_F + l] *= 0.85;
+            int n = (int)((double)si[BNN_I_MAX_N + l] * sf[BNN_F_UPDATE_F + l]);
+            si[BNN_I_UPDATE_N + l] = n < 1 ? 1 : n;
+            sf[BNN_F_UPDATE_WS + l] *= 0.9;
+          }
+        }
+        int tot = 0;
+        for (int l = 0; l < g.L; ++l) tot += si[BNN_I_UPDATE_N + l];
+        if (ar > d.cfg.adapt_fM && tot < g.P) {
+          for (int l = 0; l < g.L; ++l) {
+            sf[BNN_F_UPDATE_F + l] = exp(log(sf[BNN_F_UPDATE_F + l]) * 0.85);
+            int n = (int)((double)si[BNN_I_MAX_N + l] * sf[BNN_F_UPDATE_F + l]);
+            si[BNN_I_UPDATE_N + l] = n < 1 ? 1 : n;
+            sf[BNN_F_UPDATE_WS + l] *= 1.2;
+          }
+        }
+      }
+      int off = 0;
+      if (d.inj_proposed) {
+        const long long base = ((long long)step * d.C + c) * g.L;
+        for (int l = 0; l < g.L; ++l) {
+          s_prop[l] = d.inj_proposed[base + l];
+          s_cnt[l] = s_prop[l] ? d.inj_count[base + l] : 0;
+          s_off[l] = off;
+          off += s_cnt[l];
+        }
+        sf[BNN_F_LOG_U] = d.inj_logu[(long long)step * d.C + c];
+      } else {
+        // rr = rs.random(L); rr[argmin] = 0; layer proposed iff rr < freq_layer_update (BNN_env.py:446-451)
+        uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
+        double rr[BNN_MAX_LAYERS];
+        int amin = 0;
+        for (int l = 0; l < g.L; ++l) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFFu, (uint32_t)l, 2u), key);
+          rr[l] = u53(r.x, r.y);
+          if (rr[l] < rr[amin]) amin = l;
+        }
+        rr[amin] = 0.0;
+        // weight indicators (BNN_env.py:449-460): the first layer is proposed only if rr[0] >= freq_indicator, otherwise
+        // its indicators move: UpdateBinomial(ind, update_f[3], shape) flips each entry with probability u * update_f[3]
+        s_ind_move = 0;
+        if (d.cfg.use_indicators && rr[0] < d.cfg.freq_indicator) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFCu, 0u, 5u), key);
+          s_ind_move = 1;
+          s_ind_p = u53(r.x, r.y) * sf[BNN_F_UPDATE_F + 3];
+        }
+        // feature indicators (BNN_env.py:423-431): past adapt_stop, with probability 0.2, flips with probability u * 0.5
+        s_fi_move = 0;
+        if (d.cfg.use_feature_indicators && it > d.cfg.adapt_stop) {
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFBu, 0u, 6u), key);
+          if (u53(r.x, r.y) < 0.2) { s_fi_move = 1; s_fi_p = u53(r.z, r.w) * 0.5; }
+        }
+        for (int l = 0; l < g.L; ++l) {
+          s_prop[l] = rr[l] < sf[BNN_F_FREQ_LAYER + l] && !(l == 0 && s_ind_move);
+          s_cnt[l] = s_prop[l] ? si[BNN_I_UPDATE_N + l] : 0;
+          s_off[l] = off;
+          off += s_cnt[l];
+        }
+        uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFEu, 0u, 3u), key);
+        sf[BNN_F_LOG_U] = log(u53(r.x, r.y));
+      }
+      for (int l = 0; l < g.L; ++l) si[BNN_I_PROPOSED + l] = s_prop[l];
+      // trainable activation parameters (BNN_env.py:416-421): UpdateNormal1D(_acc_prm, d=0.05, n=1, Mb=1, mb=0) with
+      // the injected draw, both reflections over every entry (BNN_mcmc.py:46-56), Exp(10) term into additional_prob
+      double addp = d.inj_add_prob ? d.inj_add_prob[(long long)step * d.C + c] : 0.0;
+      for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
+      if (d.cfg.n_act_prm > 0 && (d.inj_alpha_ix || !d.inj_proposed)) {
+        int ix;
+        double adz;
+        if (d.inj_alpha_ix) {
+          ix = d.inj_alpha_ix[(long long)step * d.C + c];
+          adz = d.inj_alpha_dz[(long long)step * d.C + c];
+        } else {                                          // rs.integers(0, n, 1), rs.normal(0, 0.05, 1) on the device
+          uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
+          uint4 r = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFDu, 0u, 4u), key);
+          ix = (int)__umulhi(r.x, (uint32_t)d.cfg.n_act_prm);
+          double sn, cs;
+          sincospi(2.0 * u53(r.y, r.z), &sn, &cs);
+          uint4 r2 = philox4x32(make_uint4((uint32_t)it, 0xFFFFFFFDu, 1u, 4u), key);
+          adz = 0.05 * sqrt(-2.0 * log(1.0 - u53(r2.x, r2.y))) * cs;
+        }
+        sf[BNN_F_ALPHA_PROP + ix] = sf[BNN_F_ALPHA + ix] + adz;
+        double sum = 0.0;
+        for (int l = 0; l < d.cfg.n_act_prm; ++l) {
+          double z = sf[BNN_F_ALPHA_PROP + l];
+          if (z > 1.0) z = 1.0 - (z - 1.0);
+          if (z < 0.0) z = 0.0 + (0.0 - z);
+          sf[BNN_F_ALPHA_PROP + l] = z;
+          sum += z;
+        }
+        addp += log(10.0) * (-sum) * 10.0;
+      }
+      sf[BNN_F_ADD_PROB] = addp;
+      for (int l = 0; l < g.L; ++l) d.alpha_fwd[(long long)c * g.L + l] = sf[BNN_F_ALPHA_PROP + l];
+    } else {
+      s_ind_move = 0; s_fi_move = 0;
+      for (int l = 0; l < g.L; ++l) { s_prop[l] = 0; s_cnt[l] = 0; s_off[l] = 0; }
+      // initial state (MCMC.__init__, BNN_env.py:313-320): stored parameters, init_additional_prob
+      for (int l = 0; l < g.L; ++l) sf[BNN_F_ALPHA_PROP + l] = sf[BNN_F_ALPHA + l];
+      sf[BNN_F_ADD_PROB] = d.cfg.init_additional_prob;
+    }
+  }
+  // zero the proposal's counters (the forward kernel accumulates into them)
+  if (g.lik == BNN_LIK_CATEGORICAL)
+    for (int i = tid; i < NC; i += (int)blockDim.x) (counts_c ? counts_c : d.counts_prop + (long long)c * NC)[i] = 0;
+  for (int i = tid; i < g.P; i += (int)blockDim.x) wn[i] = wc[i];
+  // indicator proposals: UpdateBinomial = |ind - flip| with the injected flips (BNN_mcmc.py:98-99), else unchanged
+  const double* ind_p = nullptr;
+  const double* fi_p = nullptr;
+  __syncthreads();                                   // s_ind_move / s_fi_move and their probabilities are visible
+  const bool gen_moves = propose_mode == 1 && !d.inj_proposed;          // free-running chains draw the flips here
+  const uint2 fkey = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
+  if (d.ind_cur) {
+    const long long sc = (long long)step * d.C + c;
+    const bool mv = propose_mode == 1 && d.inj_ind_move && d.inj_ind_move[sc];
+    double* dst = d.ind_prop + (long long)c * P0;
+    for (int i = tid; i < P0; i += (int)blockDim.x) {
+      double v = d.ind_cur[(long long)c * P0 + i];
+      bool flip = mv && d.inj_ind_flip[sc * P0 + i];
+      if (gen_moves && s_ind_move) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)it, (uint32_t)i, 0u, 7u), fkey);
+        flip = u53(r.x, r.y) < s_ind_p;
+      }
+      if (flip) v = fabs(v - 1.0);
+      dst[i] = v;
+    }
+    ind_p = dst;
+  }
+  if (d.fi_cur) {
+    const long long sc = (long long)step * d.C + c;
+    const bool mv = propose_mode == 1 && d.inj_fi_move && d.inj_fi_move[sc];
+    double* dst = d.fi_prop + (long long)c * g.F;
+    for (int i = tid; i < g.F; i += (int)blockDim.x) {
+      double v = d.fi_cur[(long long)c * g.F + i];
+      bool flip = mv && d.inj_fi_flip[sc * g.F + i];
+      if (gen_moves && s_fi_move) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)it, (uint32_t)i, 0u, 8u), fkey);
+        flip = u53(r.x, r.y) < s_fi_p;
+      }
+      if (flip) v = fabs(v - 1.0);
+      dst[i] = v;
+    }
+    fi_p = dst;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ UpdateNormal (BNN_mcmc.py:57-69)
+  // z[Ix,Iy] = z[Ix,Iy] + N(0, d): fancy assignment => for duplicate (ix,iy) the LAST draw wins and
+  // increments are not accumulated.  owner[idx] = largest draw index touching idx.
+  int* owner = d.owner + (long long)c * g.P;
+  const long long inj_base = ((long long)step * d.C + c) * d.inj_cap;
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int l = 0; l < g.L; ++l) {
+      if (!s_prop[l]) continue;
+      const LayerGeom& lg = g.l[l];
+      const int cols = lg.in + lg.bias;
+      const double ws = sf[BNN_F_UPDATE_WS + l];
+      for (int k = tid; k < s_cnt[l]; k += (int)blockDim.x) {
+        Draw dr;
+        if (d.inj_proposed) {
+          dr.ix = d.inj_ix[inj_base + s_off[l] + k];
+          dr.iy = d.inj_iy[inj_base + s_off[l] + k];
+          dr.dz = d.inj_dz[inj_base + s_off[l] + k];
+        } else {
+          dr = philox_draw(d.cfg.seed, d.cfg.chain_offset + c, it, l, k, lg.out, cols, ws);
+        }
+        const int idx = lg.c_off + dr.ix * cols + dr.iy;
+        if (pass == 0) atomicMax(&owner[idx], k);
+        else if (pass == 1) { if (owner[idx] == k) wn[idx] = wc[idx] + dr.dz; }
+        else owner[idx] = -1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ reflect, mask, prior, pack
+  const double hi = d.cfg.w_bound, lo = -d.cfg.w_bound;
+  double lp = 0.0;
+  double* wpk = d.wp_prop + (long long)c * g.PB;
+  for (int i = tid; i < g.P; i += (int)blockDim.x) {
+    const int l = layer_of(g, i);
+    const LayerGeom& lg = g.l[l];
+    double z = wn[i];
+    if (propose_mode == 1) {
+      if (s_prop[l]) {                 // single reflection at the bounds (BNN_mcmc.py:66-67)
+        if (z > hi) z = hi - (z - hi);
+        if (z < lo) z = lo + (lo - z);
+      }
+      if (d.mask) z *= d.mask[i];      // w' *= mask for every layer (BNN_env.py:461-462)
+      wn[i] = z;
+    }
+    if (d.cfg.prior != BNN_PRIOR_UNIFORM) {
+      const long long e = (long long)c * g.P + i;
+      lp += logpdf_prior(z, d.cfg.prior, d.ps_entry ? d.ps_entry[e] : d.ps.s[l], d.ps_entry ? d.pls_entry[e] : d.ps.ls[l]);
+    }
+    const int cols = lg.in + lg.bias;
+    const int r = (i - lg.c_off) / cols, cc = (i - lg.c_off) % cols;
+    // the forward pass sees w0' * indicators' (BNN_env.py:463-466; the prior above does not), and a feature whose
+    // indicator is 0 is replaced by its mean: its weight column leaves the contraction and enters the bias below
+    if (l == 0 && ind_p) z *= ind_p[i];
+    if (l == 0 && fi_p && !(lg.bias && cc == 0) && fi_p[cc - lg.bias] == 0.0) z = 0.0;
+    wpk[bnn_packed_index(lg, r, cc)] = z;
+  }
+  double s = block_sum_fixed(lp, sh);
+  if (ind_p && d.cfg.use_indicators) {
+    // + sum(ind) log(pi1) + (size - sum(ind)) log(1 - pi1)   (BNN_env.py:191-193)
+    double n1 = 0.0;
+    for (int i = tid; i < P0; i += (int)blockDim.x) n1 += ind_p[i];
+    n1 = block_sum_fixed(n1, sh);
+    s += n1 * log(d.cfg.prior_ind1) + ((double)P0 - n1) * log(1.0 - d.cfg.prior_ind1);
+  }
+  if (fi_p) {
+    // data_transform (BNN_env.py:14-17): x'[:, j] = mean_j where the feature indicator is 0, i.e. every first-layer
+    // node gets the constant  sum_j mean_j * w0'[r, j] * ind'[r, j]  on top of its bias
+    __syncthreads();
+    const LayerGeom& l0 = g.l[0];
+    const int cols0 = l0.in + l0.bias;
+    for (int r = tid; r < l0.out; r += (int)blockDim.x) {
+      double adj = 0.0;
+      for (int j = 0; j < l0.in; ++j)
+        if (fi_p[j] == 0.0) {
+          const int e = r * cols0 + l0.bias + j;
+          adj += d.feat_mean[j] * wn[e] * (ind_p ? ind_p[e] : 1.0);
+        }
+      const double b = l0.bias ? wn[r * cols0] * (ind_p ? ind_p[r * cols0] : 1.0) : 0.0;
+      wpk[l0.b_off + r] = b + adj;
+    }
+  }
+  if (tid == 0) sf[BNN_F_LOGPRIOR_PROP] = s + sf[BNN_F_ADD_PROB];     // calc_prior(...) + additional_prob (BNN_env.py:481)
+  write_back();
+}

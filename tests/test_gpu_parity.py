@@ -839,3 +839,74 @@ def test_row_sharding_matches_unsharded_chains():
     assert np.array_equal(shards[0].read_state().f64, shards[1].read_state().f64)      # ranks stay bit-identical
     for e in shards + [one, full]:
         e.close()
+
+
+def _chain_loop_cases():
+    rng = np.random.default_rng(21)
+    cases = {}
+    # config-1 shape: [5,5] tanh classifier, X resident in the cluster's shared memory
+    x = rng.standard_normal((2500, 128))
+    y = rng.integers(0, 5, 2500)
+    shp = [(5, 129), (5, 6), (5, 5)]
+    cases["c1"] = dict(x=x, y=y, n_test=300, feat=128, act="tanh", lik=0, sets=[[rng.normal(0, 0.2, s) for s in shp] for _ in range(2)],
+                       kw=dict(temperature=[1.0, 0.7], adapt_f=0.2, adapt_fM=0.6, adapt_freq=5, adapt_stop=40))
+    # config-2 shape: [10,5] ReLU regression with the empirical error, 999 rows
+    x = rng.standard_normal((999, 3))
+    t = rng.standard_normal((999, 2))
+    shp = [(10, 4), (5, 11), (2, 5)]
+    cases["c2"] = dict(x=x, y=t, n_test=0, feat=3, act="ReLU", lik=1, sets=[[rng.normal(0, 0.3, s) for s in shp]],
+                       kw=dict(sigma_mode=1, prior=1, prior_scale=2.0))
+    # wide rows: the tiles of a CTA do not fit in shared memory -> X is streamed from L2 every step
+    x = rng.standard_normal((6000, 230))
+    y = rng.integers(0, 3, 6000)
+    shp = [(8, 231), (7, 9), (3, 8)]
+    cases["streamed"] = dict(x=x, y=y, n_test=500, feat=230, act="swish", lik=0,
+                             sets=[[rng.normal(0, 0.1, s) for s in shp] for _ in range(3)], kw=dict(w_bound=1.5, prior=2))
+    # trainable slopes (genReLU), many chains -> small clusters
+    x = rng.standard_normal((700, 9))
+    y = rng.integers(0, 4, 700)
+    shp = [(6, 10), (5, 7), (4, 6)]
+    cases["leaky16"] = dict(x=x, y=y, n_test=0, feat=9, act="genReLU", lik=0,
+                            sets=[[rng.normal(0, 0.3, s) for s in shp] for _ in range(16)],
+                            kw=dict(alphas=[0.1, 0.2, 0.0], n_act_prm=2, temperature=list(np.linspace(1.0, 0.4, 16))))
+    return cases
+
+
+@pytest.mark.parametrize("case", ["c1", "c2", "streamed", "leaky16"])
+def test_chain_loop_matches_launch_sequence(case):
+    """Small data sets step inside ONE persistent launch (k_chain_loop: a thread-block cluster per chain, leader CTA =
+    update body, all CTAs = forward body, partials / counters through distributed shared memory).  The chains must be
+    bit-identical to the per-step launch sequence (option chain_loop=0), for every cluster size, across calls, a
+    temperature change and different chunk lengths."""
+    from npbnn_b200.engine import Engine, NetShape
+    cs = _chain_loop_cases()[case]
+    net = NetShape.from_weights(cs["sets"][0], cs["feat"], act=cs["act"], lik=cs["lik"])
+    n_chains = len(cs["sets"])
+    states = []
+    modes = {"c1": ("loop16", "loop4"), "c2": ("loop16", "loop4", "loop1"), "streamed": ("loop16", "loop8"),
+             "leaky16": ("loop16", "loop4", "loop1")}[case] + ("sequence",)
+    for mode in modes:
+        eng = Engine(net)
+        n_tr = len(cs["x"]) - cs["n_test"]
+        if cs["n_test"]:
+            eng.set_data(cs["x"][:n_tr], cs["y"][:n_tr], x_test=cs["x"][n_tr:], y_test=cs["y"][n_tr:])
+        else:
+            eng.set_data(cs["x"], cs["y"])
+        eng.chains_init(cs["sets"], seed=99, **cs["kw"])
+        eng.set_option("chain_loop", 0 if mode == "sequence" else 1)
+        if mode.startswith("loop"):
+            eng.set_option("chain_loop_cluster", int(mode[4:]))
+        eng.mh_steps(1)
+        eng.mh_steps(25)
+        assert eng.last_kernel == ("k_fwd_generic" if mode == "sequence" else "k_chain_loop"), eng.last_kernel
+        temp = cs["kw"].get("temperature", [1.0] * n_chains)
+        eng.set_temperature(list(temp)[::-1])
+        eng.mh_steps(13)
+        st = eng.read_state()
+        states.append((st.f64.copy(), st.i32.copy(), st.w.copy()))
+        eng.close()
+    ref = states[-1]
+    assert np.all(ref[1][:, 0] == 39)
+    assert 0 < ref[1][:, 2].sum() < 39 * n_chains         # some proposals accepted, some rejected
+    for f64, i32, w in states[:-1]:
+        assert np.array_equal(f64, ref[0], equal_nan=True) and np.array_equal(i32, ref[1]) and np.array_equal(w, ref[2])
