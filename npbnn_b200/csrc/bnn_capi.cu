@@ -1073,7 +1073,7 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
   // proposals alike.  Same update / forward bodies and reduction order as the launch sequence below: identical chains.
   if (c->opt_chain_loop && !c->time_forward && !c->opt_tensor && !(c->use_sparse && c->opt_sparse) &&
       (c->force_generic || !bnn_fwd3_family(c->g)) && !bnn_part_slices(c->n_tiles16) &&
-      bnn_chain_loop_fits(c->g, d.NF, d.n_tiles16, c->C, c->n_sms)) {
+      bnn_chain_loop_fits(c->g, d.NF, d.n_tiles16, c->C, c->n_sms, c->opt_chain_cluster)) {
     FwdParams p = base_params(c);
     p.C = 1;
     int cl = 0;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
   const int PW = bnn_pred_width(g);
 
   double* tab = reinterpret_cast<double*>(smem_raw);
-  double* hbase = tab + BNN_EXP_TAB_SIZE;
+  double* hbase = tab + GEN_TAB_SIZE;
   const int per_warp = 2 * 16 * g.max_w + 16 * ZS + (PREDICT ? 16 * PW : 0);
   double* h0 = hbase + warp * per_warp;
   double* h1 = h0 + 16 * g.max_w;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
   int* cnt = ibase;   // likelihood mode: [C][2+2K]
   const int n_cnt = (!PREDICT && g.lik == BNN_LIK_CATEGORICAL) ? p.C * (2 + 2 * g.K) : 0;
 
-  for (int i = threadIdx.x; i < BNN_EXP_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab[i];
+  for (int i = threadIdx.x; i < GEN_TAB_SIZE; i += blockDim.x) tab[i] = p.exp_tab_small[i];
   for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
 
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) k_fwd_generic(const __grid_con
       fwd_generic_layers<ACT, true, true>(g, xrow0, xrow1, p.wp + (long long)c * g.PB,
                                     (ACT == BNN_ACT_LEAKY && p.alpha) ? p.alpha + (long long)c * g.L : nullptr, h0, h1, zs, ZS,
                                     tab, lane);
-      bnn_epilogue<PREDICT>(p, c, wt, lane, zs, ZS, tab, cnt, pacc, pvote);
+      bnn_epilogue<PREDICT, false, GEN_TB>(p, c, wt, lane, zs, ZS, tab, cnt, pacc, pvote);
       __syncwarp();
     }
     bnn_pred_flush<PREDICT>(p, wt, lane, pacc, pvote);
@@ -2133,7 +2133,7 @@ static cudaError_t launch_generic_t(const FwdParams& p, int n_sms, cudaStream_t 
   const int ZS = p.g.l[p.g.L - 1].out_pad + 1;
   const int PW = (p.g.lik == BNN_LIK_CATEGORICAL) ? p.g.K : p.g.O;
   size_t per_warp = 2 * 16 * (size_t)p.g.max_w + 16 * ZS + (PREDICT ? 16 * PW : 0);
-  size_t bytes = (BNN_EXP_TAB_SIZE + GEN_WARPS * per_warp) * sizeof(double);
+  size_t bytes = (GEN_TAB_SIZE + GEN_WARPS * per_warp) * sizeof(double);
   size_t ints = PREDICT ? (size_t)GEN_WARPS * 16 * PW
                         : (p.g.lik == BNN_LIK_CATEGORICAL ? (size_t)p.C * (2 + 2 * p.g.K) : 0);
   bytes += ints * sizeof(int);

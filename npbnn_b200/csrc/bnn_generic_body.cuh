@@ -7,6 +7,12 @@
 
 #define FULL_MASK 0xffffffffu
 
+// The generic path evaluates its exponentials with the 256-entry table (+ fourth-order term: one more FMA, same 3e-16
+// accuracy): 2 KB of shared memory instead of 16 KB, which is what lets k_chain_loop keep the config-1 feature matrix
+// resident next to it.  k_fwd_generic uses the same table so that both run the identical arithmetic.
+constexpr int GEN_TB = 8;
+constexpr int GEN_TAB_SIZE = 1 << GEN_TB;
+
 // compile-time loop: f(std::integral_constant<int, I>{}) for I in [I0, N)
 template <int I0, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
@@ -42,9 +48,10 @@ __device__ __forceinline__ double softplus_ref(double z) {
 // optionally writes the dense tensor.
 // R32 (likelihood mode only): the warp owns 32 rows = warp tiles wt and wt + 1, lane r owns row r; the xor
 // trees of warp16_sum stay inside each half-warp, so lanes 0 and 16 hold the two warp-tile sums.
-template <bool PREDICT, bool R32 = false>
+template <bool PREDICT, bool R32 = false, int TB = BNN_EXP_TAB_BITS>
 __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long long wt, int lane, const double* zs,
-                                             int ZS, const double* tab, int* cnt_smem, double* pacc, int* pvote) {
+                                             int ZS, const double* tab, int* cnt_smem, double* pacc, int* pvote,
+                                             const int* lab16 = nullptr, const double* tgt16 = nullptr) {
   const NetGeom& g = p.g;
   const int rl = R32 ? lane : (lane & 15);
   const long long row = wt * 16 + rl;
@@ -69,13 +76,13 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
         if (v > m) { m = v; arg = k; }   // first maximum wins, as np.argmax
       }
       if (!PREDICT && is_train) {
-        for (int k = 0; k < K; ++k) S += bnn_exp_neg(z[k] - m, tab);
+        for (int k = 0; k < K; ++k) S += bnn_exp_neg<TB>(z[k] - m, tab);
       }
     }
     if (!PREDICT) {
       int y = 0;
       if (active) {
-        y = p.labels[row];
+        y = lab16 ? lab16[rl] : p.labels[row];
         bool ok = (arg == y);
         if (is_train) {
           double d = z[y] - m;
@@ -96,7 +103,7 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
     } else {
       if (active) {
         double* zw = const_cast<double*>(z);     // the staged row is private to this lane: reuse as scratch
-        for (int k = 0; k < K; ++k) { double e = bnn_exp_neg(z[k] - m, tab); zw[k] = e; S += e; }
+        for (int k = 0; k < K; ++k) { double e = bnn_exp_neg<TB>(z[k] - m, tab); zw[k] = e; S += e; }
         double inv = 1.0 / S;
         double* pa = pacc + (lane & 15) * K;
         // sample_from_categorical: first class whose running sum (np.cumsum order) reaches u; none => class 0
@@ -134,7 +141,7 @@ __device__ __forceinline__ void bnn_epilogue(const FwdParams& p, int c, long lon
     for (int j = 0; j < K; ++j) {
       double r = 0.0;
       if (active) {
-        double t = p.targets[row * K + j];
+        double t = tgt16 ? tgt16[rl * K + j] : p.targets[row * K + j];
         r = z[j] - t;
         if (head && is_train) {
           double s = softplus_ref(z[K + j]);
@@ -191,6 +198,75 @@ __device__ __forceinline__ double2 gen_ld2(const double* p) {
   return *reinterpret_cast<const double2*>(p);
 }
 
+// One block of NT output tiles (8 columns each) of one layer over the warp's 16 rows: accumulators start at the
+// bias, k-groups in ascending order (the summation order every caller shares), then activation + staging store for
+// the next layer (or the plain store of the last layer's outputs).  Everything loop-invariant is in registers and
+// the n-tile loop is unrolled at compile time: the k-loop is loads + DMMAs only.
+//   arow0 / arow1 : A rows gq and gq + 8, already offset by 2t;  wrow : W row (n0 + gq), offset by 2t;
+//   sx : 1 if this lane's rows are swizzled (k-group kg lives at column group kg ^ 1)
+template <int ACT, bool ANC, bool WNC, int NT>
+__device__ __forceinline__ void gen_layer_block(const double* arow0, const double* arow1, const double* wrow, int stride,
+                                                int nkg, int sx, const double* bias, bool last, double alpha,
+                                                double* dst0, double* dst1, int dsx, double* z0, double* z1,
+                                                const double* tab) {
+  // A lone warp is bound by the latency of the dependent DMMA chain (~280 clk per k-group measured), not by the pipe
+  // (64 clk per m16n8k8): narrow blocks split the k-groups round-robin over NCH independent accumulator sets, summed
+  // at the end in a fixed order (set 0 carries the bias).
+  constexpr int NCH = (NT == 1) ? 4 : (NT == 2 ? 2 : 1);
+  double accs[NCH][NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const double2 bb = *reinterpret_cast<const double2*>(bias + 8 * j);
+    accs[0][j][0] = bb.x; accs[0][j][1] = bb.y; accs[0][j][2] = bb.x; accs[0][j][3] = bb.y;
+#pragma unroll
+    for (int q = 1; q < NCH; ++q) accs[q][j][0] = accs[q][j][1] = accs[q][j][2] = accs[q][j][3] = 0.0;
+  }
+  const int stride8 = 8 * stride;
+  auto kgroup = [&](int kg, double (&a)[NT][4]) {
+    const int off = (kg ^ sx) << 3;
+    const double2 a_lo = gen_ld2<ANC>(arow0 + off);
+    const double2 a_hi = gen_ld2<ANC>(arow1 + off);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const double2 bb = gen_ld2<WNC>(wrow + j * stride8 + off);
+      dmma16x8x8(a[j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bb.x, bb.y);
+    }
+  };
+  int kg = 0;
+  for (; kg + NCH <= nkg; kg += NCH) {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) kgroup(kg + q, accs[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < NCH - 1; ++q)
+    if (kg + q < nkg) kgroup(kg + q, accs[q]);
+  double (&acc)[NT][4] = accs[0];
+  if (NCH == 2) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] += accs[NCH - 1][j][e];
+  } else if (NCH == 4) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = (accs[0][j][e] + accs[1][j][e]) + (accs[2][j][e] + accs[NCH - 1][j][e]);
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (!last) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = bnn_act<ACT, GEN_TB>(acc[j][e], alpha, tab);
+      const int o = ((j ^ dsx) << 3);
+      *reinterpret_cast<double2*>(dst0 + o) = make_double2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<double2*>(dst1 + o) = make_double2(acc[j][2], acc[j][3]);
+    } else {
+      z0[8 * j] = acc[j][0]; z0[8 * j + 1] = acc[j][1];
+      z1[8 * j] = acc[j][2]; z1[8 * j + 1] = acc[j][3];
+    }
+  }
+}
+
 // All layers of one weight set over one 16-row warp tile; leaves the last layer's pre-transform outputs in zs [16][ZS].
 //   xrow0 / xrow1 : rows gq and gq + 8 of the tile in the swizzled-row layout (stride F_pad); W : packed weight set;
 //   alpha_c : this set's activation slopes (leaky) or null; h0 / h1 : per-warp staging [16][max_w] each
@@ -201,60 +277,46 @@ __device__ __forceinline__ void fwd_generic_layers(const NetGeom& g, const doubl
   const int gq = lane >> 2, t = lane & 3;
   const double* src = nullptr;
   double* dst = h0;
+#pragma unroll 1
   for (int l = 0; l < g.L; ++l) {
-    const LayerGeom& lg = g.l[l];
+    const LayerGeom lg = g.l[l];
     const bool last = (l == g.L - 1);
     const double alpha = alpha_c ? alpha_c[l] : 0.0;
-    const int sw = (gq & 1) * lg.swz;
+    const int sx = (gq & 1) & (lg.swz >> 3);
     const int nkg = lg.in_pad >> 3;
     // destination geometry = next layer's A operand
     const int dstride = last ? ZS : g.l[l + 1].stride;
-    const int dsw = last ? 0 : (gq & 1) * g.l[l + 1].swz;
+    const int dsx = last ? 0 : ((gq & 1) & (g.l[l + 1].swz >> 3));
+    const double* arow0 = (l == 0) ? xrow0 + 2 * t : src + gq * lg.stride + 2 * t;
+    const double* arow1 = (l == 0) ? xrow1 + 2 * t : src + (gq + 8) * lg.stride + 2 * t;
+#pragma unroll 1
     for (int n0 = 0; n0 < lg.out_pad; n0 += 32) {
       const int ntile = min(4, (lg.out_pad - n0) >> 3);
-      double acc[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double b0 = 0.0, b1 = 0.0;
-        if (j < ntile) {
-          const double2 bb = *reinterpret_cast<const double2*>(W + lg.b_off + n0 + 8 * j + 2 * t);
-          b0 = bb.x; b1 = bb.y;
-        }
-        acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
+      const double* wrow = W + lg.w_off + (long long)(n0 + gq) * lg.stride + 2 * t;
+      const double* bias = W + lg.b_off + n0 + 2 * t;
+      // staging stores: column n0 + 8j + 2t of rows gq / gq + 8, k-group j of the block swizzled like the consumer reads it
+      double* dst0 = dst + gq * dstride + n0 + 2 * t;
+      double* dst1 = dst + (gq + 8) * dstride + n0 + 2 * t;
+      double* z0 = zs + gq * ZS + n0 + 2 * t;
+      double* z1 = zs + (gq + 8) * ZS + n0 + 2 * t;
+      // (X in shared memory loads like the staged activations: one instantiation serves every layer, which keeps the
+      // executed code of k_chain_loop inside the instruction cache)
+#define GEN_BLOCK(NT)                                                                                                     \
+  do {                                                                                                                    \
+    if (XNC && l == 0)                                                                                                    \
+      gen_layer_block<ACT, true, WNC, NT>(arow0, arow1, wrow, lg.stride, nkg, sx, bias, last, alpha, dst0, dst1, dsx, z0,  \
+                                          z1, tab);                                                                       \
+    else                                                                                                                  \
+      gen_layer_block<ACT, false, WNC, NT>(arow0, arow1, wrow, lg.stride, nkg, sx, bias, last, alpha, dst0, dst1, dsx, z0, \
+                                           z1, tab);                                                                      \
+  } while (0)
+      switch (ntile) {
+        case 1: GEN_BLOCK(1); break;
+        case 2: GEN_BLOCK(2); break;
+        case 3: GEN_BLOCK(3); break;
+        default: GEN_BLOCK(4); break;
       }
-      for (int kg = 0; kg < nkg; ++kg) {
-        const int col = (8 * kg + 2 * t) ^ sw;
-        double2 a_lo, a_hi;
-        if (l == 0) {
-          a_lo = gen_ld2<XNC>(xrow0 + col);
-          a_hi = gen_ld2<XNC>(xrow1 + col);
-        } else {
-          a_lo = *reinterpret_cast<const double2*>(src + gq * lg.stride + col);
-          a_hi = *reinterpret_cast<const double2*>(src + (gq + 8) * lg.stride + col);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < ntile) {
-            const double2 bb = gen_ld2<WNC>(W + lg.w_off + (long long)(n0 + 8 * j + gq) * lg.stride + col);
-            dmma16x8x8(acc[j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bb.x, bb.y);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < ntile) {
-          const int cn = n0 + 8 * j + 2 * t;
-          if (!last) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = bnn_act<ACT>(acc[j][e], alpha, tab);
-            *reinterpret_cast<double2*>(dst + gq * dstride + (cn ^ dsw)) = make_double2(acc[j][0], acc[j][1]);
-            *reinterpret_cast<double2*>(dst + (gq + 8) * dstride + (cn ^ dsw)) = make_double2(acc[j][2], acc[j][3]);
-          } else {
-            zs[gq * ZS + cn] = acc[j][0]; zs[gq * ZS + cn + 1] = acc[j][1];
-            zs[(gq + 8) * ZS + cn] = acc[j][2]; zs[(gq + 8) * ZS + cn + 1] = acc[j][3];
-          }
-        }
-      }
+#undef GEN_BLOCK
     }
     __syncwarp();
     src = dst;

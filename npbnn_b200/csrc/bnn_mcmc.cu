@@ -50,10 +50,9 @@ __global__ void __launch_bounds__(UPD_THREADS) k_finalize_lik(const __grid_const
                                                                double* loglik, double* sums, int set0) {
   __shared__ double red[1 + 3 * BNN_MAX_OUT];
   __shared__ double sig[BNN_MAX_OUT];
-  __shared__ double sh[32];
   const int c = blockIdx.x;
   const double* sg = sigma ? sigma + (long long)(set0 + c) * g.K : nullptr;
-  double ll = finalize_loglik(g, part, NF, nt, c, n_train, lik_temp, sigma_mode, sg, red, sig, sh);
+  double ll = finalize_loglik(g, part + (long long)c * NF * nt, NF, nt, n_train, lik_temp, sigma_mode, sg, red, sig);
   if (threadIdx.x == 0) loglik[set0 + c] = ll;
   if (sums && g.lik != BNN_LIK_CATEGORICAL)
     for (int i = threadIdx.x; i < 3 * g.K; i += blockDim.x) sums[(long long)(set0 + c) * 3 * g.K + i] = red[1 + i];
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_prior_refresh(const __grid_cons
 // one CTA per chain: [accept previous proposal] + [adapt, propose, prior, pack] (body: bnn_mh_body.cuh)
 __global__ void __launch_bounds__(UPD_THREADS) k_mh_update(const __grid_constant__ ChainDev d, int accept_mode,
                                                             int propose_mode, int step) {
-  mh_update_body<false>(d, blockIdx.x, accept_mode, propose_mode, step);
+  mh_update_body<false>(d, blockIdx.x, accept_mode, propose_mode, step, UpdLoop{});
 }
 
 
