@@ -910,3 +910,58 @@ def test_chain_loop_matches_launch_sequence(case):
     assert 0 < ref[1][:, 2].sum() < 39 * n_chains         # some proposals accepted, some rejected
     for f64, i32, w in states[:-1]:
         assert np.array_equal(f64, ref[0], equal_nan=True) and np.array_equal(i32, ref[1]) and np.array_equal(w, ref[2])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_chain_loop_random_shapes_match_launch_sequence(seed):
+    """Randomised differential test of k_chain_loop against the per-step launch sequence: depth 2-4, ragged widths, with
+    and without bias columns, categorical / Gaussian / sigma-head likelihoods, class and instance weights, every prior,
+    bounded weights, adaptation on, test rows, 1-7 chains, injected-free (device Philox) proposals.  Bit-identical states."""
+    from npbnn_b200.engine import Engine, NetShape
+    from npbnn_b200 import _lib as L
+    rng = np.random.default_rng(1000 + seed)
+    depth = int(rng.integers(2, 5))
+    f = int(rng.integers(2, 70))
+    lik = int(rng.integers(0, 3))
+    k = int(rng.integers(2, 9)) if lik == L.LIK_CATEGORICAL else int(rng.integers(1, 4))
+    out = k if lik != L.LIK_GAUSSIAN_HEAD else 2 * k
+    widths = [int(rng.integers(2, 20)) for _ in range(depth - 1)] + [out]
+    shapes, w_in = [], f
+    for wdt in widths:
+        shapes.append((wdt, w_in + int(rng.integers(0, 2))))
+        w_in = wdt
+    n, n_test = int(rng.integers(20, 3000)), int(rng.integers(0, 200))
+    x = rng.standard_normal((n + n_test, f))
+    y = rng.integers(0, k, n + n_test) if lik == L.LIK_CATEGORICAL else rng.standard_normal((n + n_test, k))
+    act = ["ReLU", "genReLU", "swish", "tanh"][int(rng.integers(0, 4))]
+    n_chains = int(rng.integers(1, 8))
+    sets = [[rng.normal(0, 0.3, s) for s in shapes] for _ in range(n_chains)]
+    net = NetShape(f, shapes, act=act, lik=lik)
+    kw = dict(prior=int(rng.integers(0, 4)), prior_scale=float(rng.uniform(0.5, 3.0)), seed=int(rng.integers(1, 10 ** 6)),
+              adapt_f=0.25, adapt_fM=0.5, adapt_freq=int(rng.integers(2, 9)), adapt_stop=30,
+              temperature=list(rng.uniform(0.3, 1.0, n_chains)), lik_temp=float(rng.uniform(0.5, 1.0)))
+    if rng.integers(0, 2):
+        kw["w_bound"] = 1.0
+    if act == "genReLU":
+        kw.update(alphas=list(rng.uniform(0.0, 0.5, depth)), n_act_prm=int(rng.integers(0, depth + 1)))
+    if lik == L.LIK_GAUSSIAN:
+        kw["sigma_mode"] = int(rng.integers(0, 2))
+    cw = rng.uniform(0.5, 2.0, k) if lik == L.LIK_CATEGORICAL and rng.integers(0, 2) else None
+    iw = rng.uniform(0.5, 2.0, n) if lik == L.LIK_CATEGORICAL and rng.integers(0, 2) else None
+    states = []
+    for loop in (1, 0):
+        eng = Engine(net)
+        eng.set_data(x[:n], y[:n], x_test=x[n:] if n_test else None, y_test=y[n:] if n_test else None, inst_w=iw, class_w=cw)
+        eng.chains_init(sets, **kw)
+        eng.set_option("chain_loop", loop)
+        eng.mh_steps(17)
+        eng.mh_steps(1)
+        eng.mh_steps(9)
+        kernel = eng.last_kernel
+        st = eng.read_state()
+        states.append((st.f64.copy(), st.i32.copy(), st.w.copy(), kernel))
+        eng.close()
+    a, b = states
+    assert a[3] == "k_chain_loop" and b[3] == "k_fwd_generic", (a[3], b[3])
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.all(a[1][:, 0] == 27)
