@@ -266,6 +266,20 @@ __device__ __forceinline__ double bnn_log_ge1(double x) {
   return fma(ed, 0.6931471675634384, fma(ed, 1.2996506893889889e-08, lm));   // ln2 split hi (26 bits) + lo
 }
 
+// softplus(z) = np.logaddexp(0, z) = max(z, 0) + log1p(exp(-|z|)) (BNN_lib.py:170-172) and its logarithm, for the
+// sigma head of the Gaussian likelihood, without libm calls (each is a 400-500 clk dependent chain that the warps of
+// k_fwd3 would all sit behind): exp from the table routine, log1p(e) = log(u) + (e - (u - 1)) / u with u = fl(1 + e)
+// (the correction restores what the rounding of 1 + e lost: full relative accuracy down to e ~ 1e-304), log by
+// bnn_log_ge1's algorithm, which holds for every positive normal argument.  |z| >= 700 / inf / NaN: caller's libm path.
+__device__ __forceinline__ double bnn_softplus_fast(double z, const double* __restrict__ tab) {
+  const double az = fabs(z);
+  const double e = bnn_exp_neg<BNN_EXP_TAB_BITS>(-az, tab);          // (0, 1]
+  const double u = 1.0 + e;
+  const double c = e - (u - 1.0);
+  const double l1p = fma(c, bnn_rcp(u), bnn_log_ge1(u));
+  return fmax(z, 0.0) + l1p;
+}
+
 // Hidden-layer activation, matching the reference formulas (BNN_lib.py:50-66):
 //   swish z*(1+exp(-z))^-1 ; tanh 1 - 2/(exp(2z)+1) ; ReLU ; leaky (alpha*z for z<0)
 template <int ACT, int TB = BNN_EXP_TAB_BITS>

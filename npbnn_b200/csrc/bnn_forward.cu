@@ -855,7 +855,7 @@ __device__ __forceinline__ void quad_epilogue_pred(const FwdParams& p, int c, lo
 // MSE statistics; with the sigma head (columns K..2K-1 through softplus) the per-row log-density is summed here.
 template <int N3>
 __device__ __forceinline__ void quad_gauss_lik(const FwdParams& p, int c, long long wt, int lane,
-                                               const double (&acc)[N3 / 8][4]) {
+                                               const double (&acc)[N3 / 8][4], const double* tab) {
   static_assert(N3 == 8, "Gaussian outputs fit one 8-column tile");
   const int K = p.g.K;
   const bool head = (p.g.lik == BNN_LIK_GAUSSIAN_HEAD);
@@ -881,9 +881,15 @@ __device__ __forceinline__ void quad_gauss_lik(const FwdParams& p, int c, long l
         r = mu - tv;
         if (head && train) {
           const double zs = (scol & 1) ? (h ? s11 : s01) : (h ? s10 : s00);
-          const double sd = softplus_ref(zs);
-          const double u = (tv - mu) / sd;
-          ll += -0.5 * u * u - kLogSqrt2Pi - log(sd);
+          if (fabs(zs) < 700.0) {
+            const double sd = bnn_softplus_fast(zs, tab);
+            const double u = (tv - mu) * bnn_rcp(sd);
+            ll += -0.5 * u * u - kLogSqrt2Pi - bnn_log_ge1(sd);
+          } else {                                                   // out of the table routine's range, inf, NaN: libm
+            const double sd = softplus_ref(zs);
+            const double u = (tv - mu) / sd;
+            ll += -0.5 * u * u - kLogSqrt2Pi - log(sd);
+          }
         }
       }
       sr[e] += train ? r : 0.0;
@@ -918,7 +924,7 @@ __device__ __forceinline__ void quad_gauss_lik(const FwdParams& p, int c, long l
 // prediction mode: transformed outputs (identity, softplus on the sigma head) accumulated over the weight sets
 template <int N3>
 __device__ __forceinline__ void quad_gauss_pred(const FwdParams& p, int c, long long wt, int lane,
-                                                const double (&acc)[N3 / 8][4], double (&pacc)[2][N3 / 4]) {
+                                                const double (&acc)[N3 / 8][4], double (&pacc)[2][N3 / 4], const double* tab) {
   static_assert(N3 == 8, "Gaussian outputs fit one 8-column tile");
   const int K = p.g.K, O = p.g.O;
   const bool head = (p.g.lik == BNN_LIK_GAUSSIAN_HEAD);
@@ -931,7 +937,7 @@ __device__ __forceinline__ void quad_gauss_pred(const FwdParams& p, int c, long 
       const int col = 2 * t + e;
       if (row < p.n_total && col < O) {
         double v = acc[0][2 * h + e];
-        if (head && col >= K) v = softplus_ref(v);
+        if (head && col >= K) v = (fabs(v) < 700.0) ? bnn_softplus_fast(v, tab) : softplus_ref(v);
         pacc[h][e] += v;
         if (p.dense_out) p.dense_out[((long long)c * p.n_total + row) * O + col] = v;
       }
@@ -1321,8 +1327,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_fwd3(const __grid_constant__
         if constexpr (CAT) {
           if (PREDICT) quad_epilogue_pred<N3>(p, c, wt, lane, acc3, tab, pacc, pvote);
         } else {
-          if (PREDICT) quad_gauss_pred<N3>(p, c, wt, lane, acc3, pacc);
-          else quad_gauss_lik<N3>(p, c, wt, lane, acc3);
+          if (PREDICT) quad_gauss_pred<N3>(p, c, wt, lane, acc3, pacc, tab);
+          else quad_gauss_lik<N3>(p, c, wt, lane, acc3, tab);
         }
       } else {
         // (a warp without a tile waits for both parts before releasing them, so that its releases cannot run ahead)
