@@ -965,3 +965,48 @@ def test_chain_loop_random_shapes_match_launch_sequence(seed):
     assert a[3] == "k_chain_loop" and b[3] == "k_fwd_generic", (a[3], b[3])
     assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.all(a[1][:, 0] == 27)
+
+
+def test_c3_full_size_block_masked_chains():
+    """BASELINE config 3 at FULL size (200,000 x 40, create_mask network [120, 80] tanh, 5 classes, 8 chains): the oracle
+    scores every chain's initial state on all rows (1e-9, counters exact), and the fused block-pair kernel and the dense
+    kernels (option sparse=0) run the same 12 device-generated MH iterations to identical decisions and weights."""
+    from npbnn_b200.engine import Engine, NetShape
+    import npbnn_b200.api as api
+    rng = np.random.default_rng(17)
+    n, f, k, C = 200_000, 40, 5, 8
+    shapes = [(120, 40), (80, 120), (5, 81)]
+    idx = [list(range(40)), sum(([g] * 3 for g in range(40)), []), []]
+    mask = api.create_mask([np.zeros(s) for s in shapes], idx, [[3] * 40, [2] * 40, []])
+    x = rng.standard_normal((n, f))
+    teacher = [rng.normal(0, 1, s) * m for s, m in zip(shapes, mask)]
+    h = np.tanh(np.tanh(x @ teacher[0].T) @ teacher[1].T)
+    labels = np.argmax(h @ teacher[2][:, 1:].T + teacher[2][:, 0], 1)
+    sets = [[rng.normal(0, 0.1, s) * m for s, m in zip(shapes, mask)] for _ in range(C)]
+    states = []
+    for sparse in (1, 0):
+        eng = Engine(NetShape(f, shapes, act="tanh", lik=0))
+        eng.set_option("sparse", sparse)
+        eng.set_data(x, labels)
+        eng.chains_init(sets, mask=mask, seed=23, temperature=list(np.linspace(1.0, 0.5, C)))
+        if sparse:
+            assert eng.last_kernel == "k_fwd_sparse<pairs>", eng.last_kernel
+            st = eng.read_state()
+            for c, ws in enumerate(sets):
+                y = orc.forward(x, ws, "tanh", None, "softmax")
+                assert rel_close(st.logLik[c], orc.loglik_categorical(y, labels)), c
+                nc, ck, _, hist = orc.class_counters(y, labels)
+                assert st.n_correct[c] == nc and np.array_equal(st.class_correct[c], ck) and np.array_equal(st.pred_hist[c], hist)
+        else:
+            assert not eng.last_kernel.startswith("k_fwd_sparse"), eng.last_kernel
+        eng.mh_steps(12)
+        states.append(eng.read_state())
+        eng.close()
+    a, b = states
+    assert np.array_equal(a.n_accepted, b.n_accepted) and 0 < a.n_accepted.sum() < 12 * C
+    assert np.array_equal(a.w, b.w)
+    assert rel_close(a.logLik, b.logLik)
+    assert np.array_equal(a.n_correct, b.n_correct) and np.array_equal(a.pred_hist, b.pred_hist)
+    for c in range(C):
+        for wl_, m in zip(a.weights(c), mask):
+            assert np.all(wl_[m == 0] == 0)
