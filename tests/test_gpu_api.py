@@ -577,3 +577,27 @@ def test_free_running_chains_draw_every_proposal_branch_on_the_device(tmp_path):
     bn.run_mcmc(bnn, mcmc, logger)
     head = open(logger._logfile).read().split("\n")[0].split("\t")
     assert "mean_ind" in head and "alpha_0" in head and "feature_ind_5" in head
+
+
+def test_predict_sharded_chunked_upload_matches_one_pass():
+    """predshard.predict_sharded with the posterior samples in pinned host memory uploads them in chunks on a side stream
+    under the kernel of the previous chunk; mean probabilities must agree with the one-pass prediction to rounding of the
+    last additions and the vote shares exactly (world = 1: no collective)."""
+    import torch
+    from npbnn_b200.engine import Engine, NetShape, flatten_weights
+    from npbnn_b200 import predshard, workloads as wl
+    rng = np.random.default_rng(8)
+    n, S = 3000, 700
+    x, _ = wl.c4_data(n, seed=2)
+    base = flatten_weights(wl.c4_init_weights(1)[0])
+    w = base[None, :] + rng.normal(0, 0.1, (S, base.size))
+    eng = Engine(NetShape(64, list(wl.C4_SHAPES), act="swish", lik=0))
+    ref = eng.predict(x, w, mean=True, votes=True)
+    xd = torch.from_numpy(x).cuda()
+    out = predshard.predict_sharded(eng, xd, torch.from_numpy(w).pin_memory(), n, 0, 1, votes=True)
+    assert out["grid"] == (1, 1) and out["sets"] == (0, S)
+    assert np.allclose(out["mean"].cpu().numpy(), ref["mean"], rtol=0, atol=1e-14)
+    assert np.array_equal(np.rint(out["votes"].cpu().numpy() * S), np.rint(ref["votes"] * S))
+    plain = predshard.predict_sharded(eng, xd, w, n, 0, 1, votes=True)                  # pageable numpy: one chunk
+    assert np.allclose(plain["mean"].cpu().numpy(), ref["mean"], rtol=0, atol=1e-15)     # (mean * S / S)
+    eng.close()
