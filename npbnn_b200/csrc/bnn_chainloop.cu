@@ -14,6 +14,7 @@
 //   * barrier.cluster; next step.
 // Chains are independent, so the C clusters of a launch need not be co-resident.
 #include <cstdio>
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "bnn_mh_body.cuh"
 #include "bnn_generic_body.cuh"
@@ -38,7 +39,7 @@ struct ChainLoopPlan {
 // shared-memory carve-up in doubles.  Common prefix, the same in every CTA of the cluster (part and cnt_leader of rank 0
 // are written by the other ranks through distributed shared memory):
 //   tab [GEN_TAB_SIZE] | part [NF * n_tiles16] | w [PB] | alpha | stage [warps * per_warp] | cnt_leader, cnt_local (ints)
-// leader only:  wstate [2P] | ddz [UPD_DRAW_CAP] | owner [P] (ints) | didx [UPD_DRAW_CAP] (ints) | pk [P] (ints)
+// leader only:  wstate [2P] | ddz [2][UPD_DRAW_CAP] | owner [P] (ints) | didx [2][UPD_DRAW_CAP] (ints) | pk [P] (ints)
 // then the resident tiles of the CTA: per tile  X [16 * F_pad] | targets [16 * K] (Gaussian) or labels [16] (ints)
 __host__ __device__ inline size_t chain_loop_per_warp(const NetGeom& g) {
   const int ZS = g.l[g.L - 1].out_pad + 1;
@@ -50,7 +51,7 @@ __host__ __device__ inline size_t chain_loop_common_doubles(const NetGeom& g, in
          (size_t)warps * chain_loop_per_warp(g) + (size_t)((NC + 3) & ~3);      // (2 * NC4 ints = NC4 doubles)
 }
 __host__ __device__ inline size_t chain_loop_leader_doubles(const NetGeom& g) {
-  return 2 * (size_t)((g.P + 1) & ~1) + UPD_DRAW_CAP + (size_t)((g.P + 3) & ~3) + UPD_DRAW_CAP / 2;
+  return 2 * (size_t)((g.P + 1) & ~1) + 2 * UPD_DRAW_CAP + (size_t)((g.P + 3) & ~3) + UPD_DRAW_CAP;
 }
 __host__ __device__ inline size_t chain_loop_tile_doubles(const NetGeom& g) {
   return 16 * (size_t)g.F_pad + (g.lik == BNN_LIK_CATEGORICAL ? 8 : 16 * (size_t)g.K);
@@ -59,7 +60,7 @@ __host__ __device__ inline size_t chain_loop_tile_doubles(const NetGeom& g) {
 template <int ACT, bool XRES>
 __global__ void __launch_bounds__(CL_MAX_WARPS * 32, 1) k_chain_loop(const __grid_constant__ ChainDev d,
                                                                       const __grid_constant__ FwdParams p0, int n_steps,
-                                                                      int tw, int tl, int n_worker_tiles) {
+                                                                      int tw, int tl, int n_worker_tiles, int pp_mode) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ FwdParams sp;                  // this chain's forward parameters (partials -> the leader's shared memory)
   cg::cluster_group cluster = cg::this_cluster();
@@ -91,9 +92,9 @@ __global__ void __launch_bounds__(CL_MAX_WARPS * 32, 1) k_chain_loop(const __gri
   // leader only
   double* wstate = role;                                                 // [2P] current | proposed weights
   double* ddz_sm = wstate + 2 * (size_t)((g.P + 1) & ~1);
-  int* owner_sm = reinterpret_cast<int*>(ddz_sm + UPD_DRAW_CAP);
+  int* owner_sm = reinterpret_cast<int*>(ddz_sm + 2 * UPD_DRAW_CAP);
   int* didx_sm = owner_sm + ((g.P + 3) & ~3);
-  int* pk_sm = didx_sm + UPD_DRAW_CAP;
+  int* pk_sm = didx_sm + 2 * UPD_DRAW_CAP;
   double* xsm = leader ? role + chain_loop_leader_doubles(g) : role;
   const size_t tile_d = chain_loop_tile_doubles(g);
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(CL_MAX_WARPS * 32, 1) k_chain_loop(const __gri
   const FwdParams& p = sp;
   UpdLoop ctx;
   ctx.part_c = part_sm; ctx.counts_c = cnt_leader; ctx.w_sm = wstate; ctx.owner_sm = owner_sm; ctx.wpk_sm = wsm;
-  ctx.didx_sm = didx_sm; ctx.ddz_sm = ddz_sm; ctx.pk_sm = pk_sm;
+  ctx.didx_sm = didx_sm; ctx.ddz_sm = ddz_sm; ctx.pk_sm = pk_sm; ctx.pp_mode = pp_mode;
   const double2* wsrc = reinterpret_cast<const double2*>(d.wp_prop + (long long)c * g.PB);
 
 #ifdef BNN_DBG_LOOPCLK
@@ -190,6 +191,12 @@ __global__ void __launch_bounds__(CL_MAX_WARPS * 32, 1) k_chain_loop(const __gri
 #ifdef BNN_DBG_LOOPCLK
       if (tid == 0) { lt[5] += f1 - f0; dbg_epi += clock64() - f1; }
 #endif
+    }
+    // the leader's team is done with its few tiles long before the workers: it pre-proposes iteration s + 1 (layer
+    // choice, scalar draws, the proposal's draws) in the time it would otherwise wait at the barrier
+    if (pp_mode && leader && tid < UPD_TEAM_THREADS && s + 1 < n_steps) {
+      ctx.first = false; ctx.last = false;
+      mh_update_body<true>(d, c, 0, 3, s + 1, ctx);
     }
     __syncthreads();
     LOOP_STAMP(3);
@@ -296,7 +303,10 @@ static cudaError_t launch_chain_loop_t(const ChainDev& d, const FwdParams& p, in
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int tw = plan.tw, tl = plan.tl, nwt = plan.n_worker_tiles;
-  return cudaLaunchKernelEx(&cfg, kern, d, p, n_steps, tw, tl, nwt);
+  // NPBNN_CHAIN_PP (debugging aid): 0 = no pre-proposal, 1 = scalar draws only, 2 (default) = scalar draws + proposal draws
+  static int pp_mode = -1;
+  if (pp_mode < 0) { const char* e = getenv("NPBNN_CHAIN_PP"); pp_mode = e ? atoi(e) : 2; }
+  return cudaLaunchKernelEx(&cfg, kern, d, p, n_steps, tw, tl, nwt, pp_mode);
 }
 
 template <int ACT>

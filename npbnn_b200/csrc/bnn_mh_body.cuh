@@ -193,9 +193,10 @@ struct UpdLoop {
   double* w_sm;
   int* owner_sm;
   double* wpk_sm;
-  int* didx_sm;               // [UPD_DRAW_CAP] draw cache (entry index) -- k_mh_update keeps its own in static shared memory
-  double* ddz_sm;             // [UPD_DRAW_CAP] draw cache (increment)
+  int* didx_sm;               // [2][UPD_DRAW_CAP] draw cache (entry index), one buffer per iteration parity -- k_mh_update
+  double* ddz_sm;             // [2][UPD_DRAW_CAP] draw cache (increment)      keeps a single one in static shared memory
   int* pk_sm;                 // [P] per canonical entry: layer << 24 | offset in the packed set (filled when `first`)
+  int pp_mode;                // pre-proposal: 0 off, 1 scalar draws, 2 scalar draws + the proposal's draws
   bool first, last;
 };
 
@@ -218,15 +219,23 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
   __shared__ int s_ind_move, s_fi_move;
   __shared__ double s_ind_p, s_fi_p;
   // the draws of this proposal (entry index, increment), generated once and used by the three owner passes
-  int* s_didx;
-  double* s_ddz;
+  int* didx_base;
+  double* ddz_base;
   if constexpr (!COH) {
     __shared__ int st_didx[UPD_DRAW_CAP];
     __shared__ double st_ddz[UPD_DRAW_CAP];
-    s_didx = st_didx; s_ddz = st_ddz;
+    didx_base = st_didx; ddz_base = st_ddz;
   } else {
-    s_didx = lp_ctx.didx_sm; s_ddz = lp_ctx.ddz_sm;
+    didx_base = lp_ctx.didx_sm; ddz_base = lp_ctx.ddz_sm;
   }
+  // Pre-proposal of the persistent loop (propose_mode 3, see below): what iteration s_pp_it will need and does not
+  // depend on the pending accept decision -- layer choice, counts, accept uniform, indicator moves, the scalar Philox
+  // blocks and (s_pp_draws) the proposal's draws in draw-cache buffer s_pp_it & 1
+  __shared__ int s_pp_it, s_pp_draws;
+  __shared__ int s_prop_n[BNN_MAX_LAYERS], s_cnt_n[BNN_MAX_LAYERS], s_off_n[BNN_MAX_LAYERS];
+  __shared__ int s_ind_move_n, s_fi_move_n;
+  __shared__ double s_ind_p_n, s_fi_p_n, s_logu_n;
+  __shared__ uint4 s_px[BNN_MAX_LAYERS + 5], s_px_n[BNN_MAX_LAYERS + 5];
   const NetGeom& g = d.g;
   const int tid = threadIdx.x;
   const int NT = upd_nthreads<COH>();
@@ -245,6 +254,7 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
   double* wn = d.w_prop + (long long)c * g.P;
   int* owner = d.owner + (long long)c * g.P;
   if (load_state) {
+    if (tid == 0) { s_pp_it = -1; s_pp_draws = 0; }          // nothing pre-proposed yet (visible after the barrier below)
 #pragma unroll 1
     for (int i = tid; i < BNN_F_STRIDE; i += NT) ssf[i] = gsf[i];
 #pragma unroll 1
@@ -283,6 +293,111 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
   };
   const int NC = 2 + 2 * g.K;
   const int P0 = g.l[0].out * (g.l[0].in + g.l[0].bias);      // size of the first weight matrix (indicator shape)
+  // The free-running generator's scalar draws of iteration it_x (layer choice, accept uniform, indicator / slope
+  // moves) are independent Philox blocks: the lanes of warp 0 evaluate them side by side, thread 0 consumes them.
+  //   slot l < L: layer uniforms | L: accept uniform | L+1: weight indicators | L+2: feature indicators | L+3, L+4: slopes
+  auto scalar_blocks = [&](int it_x, uint4* px) {
+    if (tid < g.L + 5) {
+      const uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
+      const int q = tid - g.L;
+      uint4 ctr;
+      if (q < 0) ctr = make_uint4((uint32_t)it_x, 0xFFFFFFFFu, (uint32_t)tid, 2u);
+      else if (q == 0) ctr = make_uint4((uint32_t)it_x, 0xFFFFFFFEu, 0u, 3u);
+      else if (q == 1) ctr = make_uint4((uint32_t)it_x, 0xFFFFFFFCu, 0u, 5u);
+      else if (q == 2) ctr = make_uint4((uint32_t)it_x, 0xFFFFFFFBu, 0u, 6u);
+      else ctr = make_uint4((uint32_t)it_x, 0xFFFFFFFDu, (uint32_t)(q - 3), 4u);
+      px[tid] = philox4x32(ctr, key);
+    }
+    __syncwarp();
+  };
+  // thread 0: which layers iteration it_x proposes, how many entries, the indicator moves and log u, from the blocks
+  // px and the CURRENT adaptation state (freq_layer_update, update_n, update_f)
+  auto select_layers = [&](int it_x, const uint4* px, int* prop, int* cnt, int* off_out, int& ind_move, double& ind_p,
+                           int& fi_move, double& fi_p, double& log_u) {
+    // rr = rs.random(L); rr[argmin] = 0; layer proposed iff rr < freq_layer_update (BNN_env.py:446-451)
+    double rr[BNN_MAX_LAYERS];
+    int amin = 0, off = 0;
+#pragma unroll 1
+    for (int l = 0; l < g.L; ++l) {
+      const uint4 r = px[l];
+      rr[l] = u53(r.x, r.y);
+      if (rr[l] < rr[amin]) amin = l;
+    }
+    rr[amin] = 0.0;
+    // weight indicators (BNN_env.py:449-460): the first layer is proposed only if rr[0] >= freq_indicator, otherwise
+    // its indicators move: UpdateBinomial(ind, update_f[3], shape) flips each entry with probability u * update_f[3]
+    ind_move = 0;
+    if (d.cfg.use_indicators && rr[0] < d.cfg.freq_indicator) {
+      const uint4 r = px[g.L + 1];
+      ind_move = 1;
+      ind_p = u53(r.x, r.y) * ssf[BNN_F_UPDATE_F + 3];
+    }
+    // feature indicators (BNN_env.py:423-431): past adapt_stop, with probability 0.2, flips with probability u * 0.5
+    fi_move = 0;
+    if (d.cfg.use_feature_indicators && it_x > d.cfg.adapt_stop) {
+      const uint4 r = px[g.L + 2];
+      if (u53(r.x, r.y) < 0.2) { fi_move = 1; fi_p = u53(r.z, r.w) * 0.5; }
+    }
+#pragma unroll 1
+    for (int l = 0; l < g.L; ++l) {
+      prop[l] = rr[l] < ssf[BNN_F_FREQ_LAYER + l] && !(l == 0 && ind_move);
+      cnt[l] = prop[l] ? ssi[BNN_I_UPDATE_N + l] : 0;
+      off_out[l] = off;
+      off += cnt[l];
+    }
+    const uint4 r = px[g.L];
+    log_u = upd_log(u53(r.x, r.y));
+  };
+  // k-th draw of layer l at iteration it_x: canonical entry index and increment (device generator)
+  auto philox_entry = [&](int it_x, int l, int k, int& idx, double& dz) {
+    const LayerGeom& lg = g.l[l];
+    const int cols = lg.in + lg.bias;
+    const Draw dr = philox_draw(d.cfg.seed, d.cfg.chain_offset + c, it_x, l, k, lg.out, cols, ssf[BNN_F_UPDATE_WS + l]);
+    idx = lg.c_off + dr.ix * cols + dr.iy;
+    dz = dr.dz;
+  };
+  auto layer_of_j = [&](const int* off, const int* cnt, int j) {
+    int l = 0;
+#pragma unroll 1
+    for (int q = 1; q < g.L; ++q) if (j >= off[q] && cnt[q] > 0) l = q;
+    return l;
+  };
+
+  // ------------------------------------------------------------------ pre-proposal (persistent loop only)
+  // Called by the leader's team while the other CTAs of the cluster are still in the forward pass of the current
+  // proposal: everything iteration it + 1 needs that does not depend on the pending accept decision.  Skipped (and
+  // recomputed on the critical path) when iteration it + 1 adapts the proposal sizes or the draws are injected.
+  if (propose_mode == 3) {
+    if constexpr (COH) {
+      const int itn = ssi[BNN_I_ITERATION] + 1;
+      const bool can = !d.inj_proposed && !(itn % d.cfg.adapt_freq == 0 && itn < d.cfg.adapt_stop);
+      if (can) scalar_blocks(itn, s_px_n);
+      if (tid == 0) {
+        s_pp_it = -1;
+        s_pp_draws = 0;
+        if (can) {
+          select_layers(itn, s_px_n, s_prop_n, s_cnt_n, s_off_n, s_ind_move_n, s_ind_p_n, s_fi_move_n, s_fi_p_n, s_logu_n);
+          s_pp_it = itn;
+        }
+      }
+      upd_sync<COH>();
+      if (can) {
+        const int nd = s_off_n[g.L - 1] + s_cnt_n[g.L - 1];
+        if (nd <= UPD_DRAW_CAP && lp_ctx.pp_mode >= 2) {
+          int* di = didx_base + (itn & 1) * UPD_DRAW_CAP;
+          double* dd = ddz_base + (itn & 1) * UPD_DRAW_CAP;
+#pragma unroll 1
+          for (int j = tid; j < nd; j += NT) {
+            const int l = layer_of_j(s_off_n, s_cnt_n, j);
+            philox_entry(itn, l, j - s_off_n[l], di[j], dd[j]);
+          }
+          if (tid == 0) s_pp_draws = 1;
+        }
+      }
+      upd_sync<COH>();
+    }
+    return;
+  }
 
   // ------------------------------------------------------------------ accept / reject
   if (accept_mode) {
@@ -364,22 +479,13 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
 
   // ------------------------------------------------------------------ adaptation + which layers
   const int it = si[BNN_I_ITERATION];
-  // The free-running generator's scalar draws of this iteration (layer choice, accept uniform, indicator / slope
-  // moves) are independent Philox blocks: the lanes of warp 0 evaluate them side by side, thread 0 consumes them.
-  //   slot l < L: layer uniforms | L: accept uniform | L+1: weight indicators | L+2: feature indicators | L+3, L+4: slopes
-  __shared__ uint4 s_px[BNN_MAX_LAYERS + 5];
-  if (propose_mode == 1 && !d.inj_proposed && tid < g.L + 5) {
-    const uint2 key = make_uint2((uint32_t)d.cfg.seed ^ (uint32_t)(d.cfg.chain_offset + c), (uint32_t)(d.cfg.seed >> 32));
-    const int q = tid - g.L;
-    uint4 ctr;
-    if (q < 0) ctr = make_uint4((uint32_t)it, 0xFFFFFFFFu, (uint32_t)tid, 2u);
-    else if (q == 0) ctr = make_uint4((uint32_t)it, 0xFFFFFFFEu, 0u, 3u);
-    else if (q == 1) ctr = make_uint4((uint32_t)it, 0xFFFFFFFCu, 0u, 5u);
-    else if (q == 2) ctr = make_uint4((uint32_t)it, 0xFFFFFFFBu, 0u, 6u);
-    else ctr = make_uint4((uint32_t)it, 0xFFFFFFFDu, (uint32_t)(q - 3), 4u);
-    s_px[tid] = philox4x32(ctr, key);
+  // pre-proposed during the previous forward pass (persistent loop)?  s_pp_it was written before the team's last barrier
+  const bool use_pp = COH && resident && propose_mode == 1 && !d.inj_proposed && s_pp_it == it;
+  const bool pp_draws = use_pp && s_pp_draws;
+  if (propose_mode == 1 && !d.inj_proposed) {
+    if (use_pp) { if (tid < g.L + 5) s_px[tid] = s_px_n[tid]; __syncwarp(); }
+    else scalar_blocks(it, s_px);
   }
-  __syncwarp();
   if (tid == 0) {
     if (propose_mode == 1) {
       // BNN_env.py:392-413
@@ -408,8 +514,8 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
           }
         }
       }
-      int off = 0;
       if (d.inj_proposed) {
+        int off = 0;
         const long long base = ((long long)step * d.C + c) * g.L;
 #pragma unroll 1
         for (int l = 0; l < g.L; ++l) {
@@ -420,39 +526,16 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
         }
         sf[BNN_F_LOG_U] = d.inj_logu[(long long)step * d.C + c];
       } else {
-        // rr = rs.random(L); rr[argmin] = 0; layer proposed iff rr < freq_layer_update (BNN_env.py:446-451)
-        double rr[BNN_MAX_LAYERS];
-        int amin = 0;
+        if (use_pp) {
 #pragma unroll 1
-        for (int l = 0; l < g.L; ++l) {
-          const uint4 r = s_px[l];
-          rr[l] = u53(r.x, r.y);
-          if (rr[l] < rr[amin]) amin = l;
+          for (int l = 0; l < g.L; ++l) { s_prop[l] = s_prop_n[l]; s_cnt[l] = s_cnt_n[l]; s_off[l] = s_off_n[l]; }
+          s_ind_move = s_ind_move_n; s_ind_p = s_ind_p_n; s_fi_move = s_fi_move_n; s_fi_p = s_fi_p_n;
+          sf[BNN_F_LOG_U] = s_logu_n;
+        } else {
+          double log_u;
+          select_layers(it, s_px, s_prop, s_cnt, s_off, s_ind_move, s_ind_p, s_fi_move, s_fi_p, log_u);
+          sf[BNN_F_LOG_U] = log_u;
         }
-        rr[amin] = 0.0;
-        // weight indicators (BNN_env.py:449-460): the first layer is proposed only if rr[0] >= freq_indicator, otherwise
-        // its indicators move: UpdateBinomial(ind, update_f[3], shape) flips each entry with probability u * update_f[3]
-        s_ind_move = 0;
-        if (d.cfg.use_indicators && rr[0] < d.cfg.freq_indicator) {
-          const uint4 r = s_px[g.L + 1];
-          s_ind_move = 1;
-          s_ind_p = u53(r.x, r.y) * sf[BNN_F_UPDATE_F + 3];
-        }
-        // feature indicators (BNN_env.py:423-431): past adapt_stop, with probability 0.2, flips with probability u * 0.5
-        s_fi_move = 0;
-        if (d.cfg.use_feature_indicators && it > d.cfg.adapt_stop) {
-          const uint4 r = s_px[g.L + 2];
-          if (u53(r.x, r.y) < 0.2) { s_fi_move = 1; s_fi_p = u53(r.z, r.w) * 0.5; }
-        }
-#pragma unroll 1
-        for (int l = 0; l < g.L; ++l) {
-          s_prop[l] = rr[l] < sf[BNN_F_FREQ_LAYER + l] && !(l == 0 && s_ind_move);
-          s_cnt[l] = s_prop[l] ? si[BNN_I_UPDATE_N + l] : 0;
-          s_off[l] = off;
-          off += s_cnt[l];
-        }
-        const uint4 r = s_px[g.L];
-        sf[BNN_F_LOG_U] = upd_log(u53(r.x, r.y));
       }
 #pragma unroll 1
       for (int l = 0; l < g.L; ++l) si[BNN_I_PROPOSED + l] = s_prop[l];
@@ -555,38 +638,35 @@ __device__ void mh_update_body(const ChainDev& d, const int c, int accept_mode, 
   const long long inj_base = ((long long)step * d.C + c) * d.inj_cap;
   const int n_draws = s_off[g.L - 1] + s_cnt[g.L - 1];
   const bool cached = n_draws <= UPD_DRAW_CAP;
+  // draw cache of this iteration (persistent loop: one buffer per iteration parity, so that the pre-proposal of the
+  // next iteration never writes the buffer in use)
+  int* s_didx = didx_base + (COH ? (it & 1) * UPD_DRAW_CAP : 0);
+  double* s_ddz = ddz_base + (COH ? (it & 1) * UPD_DRAW_CAP : 0);
   auto make_draw = [&](int l, int k, int& idx, double& dz) {
-    const LayerGeom& lg = g.l[l];
-    const int cols = lg.in + lg.bias;
-    Draw dr;
     if (d.inj_proposed) {
-      dr.ix = d.inj_ix[inj_base + s_off[l] + k];
-      dr.iy = d.inj_iy[inj_base + s_off[l] + k];
-      dr.dz = d.inj_dz[inj_base + s_off[l] + k];
+      const LayerGeom& lg = g.l[l];
+      const int cols = lg.in + lg.bias;
+      idx = lg.c_off + d.inj_ix[inj_base + s_off[l] + k] * cols + d.inj_iy[inj_base + s_off[l] + k];
+      dz = d.inj_dz[inj_base + s_off[l] + k];
     } else {
-      dr = philox_draw(d.cfg.seed, d.cfg.chain_offset + c, it, l, k, lg.out, cols, sf[BNN_F_UPDATE_WS + l]);
+      philox_entry(it, l, k, idx, dz);
     }
-    idx = lg.c_off + dr.ix * cols + dr.iy;
-    dz = dr.dz;
   };
   // one flat loop over the draws of all layers (s_off are prefix sums of s_cnt): the draws of the small layers are
   // generated by other threads at the same time instead of in a loop of their own
-  auto layer_of_draw = [&](int j) { int l = 0; for (int q = 1; q < g.L; ++q) if (j >= s_off[q] && s_cnt[q] > 0) l = q; return l; };
   if (cached) {
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll 1
       for (int j = tid; j < n_draws; j += NT) {
-        int idx, k;
+        int idx;
         double dz;
-        if (pass == 0) {
-          const int l = layer_of_draw(j);
-          k = j - s_off[l];
-          make_draw(l, k, idx, dz);
+        const int k = j - s_off[layer_of_j(s_off, s_cnt, j)];
+        if (pass == 0 && !pp_draws) {
+          make_draw(layer_of_j(s_off, s_cnt, j), k, idx, dz);
           s_didx[j] = idx; s_ddz[j] = dz;
         } else {
           idx = s_didx[j]; dz = s_ddz[j];
-          k = j - s_off[layer_of_draw(j)];
         }
         if (pass == 0) atomicMax(&owner[idx], k);
         else if (pass == 1) { if (owner[idx] == k) wn[idx] = wc[idx] + dz; }
