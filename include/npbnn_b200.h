@@ -313,8 +313,9 @@ int bnn_debug_set_trace(bnn_ctx* ctx, unsigned long long* trace_dev);
 /* Options: "force_generic" = 1 disables the shape-specialised forward kernels (cross-check in tests);
  * "time_forward" = 1 enables bnn_forward_time; "sparse" = 0 evaluates masked chains with the dense kernels;
  * "graphs" = 0 launches the free-running bnn_mh_steps loop eagerly instead of replaying a CUDA graph;
- * "chain_loop" = 0 steps small data sets with one launch pair per iteration instead of one persistent launch per
- * bnn_mh_steps call (k_chain_loop: a thread-block cluster per chain; results are bit-identical either way);
+ * "chain_loop" = 1 (default) steps small data sets inside one persistent launch per bnn_mh_steps call (k_chain_loop: a
+ * thread-block cluster per chain) where that beats one launch pair per iteration, 2 = wherever the problem fits, 0 = never
+ * (results are bit-identical either way);
  * "chain_loop_cluster" = 1 | 2 | 4 | 8 | 16 caps the cluster size of that kernel (default 16);
  * "tensor_l1" = 1 (layer 1 of the 64-64-32-10 swish network as exact int8 tensor-core products, k_fwd3t) exists only in
  * builds with -DBNN_EXPERIMENTAL_TENSOR_L1; the shipped library refuses it. */

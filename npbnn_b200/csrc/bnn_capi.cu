@@ -116,7 +116,8 @@ struct bnn_ctx {
   std::vector<StepGraph> graphs;
   cudaStream_t capture_stream = nullptr;
   int opt_graphs = 1;               // option "graphs"
-  int opt_chain_loop = 1;           // option "chain_loop": small data sets step inside one persistent launch (k_chain_loop)
+  int opt_chain_loop = 1;           // option "chain_loop": 1 = small data sets step inside one persistent launch (k_chain_loop)
+                                    // where that beats the launch sequence, 2 = wherever it fits (tests), 0 = never
   int opt_chain_cluster = 16;       // option "chain_loop_cluster": largest thread-block cluster per chain
   bool mh_warm = false;             // one eager bnn_mh_steps has run since the last (re)configuration
 };
@@ -1073,11 +1074,11 @@ int bnn_mh_steps(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj, void* st
   // proposals alike.  Same update / forward bodies and reduction order as the launch sequence below: identical chains.
   if (c->opt_chain_loop && !c->time_forward && !c->opt_tensor && !(c->use_sparse && c->opt_sparse) &&
       (c->force_generic || !bnn_fwd3_family(c->g)) && !bnn_part_slices(c->n_tiles16) &&
-      bnn_chain_loop_fits(c->g, d.NF, d.n_tiles16, c->C, c->n_sms, c->opt_chain_cluster)) {
+      bnn_chain_loop_fits(c->g, d.NF, d.n_tiles16, c->C, c->n_sms, c->opt_chain_cluster, c->opt_chain_loop)) {
     FwdParams p = base_params(c);
     p.C = 1;
     int cl = 0;
-    cudaError_t e = bnn_launch_chain_loop(d, p, n_steps, c->n_sms, c->opt_chain_cluster, st, &cl);
+    cudaError_t e = bnn_launch_chain_loop(d, p, n_steps, c->n_sms, c->opt_chain_cluster, c->opt_chain_loop, st, &cl);
     if (e == cudaSuccess) {
       c->launches++;
       c->last_kernel = "k_chain_loop";

@@ -233,12 +233,33 @@ static size_t chain_loop_static_smem() {
   return v;
 }
 
-static bool chain_loop_plan(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster, ChainLoopPlan* plan) {
-  if (g.P > 2048 || nt < 1 || nt >= 4096 || g.PB % 2) return false;      // (k_mh_update would run 1,024 threads / slice partials)
+// clusters of `cl` CTAs (warps * 32 threads, smem bytes each) the GPU can hold at the same time; cached per shape
+static int chain_loop_max_clusters(int cl, int warps, size_t smem) {
+  struct Key { int cl, warps; size_t smem; int n; };
+  static Key cache[16];
+  static int n_cache = 0;
+  for (int i = 0; i < n_cache; ++i)
+    if (cache[i].cl == cl && cache[i].warps == warps && cache[i].smem == smem) return cache[i].n;
+  auto kern = k_chain_loop<BNN_ACT_TANH, true>;          // (every instantiation has the same footprint up to a few registers)
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(232448 - chain_loop_static_smem()));
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cl);
+  cfg.blockDim = dim3((unsigned)warps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (n_cache < 16) cache[n_cache++] = Key{cl, warps, smem, n};
+  return n;
+}
+
+// The tile assignment of one cluster size: warps per CTA, tile slots, residency.
+static bool chain_loop_plan_for(const NetGeom& g, int NF, long long nt, int cl, ChainLoopPlan* plan) {
   const size_t cap = (232448 - chain_loop_static_smem()) / sizeof(double);
-  // CTAs per chain: as many as there are tiles for (one tile per warp at 8 warps), within the GPU when all chains run at once
-  int cl = 16;
-  while (cl > 1 && (cl > max_cluster || (long long)(cl / 2) * 8 >= nt || (long long)C * cl > n_sms)) cl >>= 1;
   const size_t tile_d = chain_loop_tile_doubles(g), lead_d = chain_loop_leader_doubles(g);
   const int workers = cl - 1;
   ChainLoopPlan best{};
@@ -268,14 +289,41 @@ static bool chain_loop_plan(const NetGeom& g, int NF, long long nt, int C, int n
       break;                                  // the smallest t that covers the tiles at this warp count
     }
   }
-  if (!have) return false;
-  *plan = best;
-  return true;
+  if (have) *plan = best;
+  return have;
 }
 
-bool bnn_chain_loop_fits(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster) {
+// mode 1 (automatic): the persistent loop is taken only where it beats the per-step launch sequence.  Measured on a B200
+// (tools/loop_threshold.py, profiles/r02_chain_loop_threshold.json: [5,5] tanh network, 128 features, 500 - 30,000 rows x
+// 1 - 32 chains, us per MH step):
+//   loop      8 + 4.7 * tiles per warp with X resident in shared memory, 12 + 8 * tiles per warp with X streamed from L2,
+//             times the number of WAVES of clusters -- so every chain's cluster must be resident at once;
+//   sequence  21.5 + 0.006 * max(0, (16-row tiles) * chains - 1500).
+// The largest cluster size whose C clusters fit the GPU together is planned; mode 2 (tests) skips both conditions.
+static bool chain_loop_plan(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster, int mode,
+                            ChainLoopPlan* plan) {
+  if (g.P > 2048 || nt < 1 || nt >= 4096 || g.PB % 2) return false;      // (k_mh_update would run 1,024 threads / slice partials)
+  // CTAs per chain: no more than there are tiles for (one tile per warp at 8 warps), within the GPU when all chains run at once
+  int cl = 16;
+  while (cl > 1 && (cl > max_cluster || (long long)(cl / 2) * 8 >= nt || (long long)C * cl > n_sms)) cl >>= 1;
+  for (; cl >= 1; cl >>= 1) {
+    ChainLoopPlan q;
+    if (!chain_loop_plan_for(g, NF, nt, cl, &q)) { if (mode >= 2) return false; continue; }
+    if (mode >= 2) { *plan = q; return true; }
+    if (chain_loop_max_clusters(q.cluster, q.warps, q.smem) < C) continue;           // more than one wave: try smaller clusters
+    const int tpw = q.tw > q.tl ? q.tw : q.tl;
+    const double loop_us = q.x_resident ? 8.0 + 4.7 * tpw : 12.0 + 8.0 * tpw;
+    const double tc = (double)nt * C;
+    const double seq_us = 21.5 + 0.006 * (tc > 1500.0 ? tc - 1500.0 : 0.0);
+    if (loop_us < 0.95 * seq_us) { *plan = q; return true; }
+    return false;
+  }
+  return false;
+}
+
+bool bnn_chain_loop_fits(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster, int mode) {
   ChainLoopPlan plan;
-  return chain_loop_plan(g, NF, nt, C, n_sms, max_cluster, &plan);
+  return chain_loop_plan(g, NF, nt, C, n_sms, max_cluster, mode, &plan);
 }
 
 template <int ACT, bool XRES>
@@ -318,10 +366,10 @@ static cudaError_t launch_chain_loop_a(const ChainDev& d, const FwdParams& p, in
 
 // n_steps MH iterations of every chain of d in one launch; cudaErrorNotSupported when the problem does not fit the
 // persistent path (the caller then issues the per-step launch sequence)
-cudaError_t bnn_launch_chain_loop(const ChainDev& d, const FwdParams& p, int n_steps, int n_sms, int max_cluster,
+cudaError_t bnn_launch_chain_loop(const ChainDev& d, const FwdParams& p, int n_steps, int n_sms, int max_cluster, int mode,
                                   cudaStream_t st, int* cluster_out) {
   ChainLoopPlan plan;
-  if (!chain_loop_plan(d.g, d.NF, d.n_tiles16, d.C, n_sms, max_cluster, &plan)) return cudaErrorNotSupported;
+  if (!chain_loop_plan(d.g, d.NF, d.n_tiles16, d.C, n_sms, max_cluster, mode, &plan)) return cudaErrorNotSupported;
   if (cluster_out) *cluster_out = plan.cluster;
   switch (d.g.act) {
     case BNN_ACT_RELU: return launch_chain_loop_a<BNN_ACT_RELU>(d, p, n_steps, plan, st);

@@ -82,8 +82,8 @@ cudaError_t bnn_launch_reduce_part(const double* part, long long nt, int n_slice
 cudaError_t bnn_launch_mh_update(const ChainDev& d, int accept_mode, int propose_mode, int step, cudaStream_t st);
 // persistent small-data MH loop (bnn_chainloop.cu): n_steps iterations of every chain in one launch, one thread-block
 // cluster per chain; cudaErrorNotSupported when the problem does not fit (bnn_chain_loop_fits)
-bool bnn_chain_loop_fits(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster);
-cudaError_t bnn_launch_chain_loop(const ChainDev& d, const FwdParams& p, int n_steps, int n_sms, int max_cluster,
+bool bnn_chain_loop_fits(const NetGeom& g, int NF, long long nt, int C, int n_sms, int max_cluster, int mode);
+cudaError_t bnn_launch_chain_loop(const ChainDev& d, const FwdParams& p, int n_steps, int n_sms, int max_cluster, int mode,
                                   cudaStream_t st, int* cluster_out);
 cudaError_t bnn_launch_rowshard_local(const NetGeom& g, const double* part, int NF, long long nt, const int* counts, int NC,
                                       double* out, int n_chains, cudaStream_t st);

@@ -893,7 +893,7 @@ def test_chain_loop_matches_launch_sequence(case):
         else:
             eng.set_data(cs["x"], cs["y"])
         eng.chains_init(cs["sets"], seed=99, **cs["kw"])
-        eng.set_option("chain_loop", 0 if mode == "sequence" else 1)
+        eng.set_option("chain_loop", 0 if mode == "sequence" else 2)        # 2: wherever it fits (1 = where it pays)
         if mode.startswith("loop"):
             eng.set_option("chain_loop_cluster", int(mode[4:]))
         eng.mh_steps(1)
@@ -949,7 +949,7 @@ def test_chain_loop_random_shapes_match_launch_sequence(seed):
     cw = rng.uniform(0.5, 2.0, k) if lik == L.LIK_CATEGORICAL and rng.integers(0, 2) else None
     iw = rng.uniform(0.5, 2.0, n) if lik == L.LIK_CATEGORICAL and rng.integers(0, 2) else None
     states = []
-    for loop in (1, 0):
+    for loop in (2, 0):
         eng = Engine(net)
         eng.set_data(x[:n], y[:n], x_test=x[n:] if n_test else None, y_test=y[n:] if n_test else None, inst_w=iw, class_w=cw)
         eng.chains_init(sets, **kw)
@@ -1010,3 +1010,23 @@ def test_c3_full_size_block_masked_chains():
     for c in range(C):
         for wl_, m in zip(a.weights(c), mask):
             assert np.all(wl_[m == 0] == 0)
+
+
+def test_chain_loop_is_taken_where_it_pays():
+    """Automatic mode (option chain_loop = 1, the default): the persistent loop is chosen for the reference's example sizes
+    (a few thousand rows, a few chains whose clusters are resident together) and NOT for mid-size data, where the
+    grid-wide launch sequence is faster (profiles/r02_chain_loop_threshold.json)."""
+    from npbnn_b200.engine import Engine, NetShape
+    rng = np.random.default_rng(3)
+    shapes = [(5, 129), (5, 6), (5, 5)]
+    net = NetShape(128, shapes, act="tanh", lik=0)
+    for n, chains, want in ((2500, 1, "k_chain_loop"), (2500, 2, "k_chain_loop"), (20000, 1, "k_fwd_generic"),
+                            (20000, 8, "k_fwd_generic"), (400, 32, "k_chain_loop")):
+        x = rng.standard_normal((n, 128))
+        y = rng.integers(0, 5, n)
+        eng = Engine(net)
+        eng.set_data(x, y)
+        eng.chains_init([[rng.normal(0, 0.1, s) for s in shapes] for _ in range(chains)], seed=5)
+        eng.mh_steps(3)
+        assert eng.last_kernel == want, (n, chains, eng.last_kernel)
+        eng.close()
