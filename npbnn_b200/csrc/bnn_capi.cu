@@ -119,6 +119,7 @@ struct bnn_ctx {
   int opt_chain_loop = 1;           // option "chain_loop": 1 = small data sets step inside one persistent launch (k_chain_loop)
                                     // where that beats the launch sequence, 2 = wherever it fits (tests), 0 = never
   int opt_chain_cluster = 16;       // option "chain_loop_cluster": largest thread-block cluster per chain
+  int opt_pred_tf32 = 0;            // option "predict_tf32": opt-in 3xTF32 prediction summaries (bnn_pred_lp.cu), never the MH path
   bool mh_warm = false;             // one eager bnn_mh_steps has run since the last (re)configuration
 };
 
@@ -351,6 +352,7 @@ int bnn_set_option(bnn_ctx* c, const char* name, int value) {
   }
   if (strcmp(name, "graphs") == 0) { c->opt_graphs = value; return 0; }
   if (strcmp(name, "chain_loop") == 0) { c->opt_chain_loop = value; return 0; }
+  if (strcmp(name, "predict_tf32") == 0) { c->opt_pred_tf32 = value; return 0; }
   if (strcmp(name, "chain_loop_cluster") == 0) {
     REQUIRE(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "bnn_set_option: chain_loop_cluster must be 1, 2, 4, 8 or 16");
     c->opt_chain_cluster = value;
@@ -1420,6 +1422,12 @@ static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double
   p.samp_u = u_dev; p.samp_counts = class_counts_dev; p.samp_dense = post_pred_dev;
   p.samp_philox = samp_philox ? 1 : 0; p.samp_seed = samp_seed;
   if (class_counts_dev) CUDA_TRY(cudaMemsetAsync(class_counts_dev, 0, sizeof(int32_t) * (size_t)n_sets * g.K, st));
+  if (c->opt_pred_tf32 && !c->force_generic && bnn_pred_tf32_fits(p)) {
+    // opt-in reduced precision (stated tolerance: class probabilities to ~1e-6 absolute); summaries only
+    CUDA_TRY(bnn_launch_pred_tf32(p, c->n_sms, st, &c->last_kernel));
+    c->launches += 3;
+    return 0;
+  }
   CUDA_TRY(timed_forward(c, p, true, st));
   c->launches += 3;
   return 0;

@@ -601,3 +601,30 @@ def test_predict_sharded_chunked_upload_matches_one_pass():
     plain = predshard.predict_sharded(eng, xd, w, n, 0, 1, votes=True)                  # pageable numpy: one chunk
     assert np.allclose(plain["mean"].cpu().numpy(), ref["mean"], rtol=0, atol=1e-15)     # (mean * S / S)
     eng.close()
+
+
+def test_predict_tf32_mode():
+    """Opt-in reduced-precision prediction (option predict_tf32: 3xTF32 tensor-core contractions, FP32 activations and
+    softmax, FP64 accumulation over the samples) against the FP64 kernel on the c4 / c5 network shape.  Stated tolerance:
+    mean class probabilities to 5e-6 absolute; the argmax votes may flip only where two classes tie to that precision."""
+    from npbnn_b200.engine import Engine, NetShape, flatten_weights
+    from npbnn_b200 import workloads as wl
+    rng = np.random.default_rng(12)
+    n, S = 5003, 37
+    x, _ = wl.c4_data(n, seed=4)
+    base = flatten_weights(wl.c4_init_weights(1)[0])
+    w = base[None, :] + rng.normal(0, 0.15, (S, base.size))
+    for act in ("swish", "tanh", "ReLU"):
+        eng = Engine(NetShape(64, list(wl.C4_SHAPES), act=act, lik=0))
+        ref = eng.predict(x, w, mean=True, votes=True)
+        assert eng.last_kernel.startswith("k_fwd3<"), eng.last_kernel
+        eng.set_option("predict_tf32", 1)
+        lp = eng.predict(x, w, mean=True, votes=True)
+        assert eng.last_kernel.startswith("k_pred_tf32x3<"), eng.last_kernel
+        eng.set_option("predict_tf32", 0)
+        err = np.abs(lp["mean"] - ref["mean"]).max()
+        assert err < 5e-6, (act, err)
+        assert np.allclose(lp["mean"].sum(1), 1.0, atol=1e-6)
+        flips = np.abs(np.rint(lp["votes"] * S) - np.rint(ref["votes"] * S)).sum() / 2
+        assert flips <= 1e-4 * n * S, (act, flips)
+        eng.close()
