@@ -289,6 +289,8 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   c->n_sms = prop.multiProcessorCount;
   const char* fg = getenv("NPBNN_FORCE_GENERIC");
   c->force_generic = (fg && fg[0] == '1') ? 1 : 0;
+  const char* pt = getenv("NPBNN_PREDICT_TF32");           // opt-in reduced-precision prediction summaries (bnn_pred_lp.cu)
+  if (pt) c->opt_pred_tf32 = (pt[0] != '0');
 #ifdef BNN_EXPERIMENTAL_TENSOR_L1
   const char* tl = getenv("NPBNN_TENSOR_L1");
   if (tl) c->opt_tensor = (tl[0] != '0');
