@@ -319,7 +319,8 @@ int bnn_debug_set_trace(bnn_ctx* ctx, unsigned long long* trace_dev);
  * "chain_loop_cluster" = 1 | 2 | 4 | 8 | 16 caps the cluster size of that kernel (default 16);
  * "predict_tf32" = 1 (default 0) evaluates bnn_predict summaries (mean / votes) of the 64-64-32-16 categorical family on the
  * TF32 tensor cores in error-compensated 3xTF32 form with FP32 activations: class probabilities agree with the FP64 kernel
- * to ~1e-6 absolute (stated tolerance 5e-6); bnn_mh_steps and the likelihood calls never use reduced precision;
+ * to ~1e-6 absolute (stated tolerance 5e-6); 2 = plain TF32 (one product, ~1e-4, stated 5e-3); bnn_mh_steps and the
+ * likelihood calls never use reduced precision;
  * "tensor_l1" = 1 (layer 1 of the 64-64-32-10 swish network as exact int8 tensor-core products, k_fwd3t) exists only in
  * builds with -DBNN_EXPERIMENTAL_TENSOR_L1; the shipped library refuses it. */
 int bnn_set_option(bnn_ctx* ctx, const char* name, int value);

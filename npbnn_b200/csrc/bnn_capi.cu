@@ -290,7 +290,7 @@ int bnn_ctx_create(bnn_ctx** out, int device) {
   const char* fg = getenv("NPBNN_FORCE_GENERIC");
   c->force_generic = (fg && fg[0] == '1') ? 1 : 0;
   const char* pt = getenv("NPBNN_PREDICT_TF32");           // opt-in reduced-precision prediction summaries (bnn_pred_lp.cu)
-  if (pt) c->opt_pred_tf32 = (pt[0] != '0');
+  if (pt) c->opt_pred_tf32 = atoi(pt);
 #ifdef BNN_EXPERIMENTAL_TENSOR_L1
   const char* tl = getenv("NPBNN_TENSOR_L1");
   if (tl) c->opt_tensor = (tl[0] != '0');
@@ -1426,7 +1426,7 @@ static int predict_impl(bnn_ctx* c, const double* x_dev, int64_t n, const double
   if (class_counts_dev) CUDA_TRY(cudaMemsetAsync(class_counts_dev, 0, sizeof(int32_t) * (size_t)n_sets * g.K, st));
   if (c->opt_pred_tf32 && !c->force_generic && bnn_pred_tf32_fits(p)) {
     // opt-in reduced precision (stated tolerance: class probabilities to ~1e-6 absolute); summaries only
-    CUDA_TRY(bnn_launch_pred_tf32(p, c->n_sms, st, &c->last_kernel));
+    CUDA_TRY(bnn_launch_pred_tf32(p, c->n_sms, c->opt_pred_tf32 >= 2 ? 1 : 3, st, &c->last_kernel));
     c->launches += 3;
     return 0;
   }

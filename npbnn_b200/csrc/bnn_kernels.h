@@ -56,7 +56,7 @@ bool bnn_sparse_fits(const FwdParams& p);
 // opt-in reduced-precision posterior prediction (bnn_pred_lp.cu): 3xTF32 tensor-core contractions, FP32 activations /
 // softmax, FP64 accumulation over the samples; summaries of the 64-64-32-16 categorical family only
 bool bnn_pred_tf32_fits(const FwdParams& p);
-cudaError_t bnn_launch_pred_tf32(const FwdParams& p, int n_sms, cudaStream_t st, const char** which);
+cudaError_t bnn_launch_pred_tf32(const FwdParams& p, int n_sms, int passes, cudaStream_t st, const char** which);
 // k_fwd3 width family the padded geometry matches exactly: 1 = 64->64->32, 2 = 32->32->16, 0 = none (generic kernel)
 int bnn_fwd3_family(const NetGeom& g);
 // tensor-core first layer (k_fwd3t): operand slicing

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int LP_WARPS = 8;
+constexpr int LP_WARPS = 10;          // 190-200 registers per thread: ten warps fill the register file of an SM
 constexpr int KP0 = 64, N1 = 64, N2 = 32, N3 = 16;
 constexpr int W1_OFF = 0, B1_OFF = N1 * KP0, W2_OFF = B1_OFF + N1, B2_OFF = W2_OFF + N2 * N1, W3_OFF = B2_OFF + N2,
               B3_OFF = W3_OFF + N3 * N2, PBF = B3_OFF + N3;
@@ -39,35 +39,53 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // one k-group of an [16 x 8k] x [8k x 8] product in 3xTF32: (ah, al) A fragments, W row pointer to (hi, lo) float pairs
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4 w) {
-  // w = (W[n][2t].hi, W[n][2t].lo, W[n][2t+1].hi, W[n][2t+1].lo)
-  const uint32_t b0h = __float_as_uint(w.x), b0l = __float_as_uint(w.y), b1h = __float_as_uint(w.z), b1l = __float_as_uint(w.w);
-  mma_tf32(c, al, b0h, b1h);       // small terms first
-  mma_tf32(c, ah, b0l, b1l);
-  mma_tf32(c, ah, b0h, b1h);
+// One k-group of a layer for all NT output tiles.  PASSES = 3: error-compensated (products to 2^-22), PASSES = 1: plain TF32
+// (10-bit mantissas, products to 2^-11).  The three products of an accumulator are issued NT instructions apart (pass by
+// pass over the tiles), never back to back: a dependent mma.sync waits ~30 clk for its accumulator.
+//   wr: W row (n0 + gq) of the layer as (hi, lo) float pairs, already offset by the swizzled column of this k-group
+template <int PASSES, int NT>
+__device__ __forceinline__ void mma_kgroup(float (&acc)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const float2* wr, int row_stride8) {
+  float4 w[NT];                                   // (W[n][2t].hi, W[n][2t+1].hi, W[n][2t].lo, W[n][2t+1].lo)
+#pragma unroll
+  for (int j = 0; j < NT; ++j) w[j] = *reinterpret_cast<const float4*>(wr + j * row_stride8);
+  if (PASSES == 3) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(acc[j], al, __float_as_uint(w[j].x), __float_as_uint(w[j].y));   // small terms first
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(acc[j], ah, __float_as_uint(w[j].z), __float_as_uint(w[j].w));
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32(acc[j], ah, __float_as_uint(w[j].x), __float_as_uint(w[j].y));
 }
 template <int ACT>
 __device__ __forceinline__ float act_f32(float z, float alpha) {
   if (ACT == BNN_ACT_RELU) return z < 0.f ? 0.f : z;
   if (ACT == BNN_ACT_LEAKY) return z < 0.f ? alpha * z : z;
-  if (ACT == BNN_ACT_SWISH) return z * __frcp_rn(1.0f + __expf(-z));
-  return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * z) + 1.0f);
+  if (ACT == BNN_ACT_SWISH) return __fdividef(z, 1.0f + __expf(-z));
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * z) + 1.0f);
 }
 
 // packed weight sets (doubles) -> (tf32 hi, tf32 lo) float pairs, in place (the scratch copy bnn_predict packs per call):
 // once per call instead of once per CTA and tile round; biases keep the full FP32 value in .x
-__global__ void k_split_w_tf32(double* wp, long long n_total) {
+__global__ void k_split_w_tf32(double* wp, long long n_pairs) {
+  // one thread per PAIR of consecutive packed entries (columns 2t', 2t'+1 of a row, or two biases): the pair becomes
+  // (hi0, hi1, lo0, lo1), so that the B operands of an MMA (b0, b1) sit in adjacent registers after one 16-byte load
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_total) return;
-  const int e = (int)(i % PBF);
-  const float v = (float)wp[i];
-  uint32_t hi, lo;
-  split_tf32(v, hi, lo);
+  if (i >= n_pairs) return;
+  const int e = (int)((2 * i) % PBF);
+  const double2 d = reinterpret_cast<const double2*>(wp)[i];
+  const float v0 = (float)d.x, v1 = (float)d.y;
+  uint32_t h0, l0, h1, l1;
+  split_tf32(v0, h0, l0);
+  split_tf32(v1, h1, l1);
   const bool is_bias = (e >= B1_OFF && e < W2_OFF) || (e >= B2_OFF && e < W3_OFF) || e >= B3_OFF;
-  reinterpret_cast<float2*>(wp)[i] = is_bias ? make_float2(v, 0.f) : make_float2(__uint_as_float(hi), __uint_as_float(lo));
+  // biases keep the full FP32 values in (.x, .y)
+  reinterpret_cast<float4*>(wp)[i] = is_bias ? make_float4(v0, v1, 0.f, 0.f)
+                                             : make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
 }
 
-template <int ACT>
+template <int ACT, int PASSES>
 __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* wbuf = reinterpret_cast<double*>(smem_raw);          // [2][PBF] (hi, lo) float pairs, 8 bytes per weight
@@ -113,13 +131,19 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
 #pragma unroll
       for (int i = 0; i < N3 / 4; ++i) { pacc[h][i] = 0.0; pvote[h][i] = 0; }
 
+    // Every CTA walks the samples in the same cyclic order but starts at its own offset: 148 CTAs reading the SAME 54 KB
+    // at the same time queue up on the few L2 slices that hold it (measured: 5.9 us per sample and round whatever the
+    // number of MMAs); rotated, the reads spread over the whole L2.  A tile is summed by one warp in a fixed order either way.
+    const int c_off = (int)(((long long)blockIdx.x * p.C) / gridDim.x);
+    auto set_of = [&](int i) { const int s = i + c_off; return s >= p.C ? s - p.C : s; };
     __syncthreads();                                            // the previous round is done with both buffers
-    stage_async(0, 0);
-    for (int c = 0; c < p.C; ++c) {
-      const int buf = c & 1;
+    stage_async(0, set_of(0));
+    for (int ci = 0; ci < p.C; ++ci) {
+      const int c = set_of(ci);
+      const int buf = ci & 1;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();                                          // set c has landed; nobody reads buffer buf ^ 1 any more
-      if (c + 1 < p.C) stage_async(buf ^ 1, c + 1);
+      if (ci + 1 < p.C) stage_async(buf ^ 1, set_of(ci + 1));
       if (have_tile) {
         const float2* W = reinterpret_cast<const float2*>(wbuf + (size_t)buf * PBF);
         const float a1 = (ACT == BNN_ACT_LEAKY && p.alpha) ? (float)p.alpha[c * 3 + 0] : 0.f;
@@ -128,7 +152,7 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
         float acc1[N1 / 8][4];
 #pragma unroll
         for (int j = 0; j < N1 / 8; ++j) {
-          const float b0 = W[B1_OFF + 8 * j + 2 * t].x, b1 = W[B1_OFF + 8 * j + 2 * t + 1].x;
+          const float b0 = W[B1_OFF + 8 * j + 2 * t].x, b1 = W[B1_OFF + 8 * j + 2 * t].y;
           acc1[j][0] = b0; acc1[j][1] = b1; acc1[j][2] = b0; acc1[j][3] = b1;
         }
         {
@@ -137,16 +161,14 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
 #pragma unroll
           for (int kg = 0; kg < KP0 / 8; ++kg) {
             const int col = (8 * kg + 2 * t) ^ sw;
-#pragma unroll
-            for (int j = 0; j < N1 / 8; ++j)
-              mma3(acc1[j], xh[kg], xl[kg], *reinterpret_cast<const float4*>(wr + j * 8 * KP0 + col));
+            mma_kgroup<PASSES, N1 / 8>(acc1, xh[kg], xl[kg], wr + col, 8 * KP0);
           }
         }
         // ---- layer 2 (A = activated acc1, split into hi / lo)
         float acc2[N2 / 8][4];
 #pragma unroll
         for (int j = 0; j < N2 / 8; ++j) {
-          const float b0 = W[B2_OFF + 8 * j + 2 * t].x, b1 = W[B2_OFF + 8 * j + 2 * t + 1].x;
+          const float b0 = W[B2_OFF + 8 * j + 2 * t].x, b1 = W[B2_OFF + 8 * j + 2 * t].y;
           acc2[j][0] = b0; acc2[j][1] = b1; acc2[j][2] = b0; acc2[j][3] = b1;
         }
         {
@@ -160,16 +182,14 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
             split_tf32(act_f32<ACT>(acc1[kg][1], a1), ah[2], al[2]);
             split_tf32(act_f32<ACT>(acc1[kg][3], a1), ah[3], al[3]);
             const int col = (8 * kg + 2 * t) ^ sw;
-#pragma unroll
-            for (int j = 0; j < N2 / 8; ++j)
-              mma3(acc2[j], ah, al, *reinterpret_cast<const float4*>(wr + j * 8 * N1 + col));
+            mma_kgroup<PASSES, N2 / 8>(acc2, ah, al, wr + col, 8 * N1);
           }
         }
         // ---- layer 3
         float acc3[N3 / 8][4];
 #pragma unroll
         for (int j = 0; j < N3 / 8; ++j) {
-          const float b0 = W[B3_OFF + 8 * j + 2 * t].x, b1 = W[B3_OFF + 8 * j + 2 * t + 1].x;
+          const float b0 = W[B3_OFF + 8 * j + 2 * t].x, b1 = W[B3_OFF + 8 * j + 2 * t].y;
           acc3[j][0] = b0; acc3[j][1] = b1; acc3[j][2] = b0; acc3[j][3] = b1;
         }
         {
@@ -183,9 +203,7 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
             split_tf32(act_f32<ACT>(acc2[kg][1], a2), ah[2], al[2]);
             split_tf32(act_f32<ACT>(acc2[kg][3], a2), ah[3], al[3]);
             const int col = (8 * kg + 2 * t) ^ sw;
-#pragma unroll
-            for (int j = 0; j < N3 / 8; ++j)
-              mma3(acc3[j], ah, al, *reinterpret_cast<const float4*>(wr + j * 8 * N2 + col));
+            mma_kgroup<PASSES, N3 / 8>(acc3, ah, al, wr + col, 8 * N2);
           }
         }
         // ---- softmax per row (rows gq and gq + 8; the 4 lanes of a quad hold the 16 columns), FP32
@@ -253,9 +271,9 @@ __global__ void __launch_bounds__(LP_WARPS * 32, 1) k_pred_tf32x3(const __grid_c
   }
 }
 
-template <int ACT>
+template <int ACT, int PASSES>
 cudaError_t launch_lp(const FwdParams& p, int n_sms, cudaStream_t st) {
-  auto kern = k_pred_tf32x3<ACT>;
+  auto kern = k_pred_tf32x3<ACT, PASSES>;
   const size_t bytes = 2 * (size_t)PBF * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
@@ -264,8 +282,8 @@ cudaError_t launch_lp(const FwdParams& p, int n_sms, cudaStream_t st) {
     attr_done = true;
   }
   {
-    const long long n_total = (long long)p.C * PBF;
-    k_split_w_tf32<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(const_cast<double*>(p.wp), n_total);
+    const long long n_pairs = (long long)p.C * PBF / 2;
+    k_split_w_tf32<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(const_cast<double*>(p.wp), n_pairs);
   }
   const long long ctas = (p.n_tiles16 + LP_WARPS - 1) / LP_WARPS;
   const int grid = (int)(ctas < n_sms ? ctas : n_sms);          // one CTA per SM (231 registers x 256 threads)
@@ -282,13 +300,22 @@ bool bnn_pred_tf32_fits(const FwdParams& p) {
          !p.samp_philox && !p.samp_counts && !p.samp_dense && (p.mean_out || p.votes_out);
 }
 
-cudaError_t bnn_launch_pred_tf32(const FwdParams& p, int n_sms, cudaStream_t st, const char** which) {
-  static const char* const names[4] = {"k_pred_tf32x3<relu>", "k_pred_tf32x3<leaky>", "k_pred_tf32x3<swish>", "k_pred_tf32x3<tanh>"};
-  if (which) *which = names[p.g.act];
+cudaError_t bnn_launch_pred_tf32(const FwdParams& p, int n_sms, int passes, cudaStream_t st, const char** which) {
+  static const char* const names[2][4] = {{"k_pred_tf32x3<relu>", "k_pred_tf32x3<leaky>", "k_pred_tf32x3<swish>", "k_pred_tf32x3<tanh>"},
+                                          {"k_pred_tf32x1<relu>", "k_pred_tf32x1<leaky>", "k_pred_tf32x1<swish>", "k_pred_tf32x1<tanh>"}};
+  if (which) *which = names[passes == 1][p.g.act];
+  if (passes == 1) {
+    switch (p.g.act) {
+      case BNN_ACT_RELU: return launch_lp<BNN_ACT_RELU, 1>(p, n_sms, st);
+      case BNN_ACT_LEAKY: return launch_lp<BNN_ACT_LEAKY, 1>(p, n_sms, st);
+      case BNN_ACT_SWISH: return launch_lp<BNN_ACT_SWISH, 1>(p, n_sms, st);
+      default: return launch_lp<BNN_ACT_TANH, 1>(p, n_sms, st);
+    }
+  }
   switch (p.g.act) {
-    case BNN_ACT_RELU: return launch_lp<BNN_ACT_RELU>(p, n_sms, st);
-    case BNN_ACT_LEAKY: return launch_lp<BNN_ACT_LEAKY>(p, n_sms, st);
-    case BNN_ACT_SWISH: return launch_lp<BNN_ACT_SWISH>(p, n_sms, st);
-    default: return launch_lp<BNN_ACT_TANH>(p, n_sms, st);
+    case BNN_ACT_RELU: return launch_lp<BNN_ACT_RELU, 3>(p, n_sms, st);
+    case BNN_ACT_LEAKY: return launch_lp<BNN_ACT_LEAKY, 3>(p, n_sms, st);
+    case BNN_ACT_SWISH: return launch_lp<BNN_ACT_SWISH, 3>(p, n_sms, st);
+    default: return launch_lp<BNN_ACT_TANH, 3>(p, n_sms, st);
   }
 }

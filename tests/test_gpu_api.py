@@ -627,4 +627,9 @@ def test_predict_tf32_mode():
         assert np.allclose(lp["mean"].sum(1), 1.0, atol=1e-6)
         flips = np.abs(np.rint(lp["votes"] * S) - np.rint(ref["votes"] * S)).sum() / 2
         assert flips <= 1e-4 * n * S, (act, flips)
+        eng.set_option("predict_tf32", 2)                 # plain TF32 (one product): quick-look precision, 5e-3 stated
+        lp1 = eng.predict(x, w, mean=True, votes=True)
+        assert eng.last_kernel.startswith("k_pred_tf32x1<"), eng.last_kernel
+        err1 = np.abs(lp1["mean"] - ref["mean"]).max()
+        assert err < err1 < 5e-3, (act, err1)
         eng.close()
