@@ -1030,3 +1030,69 @@ def test_chain_loop_is_taken_where_it_pays():
         eng.mh_steps(3)
         assert eng.last_kernel == want, (n, chains, eng.last_kernel)
         eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 17, 33])
+def test_tiny_and_ragged_row_counts(n):
+    """Edge sizes: fewer rows than one 16-row tile, one row more / less than a tile boundary.  The reference has no
+    size restriction (np.dot on [N, F], BNN_lib.py:154-162); the padded rows of the device layout must not reach the
+    likelihood, the counters or the predictions -- on the specialised kernel, the generic kernel and inside the
+    persistent chain loop."""
+    from npbnn_b200.engine import Engine, NetShape
+    # (a) the c4 network: k_fwd3 and the generic kernel against the oracle
+    x, labels, sets = _c4_like(n, 3, seed=n)
+    m = orc.Model(x=x, labels=labels, weights=sets[0], act="swish", mode="classification")
+    eng = Engine(NetShape.from_weights(sets[0], 64, act="swish", lik=0))
+    eng.set_data(x, labels)
+    res = eng.forward_lik(sets)
+    assert eng.last_kernel.startswith("k_fwd3"), eng.last_kernel
+    eng.set_option("force_generic", 1)
+    gen = eng.forward_lik(sets)
+    assert eng.last_kernel == "k_fwd_generic"
+    eng.set_option("force_generic", 0)
+    for i, w in enumerate(sets):
+        ref = oracle_score(m, w)
+        for r in (res, gen):
+            assert rel_close(r["loglik"][i], ref["loglik"]), (n, i, r["loglik"][i], ref["loglik"])
+            assert r["counts"][i][0] == ref["n_correct"]
+            assert np.array_equal(r["counts"][i][12:22], ref["pred_hist"]) and ref["pred_hist"].sum() == n
+    out = eng.predict(x, sets, mean=True, votes=True, dense=True)
+    dense_ref, mean_ref = orc.posterior_predict(x, sets, "swish", None, "softmax", 1)
+    assert out["dense"].shape == dense_ref.shape and np.allclose(out["dense"], dense_ref, rtol=1e-10, atol=1e-300)
+    assert np.allclose(out["mean"], mean_ref, rtol=1e-10, atol=1e-300)
+    eng.close()
+    # (b) a small tanh classifier: the persistent chain loop against the per-step launch sequence, bit for bit
+    rng = np.random.default_rng(100 + n)
+    xs = rng.standard_normal((n, 7))
+    ys = rng.integers(0, 3, n).astype(np.int64)
+    ws = [[rng.normal(0, 0.4, s) for s in ((5, 8), (4, 6), (3, 4))] for _ in range(2)]
+    ms = orc.Model(x=xs, labels=ys, weights=ws[0], act="tanh", mode="classification")
+    states = []
+    for mode in (2, 0):
+        eng = Engine(NetShape.from_weights(ws[0], 7, act="tanh", lik=0))
+        eng.set_data(xs, ys)
+        if mode == 2:
+            sc = eng.forward_lik(ws)
+            for i, w in enumerate(ws):
+                ref = oracle_score(ms, w)
+                assert rel_close(sc["loglik"][i], ref["loglik"]) and sc["counts"][i][0] == ref["n_correct"]
+        eng.chains_init(ws, seed=5)
+        eng.set_option("chain_loop", mode)
+        eng.mh_steps(12)
+        assert eng.last_kernel == ("k_chain_loop" if mode == 2 else "k_fwd_generic"), eng.last_kernel
+        st = eng.read_state()
+        states.append((st.f64.copy(), st.i32.copy(), st.w.copy()))
+        eng.close()
+    for a, b in zip(*states):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_empty_training_set_is_refused():
+    """Zero rows: the reference fails inside numpy (np.argmax of an empty axis, BNN_lib.py:203-209); the library
+    refuses the data set up front instead of launching over nothing."""
+    from npbnn_b200.engine import Engine, NetShape
+    ws = [np.zeros(s) for s in ((5, 8), (3, 6))]
+    eng = Engine(NetShape.from_weights(ws, 7, act="tanh", lik=0))
+    with pytest.raises(Exception):
+        eng.set_data(np.zeros((0, 7)), np.zeros(0, dtype=np.int64))
+    eng.close()
