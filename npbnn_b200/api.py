@@ -372,10 +372,13 @@ class _ChainGroup:
         if bnn._estimation_mode == "classification":
             self.labels_count = np.bincount(bnn._labels, minlength=bnn._size_output)
 
-    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None, additional_prob=0, adapt_stop=0):
+    def draw_steps(self, rngs, state, chain_ids, n_steps, reseed=None, additional_prob=0, adapt_stop=0, step0=0):
         """Consume each chain's generator exactly as mh_step + UpdateNormal do (BNN_env.py:446-453,493;
         BNN_mcmc.py:62-65) for n_steps iterations during which no adaptation fires.
-        reseed(chain, iteration) -> Generator implements randomize_seed (BNN_env.py:383-384)."""
+        reseed(chain, iteration) -> Generator implements randomize_seed (BNN_env.py:383-384).
+        step0: the draws are those of iterations state.iteration + step0 ... + step0 + n_steps - 1 (a later slice of
+        the same adaptation-free stretch; only meaningful with reseed, whose generators do not depend on the slicing)."""
+        assert step0 == 0 or reseed is not None
         nl = self.net.n_layers
         shapes = self.net.shapes
         cap = max(1, int(np.max(np.sum(state.update_n, axis=1))))
@@ -397,13 +400,13 @@ class _ChainGroup:
         for c in range(self.n):
             flu, un, uws = state.freq_layer_update[c], state.update_n[c], state.update_ws[c]
             for s in range(n_steps):
-                rs = rngs[c] if reseed is None else reseed(chain_ids[c], int(state.iteration[c]) + s)
+                rs = rngs[c] if reseed is None else reseed(chain_ids[c], int(state.iteration[c]) + step0 + s)
                 if self.n_act_prm:        # UpdateNormal1D(_acc_prm, d=0.05, n=1, ...) comes first (BNN_env.py:416-417)
                     inj["alpha_ix"][s, c] = rs.integers(0, self.n_act_prm, 1)[0]
                     inj["alpha_dz"][s, c] = rs.normal(0, 0.05, 1)[0]
                 # feature indicators (BNN_env.py:423-431): once past adapt_stop, with probability 0.2 the indicators are
                 # flipped by UpdateBinomial(ind, 0.5, shape) -- numpy's GLOBAL generator (BNN_mcmc.py:98-99)
-                if self.use_fi and int(state.iteration[c]) + s > adapt_stop and rs.random() < 0.2:
+                if self.use_fi and int(state.iteration[c]) + step0 + s > adapt_stop and rs.random() < 0.2:
                     inj["fi_move"][s, c] = 1
                     inj["fi_flip"][s, c] = np.random.binomial(1, np.random.random() * 0.5, self.net.n_features)
                 rr = rs.random(nl)
@@ -863,13 +866,47 @@ class MC3:
                 _mirror_adaptation(st, c, it, self.adapt_freq, self.adapt_stop, self.adapt_f, self.adapt_fM, max_n,
                                    int(np.sum(max_n)))
             k = min(n - done, _steps_to_adaptation(it, self.adapt_freq, self.adapt_stop))
-            # randomize_seed=True: every step reseeds default_rng(iteration + mcmc_id) (BNN_env.py:383-384)
-            inj = g.draw_steps([None] * self.n_local, st, [self.start + c for c in range(self.n_local)], k,
-                               reseed=lambda cid, i: np.random.default_rng(i + cid), adapt_stop=self.adapt_stop)
-            g.eng.mh_steps(k, inj)
+            # randomize_seed=True: every step reseeds default_rng(iteration + mcmc_id) (BNN_env.py:383-384), so the
+            # draws of an iteration depend on nothing but (iteration, chain) and the adaptation state read above
+            def draw(s0, m):
+                return g.draw_steps([None] * self.n_local, st, [self.start + c for c in range(self.n_local)], m,
+                                    reseed=lambda cid, i: np.random.default_rng(i + cid), adapt_stop=self.adapt_stop,
+                                    step0=s0)
+            sub = max(4, k // 16)
+            if k <= sub or g.freq_indicator or g.use_fi:      # (the indicator moves consume numpy's GLOBAL generator
+                g.eng.mh_steps(k, draw(0, k))                  #  chain by chain: keep that order)
+            else:
+                # The host needs ~80 us per (chain, iteration) for the reference's generator calls -- 0.26 s per 100
+                # iterations of 32 chains, 15 % of the device time at BASELINE config 4: a worker thread draws slice
+                # j + 1 while this thread waits inside bnn_mh_steps for slice j (ctypes releases the GIL).
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=1) as pool:
+                    s0 = 0
+                    fut = pool.submit(draw, 0, min(sub, k))
+                    while s0 < k:
+                        m = min(sub, k - s0)
+                        inj = fut.result()
+                        s0 += m
+                        if s0 < k:
+                            fut = pool.submit(draw, s0, min(sub, k - s0))
+                        g.eng.mh_steps(m, inj)
             done += k
 
     def run_mcmc(self):
+        # The reference rewrites the [bnn, mcmc, logger] pickle -- the feature matrix included, 512 MB at BASELINE config 4
+        # -- after every swap period (BNN_mc3.py:118-122 -> BNN_env.py:658).  As in run_mcmc above the writes go to the
+        # logger's background writer (newest snapshot wins, the last one is on disk when this returns) so that the
+        # device does not idle while the host pickles: tools/mc3_api_c4.py.
+        lg = self.logger if hasattr(self.logger, "begin_async") and self.__dict__.get("async_pickle", True) else None
+        if lg is not None:
+            lg.begin_async()
+        try:
+            self._run_mcmc()
+        finally:
+            if lg is not None:
+                lg.end_async()
+
+    def _run_mcmc(self):
         g = self._group
         for mc3_it in range(self.n_mc3_iteration):
             self._run_period()

@@ -171,7 +171,44 @@ def test_mc3_reproduces_reference_run(tmp_path):
             for li in range(3):
                 assert np.array_equal(mc3.singleChainArgs[c][0]._w_layers[li], z["it%d_c%d_w%d" % (it, c, li)]), (it, c, li)
     assert os.path.exists(logger._pklfile)
-    assert pickle.load(open(logger._pklfile, "rb"))[2]._post_weight_samples
+    lg = pickle.load(open(logger._pklfile, "rb"))[2]
+    assert lg._post_weight_samples
+    # the pickle on disk when run_mcmc returns is the LAST snapshot (background writer): the cold chain's final state
+    cold = [a for a in mc3.singleChainArgs if a[1]._temperature == 1][0]
+    assert lg._post_weight_samples[-1]["mcmc_it"] == cold[1]._current_iteration
+    for wa, wb in zip(lg._post_weight_samples[-1]["weights"], cold[0]._w_layers):
+        assert np.array_equal(wa, wb)
+
+
+def test_mc3_background_pickle_matches_synchronous_writes(tmp_path):
+    """MC3.run_mcmc hands the per-period [bnn, mcmc, logger] pickle (BNN_env.py:658) to the logger's background
+    writer; with async_pickle = False every period writes synchronously as the reference does.  Same .log rows, same
+    posterior samples in the final pickle."""
+    import npbnn_b200 as bn
+    z, meta = G.load("mc3")
+    dat = {"data": np.array(z["x"]), "labels": np.array(z["labels"]), "test_data": [], "test_labels": []}
+    runs = []
+    for tag, flag in (("bg", True), ("sync", False)):
+        np.random.seed(3)                 # MC3 draws its chain seeds from numpy's global generator (BNN_mc3.py:40)
+        bnn = bn.npBNN(dat, n_nodes=[4, 3], use_bias_node=-1, seed=1, actFun=bn.ActFun(fun="swish"),
+                       init_weights=[np.array(z["w0_%d" % i]) for i in range(3)])
+        logger = bn.postLogger(bnn, filename="mc3_" + tag, wdir=str(tmp_path))
+        mc3 = bn.MC3(bnn, logger=logger, n_post_samples=6, sampling_f=5, n_iteration=60, n_chains=3, swap_frequency=5,
+                     verbose=0, rng="philox", swap_seed=11)
+        mc3.async_pickle = flag
+        mc3.run_mcmc()
+        assert logger.__dict__.get("_async") is None
+        saved = pickle.load(open(logger._pklfile, "rb"))
+        runs.append((open(logger._logfile).read().splitlines(), saved[2]._post_weight_samples, saved[0]._w_layers))
+    a, b = runs
+    assert a[0] == b[0] and len(a[0]) == 1 + 12
+    assert len(a[1]) == len(b[1]) == 6
+    for sa, sb in zip(a[1], b[1]):
+        assert sa["mcmc_it"] == sb["mcmc_it"]
+        for wa, wb in zip(sa["weights"], sb["weights"]):
+            assert np.array_equal(wa, wb)
+    for wa, wb in zip(a[2], b[2]):
+        assert np.array_equal(wa, wb)
 
 
 def test_unsupported_options_raise():
