@@ -27,9 +27,9 @@ y = np.argmax(x @ w_true + rng.normal(0, 1.0, (n, 6)), 1)
 dat = {"data": x[:18000], "labels": y[:18000], "label_dict": np.arange(6), "test_data": x[18000:], "test_labels": y[18000:]}
 np.random.seed(1234)
 bnn = bn.npBNN(dat, n_nodes=[32, 16], use_bias_node=-1, seed=1, actFun=bn.ActFun(fun="swish"))
-logger = bn.postLogger(bnn, filename="mc3_w%d" % world, wdir=outdir)
+logger = bn.postLogger(bnn, filename="mc3_%s_w%d" % (os.environ.get("MC3_RNG", "philox"), world), wdir=outdir)
 mc3 = bn.MC3(bnn, logger=logger, n_post_samples=20, sampling_f=50, n_iteration=2000, n_chains=8, swap_frequency=50,
-             verbose=0, print_f=10 ** 9, adapt_f=0.3, adapt_fM=0.6, adapt_freq=25, adapt_stop=500, rng="philox", swap_seed=77,
+             verbose=0, print_f=10 ** 9, adapt_f=0.3, adapt_fM=0.6, adapt_freq=25, adapt_stop=500, rng=os.environ.get("MC3_RNG", "philox"), swap_seed=77,
              device=int(os.environ.get("LOCAL_RANK", "0")))
 t0 = time.perf_counter()
 mc3.run_mcmc()
