@@ -788,6 +788,19 @@ def run_mcmc(bnn, mcmc, logger, pipeline_depth=4):
             logger.end_async()
 
 
+def _chain_view(bnn):
+    """A per-chain copy of the model object that SHARES the row-sized read-only arrays (features, labels, sample ids,
+    instance weights) with the original: the reference deep-copies / pickles the whole object per chain
+    (BNN_mc3.py:42-47), which at BASELINE config 4 is 32 x 512 MB of host memory and 4 s for views whose data nobody
+    writes (update_data rebinds the attributes).  Weights, indicators, prior scales ... stay private copies."""
+    memo = {}
+    for k in ("_data", "_labels", "_test_data", "_test_labels", "_sample_id", "_instance_weights", "_instance_id"):
+        v = bnn.__dict__.get(k)
+        if isinstance(v, np.ndarray):
+            memo[id(v)] = v
+    return deepcopy(bnn, memo)
+
+
 class MC3:
     """Metropolis-coupled chains (BNN_mc3.py:8-126).  All chains live on the GPU(s); there is no fork pool
     and nothing is pickled between swap periods.  With torch.distributed initialised the chains are
@@ -841,7 +854,7 @@ class MC3:
         # per-chain views with the reference's attribute surface (singleChainArgs[i] = [bnn, mcmc])
         self.singleChainArgs = []
         for i in range(self.n_local):
-            b = deepcopy(data)
+            b = _chain_view(data)
             b.reset_seed(self.rseeds[self.start + i])
             m = MCMC(b, temperature=self.temperatures[self.start + i], n_iteration=swap_frequency, sampling_f=sampling_f,
                      print_f=swap_frequency * 10, n_post_samples=n_post_samples, mcmc_id=self.start + i, randomize_seed=True,
@@ -960,7 +973,7 @@ class MC3:
             b, m = cold
         else:
             if getattr(self, "_cold_view", None) is None:
-                b = deepcopy(self._bnn)
+                b = _chain_view(self._bnn)
                 m = object.__new__(MCMC)
                 self._cold_view = (b, m)
             b, m = self._cold_view
