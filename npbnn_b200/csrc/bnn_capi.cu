@@ -82,6 +82,12 @@ struct bnn_ctx {
   DevBuf part_red;
   DevBuf part_sl;                   // [C, NF, n_slices]: slice sums of the tile partials (k_reduce_part), read by k_mh_update
   DevBuf inj_proposed, inj_count, inj_ix, inj_iy, inj_dz, inj_logu, inj_alpha_ix, inj_alpha_dz, inj_add_prob;
+  // the six arrays every injection carries travel in ONE host-to-device transfer: packed into a pinned staging buffer
+  // (so the caller's arrays are free on return whatever memory they live in), copied into one device arena
+  DevBuf inj_arena;
+  void* inj_host = nullptr;
+  size_t inj_host_bytes = 0;
+  cudaEvent_t inj_copied = nullptr;   // the last transfer out of inj_host
   const char* last_kernel = "";
   // block-masked networks: dataflow program of the chains' mask (k_fwd_sparse)
   // tensor-core first layer (k_fwd3t): int8 slices of X (made once per data set) and of W1 (per scored batch)
@@ -330,6 +336,9 @@ int bnn_ctx_destroy(bnn_ctx* c) {
     if (sn.staged) cudaEventDestroy(sn.staged);
     if (sn.done) cudaEventDestroy(sn.done);
   }
+  c->inj_arena.release();
+  if (c->inj_host) cudaFreeHost(c->inj_host);
+  if (c->inj_copied) cudaEventDestroy(c->inj_copied);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   invalidate_graphs(c);
   if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
@@ -1002,22 +1011,40 @@ static int stage_injection(bnn_ctx* c, int32_t n_steps, const bnn_injection* inj
         off += cnt;
       }
     }
-    int rc = 0;
-    rc |= upload(c->inj_proposed, inj->proposed, nl, st);
-    rc |= upload(c->inj_count, inj->count, nl, st);
-    rc |= upload(c->inj_ix, inj->ix, nc, st);
-    rc |= upload(c->inj_iy, inj->iy, nc, st);
-    rc |= upload(c->inj_dz, inj->dz, nc, st);
-    rc |= upload(c->inj_logu, inj->log_u, (size_t)n_steps * c->C, st);
-    if (rc) return rc;
-    d.inj_proposed = c->inj_proposed.as<int>();
-    d.inj_count = c->inj_count.as<int>();
-    d.inj_ix = c->inj_ix.as<int>();
-    d.inj_iy = c->inj_iy.as<int>();
-    d.inj_dz = c->inj_dz.as<double>();
-    d.inj_logu = c->inj_logu.as<double>();
-    d.inj_cap = inj->cap;
     const size_t ns = (size_t)n_steps * c->C;
+    {
+      // one transfer instead of six (a single-step injection is latency, not bandwidth: 6 x ~8 us of copy-engine
+      // round trips in front of the step's first kernel)
+      auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+      const size_t o_dz = 0, o_lu = o_dz + al(8 * nc), o_pr = o_lu + al(8 * ns), o_ct = o_pr + al(4 * nl),
+                   o_ix = o_ct + al(4 * nl), o_iy = o_ix + al(4 * nc), total = o_iy + al(4 * nc);
+      if (c->inj_copied) CUDA_TRY(cudaEventSynchronize(c->inj_copied));      // the staging buffer is free again
+      else CUDA_TRY(cudaEventCreateWithFlags(&c->inj_copied, cudaEventDisableTiming));
+      if (total > c->inj_host_bytes) {
+        if (c->inj_host) CUDA_TRY(cudaFreeHost(c->inj_host));
+        c->inj_host = nullptr; c->inj_host_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&c->inj_host, 2 * total));
+        c->inj_host_bytes = 2 * total;
+      }
+      CUDA_TRY(c->inj_arena.ensure(total, false, st));
+      char* h = static_cast<char*>(c->inj_host);
+      memcpy(h + o_dz, inj->dz, 8 * nc);
+      memcpy(h + o_lu, inj->log_u, 8 * ns);
+      memcpy(h + o_pr, inj->proposed, 4 * nl);
+      memcpy(h + o_ct, inj->count, 4 * nl);
+      memcpy(h + o_ix, inj->ix, 4 * nc);
+      memcpy(h + o_iy, inj->iy, 4 * nc);
+      CUDA_TRY(cudaMemcpyAsync(c->inj_arena.p, h, total, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaEventRecord(c->inj_copied, st));
+      char* dv = static_cast<char*>(c->inj_arena.p);
+      d.inj_dz = reinterpret_cast<double*>(dv + o_dz);
+      d.inj_logu = reinterpret_cast<double*>(dv + o_lu);
+      d.inj_proposed = reinterpret_cast<int*>(dv + o_pr);
+      d.inj_count = reinterpret_cast<int*>(dv + o_ct);
+      d.inj_ix = reinterpret_cast<int*>(dv + o_ix);
+      d.inj_iy = reinterpret_cast<int*>(dv + o_iy);
+    }
+    d.inj_cap = inj->cap;
     if (c->cfg.n_act_prm > 0) {
       REQUIRE(inj->alpha_ix && inj->alpha_dz, "bnn_mh_steps: trainable activation parameters need alpha_ix / alpha_dz");
       for (size_t s = 0; s < ns; ++s)
