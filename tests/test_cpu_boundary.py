@@ -349,3 +349,27 @@ def test_prediction_grid_and_combine_two_ranks_gloo(tmp_path):
     a, b = np.load(tmp_path / "pred_0.npy"), np.load(tmp_path / "pred_1.npy")
     probs = np.random.default_rng(0).random((7, 1000, 3))
     assert np.array_equal(a, b) and np.allclose(a, probs.mean(0), rtol=1e-14)
+
+
+def test_host_draws_do_not_depend_on_how_a_stretch_is_sliced():
+    """MC3 with the reference's generator (randomize_seed: default_rng(iteration + chain id) per step, BNN_env.py:383-384)
+    draws slice j + 1 on a worker thread while the device runs slice j: the draws of an adaptation-free stretch must be
+    the same whether they are made in one call or in slices (draw_steps(..., step0=...))."""
+    from types import SimpleNamespace
+    from npbnn_b200 import api
+    shapes = [(6, 9), (4, 7), (3, 5)]
+    g = object.__new__(api._ChainGroup)
+    g.net = SimpleNamespace(n_layers=3, shapes=shapes, n_features=8)
+    g.n, g.n_act_prm, g.freq_indicator, g.use_fi = 3, 0, 0.0, False
+    st = SimpleNamespace(update_n=np.array([[5, 3, 2]] * 3), freq_layer_update=np.array([[0.6, 0.5, 0.4]] * 3),
+                         update_ws=np.array([[0.07, 0.08, 0.09]] * 3), update_f=np.array([[0.05] * 3] * 3),
+                         iteration=np.array([40, 40, 40]))
+    reseed = lambda cid, i: np.random.default_rng(i + cid)
+    ids = [4, 5, 6]
+    whole = g.draw_steps([None] * 3, st, ids, 10, reseed=reseed)
+    parts = [g.draw_steps([None] * 3, st, ids, m, reseed=reseed, step0=s0) for s0, m in ((0, 4), (4, 4), (8, 2))]
+    assert whole["proposed"].sum() > 0
+    for k in whole:
+        assert np.array_equal(whole[k], np.concatenate([p[k] for p in parts], axis=0)), k
+    with pytest.raises(AssertionError):                        # a stateful generator cannot be sliced out of order
+        g.draw_steps([np.random.default_rng(0)] * 3, st, ids, 2, step0=3)
