@@ -885,7 +885,9 @@ class MC3:
                 return g.draw_steps([None] * self.n_local, st, [self.start + c for c in range(self.n_local)], m,
                                     reseed=lambda cid, i: np.random.default_rng(i + cid), adapt_stop=self.adapt_stop,
                                     step0=s0)
-            sub = max(4, k // 16)
+            # slices: many on large data (the first slice's draw is the only one the device waits for), few on small
+            # data, where every bnn_mh_steps call costs about as much as several device iterations
+            sub = max(4, k // (16 if self._bnn._n_samples >= 20000 else 4))
             if k <= sub or g.freq_indicator or g.use_fi:      # (the indicator moves consume numpy's GLOBAL generator
                 g.eng.mh_steps(k, draw(0, k))                  #  chain by chain: keep that order)
             else:
